@@ -1,0 +1,86 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (/root/reference).
+
+TEST INFRASTRUCTURE.  Run in the build container only (the reference tree does not exist
+on the GPU box):
+
+    python -m oracle.make_golden            # all cases of tests/cases.py
+    python -m oracle.make_golden tiny_all   # one case
+
+Each fixture stores the sha256 of the synthetic inputs it was made from, the
+representations a plugin sees every analysed frame (wrapped / unwrapped lipid COMs,
+membrane COM, leaflet labels, and for grid cases the lipid grids of both
+lipid_grid_opt.py -- what BilayerAnalyzer builds -- and the exact lipid_grid.py), and
+``get_analysis_data`` of every analysis.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh          # noqa: E402
+from tests import cases                       # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def make(name: str) -> str:
+    c = cases.CASES[name]
+    top, traj = cases.make_inputs(name)
+    wants_grid = any(a.split()[0] in ("apl_grid", "thickness_grid") for a in c["analyses"])
+    out, frames, ba = rh.run_reference(top, traj, analyses=c["analyses"],
+                                       rep_settings=c.get("rep_settings"),
+                                       frame_range=c.get("frame_range"),
+                                       settings=c.get("settings"), capture_grid=wants_grid)
+    flat = cases.flatten_outputs(out)
+    N = len(frames[0]["com"])
+    labels = np.zeros((len(frames), N), dtype=np.uint8)
+    for f, fr in enumerate(frames):
+        labels[f][fr["upper"]] = 1
+        assert len(fr["upper"]) + len(fr["lower"]) == N
+    flat["rep/com"] = np.array([fr["com"] for fr in frames])
+    flat["rep/com_unwrap"] = np.array([fr["com_unwrap"] for fr in frames])
+    flat["rep/mem_com"] = np.array([fr["mem_com"] for fr in frames])
+    flat["rep/mass"] = frames[0]["mass"]
+    flat["rep/labels"] = labels
+    flat["rep/time"] = np.array([fr["time"] for fr in frames])
+    flat["rep/u_last"] = frames[-1]["u"]
+    flat["rep/types"] = np.array(frames[0]["types"])
+    if wants_grid:
+        import pybilt.lipid_grid.lipid_grid as lg_exact
+        for leaf in ("upper", "lower"):
+            flat[f"rep/grid_{leaf}"] = np.array([fr["grid_" + leaf] for fr in frames])
+            flat[f"rep/gridz_{leaf}"] = np.array([fr["gridz_" + leaf] for fr in frames])
+        flat["rep/thickness"] = np.array([fr["thickness"] for fr in frames])
+        flat["rep/apl_lipid"] = np.array([fr["apl_lipid"] for fr in frames])
+        # the exact (brute force) grids of lipid_grid.py on the same frames
+        ba2 = rh.make_analyzer(top, traj, [], rep_settings=c.get("rep_settings"),
+                               frame_range=c.get("frame_range"))
+        nx = c["rep_settings"]["lipid_grid"]["n_xbins"]
+        ny = c["rep_settings"]["lipid_grid"]["n_ybins"]
+        ex = {"upper": [], "lower": []}
+        with rh.quiet():
+            for _ in ba2:
+                g = lg_exact.LipidGrids(ba2.reps["com_frame"], ba2.reps["leaflets"], [0, 1],
+                                        nxbins=nx, nybins=ny)
+                for leaf in ex:
+                    ex[leaf].append(np.array(g.leaf_grid[leaf].lipid_grid))
+        for leaf in ex:
+            flat[f"rep/grid_exact_{leaf}"] = np.array(ex[leaf])
+    flat["meta/input_sha256"] = np.array(cases.input_digest(traj))
+    flat["meta/numpy"] = np.array(np.__version__)
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **flat)
+    return path
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(cases.CASES)
+    for n in names:
+        p = make(n)
+        print(n, "->", p, os.path.getsize(p), "bytes")

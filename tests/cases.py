@@ -1,0 +1,110 @@
+"""Parity cases shared by oracle/make_golden.py (which runs the literal reference on them)
+and the tests (which run the oracle port and the CUDA path on the same inputs).
+
+Every case is fully described by a deterministic synthetic bilayer (pybilt_b200.synthetic),
+the analysis strings in the reference's own syntax, and BilayerAnalyzer settings.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from pybilt_b200 import synthetic as syn
+
+MIX3 = (syn.POPC_AA.with_fraction(0.5), syn.DOPE_AA.with_fraction(0.3),
+        syn.TLCL2_AA.with_fraction(0.2))
+CG3 = (syn.POPC.with_fraction(0.5), syn.DOPE.with_fraction(0.3), syn.CHOL.with_fraction(0.2))
+
+ALL6 = ["msd msd_1",
+        "msd msd_up_dope leaflet upper resname DOPE",
+        "msd_multi mm n_tau 3 n_sigma 3",
+        "msd_multi mm_overlap n_tau 4 n_sigma 2",
+        "nnf nnf_a resname_1 DOPE resname_2 POPC leaflet upper n_neighbors 6",
+        "nnf nnf_default",
+        "com_lateral_rdf rdf_pp resname_1 POPC resname_2 POPC leaflet upper n_bins 80 range_outer 40.0",
+        "com_lateral_rdf rdf_pd resname_1 POPC resname_2 DOPE",
+        "com_lateral_rdf rdf_all_d resname_1 all resname_2 DOPE leaflet lower",
+        "apl_grid apl",
+        "thickness_grid bt"]
+
+CASES = {
+    # tiny, everything on, NPT box, mixed masses
+    "tiny_all": dict(
+        spec=syn.BilayerSpec(64, MIX3, seed=7, box_z=72.0, npt=1e-3), n_frames=12,
+        analyses=ALL6, rep_settings={"lipid_grid": {"n_xbins": 8, "n_ybins": 8}}),
+    # stand-in for BASELINE configs[0] (missing sample_bilayer): 600 lipids, 10 frames
+    "c1_sample": dict(
+        spec=syn.config_spec("C1")[0], n_frames=10,
+        analyses=["msd msd_1",
+                  "msd msd_popc resname POPC",
+                  "com_lateral_rdf rdf resname_1 POPC resname_2 POPC leaflet upper n_bins 80 range_outer 40.0",
+                  "nnf nnf_a resname_1 DOPE resname_2 POPC leaflet upper n_neighbors 6"]),
+    # name_dict gather lists, leaflet update interval, strided frame range
+    "name_dict": dict(
+        spec=syn.BilayerSpec(96, MIX3, seed=11, box_z=72.0), n_frames=20,
+        analyses=["msd msd_1", "msd_multi mm n_tau 3 n_sigma 4",
+                  "nnf nnf_a resname_1 POPC resname_2 DOPE n_neighbors 4",
+                  "com_lateral_rdf rdf resname_1 DOPE resname_2 TLCL2 n_bins 30 range_inner 2.0 range_outer 32.0"],
+        rep_settings={"com_frame": {"name_dict": {"POPC": ["P", "N"], "DOPE": ["P", "N"],
+                                                  "TLCL2": ["P1", "P3"]}},
+                      "leaflets": {"update_interval": 3}},
+        frame_range=(2, -2, 2)),
+    # first frames of BASELINE configs[1]: 512-lipid POPC CG bilayer, MSD + multi-origin MSD
+    "c2_prefix": dict(
+        spec=syn.config_spec("C2")[0], n_frames=60,
+        analyses=["msd msd_1", "msd msd_up leaflet upper",
+                  "msd_multi mm n_tau 10 n_sigma 10", "msd_multi mm5 n_tau 20 n_sigma 5"]),
+    # adversarial unwrap: steps comparable with the box, so shifts of several images occur
+    "big_steps": dict(
+        spec=syn.BilayerSpec(32, (syn.POPC_AA,), seed=3, box_z=60.0, step=45.0, z_step=0.1,
+                             bead_jitter=3.0, npt=5e-3, drift=(7.0, -11.0, 0.0)), n_frames=16,
+        analyses=["msd msd_1"]),
+    # lipid grids at >= 1 cell per lipid and at 0.5 cells per lipid (opt != exact there)
+    "grid_dense": dict(
+        spec=syn.BilayerSpec(256, CG3, seed=5), n_frames=3,
+        analyses=["apl_grid apl", "thickness_grid bt"],
+        rep_settings={"lipid_grid": {"n_xbins": 16, "n_ybins": 16}}),
+    "grid_sparse": dict(
+        spec=syn.BilayerSpec(256, CG3, seed=6, lattice_jitter=0.49), n_frames=2,
+        analyses=["apl_grid apl", "thickness_grid bt"],
+        rep_settings={"lipid_grid": {"n_xbins": 8, "n_ybins": 8}}),
+    # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
+    "c3_small": dict(
+        spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,
+        analyses=["com_lateral_rdf rdf_pp resname_1 POPC resname_2 POPC leaflet upper n_bins 80 range_outer 40.0",
+                  "com_lateral_rdf rdf_dc resname_1 DOPE resname_2 CHOL leaflet lower n_bins 80 range_outer 40.0",
+                  "com_lateral_rdf rdf_aa resname_1 all resname_2 all",
+                  "nnf nnf_pd resname_1 POPC resname_2 DOPE",
+                  "nnf nnf_cc resname_1 CHOL resname_2 CHOL leaflet lower n_neighbors 5"]),
+}
+
+
+def make_inputs(name):
+    c = CASES[name]
+    top, traj = syn.generate(c["spec"], c["n_frames"])
+    return top, traj
+
+
+def input_digest(traj) -> str:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(traj.positions).tobytes())
+    h.update(np.ascontiguousarray(traj.dimensions).tobytes())
+    return h.hexdigest()
+
+
+def flatten_outputs(out: dict) -> dict:
+    """analysis outputs -> flat {key: ndarray} (npz friendly)."""
+    flat = {}
+    for a_id, v in out.items():
+        if isinstance(v, dict):
+            for k, arr in v.items():
+                flat[f"out/{a_id}/{k}"] = np.asarray(arr)
+        elif isinstance(v, tuple):
+            flat[f"out/{a_id}/rdf"] = np.asarray(v[0])
+            flat[f"out/{a_id}/bins"] = np.asarray(v[1])
+        elif isinstance(v, list):
+            continue
+        else:
+            flat[f"out/{a_id}"] = np.asarray(v)
+    return flat
