@@ -1,0 +1,160 @@
+/* pbk.h -- C ABI of libpbk, the B200 (sm_100a) kernels behind PyBILT's BilayerAnalyzer
+ * analysis-plugin API (frame-batched lipid reduction hot path).
+ *
+ * Every entry point replaces a piece of the reference's pure-Python per-frame loop; the
+ * file:line each one restates is given beside it (paths relative to the PyBILT tree).
+ * The reference has no FFI of its own (it is 100 % Python), so the binding a maintainer
+ * adds is the ctypes stub shown in INTEGRATION.md; pybilt_b200/_native.py is that stub.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers owned by the caller (allocated e.g. with
+ *     torch.empty(..., device='cuda')); the library allocates nothing that outlives a call;
+ *   - F = analysed frames in this batch, M = selected atoms, N = lipids (COM beads);
+ *   - positions are float32 [F][M][3] exactly as MDAnalysis hands them over, boxes float32
+ *     [F][3], masses float64 [M]; COM outputs float64 [F][N][3]; labels uint8 [F][N]
+ *     (1 = upper, 0 = lower);
+ *   - every call enqueues on the given cudaStream_t (passed as void*) and returns without
+ *     synchronising; data-dependent failures (a lipid exactly on the leaflet mid-plane, an
+ *     image count that does not fit int16) are written to the int32 `status` word the
+ *     caller supplies and reads after synchronising;
+ *   - return value: 0 on success, <0 = PBK_E*; pbk_last_error() gives the text.
+ *     No C++ exception crosses this boundary.
+ */
+#ifndef PBK_H
+#define PBK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBK_ABI_VERSION 1
+
+#define PBK_OK 0
+#define PBK_EINVAL (-1) /* bad argument */
+#define PBK_ECUDA (-2)  /* CUDA runtime error (launch, attribute ...) */
+
+/* bits of the device-side status word */
+#define PBK_ST_IMAGE_OVERFLOW 1 /* |image count| > 32767 or non-positive box length */
+#define PBK_ST_LEAFLET_TIE 2    /* com_unwrap[norm] == zavg: reference raises KeyError('') */
+
+typedef struct pbk_ctx pbk_ctx;
+
+int pbk_abi_version(void);
+int pbk_ctx_create(int device, pbk_ctx **out);
+void pbk_ctx_destroy(pbk_ctx *ctx);
+const char *pbk_last_error(const pbk_ctx *ctx);
+
+/* ---- A1  PBC unwrap ---------------------------------------------------------------------
+ * wrap_coordinates(abc, coord, refcoord)      pybilt/mda_tools/mda_unwrap_vectorized.py:12-93
+ * + the _oldcoords recurrence                 pybilt/bilayer_analyzer/bilayer_analyzer.py:936-954
+ * Per atom and axis: d = f32(x_t - u_{t-1}); image shift s_t from the strict >/< loops
+ * evaluated in float64; u_t = f32(f64(x_t) + s_t*L_t).  Writes the integer image counts
+ * img[F][M][3]; u_state[M][3] (float32) carries u of the last frame in and out so batches
+ * chain.  first_frame != 0: frame 0 of the batch is its own reference (u_0 = x_0). */
+int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
+                      int first_frame, int64_t F, int64_t M, int16_t *img, int32_t *status,
+                      void *stream);
+
+/* ---- A3  membrane centre of mass --------------------------------------------------------
+ * mem_com_k = (f64(u[:,k]) * masses).sum() / masses.sum()   pybilt/bilayer_analyzer/com_frame.py:175-179
+ * evaluated in NumPy's pairwise-summation order so that it is bit-identical (the value is
+ * subtracted from every coordinate before a float32 rounding, com_frame.py:180).  The
+ * summation tree is passed as a plan built by the host (pybilt_b200/pairwise.py):
+ * leaf_start/leaf_len[L] (<=128-element blocks), node_left/node_right[K] (internal nodes,
+ * children numbered leaves 0..L-1 then nodes L..L+K-1, ordered by height),
+ * level_off[H+1] (node ranges per height).  node_vals is scratch [F][L+K][3] float64. */
+int pbk_membrane_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                     const double *mass, int64_t F, int64_t M, const int32_t *leaf_start,
+                     const int32_t *leaf_len, int32_t L, const int32_t *node_left,
+                     const int32_t *node_right, int32_t K, const int32_t *level_off, int32_t H,
+                     double total_mass, double *node_vals, double *mem_com, void *stream);
+
+/* ---- A2 + A4  per-lipid centres of mass -------------------------------------------------
+ * LipidCOM.extract wrapped / unwrapped passes  pybilt/bilayer_analyzer/com_frame.py:43-96,163-185
+ * com_i        = sum_a m_a*f64(x_a)                    / lipid_mass_i   (raw wrapped positions)
+ * com_unwrap_i = sum_a m_a*f64(f32(f64(u_a) - mem_com)) / lipid_mass_i
+ * atoms of lipid i are gather[seg[i] .. seg[i+1]) in that order (gather == NULL: identity,
+ * i.e. lipids are contiguous atom ranges); accumulated in atom order like MDAnalysis'
+ * (pos*w[:,None]).sum(axis=0). */
+int pbk_lipid_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                  const double *mass, const double *mem_com, const int32_t *seg,
+                  const int32_t *gather, const double *lipid_mass, int64_t F, int64_t M, int64_t N,
+                  double *com, double *com_unwrap, void *stream);
+
+/* ---- B1  leaflet assignment -------------------------------------------------------------
+ * BilayerAnalyzer._build_leaflets             pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847
+ * label = 1 (upper) if com_unwrap[norm] > zavg, 0 (lower) if < zavg, zavg = Welford running
+ * mean in lipid order (pybilt/common/running_stats.py:34-52).  Frames whose global index
+ * (frame0 + f) is not a multiple of update_interval copy the previous frame's labels
+ * (bilayer_analyzer.py:969-981); prev_labels[N] is the row before this batch (may be NULL
+ * when frame0 % update_interval == 0). */
+int pbk_leaflets(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N, int norm,
+                 int64_t frame0, int update_interval, const uint8_t *prev_labels,
+                 uint8_t *labels, int32_t *status, void *stream);
+
+/* ---- C1 / C2  mean squared displacement -------------------------------------------------
+ * MSDProtocol.run_analysis / MSDMultiProtocol.run_analysis
+ *                                  pybilt/bilayer_analyzer/analysis_protocols.py:582-667, 781-895
+ * out[p] = mean_{i in idx} |r_{end[p], i} - r_{origin[p], i}|^2 over the two lateral
+ * components lat0, lat1 of com_unwrap.  Single-origin MSD is pairs (0, t); multi-origin
+ * MSD passes one pair per finished time block. */
+int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
+                  const int32_t *idx, int32_t n_idx, int lat0, int lat1,
+                  const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
+                  double *out, void *stream);
+
+/* ---- D1 + D2  COM lateral RDF -----------------------------------------------------------
+ * COMLateralRDFProtocol.run_analysis   pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006
+ * distance_euclidean_pbc               pybilt/common/distance_cutoff_clustering.py:27-71
+ * np.histogram fast path               numpy/lib/_histograms_impl.py
+ * Per frame and per leaflet in leaflet_mask (bit0 upper, bit1 lower) that holds at least one
+ * lipid of type_a and one of type_b (type < 0 = 'all'): every ordered pair i in A, j in B,
+ * i != j, minimum-image lateral distance of the wrapped COMs, binned on edges[n_bins+1]
+ * (the float64 linspace np.histogram builds).  count[n_bins] (uint64) is accumulated;
+ * frame_counts[F][2][3] int32 receives (N_a, N_b, N_leaflet) per frame and leaflet
+ * (upper row 0, lower row 1), N_a = N_b = 0 where the leaflet was skipped. */
+int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+            const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+            int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
+            const double *edges, unsigned long long *count, int32_t *frame_counts, void *stream);
+
+/* ---- D3  nearest-neighbour fraction -----------------------------------------------------
+ * NNFProtocol.run_analysis             pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257
+ * For every lipid i of type_a in a leaflet that holds both types: the k nearest other
+ * members of the leaflet (stable order: equal distances keep ascending lipid index);
+ * n_b[F][N] = number of them of type_b (-1 for lipids that are not reference lipids);
+ * frac[F] = Welford mean over reference lipids (upper members first) of n_b/k, 0 if none. */
+int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+            const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+            int leaflet_mask, int k, int32_t *n_b, double *frac, void *stream);
+
+/* ---- G1 / G2  lipid grids ---------------------------------------------------------------
+ * lipid_grid_opt.LipidGrid2d.__init__ + _knn  pybilt/lipid_grid/lipid_grid_opt.py:155-334,435-468
+ * lipid_grid.LipidGrid2d.__init__ (exact)     pybilt/lipid_grid/lipid_grid.py:150-248
+ * mode 1 ('opt', what BilayerAnalyzer builds): 24 nearest neighbours per lipid, cell (0,0)
+ * exact, every other cell searches the lipid of cell (max(0,cx-1), max(0,cy-1)) and its 24
+ * neighbours; mode 0 ('exact'): nearest lipid of the leaflet per cell.  Grid geometry is
+ * the float32 linspace of NumPy >= 2 (lipid_grid_opt.py:204-227).  grid_idx[F][2][nx][ny]
+ * int32 (leaflet 0 = upper), grid_z[F][2][nx][ny] float64 = com_unwrap[norm] of that lipid.
+ * knn_scratch: int32 [F][N][24] (mode 1 only). */
+int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com_unwrap,
+                   const uint8_t *labels, const float *box, int64_t F, int64_t N, int lat0,
+                   int lat1, int norm, int nx, int ny, int mode, int32_t *knn_scratch,
+                   int32_t *grid_idx, double *grid_z, void *stream);
+
+/* ---- G3  grid reductions ----------------------------------------------------------------
+ * LipidGrids.average_thickness / area_per_lipid   pybilt/lipid_grid/lipid_grid_opt.py:496-526,553-597
+ * thickness[F][2] = (mean, population std) over cells of grid_z[upper]-grid_z[lower];
+ * cells_per_lipid[F][N] int32; apl[F][1+2*T]: composite Welford mean, then per type code
+ * (mean, sample deviation) in the float32/float64 promotion order of the reference. */
+int pbk_grid_reduce(pbk_ctx *ctx, const int32_t *grid_idx, const double *grid_z,
+                    const uint8_t *labels, const int32_t *type_code, const float *box, int64_t F,
+                    int64_t N, int lat0, int lat1, int nx, int ny, int n_types,
+                    int32_t *cells_per_lipid, double *thickness, double *apl, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBK_H */

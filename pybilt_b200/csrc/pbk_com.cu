@@ -1,0 +1,368 @@
+// pbk_com.cu -- unwrap, membrane COM, per-lipid COM, leaflets, MSD (generic multi-kernel path).
+//
+// Reference arithmetic restated here (paths relative to the PyBILT tree):
+//   unwrap        pybilt/mda_tools/mda_unwrap_vectorized.py:12-93
+//   membrane COM  pybilt/bilayer_analyzer/com_frame.py:172-181 (NumPy pairwise sums)
+//   lipid COM     pybilt/bilayer_analyzer/com_frame.py:43-96,163-185 (MDAnalysis center_of_mass)
+//   leaflets      pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847
+//   msd           pybilt/bilayer_analyzer/analysis_protocols.py:582-667, 781-895
+#include "pbk_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// K1  image counts: one thread per atom component, marching over the frames of the batch.
+// Loads are independent of the recurrence, so they are issued UNR frames ahead.
+// ---------------------------------------------------------------------------------------
+#define UNR 8
+
+__device__ __forceinline__ int pbk_image_shift(float x, float uprev, float L, int *bad)
+{
+    float d = __fsub_rn(x, uprev);
+    float h = L * 0.5f;
+    int s = 0;
+    if (!(L > 0.0f)) { *bad = 1; return 0; }
+    double dd = (double)d, Ld = (double)L, hd = (double)h;
+    if (d > h) {
+        do { s -= 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) > hd && s > -32768);
+    } else if (d < -h) {
+        do { s += 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) < -hd && s < 32768);
+    }
+    if (s <= -32768 || s >= 32768) { *bad = 1; s = 0; }
+    return s;
+}
+
+__global__ void __launch_bounds__(128)
+k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, float *u_state,
+                int first_frame, int64_t F, int64_t C, int16_t *__restrict__ img, int32_t *status)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int k = (int)(c % 3);
+    int bad = 0;
+    float up;
+    int64_t t = 0;
+    if (first_frame) {
+        up = x[c];
+        img[c] = 0;
+        t = 1;
+    } else {
+        up = u_state[c];
+    }
+    for (; t + UNR <= F; t += UNR) {
+        float xv[UNR], Lv[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; j++) {
+            xv[j] = __ldg(x + (t + j) * C + c);
+            Lv[j] = __ldg(box + (t + j) * 3 + k);
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; j++) {
+            int s = pbk_image_shift(xv[j], up, Lv[j], &bad);
+            up = pbk_unwrapped(xv[j], s, Lv[j]);
+            img[(t + j) * C + c] = (int16_t)s;
+        }
+    }
+    for (; t < F; t++) {
+        float xv = __ldg(x + t * C + c), L = __ldg(box + t * 3 + k);
+        int s = pbk_image_shift(xv, up, L, &bad);
+        up = pbk_unwrapped(xv, s, L);
+        img[t * C + c] = (int16_t)s;
+    }
+    u_state[c] = up;
+    if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
+}
+
+extern "C" int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
+                                 int first_frame, int64_t F, int64_t M, int16_t *img,
+                                 int32_t *status, void *stream)
+{
+    if (!ctx || !x || !box || !u_state || !img || !status || F < 0 || M <= 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_unwrap_images: bad argument");
+    if (F == 0) return PBK_OK;
+    int64_t C = 3 * M;
+    int threads = 128;
+    int64_t blocks = (C + threads - 1) / threads;
+    k_unwrap_images<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        x, box, u_state, first_frame, F, C, img, status);
+    PBK_CHECK_LAUNCH(ctx, "k_unwrap_images");
+    return PBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2  membrane COM, step 1: NumPy pairwise leaf sums.  One warp per (frame, leaf); lanes
+// 0..23 = 8 accumulator lanes x 3 axes reading 96 contiguous bytes per step.
+//   r[j] = a[j]; for i = 8; i < n - n%8; i += 8: r[j] += a[i+j];
+//   res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); then the n%8 tail sequentially.
+// with a[i] = m_i * f64(u_i).   n < 8: res = 0 + a0 + a1 + ... sequentially.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mem_leaf_sums(const float *__restrict__ x, const float *__restrict__ box,
+                const int16_t *__restrict__ img, const double *__restrict__ mass, int64_t F,
+                int64_t M, const int32_t *__restrict__ leaf_start,
+                const int32_t *__restrict__ leaf_len, int32_t L, int32_t nodes_per_frame,
+                double *__restrict__ node_vals)
+{
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= F * (int64_t)L) return;
+    int64_t f = w / L;
+    int leaf = (int)(w % L);
+    int start = leaf_start[leaf], n = leaf_len[leaf];
+    int j = lane / 3, k = lane % 3;             // accumulator lane, axis (lanes >= 24 idle)
+    bool act = lane < 24;
+    const float *xf = x + (f * M + start) * 3;
+    const int16_t *sf = img + (f * M + start) * 3;
+    const double *mf = mass + start;
+    float Lk = box[f * 3 + k];
+    double r = 0.0;
+    int nfull = n - (n % 8);
+    if (n >= 8 && act) {
+        r = __dmul_rn(mf[j], (double)pbk_unwrapped(xf[j * 3 + k], sf[j * 3 + k], Lk));
+        for (int i = 8; i < nfull; i += 8) {
+            int a = i + j;
+            double p = __dmul_rn(mf[a], (double)pbk_unwrapped(xf[a * 3 + k], sf[a * 3 + k], Lk));
+            r = __dadd_rn(r, p);
+        }
+    }
+    // butterfly over the accumulator index j (lane = 3*j + k): j^1, j^2, j^4
+    {
+        int src1 = ((j ^ 1) * 3 + k) & 31, src2 = ((j ^ 2) * 3 + k) & 31, src4 = ((j ^ 4) * 3 + k) & 31;
+        double o = __shfl_sync(0xffffffffu, r, act ? src1 : lane);
+        r = __dadd_rn(r, o);
+        o = __shfl_sync(0xffffffffu, r, act ? src2 : lane);
+        r = __dadd_rn(r, o);
+        o = __shfl_sync(0xffffffffu, r, act ? src4 : lane);
+        r = __dadd_rn(r, o);
+    }
+    if (lane < 3) {
+        int i0 = nfull;
+        if (n < 8) { r = 0.0; i0 = 0; }
+        for (int i = i0; i < n; i++) {
+            double p = __dmul_rn(mf[i], (double)pbk_unwrapped(xf[i * 3 + k], sf[i * 3 + k], Lk));
+            r = __dadd_rn(r, p);
+        }
+        node_vals[(f * nodes_per_frame + leaf) * 3 + k] = r;
+    }
+}
+
+// K2b  step 2: combine the leaf sums along the recursion tree, level by level.
+__global__ void __launch_bounds__(256)
+k_mem_tree(const int32_t *__restrict__ node_left, const int32_t *__restrict__ node_right,
+           const int32_t *__restrict__ level_off, int32_t H, int32_t L, int32_t K,
+           double total_mass, double *__restrict__ node_vals, double *__restrict__ mem_com)
+{
+    int64_t f = blockIdx.x;
+    double *v = node_vals + f * (int64_t)(L + K) * 3;
+    for (int h = 0; h < H; h++) {
+        int a = level_off[h], b = level_off[h + 1];
+        for (int w = threadIdx.x; w < (b - a) * 3; w += blockDim.x) {
+            int node = a + w / 3, k = w % 3;
+            v[(L + node) * 3 + k] = __dadd_rn(v[node_left[node] * 3 + k], v[node_right[node] * 3 + k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) {
+        int root = L + K - 1;
+        mem_com[f * 3 + threadIdx.x] = __ddiv_rn(v[root * 3 + threadIdx.x], total_mass);
+    }
+}
+
+extern "C" int pbk_membrane_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                                const double *mass, int64_t F, int64_t M,
+                                const int32_t *leaf_start, const int32_t *leaf_len, int32_t L,
+                                const int32_t *node_left, const int32_t *node_right, int32_t K,
+                                const int32_t *level_off, int32_t H, double total_mass,
+                                double *node_vals, double *mem_com, void *stream)
+{
+    if (!ctx || !x || !box || !img || !mass || !leaf_start || !leaf_len || !node_vals || !mem_com ||
+        F < 0 || M <= 0 || L <= 0 || K < 0 || (K > 0 && (!node_left || !node_right || !level_off)))
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_membrane_com: bad argument");
+    if (F == 0) return PBK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t warps = F * (int64_t)L;
+    int64_t blocks = (warps * 32 + 255) / 256;
+    k_mem_leaf_sums<<<(unsigned)blocks, 256, 0, st>>>(x, box, img, mass, F, M, leaf_start, leaf_len,
+                                                      L, L + K, node_vals);
+    PBK_CHECK_LAUNCH(ctx, "k_mem_leaf_sums");
+    k_mem_tree<<<(unsigned)F, 256, 0, st>>>(node_left, node_right, level_off, H, L, K, total_mass,
+                                            node_vals, mem_com);
+    PBK_CHECK_LAUNCH(ctx, "k_mem_tree");
+    return PBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3  per-lipid COM, wrapped (raw x) and unwrapped (v = f32(f64(u) - mem_com)), one thread
+// per (frame, lipid), atoms accumulated in list order.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_lipid_com(const float *__restrict__ x, const float *__restrict__ box,
+            const int16_t *__restrict__ img, const double *__restrict__ mass,
+            const double *__restrict__ mem_com, const int32_t *__restrict__ seg,
+            const int32_t *__restrict__ gather, const double *__restrict__ lipid_mass, int64_t F,
+            int64_t M, int64_t N, double *__restrict__ com, double *__restrict__ com_unwrap)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= F * N) return;
+    int64_t f = g / N;
+    int i = (int)(g % N);
+    const float *xf = x + f * M * 3;
+    const int16_t *sf = img + f * M * 3;
+    float L0 = box[f * 3], L1 = box[f * 3 + 1], L2 = box[f * 3 + 2];
+    double m0 = mem_com[f * 3], m1 = mem_com[f * 3 + 1], m2 = mem_com[f * 3 + 2];
+    double c0 = 0, c1 = 0, c2 = 0, w0 = 0, w1 = 0, w2 = 0;
+    int a0 = seg[i], a1 = seg[i + 1];
+    for (int p = a0; p < a1; p++) {
+        int a = gather ? gather[p] : p;
+        double m = mass[a];
+        float x0 = xf[a * 3], x1 = xf[a * 3 + 1], x2 = xf[a * 3 + 2];
+        c0 = __dadd_rn(c0, __dmul_rn((double)x0, m));
+        c1 = __dadd_rn(c1, __dmul_rn((double)x1, m));
+        c2 = __dadd_rn(c2, __dmul_rn((double)x2, m));
+        float u0 = pbk_unwrapped(x0, sf[a * 3], L0);
+        float u1 = pbk_unwrapped(x1, sf[a * 3 + 1], L1);
+        float u2 = pbk_unwrapped(x2, sf[a * 3 + 2], L2);
+        float v0 = __double2float_rn(__dsub_rn((double)u0, m0));
+        float v1 = __double2float_rn(__dsub_rn((double)u1, m1));
+        float v2 = __double2float_rn(__dsub_rn((double)u2, m2));
+        w0 = __dadd_rn(w0, __dmul_rn((double)v0, m));
+        w1 = __dadd_rn(w1, __dmul_rn((double)v1, m));
+        w2 = __dadd_rn(w2, __dmul_rn((double)v2, m));
+    }
+    double lm = lipid_mass[i];
+    double *co = com + g * 3, *cu = com_unwrap + g * 3;
+    co[0] = __ddiv_rn(c0, lm); co[1] = __ddiv_rn(c1, lm); co[2] = __ddiv_rn(c2, lm);
+    cu[0] = __ddiv_rn(w0, lm); cu[1] = __ddiv_rn(w1, lm); cu[2] = __ddiv_rn(w2, lm);
+}
+
+extern "C" int pbk_lipid_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                             const double *mass, const double *mem_com, const int32_t *seg,
+                             const int32_t *gather, const double *lipid_mass, int64_t F, int64_t M,
+                             int64_t N, double *com, double *com_unwrap, void *stream)
+{
+    if (!ctx || !x || !box || !img || !mass || !mem_com || !seg || !lipid_mass || !com ||
+        !com_unwrap || F < 0 || M <= 0 || N <= 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_lipid_com: bad argument");
+    if (F == 0) return PBK_OK;
+    int64_t total = F * N;
+    int64_t blocks = (total + 127) / 128;
+    k_lipid_com<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+        x, box, img, mass, mem_com, seg, gather, lipid_mass, F, M, N, com, com_unwrap);
+    PBK_CHECK_LAUNCH(ctx, "k_lipid_com");
+    return PBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K4  leaflets.  One CTA per frame.  The label only depends on the sign of z - zavg, so a
+// tree mean decides every lipid that is further from it than the worst-case difference
+// between the tree mean and the reference's sequential Welford mean; if any lipid is
+// closer, thread 0 replays the sequential Welford recurrence and all lipids are compared
+// with that exact value.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_leaflets(const double *__restrict__ com_unwrap, int64_t F, int64_t N, int norm, int64_t frame0,
+           int interval, const uint8_t *__restrict__ prev, uint8_t *__restrict__ labels,
+           int32_t *status)
+{
+    __shared__ double red[32];
+    __shared__ double zexact;
+    __shared__ int need_exact;
+    int64_t f = blockIdx.x;
+    int64_t g = frame0 + f;
+    int64_t src = g - (g % interval);
+    uint8_t *out = labels + f * N;
+    if (src < frame0) {
+        // copied from the row before this batch (or from an earlier copy of it)
+        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) out[i] = prev ? prev[i] : 0;
+        return;
+    }
+    const double *z = com_unwrap + (src - frame0) * N * 3 + norm;
+    double s = 0.0, mx = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        double v = z[i * 3];
+        s += v;
+        mx = fmax(mx, fabs(v));
+    }
+    s = pbk_block_sum(s, red);
+    mx = pbk_block_max(mx, red);
+    double mean = s / (double)N;
+    double tol = 64.0 * (double)N * 2.220446049250313e-16 * mx;
+    if (threadIdx.x == 0) need_exact = 0;
+    __syncthreads();
+    int close = 0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x)
+        if (fabs(z[i * 3] - mean) <= tol) close = 1;
+    if (close) need_exact = 1;
+    __syncthreads();
+    if (need_exact) {
+        if (threadIdx.x == 0) {
+            double m = 0.0;                       // running_stats.py:34-52
+            for (int64_t i = 0; i < N; i++) {
+                double v = z[i * 3];
+                m = (i == 0) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)(i + 1)));
+            }
+            zexact = m;
+        }
+        __syncthreads();
+        mean = zexact;
+    }
+    int tie = 0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        double v = z[i * 3];
+        if (v > mean) out[i] = 1;
+        else if (v < mean) out[i] = 0;
+        else { out[i] = 0; tie = 1; }
+    }
+    if (tie) atomicOr(status, PBK_ST_LEAFLET_TIE);
+}
+
+extern "C" int pbk_leaflets(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N, int norm,
+                            int64_t frame0, int update_interval, const uint8_t *prev_labels,
+                            uint8_t *labels, int32_t *status, void *stream)
+{
+    if (!ctx || !com_unwrap || !labels || !status || F < 0 || N <= 0 || norm < 0 || norm > 2 ||
+        update_interval < 1 || frame0 < 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_leaflets: bad argument");
+    if (F == 0) return PBK_OK;
+    k_leaflets<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(com_unwrap, F, N, norm, frame0,
+                                                             update_interval, prev_labels, labels,
+                                                             status);
+    PBK_CHECK_LAUNCH(ctx, "k_leaflets");
+    return PBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K5  MSD over (origin, end) frame pairs; one CTA per pair, fixed-order tree mean.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_msd_pairs(const double *__restrict__ cu, int64_t N, const int32_t *__restrict__ idx, int32_t n,
+            int lat0, int lat1, const int32_t *__restrict__ po, const int32_t *__restrict__ pe,
+            double *__restrict__ out)
+{
+    __shared__ double red[32];
+    int p = blockIdx.x;
+    const double *a = cu + (int64_t)pe[p] * N * 3;
+    const double *b = cu + (int64_t)po[p] * N * 3;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int64_t i = idx[t];
+        double dx = __dsub_rn(a[i * 3 + lat0], b[i * 3 + lat0]);
+        double dy = __dsub_rn(a[i * 3 + lat1], b[i * 3 + lat1]);
+        s += __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    }
+    s = pbk_block_sum(s, red);
+    if (threadIdx.x == 0) out[p] = n > 0 ? s / (double)n : 0.0;
+}
+
+extern "C" int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
+                             const int32_t *idx, int32_t n_idx, int lat0, int lat1,
+                             const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
+                             double *out, void *stream)
+{
+    if (!ctx || !com_unwrap || !idx || !pair_origin || !pair_end || !out || F <= 0 || N <= 0 ||
+        n_idx < 0 || n_pairs < 0 || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_msd_pairs: bad argument");
+    if (n_pairs == 0) return PBK_OK;
+    k_msd_pairs<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
+        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out);
+    PBK_CHECK_LAUNCH(ctx, "k_msd_pairs");
+    return PBK_OK;
+}

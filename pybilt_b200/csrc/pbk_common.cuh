@@ -1,0 +1,93 @@
+// pbk_common.cuh -- shared device helpers of libpbk (sm_100a).
+//
+// Arithmetic contract (see DESIGN.md "Arithmetic"): the library is compiled with
+// -fmad=false so that no multiply-add is fused behind our back; the only fused operation
+// is the explicit fma() in pbc_dist2(), which restates the FMA accumulation OpenBLAS' ddot
+// performs for the reference's np.dot(d_v, d_v).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pbk.h"
+
+struct pbk_ctx {
+    int device;
+    int sm_count;
+    char err[512];
+};
+
+#define PBK_WARP 32
+
+__device__ __forceinline__ float pbk_unwrapped(float x, int s, float L)
+{
+    // u = f32(f64(x) + s*L)      mda_unwrap_vectorized.py:49,70,92
+    return s == 0 ? x : __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)s, (double)L)));
+}
+
+// distance_euclidean_pbc(a, b, l_box, center='box_half') with a' = a - c, b' = b - c already
+// formed (c = f32 box / 2).  Returns d^2 = fma(dy, dy, dx*dx); distance_cutoff_clustering.py:50-70.
+__device__ __forceinline__ double pbk_pbc_dist2(double apx, double apy, double bpx, double bpy,
+                                                double Lx, double Ly, double hx, double hy)
+{
+    double dx = __dsub_rn(apx, bpx);
+    double dy = __dsub_rn(apy, bpy);
+    if (fabs(dx) > hx) dx = __dsub_rn(__dsub_rn(Lx, fabs(apx)), fabs(bpx));
+    if (fabs(dy) > hy) dy = __dsub_rn(__dsub_rn(Ly, fabs(apy)), fabs(bpy));
+    return fma(dy, dy, __dmul_rn(dx, dx));
+}
+
+// np.histogram uniform-bin rule (numpy/lib/_histograms_impl.py): -1 when out of range.
+__device__ __forceinline__ int pbk_hist_bin(double r, double lo, double hi, int nb,
+                                            const double *edges)
+{
+    if (!(r >= lo) || !(r <= hi)) return -1;
+    double f = __dmul_rn(__ddiv_rn(__dsub_rn(r, lo), __dsub_rn(hi, lo)), (double)nb);
+    int k = (int)f;
+    if (k == nb) k -= 1;
+    if (r < edges[k]) k -= 1;
+    else if (r >= edges[k + 1] && k != nb - 1) k += 1;
+    return k;
+}
+
+template <typename T>
+__device__ __forceinline__ T pbk_warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum (fixed tree), result valid in every thread; red must hold 32 T's
+template <typename T>
+__device__ __forceinline__ T pbk_block_sum(T v, T *red)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = pbk_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    T t = (lane < nw) ? red[lane] : T(0);
+    t = pbk_warp_sum(t);
+    return t;
+}
+
+__device__ __forceinline__ double pbk_block_max(double v, double *red)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (lane < nw) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+
+int pbk_fail(pbk_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
+#define PBK_CHECK_LAUNCH(ctx, name)                                      \
+    do {                                                                 \
+        cudaError_t _e = cudaGetLastError();                             \
+        if (_e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, name, _e); \
+    } while (0)

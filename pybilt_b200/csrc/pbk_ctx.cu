@@ -1,0 +1,40 @@
+// pbk_ctx.cu -- context handling and error reporting of libpbk.
+#include <stdio.h>
+#include <string.h>
+
+#include "pbk_common.cuh"
+
+int pbk_fail(pbk_ctx *ctx, int code, const char *what, cudaError_t e)
+{
+    if (ctx) {
+        if (e != cudaSuccess)
+            snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(ctx->err, sizeof(ctx->err), "%s", what);
+    }
+    return code;
+}
+
+extern "C" int pbk_abi_version(void) { return PBK_ABI_VERSION; }
+
+extern "C" int pbk_ctx_create(int device, pbk_ctx **out)
+{
+    if (!out) return PBK_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) return PBK_ECUDA;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return PBK_ECUDA;
+    pbk_ctx *c = new pbk_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->err[0] = 0;
+    *out = c;
+    return PBK_OK;
+}
+
+extern "C" void pbk_ctx_destroy(pbk_ctx *ctx) { delete ctx; }
+
+extern "C" const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err : "null context"; }

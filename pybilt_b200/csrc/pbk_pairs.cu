@@ -1,0 +1,266 @@
+// pbk_pairs.cu -- minimum-image lateral pair work per leaflet: COM lateral RDF histograms and
+// nearest-neighbour fractions.
+//
+// Reference arithmetic restated here (paths relative to the PyBILT tree):
+//   distance       pybilt/common/distance_cutoff_clustering.py:27-71
+//   com_lateral_rdf pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006
+//   nnf            pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257
+#include "pbk_common.cuh"
+
+#define PAIR_TJ 1024         // lipids staged in shared memory per tile
+#define PAIR_THREADS 256
+
+// class byte of a lipid in a frame: bit0 = leaflet label, bit1 = is type A, bit2 = is type B
+__device__ __forceinline__ unsigned pbk_cls(uint8_t label, int type, int ta, int tb)
+{
+    return (unsigned)(label & 1) | ((ta < 0 || type == ta) ? 2u : 0u) | ((tb < 0 || type == tb) ? 4u : 0u);
+}
+
+// counts[leaf][0..2] = (N_a, N_b, N_leaflet) of the frame; every thread gets the result
+__device__ void pbk_frame_class_counts(const uint8_t *lab, const int32_t *type_code, int64_t N,
+                                       int ta, int tb, int *sh_counts /*[6]*/)
+{
+    if (threadIdx.x < 6) sh_counts[threadIdx.x] = 0;
+    __syncthreads();
+    int c[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned cl = pbk_cls(lab[i], type_code[i], ta, tb);
+        int leaf = (cl & 1) ? 0 : 1;                 // row 0 = upper (label 1), row 1 = lower
+        c[leaf * 3 + 0] += (cl >> 1) & 1;
+        c[leaf * 3 + 1] += (cl >> 2) & 1;
+        c[leaf * 3 + 2] += 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        int v = pbk_warp_sum(c[q]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh_counts[q], v);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// K6  RDF.  grid = (frames, i-tiles); each thread owns one reference lipid i and sweeps all
+// j staged through shared memory; bins go to warp-private shared histograms.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAIR_THREADS)
+k_rdf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
+      const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N, int lat0,
+      int lat1, int ta, int tb, int leaflet_mask, int nb, double lo, double hi,
+      const double *__restrict__ edges, unsigned long long *__restrict__ count,
+      int32_t *__restrict__ frame_counts, int hist_copies)
+{
+    extern __shared__ unsigned char smem_raw[];
+    double *s_edges = reinterpret_cast<double *>(smem_raw);                 // nb+1
+    double *s_px = s_edges + (nb + 1);                                      // PAIR_TJ
+    double *s_py = s_px + PAIR_TJ;                                          // PAIR_TJ
+    unsigned *s_hist = reinterpret_cast<unsigned *>(s_py + PAIR_TJ);        // hist_copies*nb
+    unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_hist + (size_t)hist_copies * nb);
+    __shared__ int sh_counts[6];
+
+    int64_t f = blockIdx.x;
+    const double *cf = com + f * N * 3;
+    const uint8_t *lab = labels + f * N;
+    float bxf = box[f * 3 + lat0], byf = box[f * 3 + lat1];
+    float cxf = bxf * 0.5f, cyf = byf * 0.5f;
+    double Lx = (double)bxf, Ly = (double)byf, hx = (double)cxf, hy = (double)cyf;
+
+    for (int q = threadIdx.x; q <= nb; q += blockDim.x) s_edges[q] = edges[q];
+    for (int q = threadIdx.x; q < hist_copies * nb; q += blockDim.x) s_hist[q] = 0u;
+    pbk_frame_class_counts(lab, type_code, N, ta, tb, sh_counts);
+    // a leaflet takes part iff selected and it holds both groups (has_group, :4965)
+    bool leaf_on[2];
+    for (int l = 0; l < 2; l++)
+        leaf_on[l] = ((leaflet_mask >> l) & 1) && sh_counts[l * 3 + 0] > 0 && sh_counts[l * 3 + 1] > 0;
+    if (blockIdx.y == 0 && threadIdx.x < 6) {
+        int l = threadIdx.x / 3, q = threadIdx.x % 3;
+        int v = sh_counts[threadIdx.x];
+        if (q < 2 && !leaf_on[l]) v = 0;
+        if (q == 2 && !((leaflet_mask >> l) & 1)) v = 0;
+        frame_counts[f * 6 + threadIdx.x] = v;
+    }
+
+    int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    bool iact = false;
+    double apx = 0, apy = 0;
+    unsigned icl = 0;
+    if (i < N) {
+        icl = pbk_cls(lab[i], type_code[i], ta, tb);
+        int leaf = (icl & 1) ? 0 : 1;
+        iact = (icl & 2u) && leaf_on[leaf];
+        apx = __dsub_rn(cf[i * 3 + lat0], hx);
+        apy = __dsub_rn(cf[i * 3 + lat1], hy);
+    }
+    unsigned *myhist = s_hist + (size_t)((threadIdx.x >> 5) % hist_copies) * nb;
+
+    for (int64_t j0 = 0; j0 < N; j0 += PAIR_TJ) {
+        int tj = (int)min((int64_t)PAIR_TJ, N - j0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < tj; q += blockDim.x) {
+            int64_t j = j0 + q;
+            s_px[q] = __dsub_rn(cf[j * 3 + lat0], hx);
+            s_py[q] = __dsub_rn(cf[j * 3 + lat1], hy);
+            s_cls[q] = (unsigned char)pbk_cls(lab[j], type_code[j], ta, tb);
+        }
+        __syncthreads();
+        if (iact) {
+            for (int q = 0; q < tj; q++) {
+                unsigned jc = s_cls[q];
+                if (!(jc & 4u) || ((jc ^ icl) & 1u) || (j0 + q) == i) continue;
+                double d2 = pbk_pbc_dist2(apx, apy, s_px[q], s_py[q], Lx, Ly, hx, hy);
+                double r = sqrt(d2);
+                int k = pbk_hist_bin(r, lo, hi, nb, s_edges);
+                if (k >= 0) atomicAdd(&myhist[k], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nb; q += blockDim.x) {
+        unsigned long long t = 0;
+        for (int c = 0; c < hist_copies; c++) t += s_hist[(size_t)c * nb + q];
+        if (t) atomicAdd(&count[q], t);
+    }
+}
+
+extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
+                       const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
+                       int lat1, int type_a, int type_b, int leaflet_mask, int32_t n_bins,
+                       double range_lo, double range_hi, const double *edges,
+                       unsigned long long *count, int32_t *frame_counts, void *stream)
+{
+    if (!ctx || !com || !labels || !type_code || !box || !edges || !count || !frame_counts ||
+        F < 0 || N <= 0 || n_bins <= 0 || !(range_hi > range_lo) || (leaflet_mask & ~3) ||
+        lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: bad argument");
+    if (F == 0) return PBK_OK;
+    int warps = PAIR_THREADS / 32;
+    int copies = warps;
+    auto smem_for = [&](int c) {
+        return (size_t)(n_bins + 1) * 8 + (size_t)PAIR_TJ * 16 + (size_t)c * n_bins * 4 + PAIR_TJ;
+    };
+    while (copies > 1 && smem_for(copies) > 96 * 1024) copies >>= 1;
+    size_t smem = smem_for(copies);
+    if (smem > 200 * 1024) return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: n_bins too large");
+    cudaError_t e = cudaFuncSetAttribute(k_rdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_rdf smem attribute", e);
+    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
+    k_rdf<<<grid, PAIR_THREADS, smem, (cudaStream_t)stream>>>(
+        com, labels, type_code, box, N, lat0, lat1, type_a, type_b, leaflet_mask, n_bins, range_lo,
+        range_hi, edges, count, frame_counts, copies);
+    PBK_CHECK_LAUNCH(ctx, "k_rdf");
+    return PBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K7  NNF.  One thread per reference lipid keeps the k best (distance, is-type-b) entries
+// in ascending order; a candidate is inserted only if strictly closer than the current
+// k-th, and behind entries of equal distance (Python's stable sort over candidates
+// visited in ascending lipid index).
+// ---------------------------------------------------------------------------------------
+#define NNF_KMAX 64
+
+__global__ void __launch_bounds__(PAIR_THREADS)
+k_nnf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
+      const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N, int lat0,
+      int lat1, int ta, int tb, int leaflet_mask, int k, int32_t *__restrict__ n_b)
+{
+    __shared__ double s_px[PAIR_TJ], s_py[PAIR_TJ];
+    __shared__ unsigned char s_cls[PAIR_TJ];
+    __shared__ int sh_counts[6];
+    int64_t f = blockIdx.x;
+    const double *cf = com + f * N * 3;
+    const uint8_t *lab = labels + f * N;
+    float bxf = box[f * 3 + lat0], byf = box[f * 3 + lat1];
+    float cxf = bxf * 0.5f, cyf = byf * 0.5f;
+    double Lx = (double)bxf, Ly = (double)byf, hx = (double)cxf, hy = (double)cyf;
+    pbk_frame_class_counts(lab, type_code, N, ta, tb, sh_counts);
+    bool leaf_on[2];
+    for (int l = 0; l < 2; l++)
+        leaf_on[l] = ((leaflet_mask >> l) & 1) && sh_counts[l * 3 + 0] > 0 && sh_counts[l * 3 + 1] > 0;
+
+    int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    bool iact = false;
+    double apx = 0, apy = 0;
+    unsigned icl = 0;
+    if (i < N) {
+        icl = pbk_cls(lab[i], type_code[i], ta, tb);
+        iact = (icl & 2u) && leaf_on[(icl & 1) ? 0 : 1];
+        apx = __dsub_rn(cf[i * 3 + lat0], hx);
+        apy = __dsub_rn(cf[i * 3 + lat1], hy);
+    }
+    double best[NNF_KMAX];
+    unsigned long long bmask = 0ull;      // bit t = entry t is of type b
+    int nbest = 0;
+    for (int64_t j0 = 0; j0 < N; j0 += PAIR_TJ) {
+        int tj = (int)min((int64_t)PAIR_TJ, N - j0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < tj; q += blockDim.x) {
+            int64_t j = j0 + q;
+            s_px[q] = __dsub_rn(cf[j * 3 + lat0], hx);
+            s_py[q] = __dsub_rn(cf[j * 3 + lat1], hy);
+            s_cls[q] = (unsigned char)pbk_cls(lab[j], type_code[j], ta, tb);
+        }
+        __syncthreads();
+        if (iact) {
+            for (int q = 0; q < tj; q++) {
+                unsigned jc = s_cls[q];
+                if (((jc ^ icl) & 1u) || (j0 + q) == i) continue;
+                double r = sqrt(pbk_pbc_dist2(apx, apy, s_px[q], s_py[q], Lx, Ly, hx, hy));
+                if (nbest == k && !(r < best[k - 1])) continue;
+                int pos = nbest < k ? nbest : k - 1;          // slot that is freed / appended
+                while (pos > 0 && best[pos - 1] > r) pos--;
+                // shift entries [pos, last) one slot up
+                int last = nbest < k ? nbest : k - 1;
+                for (int t = last; t > pos; t--) best[t] = best[t - 1];
+                unsigned long long lowm = (pos == 0) ? 0ull : ((~0ull) >> (64 - pos));
+                unsigned long long keep = bmask & lowm;
+                unsigned long long up = (bmask & ~lowm) << 1;
+                bmask = keep | up | (((jc >> 2) & 1ull) << pos);
+                if (k < 64) bmask &= ((1ull << k) - 1ull);
+                best[pos] = r;
+                if (nbest < k) nbest++;
+            }
+        }
+    }
+    if (i < N) n_b[f * N + i] = iact ? __popcll(bmask) : -1;
+}
+
+// Welford mean of n_b/k over the reference lipids of a frame, upper members first
+// (analysis_protocols.py:2219-2250); one thread per frame.
+__global__ void k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels,
+                                 int64_t F, int64_t N, int k, double *__restrict__ frac)
+{
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int32_t *c = n_b + f * N;
+    const uint8_t *lab = labels + f * N;
+    double m = 0.0;
+    int64_t n = 0;
+    for (int pass = 1; pass >= 0; pass--) {
+        for (int64_t i = 0; i < N; i++) {
+            if (lab[i] != pass || c[i] < 0) continue;
+            double v = __ddiv_rn((double)c[i], (double)k);
+            n++;
+            m = (n == 1) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)n));
+        }
+    }
+    frac[f] = m;
+}
+
+extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
+                       const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
+                       int lat1, int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b,
+                       double *frac, void *stream)
+{
+    if (!ctx || !com || !labels || !type_code || !box || !n_b || !frac || F < 0 || N <= 0 ||
+        k < 1 || k > NNF_KMAX || (leaflet_mask & ~3) || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_nnf: bad argument (1 <= k <= 64)");
+    if (F == 0) return PBK_OK;
+    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
+    k_nnf<<<grid, PAIR_THREADS, 0, (cudaStream_t)stream>>>(com, labels, type_code, box, N, lat0,
+                                                           lat1, type_a, type_b, leaflet_mask, k, n_b);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf");
+    k_nnf_frame_mean<<<(unsigned)((F + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N,
+                                                                                  k, frac);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
+    return PBK_OK;
+}

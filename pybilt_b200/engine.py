@@ -1,0 +1,257 @@
+"""Device-resident lipid reduction: frames in, per-lipid COMs / leaflets / analyses out.
+
+This is the frame-batched replacement of the body of ``BilayerAnalyzer.__next__``
+(pybilt/bilayer_analyzer/bilayer_analyzer.py:901-1031): instead of one Python iteration
+per frame, the analysed frames are pushed through libpbk (include/pbk.h) in batches and
+the representations every analysis plugin reads -- wrapped and unwrapped lipid COMs,
+membrane COM, leaflet labels -- stay resident in HBM for the plugins' kernels.
+
+PyTorch is used for device buffers, streams and copies only; every computation on the hot
+path is a libpbk kernel.  No CPU fallback exists: constructing an engine without a CUDA
+device raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from .pairwise import build_plan
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class BeadLayout:
+    """Which atoms make up each COM bead (lipid): CSR ``seg`` into ``gather``.
+
+    default (``name_dict`` None): one bead per residue over all its atoms, contiguous
+    (com_frame.py:163-168); ``name_dict``: atoms named name_dict[resname][0], then [1], ...
+    (com_frame.py:63-77); ``multi_bead``: one bead per listed name (com_frame.py:188-231).
+    """
+    seg: np.ndarray            # int32 [N+1]
+    gather: Optional[np.ndarray]   # int32 [T] or None when beads are contiguous atom ranges
+    types: List[str]           # resname of every bead
+    resids: np.ndarray         # int64 [N]
+    bead_mass: np.ndarray      # f64 [N]  = masses[atoms].sum()  (LipidCOM.mass, com_frame.py:95)
+
+    @property
+    def n_beads(self) -> int:
+        return len(self.types)
+
+
+def build_bead_layout(masses, names, resindex, resnames, resids, name_dict=None,
+                      multi_bead=False) -> BeadLayout:
+    masses = np.asarray(masses, dtype=np.float64)
+    resindex = np.asarray(resindex, dtype=np.int64)
+    n_res = len(resnames)
+    counts = np.bincount(resindex, minlength=n_res)
+    rseg = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if name_dict is None:
+        seg = rseg.astype(np.int32)
+        bead_mass = np.array([masses[rseg[r]:rseg[r + 1]].sum() for r in range(n_res)])
+        return BeadLayout(seg, None, list(resnames), np.asarray(resids, dtype=np.int64), bead_mass)
+    names = np.asarray(names, dtype=object)
+    gather, seg, types, rid = [], [0], [], []
+    for r in range(n_res):
+        lo, hi = int(rseg[r]), int(rseg[r + 1])
+        rn = resnames[r]
+        if rn not in name_dict:
+            raise RuntimeError("name_dict has no entry for resname '%s'" % rn)
+        per_name = [lo + np.nonzero(names[lo:hi] == nm)[0] for nm in name_dict[rn]]
+        groups = per_name if multi_bead else [np.concatenate(per_name)]
+        for g in groups:
+            gather.append(g)
+            seg.append(seg[-1] + len(g))
+            types.append(rn)
+            rid.append(int(resids[r]))
+    gather = np.concatenate(gather).astype(np.int32)
+    seg = np.asarray(seg, dtype=np.int32)
+    bead_mass = np.array([masses[gather[seg[i]:seg[i + 1]]].sum() for i in range(len(types))])
+    return BeadLayout(seg, gather, types, np.asarray(rid, dtype=np.int64), bead_mass)
+
+
+class LipidReductionEngine:
+    """Runs unwrap -> membrane COM -> lipid COM -> leaflets for batches of frames and keeps
+    the results for all analysed frames resident on the device."""
+
+    def __init__(self, masses, layout: BeadLayout, n_frames: int, device: int = 0, norm: int = 2,
+                 leaflet_update_interval: int = 1, batch_frames: Optional[int] = None,
+                 scratch_bytes: int = 4 << 30):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pybilt_b200: a CUDA device is required (no CPU fallback)")
+        self.ctx = _native.Context(device)
+        self.dev = torch.device("cuda", device)
+        self.masses_h = np.ascontiguousarray(masses, dtype=np.float64)
+        self.M = int(self.masses_h.shape[0])
+        self.layout = layout
+        self.N = layout.n_beads
+        self.F = int(n_frames)
+        self.norm = int(norm)
+        self.update_interval = int(leaflet_update_interval)
+        self.total_mass = float(self.masses_h.sum())            # com_frame.py:175
+        plan = build_plan(self.M)
+        self.plan = plan
+        d = self.dev
+        self.d_mass = torch.from_numpy(self.masses_h).to(d)
+        self.d_seg = torch.from_numpy(layout.seg).to(d)
+        self.d_gather = None if layout.gather is None else torch.from_numpy(layout.gather).to(d)
+        self.d_bead_mass = torch.from_numpy(np.ascontiguousarray(layout.bead_mass)).to(d)
+        self.d_leaf_start = torch.from_numpy(plan.leaf_start).to(d)
+        self.d_leaf_len = torch.from_numpy(plan.leaf_len).to(d)
+        self.d_node_left = torch.from_numpy(plan.node_left).to(d) if plan.n_nodes else torch.zeros(1, dtype=torch.int32, device=d)
+        self.d_node_right = torch.from_numpy(plan.node_right).to(d) if plan.n_nodes else torch.zeros(1, dtype=torch.int32, device=d)
+        self.d_level_off = torch.from_numpy(plan.level_off).to(d)
+        # per-frame scratch: image counts (6 B/atom) + tree nodes
+        per_frame = self.M * 6 + (plan.n_leaves + plan.n_nodes) * 24
+        if batch_frames is None:
+            batch_frames = max(1, min(self.F, scratch_bytes // max(per_frame, 1)))
+        self.B = int(batch_frames)
+        self.d_img = torch.empty((self.B, self.M, 3), dtype=torch.int16, device=d)
+        self.d_nodes = torch.empty((self.B, plan.n_leaves + plan.n_nodes, 3), dtype=torch.float64, device=d)
+        self.d_u_state = torch.empty((self.M, 3), dtype=torch.float32, device=d)
+        self.d_status = torch.zeros(1, dtype=torch.int32, device=d)
+        # resident representations of every analysed frame
+        self.com = torch.empty((self.F, self.N, 3), dtype=torch.float64, device=d)
+        self.com_unwrap = torch.empty((self.F, self.N, 3), dtype=torch.float64, device=d)
+        self.mem_com = torch.empty((self.F, 3), dtype=torch.float64, device=d)
+        self.labels = torch.empty((self.F, self.N), dtype=torch.uint8, device=d)
+        self.box = torch.empty((self.F, 3), dtype=torch.float32, device=d)
+        self.n_done = 0
+        self.launches = 0
+
+    # ---------------------------------------------------------------------------------
+    def reset(self):
+        self.n_done = 0
+        self.d_status.zero_()
+
+    def stream_ptr(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def push(self, x: torch.Tensor, box: torch.Tensor):
+        """Process the next ``x.shape[0]`` analysed frames.  ``x`` float32 [f, M, 3] and ``box``
+        float32 [f, 3] are device tensors (any f; split into scratch-sized batches here)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert box.is_cuda and box.dtype == torch.float32 and box.is_contiguous()
+        f_total = int(x.shape[0])
+        if self.n_done + f_total > self.F:
+            raise RuntimeError("more frames pushed than the engine was sized for")
+        st = self.stream_ptr()
+        c = self.ctx
+        for b0 in range(0, f_total, self.B):
+            b1 = min(f_total, b0 + self.B)
+            nb = b1 - b0
+            xb, bb = x[b0:b1], box[b0:b1]
+            g0 = self.n_done
+            self.box[g0:g0 + nb].copy_(bb)
+            c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
+                   1 if g0 == 0 else 0, nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+            p = self.plan
+            c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
+                   self.d_mass.data_ptr(), nb, self.M, self.d_leaf_start.data_ptr(),
+                   self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(),
+                   self.d_node_right.data_ptr(), p.n_nodes, self.d_level_off.data_ptr(), p.n_levels,
+                   self.total_mass, self.d_nodes.data_ptr(), self.mem_com[g0:].data_ptr(), st)
+            c.call("pbk_lipid_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
+                   self.d_mass.data_ptr(), self.mem_com[g0:].data_ptr(), self.d_seg.data_ptr(),
+                   _ptr(self.d_gather), self.d_bead_mass.data_ptr(), nb, self.M, self.N,
+                   self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(), st)
+            prev = self.labels[g0 - 1].data_ptr() if g0 > 0 else None
+            c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
+                   self.update_interval, prev, self.labels[g0:].data_ptr(), self.d_status.data_ptr(), st)
+            self.launches += 5
+            self.n_done += nb
+
+    def check_status(self):
+        """Synchronises; raises like the reference does for data-dependent failures."""
+        s = int(self.d_status.item())
+        if s & _native.ST_LEAFLET_TIE:
+            raise KeyError("")      # bilayer_analyzer.py:838-845: pos stays '' -> leaflets['']
+        if s & _native.ST_IMAGE_OVERFLOW:
+            raise RuntimeError("unwrap: image count outside int16 or non-positive box length")
+
+    # ---------------------------------------------------------------------------------
+    # analyses over the resident representations
+    # ---------------------------------------------------------------------------------
+    def msd_pairs(self, idx: np.ndarray, origins: Sequence[int], ends: Sequence[int],
+                  lateral=(0, 1)) -> torch.Tensor:
+        d = self.dev
+        d_idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=d)
+        d_o = torch.as_tensor(np.ascontiguousarray(origins, dtype=np.int32), device=d)
+        d_e = torch.as_tensor(np.ascontiguousarray(ends, dtype=np.int32), device=d)
+        out = torch.empty(len(d_o), dtype=torch.float64, device=d)
+        self.ctx.call("pbk_msd_pairs", self.com_unwrap.data_ptr(), self.n_done, self.N,
+                      d_idx.data_ptr(), int(d_idx.numel()), int(lateral[0]), int(lateral[1]),
+                      d_o.data_ptr(), d_e.data_ptr(), int(d_o.numel()), out.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return out
+
+    def rdf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int,
+            edges: np.ndarray, lateral=(0, 1), frames: Optional[slice] = None):
+        d = self.dev
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        nb = len(edges) - 1
+        d_edges = torch.as_tensor(np.ascontiguousarray(edges, dtype=np.float64), device=d)
+        count = torch.zeros(nb, dtype=torch.int64, device=d)
+        fc = torch.empty((F, 2, 3), dtype=torch.int32, device=d)
+        self.ctx.call("pbk_rdf", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
+                      type_code.data_ptr(), self.box[sl.start:].data_ptr(), F, self.N,
+                      int(lateral[0]), int(lateral[1]), int(type_a), int(type_b), int(leaflet_mask),
+                      nb, float(edges[0]), float(edges[-1]), d_edges.data_ptr(), count.data_ptr(),
+                      fc.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return count, fc
+
+    def nnf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int, k: int,
+            lateral=(0, 1)):
+        d = self.dev
+        F = self.n_done
+        n_b = torch.empty((F, self.N), dtype=torch.int32, device=d)
+        frac = torch.empty(F, dtype=torch.float64, device=d)
+        self.ctx.call("pbk_nnf", self.com.data_ptr(), self.labels.data_ptr(), type_code.data_ptr(),
+                      self.box.data_ptr(), F, self.N, int(lateral[0]), int(lateral[1]), int(type_a),
+                      int(type_b), int(leaflet_mask), int(k), n_b.data_ptr(), frac.data_ptr(),
+                      self.stream_ptr())
+        self.launches += 2
+        return n_b, frac
+
+    def lipid_grid(self, nx: int, ny: int, mode: str = "opt", lateral=(0, 1),
+                   frames: Optional[slice] = None):
+        d = self.dev
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        gi = torch.empty((F, 2, nx, ny), dtype=torch.int32, device=d)
+        gz = torch.empty((F, 2, nx, ny), dtype=torch.float64, device=d)
+        m = 1 if mode == "opt" else 0
+        knn = torch.empty((F, self.N, 24), dtype=torch.int32, device=d) if m == 1 else None
+        norm = [i for i in (0, 1, 2) if i not in tuple(lateral)][0]
+        s = sl.start
+        self.ctx.call("pbk_lipid_grid", self.com[s:].data_ptr(), self.com_unwrap[s:].data_ptr(),
+                      self.labels[s:].data_ptr(), self.box[s:].data_ptr(), F, self.N, int(lateral[0]),
+                      int(lateral[1]), norm, int(nx), int(ny), m, _ptr(knn), gi.data_ptr(),
+                      gz.data_ptr(), self.stream_ptr())
+        self.launches += 2 if m == 1 else 1
+        return gi, gz, knn
+
+    def grid_reduce(self, gi: torch.Tensor, gz: torch.Tensor, type_code: torch.Tensor, n_types: int,
+                    lateral=(0, 1), frames: Optional[slice] = None):
+        d = self.dev
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        nx, ny = int(gi.shape[2]), int(gi.shape[3])
+        cells = torch.empty((F, self.N), dtype=torch.int32, device=d)
+        thick = torch.empty((F, 2), dtype=torch.float64, device=d)
+        apl = torch.empty((F, 1 + 2 * n_types), dtype=torch.float64, device=d)
+        s = sl.start
+        self.ctx.call("pbk_grid_reduce", gi.data_ptr(), gz.data_ptr(), self.labels[s:].data_ptr(),
+                      type_code.data_ptr(), self.box[s:].data_ptr(), F, self.N, int(lateral[0]),
+                      int(lateral[1]), nx, ny, int(n_types), cells.data_ptr(), thick.data_ptr(),
+                      apl.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return cells, thick, apl
