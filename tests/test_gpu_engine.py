@@ -63,3 +63,123 @@ def test_representations_match_reference(name, batch):
     # stronger than required: the COMs come out bit-identical too
     assert np.array_equal(com, gold["rep/com"])
     assert np.array_equal(comu, gold["rep/com_unwrap"])
+
+
+def type_codes(types):
+    names = []
+    for t in types:
+        if t not in names:
+            names.append(t)
+    return names, np.array([names.index(t) for t in types], dtype=np.int32)
+
+
+def port_reps(name):
+    c = cases.CASES[name]
+    top, traj = cases.make_inputs(name)
+    out, reps = port.run(top, traj, [], c.get("rep_settings"), c.get("settings"),
+                         c.get("frame_range", (0, -1, 1)), return_reps=True)
+    return reps
+
+
+@pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c2_prefix", "name_dict"])
+def test_msd_pairs_match_port(name):
+    e, top, traj, fr, layout = run_engine(name)
+    reps = port_reps(name)
+    F = len(fr)
+    views0 = port.leaflet_views(reps["labels"][0], reps["types"])
+    for leaflet, group in [("both", "all"), ("upper", "all"), ("lower", layout.types[0])]:
+        idx = port._indices_for(views0, leaflet, group)
+        want = port.msd(reps["com_unwrap"], reps["times"], idx)[:, 1]
+        got = e.msd_pairs(idx, np.zeros(F, dtype=np.int32), np.arange(F, dtype=np.int32)).cpu().numpy()
+        rel_close(got, want, COM_RTOL)
+        assert got[0] == 0.0
+    pairs, _ = port.msd_multi_blocks(F, 3, 2)
+    idx = port._indices_for(views0, "both", "all")
+    r = reps["com_unwrap"][:, idx][:, :, [0, 1]]
+    want = np.array([port._frame_msd(r[b:b + 1], r[a:a + 1])[0] for a, b in pairs])
+    got = e.msd_pairs(idx, [a for a, _ in pairs], [b for _, b in pairs]).cpu().numpy()
+    rel_close(got, want, COM_RTOL)
+
+
+RDF_SETTINGS = [("all", "all", 3, 25, 0.0, 25.0), ("A0", "A0", 1, 80, 0.0, 40.0),
+                ("A0", "A1", 3, 30, 2.0, 32.0), ("all", "A1", 2, 25, 0.0, 25.0),
+                ("A1", "all", 3, 7, 1.0, 9.0)]
+
+
+@pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
+def test_rdf_counts_match_port(name):
+    e, top, traj, fr, layout = run_engine(name)
+    reps = port_reps(name)
+    names, codes = type_codes(layout.types)
+    d_codes = torch.from_numpy(codes).cuda()
+    for (ra, rb, mask, nb, lo, hi) in RDF_SETTINGS:
+        def resolve(r):
+            if r == "all":
+                return "all", -1
+            i = int(r[1:]) % len(names)
+            return names[i], i
+        (na, ca), (nbn, cb) = resolve(ra), resolve(rb)
+        leaflet = {3: "both", 1: "upper", 2: "lower"}[mask]
+        (g, bins), want = port.rdf(reps["com"], reps["labels"], reps["types"], reps["box"], leaflet,
+                                   na, nbn, nb, lo, hi)
+        edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
+        count, fc = e.rdf(d_codes, ca, cb, mask, edges)
+        got = count.cpu().numpy()
+        assert np.array_equal(got, want), (name, ra, rb, mask, np.abs(got - want).max())
+        assert want.sum() > 0 or name == "tiny_all"
+
+
+@pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
+def test_nnf_counts_match_port(name):
+    e, top, traj, fr, layout = run_engine(name)
+    reps = port_reps(name)
+    names, codes = type_codes(layout.types)
+    d_codes = torch.from_numpy(codes).cuda()
+    for (ia, ib, mask, k) in [(0, 1, 3, 5), (1, 0, 1, 6), (0, 0, 2, 3), (2, 1, 3, 24)]:
+        ia, ib = ia % len(names), ib % len(names)
+        leaflet = {3: "both", 1: "upper", 2: "lower"}[mask]
+        res, counts = port.nnf(reps["com"], reps["labels"], reps["types"], reps["box"], reps["times"],
+                               leaflet, names[ia], names[ib], k, return_counts=True)
+        n_b, frac = e.nnf(d_codes, ia, ib, mask, k)
+        n_b = n_b.cpu().numpy()
+        lab = reps["labels"]
+        for f in range(len(fr)):
+            got = np.concatenate([n_b[f][(lab[f] == 1) & (n_b[f] >= 0)],
+                                  n_b[f][(lab[f] == 0) & (n_b[f] >= 0)]])
+            assert np.array_equal(got, counts[f]), (name, f)              # bit-exact neighbour counts
+        rel_close(frac.cpu().numpy(), res[:, 1], 1e-15)
+
+
+@pytest.mark.parametrize("name,nx", [("tiny_all", 8), ("grid_dense", 16), ("grid_sparse", 8),
+                                     ("c3_small", 32)])
+@pytest.mark.parametrize("mode", ["opt", "exact"])
+def test_lipid_grid_matches_port(name, nx, mode):
+    e, top, traj, fr, layout = run_engine(name)
+    reps = port_reps(name)
+    names, codes = type_codes(layout.types)
+    d_codes = torch.from_numpy(codes).cuda()
+    gi, gz, knn = e.lipid_grid(nx, nx, mode)
+    cells, thick, apl = e.grid_reduce(gi, gz, d_codes, len(names))
+    gi, gz = gi.cpu().numpy(), gz.cpu().numpy()
+    cells, thick, apl = cells.cpu().numpy(), thick.cpu().numpy(), apl.cpu().numpy()
+    gold = load(name)
+    for f in range(len(fr)):
+        g = port.lipid_grid_frame(reps["com"][f], reps["com_unwrap"][f], reps["labels"][f],
+                                  reps["box"][f], nx, nx, mode)
+        for li, leaf in enumerate(("upper", "lower")):
+            assert np.array_equal(gi[f, li], g[leaf][0]), (name, f, leaf)   # bit-exact cell indices
+            assert np.array_equal(gz[f, li], g[leaf][1])
+            key = f"rep/grid_{leaf}" if mode == "opt" else f"rep/grid_exact_{leaf}"
+            if key in gold and gold[key].shape[1] == nx:
+                assert np.array_equal(gi[f, li], gold[key][f])              # literal reference
+        t = port.grid_thickness(g)
+        rel_close(thick[f], np.array(t), 1e-12)
+        avg, by_res, area_of = port.grid_apl(g, reps["labels"][f], reps["types"])
+        rel_close(apl[f, 0], avg, 1e-15)
+        for ti, nm in enumerate(names):
+            rel_close(apl[f, 1 + 2 * ti], by_res[nm][0], 1e-15)
+            rel_close(apl[f, 2 + 2 * ti], by_res[nm][1], 1e-12)
+        cnt_want = np.zeros(len(layout.types), dtype=np.int64)
+        for li, leaf in enumerate(("upper", "lower")):
+            cnt_want += np.bincount(g[leaf][0].reshape(-1), minlength=len(cnt_want))
+        assert np.array_equal(cells[f], cnt_want)
