@@ -110,7 +110,7 @@ int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
  * distance_euclidean_pbc               pybilt/common/distance_cutoff_clustering.py:27-71
  * np.histogram fast path               numpy/lib/_histograms_impl.py
  * Per frame and per leaflet in leaflet_mask (bit0 upper, bit1 lower) that holds at least one
- * lipid of type_a and one of type_b (type < 0 = 'all'): every ordered pair i in A, j in B,
+ * lipid of type_a and one of type_b (type -1 = 'all', any other negative = no lipid): every ordered pair i in A, j in B,
  * i != j, minimum-image lateral distance of the wrapped COMs, binned on edges[n_bins+1]
  * (the float64 linspace np.histogram builds).  count[n_bins] (uint64) is accumulated;
  * frame_counts[F][2][3] int32 receives (N_a, N_b, N_leaflet) per frame and leaflet

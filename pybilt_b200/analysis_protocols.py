@@ -1,0 +1,534 @@
+"""Analysis plugin registry and the in-scope analysis protocols, frame-batched on the device.
+
+Drop-in mirror of the plugin surface of pybilt/bilayer_analyzer/analysis_protocols.py:
+module registries ``command_protocols`` / ``valid_analysis`` / ``analysis_obj_name_dict`` /
+``use_objects`` (:70-76), the ``Analyses`` container (:119-329) and the ``AnalysisProtocol``
+base class (:332-501) with the same constructor argument forms ("id key value ..." strings
+or dicts), settings handling, ``get_data()`` shapes, ``save_data`` pickles and error
+behaviour (``RuntimeError`` for bad input, ``warnings.warn`` for unknown setting keys).
+
+What changes is *when* the work happens.  The reference calls ``run_analysis`` once per
+frame and computes in Python; the six protocols registered here ('msd', 'msd_multi',
+'com_lateral_rdf', 'nnf', 'apl_grid', 'thickness_grid') implement ``run_batch`` instead,
+which receives the device-resident representations of all analysed frames and launches
+libpbk kernels over them.  A user plugin written against the reference recipe (a subclass
+with a per-frame ``run_analysis(ba_settings, ba_reps, ba_mda_data)``) still works: the
+analyzer feeds it host views frame by frame.
+"""
+from __future__ import annotations
+
+import pickle
+import warnings
+
+import numpy as np
+
+from .running_stats import RunningStats, running_rows
+
+command_protocols = {}
+valid_analysis = []
+analysis_obj_name_dict = {}
+use_objects = {"mda_frame": True, "com_frame": True, "lipid_grid": False, "vector_frame": False}
+
+
+def word_list_to_string(word_list, delimeter=" "):
+    return str(delimeter.join(word_list))
+
+
+class Analyses(object):
+    """The set of analyses a BilayerAnalyzer runs (analysis_protocols.py:119-329)."""
+
+    def __init__(self, analysis_commands):
+        self.use_objects = use_objects.copy()
+        self.in_commands = analysis_commands
+        self.arguments = []
+        self.analysis_keys = []
+        self.analysis_ids = []
+        self.command_protocol = dict()
+        self.n_commands = 0
+        for command in analysis_commands:
+            self.add_analysis(command)
+        if self.use_objects['lipid_grid']:
+            self.use_objects['com_frame'] = True
+
+    def __getitem__(self, item):
+        return self.command_protocol[item]
+
+    def __len__(self):
+        return len(self.analysis_ids)
+
+    def add_analysis(self, inputs):
+        if isinstance(inputs, str):
+            words = inputs.split()
+            if len(words) < 2:
+                raise RuntimeError("wrong number of arguments for analysis {}".format(words))
+            self._register(words[0], words[1], word_list_to_string(words[1:]))
+        elif isinstance(inputs, (list, tuple)):
+            if len(inputs) != 3:
+                raise RuntimeError("wrong number of arguments in the input list/tuple. Should be "
+                                   "three: [a_key, a_id, a_set_dict]")
+            args = inputs[2]
+            args['analysis_id'] = inputs[1]
+            self._register(inputs[0], inputs[1], args)
+        elif isinstance(inputs, dict):
+            for key in ['analysis_key', 'analysis_id', "analysis_settings"]:
+                if key not in inputs:
+                    raise RuntimeError("required key: {} , not in the input dictionary.".format(key))
+            args = inputs['analysis_settings']
+            args['analysis_id'] = inputs['analysis_id']
+            self._register(inputs['analysis_key'], inputs['analysis_id'], args)
+
+    def _register(self, key, a_id, args):
+        if key not in valid_analysis:
+            raise RuntimeError("invalid analysis_key '{}' : {}".format(key, args))
+        if a_id in self.analysis_ids:
+            raise RuntimeError("analysis_id '{}' has already been used!".format(a_id))
+        self.use_objects[analysis_obj_name_dict[key]] = True
+        self.arguments.append(args)
+        self.analysis_ids.append(a_id)
+        self.analysis_keys.append(key)
+        self.command_protocol[a_id] = command_protocols[key](args)
+        self.n_commands += 1
+
+    def remove_analysis(self, analysis_id):
+        if analysis_id in self.analysis_ids:
+            del self.command_protocol[analysis_id]
+            index = self.analysis_ids.index(analysis_id)
+            del self.arguments[index]
+            del self.analysis_keys[index]
+            del self.analysis_ids[index]
+            self.n_commands -= 1
+        else:
+            warnings.warn("no analysis with id '{}'".format(analysis_id))
+
+    def remove_all(self):
+        for a_id in list(self.analysis_ids):
+            self.remove_analysis(a_id)
+
+    def print_protocol(self):
+        print('build objects:')
+        for key in self.use_objects.keys():
+            if self.use_objects[key]:
+                print(key)
+        print("with analysis:")
+        for analysis_id in self.analysis_ids:
+            self.command_protocol[analysis_id].print_protocol()
+
+    def dump_data(self, path=None):
+        print('dumping analysis data to pickle files...')
+        for analysis_id in self.analysis_ids:
+            print("analysis id: {} ---> {} ".format(
+                analysis_id, self.command_protocol[analysis_id].save_file_name))
+            self.command_protocol[analysis_id].save_data(path=path)
+
+    def reset(self):
+        for analysis_id in self.analysis_ids:
+            self.command_protocol[analysis_id].reset()
+
+
+class AnalysisProtocol(object):
+    """Base class of every analysis plugin (analysis_protocols.py:332-501)."""
+    _pickleable = True
+    _short_description = 'None'
+    analysis_key = 'none'
+    _related = None
+    batched = False         # True: implements run_batch(ba_settings, batch, ba_mda_data)
+
+    def __init__(self, args):
+        self._short_description = "parent analysis protocol"
+        self._return_length = 1
+        self.analysis_key = 'none'
+        self.analysis_id = 'none'
+        self.settings = dict()
+        self.settings['none'] = None
+        self._valid_settings = list(self.settings.keys())
+        self.save_file_name = self.analysis_id + ".pickle"
+        self._parse_args(args)
+        self.analysis_output = []
+
+    def _setup(self, defaults, args):
+        """Common constructor tail of the concrete protocols."""
+        self.analysis_id = 'none'
+        self.settings = dict(defaults)
+        self._valid_settings = list(self.settings.keys())
+        self._parse_args(args)
+        self.save_file_name = self.analysis_id + ".pickle"
+        self.analysis_output = []
+
+    def _parse_args(self, args):
+        if isinstance(args, str):
+            self._parse_string(args)
+        elif isinstance(args, dict):
+            self._parse_dict(args)
+        else:
+            raise RuntimeError("Invalid input structure for arguments/settings to analysis type "
+                               + self.analysis_key)
+
+    def _parse_string(self, args):
+        self._parse_dict(self._cast_settings(self._parse_str_to_dict(args)))
+
+    def _parse_str_to_dict(self, args):
+        words = args.split()
+        arg_dict = {'analysis_id': words[0]}
+        for i in range(1, len(words) - 1, 2):
+            if words[i] in self._valid_settings:
+                arg_dict[words[i]] = words[i + 1]
+            else:
+                warnings.warn("ignoring invalid argument key " + words[i] + " for analysis "
+                              + self.analysis_key)
+        return arg_dict
+
+    _casts = {}
+
+    def _cast_settings(self, arg_dict):
+        for key, cast in self._casts.items():
+            if key in arg_dict:
+                arg_dict[key] = cast(arg_dict[key])
+        return arg_dict
+
+    def _parse_dict(self, args):
+        if 'analysis_id' not in args:
+            raise RuntimeError("required key 'anlaysis_id' not assigned in input dict for analysis "
+                               "type: '" + self.analysis_key + "'")
+        for key, value in args.items():
+            if key in self._valid_settings:
+                self.settings[key] = value
+            elif key == 'analysis_id':
+                self.analysis_id = value
+            else:
+                warnings.warn("ignoring invalid argument key " + key + " for analysis "
+                              + self.analysis_key)
+
+    def short_description(self):
+        return self._short_description
+
+    def pickleable(self):
+        return self._pickleable
+
+    def print_protocol(self):
+        print("Analysis: " + self._short_description)
+        print("  with analysis_id: {} ".format(self.analysis_id))
+        print("   and settings: ")
+        for key in self.settings.keys():
+            print("    {}: {} ".format(key, self.settings[key]))
+
+    def run_analysis(self, ba_settings, ba_reps, ba_mda_data):
+        """Per-frame entry point of the reference recipe.  Batched protocols do their work in
+        run_batch and ignore per-frame calls; plain plugins override this."""
+        if not self.batched:
+            self.analysis_output.append(np.zeros(self._return_length))
+
+    def save_data(self, path=None):
+        save_file = self.save_file_name if path is None else path + self.save_file_name
+        with open(save_file, 'wb') as outfile:
+            pickle.dump(self.get_data(), outfile)
+
+    def get_data(self):
+        return np.array(self.analysis_output)
+
+    def reset(self):
+        self.analysis_output = []
+
+
+def _protocol(key, rep):
+    def deco(cls):
+        valid_analysis.append(key)
+        analysis_obj_name_dict[key] = rep
+        command_protocols[key] = cls
+        cls.analysis_key = key
+        return cls
+    return deco
+
+
+def _first_frame_indices(leaflets, leaflet, group):
+    """Index list frozen at the first analysed frame (analysis_protocols.py:586-605):
+    'both' (and any unknown name, after a warning) = upper members then lower members."""
+    if leaflet in ("upper", "lower"):
+        return list(leaflets[leaflet].get_group_indices(group))
+    if leaflet != "both":
+        print("!! Warning - request for unknown leaflet name \'", leaflet)
+        print("!! the options are \"upper\", \"lower\", or \"both\"--using the default \"both\"")
+    out = []
+    for name in leaflets:
+        out += leaflets[name].get_group_indices(group)
+    return out
+
+
+def _leaflet_mask(leaflet):
+    return {"both": 3, "upper": 1, "lower": 2}.get(leaflet, 0)
+
+
+def _lipid_types_in(leaflets, do_leaflet):
+    names, nlipids = [], 0
+    for leaf in do_leaflet:
+        nlipids += len(leaflets[leaf].get_member_indices())
+        for g in leaflets[leaf].get_group_names():
+            if g not in names:
+                names.append(g)
+    return names, nlipids
+
+
+# ---------------------------------------------------------------------------------------
+@_protocol('msd', 'com_frame')
+class MSDProtocol(AnalysisProtocol):
+    """Single time origin lateral MSD, rows [time, msd] (analysis_protocols.py:509-667)."""
+    _short_description = "Single time origin mean squared displacement."
+    _related = list(['msd_multi'])
+    batched = True
+
+    def __init__(self, args):
+        self._indices = []
+        self._setup({'leaflet': 'both', 'resname': 'all'}, args)
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
+                                             self.settings['resname'])
+        F = batch.n_frames
+        vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
+                                      np.zeros(F, dtype=np.int32), np.arange(F, dtype=np.int32),
+                                      ba_settings['lateral']).cpu().numpy()
+        self.analysis_output = [np.array([batch.times[f], vals[f]]) for f in range(F)]
+
+
+def msd_multi_schedule(n_frames, n_tau, n_sigma):
+    """Replay of the block counters of MSDMultiProtocol.run_analysis
+    (analysis_protocols.py:833-888): returns ({block: (origin, end frame)}, n_blocks)."""
+    finished = {}
+    origins, counters = [0], [0]
+    tau_counter = sigma_counter = 0
+    for f in range(n_frames):
+        opening = sigma_counter == n_sigma
+        if opening:
+            origins.append(f)
+            counters.append(0)
+        if sigma_counter < n_sigma or opening:
+            for b in range(tau_counter, len(origins)):
+                if counters[b] < n_tau:
+                    counters[b] += 1
+                if counters[b] == n_tau:
+                    finished[b] = (origins[b], f)
+                    tau_counter += 1
+        if opening:
+            sigma_counter = 0
+        sigma_counter += 1
+    return finished, len(origins)
+
+
+@_protocol('msd_multi', 'com_frame')
+class MSDMultiProtocol(AnalysisProtocol):
+    """Multiple time origin MSD -> [msd, stderr, D, D stderr] (analysis_protocols.py:678-935)."""
+    _short_description = "Multiple time origin mean squared displacement."
+    _related = list(['msd'])
+    _casts = {'n_tau': int, 'n_sigma': int}
+    batched = True
+
+    def __init__(self, args):
+        self._indices = []
+        self._tau = 0.0
+        self._setup({'leaflet': 'both', 'resname': 'all', 'n_tau': 50, 'n_sigma': 50}, args)
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
+                                             self.settings['resname'])
+        n_tau, n_sigma = self.settings['n_tau'], self.settings['n_sigma']
+        F = batch.n_frames
+        finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
+        out = [0.0] * n_blocks
+        if finished:
+            blocks = sorted(finished)
+            vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
+                                          [finished[b][0] for b in blocks],
+                                          [finished[b][1] for b in blocks],
+                                          ba_settings['lateral']).cpu().numpy()
+            for b, v in zip(blocks, vals):
+                out[b] = v
+        self.analysis_output = out
+        self._tau = batch.times[n_tau - 1] - batch.times[0] if F >= n_tau else 0.0
+
+    def _process_output(self, analysis_output):
+        vals = np.array([v for v in analysis_output if v > 0.0])
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            avg = vals.mean()
+            err = vals.std() / np.sqrt(len(vals))
+            return np.array([avg, err, avg / (4.0 * self._tau), err / (4.0 * self._tau)])
+
+    def get_data(self):
+        return self._process_output(self.analysis_output)
+
+    def reset(self):
+        self.analysis_output = []
+        self._indices = []
+
+
+# ---------------------------------------------------------------------------------------
+@_protocol('com_lateral_rdf', 'com_frame')
+class COMLateralRDFProtocol(AnalysisProtocol):
+    """2-d lateral RDF of lipid COMs -> (rdf[n_bins], bin centres)
+    (analysis_protocols.py:4792-5062)."""
+    _short_description = "Lipid-lipid RDF in the bilayer lateral plane."
+    _related = list(['nnf'])
+    _casts = {'n_bins': int, 'range_inner': float, 'range_outer': float}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'leaflet': 'both', 'resname_1': 'first', 'resname_2': 'first', 'n_bins': 25,
+                     'range_inner': 0.0, 'range_outer': 25.0}, args)
+        self.reset()
+
+    def reset(self):
+        self.analysis_output = []
+        self._count = None
+        self._edges = None
+        self._bins = None
+        self._n_frames = 0
+        self._area_run = RunningStats()
+        self._N_a = self._N_b = self._N = 0
+        self._n_leaf = 0
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        s = self.settings
+        do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
+        rdf_range = [s['range_inner'], s['range_outer']]
+        # same call the reference uses to lay out the bins (:4909-4916)
+        _c, edges = np.histogram([-1], bins=s['n_bins'], range=rdf_range)
+        self._edges = edges
+        self._bins = 0.5 * (edges[:-1] + edges[1:])
+        lipid_types, _n = _lipid_types_in(batch.first_leaflets, do_leaflet)
+        if s['resname_1'] == 'first':
+            s['resname_1'] = lipid_types[0]
+        if s['resname_2'] == 'first':
+            s['resname_2'] = lipid_types[0]
+        self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
+        self._n_leaf = float(len(do_leaflet))
+        count, fc = batch.engine.rdf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
+                                     batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
+                                     edges, ba_settings['lateral'])
+        fc = fc.cpu().numpy().astype(np.int64)
+        self._count = count.cpu().numpy().astype(np.float64)
+        self._N_a += int(fc[:, :, 0].sum())
+        self._N_b += int(fc[:, :, 1].sum())
+        self._N += int(fc[:, :, 2].sum())
+        lat = list(ba_settings['lateral'])
+        for f in range(batch.n_frames):
+            self._area_run.push(batch.box_host[f][lat].prod())      # float32 product (:5004)
+        self._n_frames += batch.n_frames
+
+    def get_data(self):
+        shell = np.power(self._edges[1:], 2) - np.power(self._edges[:-1], 2)
+        shell *= np.pi
+        n_a = self._N_a / (self._n_leaf * self._n_frames)
+        n_b = self._N_b / (self._n_leaf * self._n_frames)
+        n_pairs = n_a * n_b
+        r1, r2 = self.settings['resname_1'], self.settings['resname_2']
+        if r1 == r2:
+            n_pairs -= n_a
+        elif r1 == 'all' and r2 != 'all':
+            n_pairs -= n_b
+        elif r2 == 'all' and r1 != 'all':
+            n_pairs -= n_a
+        with np.errstate(all="ignore"):
+            pair_density = n_pairs / self._area_run.mean()
+            rdf = (self._count * (1.0 / (pair_density * shell))) / self._n_frames
+        return rdf, self._bins
+
+
+# ---------------------------------------------------------------------------------------
+@_protocol('nnf', 'com_frame')
+class NNFProtocol(AnalysisProtocol):
+    """Nearest-neighbour fraction, rows [time, f, running mean, running deviation]
+    (analysis_protocols.py:2075-2257)."""
+    _short_description = "Lateral order nearest neighbor fraction."
+    _casts = {'n_neighbors': int}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'leaflet': 'both', 'n_neighbors': 5, 'resname_1': 'first',
+                     'resname_2': 'first'}, args)
+        self.running = RunningStats()
+        self.neighbor_counts = None
+
+    def reset(self):
+        self.running.reset()
+        self.analysis_output = []
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        s = self.settings
+        do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
+        lipid_types, nlipids = _lipid_types_in(batch.first_leaflets, do_leaflet)
+        if s['resname_1'] == 'first':
+            s['resname_1'] = lipid_types[0]
+        if s['resname_2'] == 'first':
+            s['resname_2'] = lipid_types[0]
+        if s['n_neighbors'] > nlipids:                       # :2197-2198
+            s['n_neighbors'] = nlipids - 1
+        self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
+        n_b, frac = batch.engine.nnf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
+                                     batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
+                                     s['n_neighbors'], ba_settings['lateral'])
+        self.neighbor_counts = n_b            # device int32 [F, N]; -1 = not a reference lipid
+        rows, self.running = running_rows(batch.times, frac.cpu().numpy())
+        self.analysis_output = [list(r) for r in rows]
+
+
+# ---------------------------------------------------------------------------------------
+@_protocol('thickness_grid', 'lipid_grid')
+class BTGridProtocol(AnalysisProtocol):
+    """Bilayer thickness from the lipid grids, rows [time, thickness, running mean, running
+    deviation] (analysis_protocols.py:1026-1095)."""
+    _short_description = "Bilayer thickness using lipid_grid."
+    _related = list(['lipid_length', 'thickness_leaflet_distance', 'thickness_peak_distance',
+                     'thickness_mass_weighted_std'])
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self.running = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        grids = batch.lipid_grids()
+        rows, self.running = running_rows(batch.times, grids.thickness_host[:, 0])
+        self.analysis_output = [r for r in rows]
+
+    def reset(self):
+        self.running.reset()
+        self.analysis_output = []
+
+
+@_protocol('apl_grid', 'lipid_grid')
+class APLGridProtocol(AnalysisProtocol):
+    """Area per lipid from the lipid grids -> {'composite': [F,4], resname: [F,4]}
+    (analysis_protocols.py:1549-1644)."""
+    _short_description = "Area per lipid using 2D lipid grids."
+    _related = list(['apl_box'])
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self.analysis_output = {}
+        self.running = RunningStats()
+        self.running_res = {}
+        self.first_comp = True
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        grids = batch.lipid_grids()
+        apl = grids.apl_host
+        rows, self.running = running_rows(batch.times, apl[:, 0])
+        out = {'composite': rows}
+        # resnames in the order LipidGrids.area_per_lipid lists them at the first frame
+        names, _n = _lipid_types_in(batch.first_leaflets, ['upper', 'lower'])
+        for name in names:
+            t = batch.type_names.index(name)
+            out[name], self.running_res[name] = running_rows(batch.times, apl[:, 1 + 2 * t])
+        self.analysis_output = out
+        self.first_comp = False
+
+    def get_data(self):
+        for key in self.analysis_output.keys():
+            self.analysis_output[key] = np.array(self.analysis_output[key])
+        return self.analysis_output
+
+    def reset(self):
+        self.running.reset()
+        self.analysis_output = {}
+        self.first_comp = True
+        self.running_res = {}

@@ -1,0 +1,577 @@
+"""``BilayerAnalyzer``: PyBILT's analysis driver with the frame loop moved onto the B200.
+
+Drop-in mirror of pybilt/bilayer_analyzer/bilayer_analyzer.py:112-1079: same constructor
+(``structure`` / ``trajectory`` / ``selection``, ``input_file`` or ``input_dict``), same
+``settings`` / ``rep_settings`` / ``reps`` dictionaries, ``add_analysis`` /
+``remove_analysis`` / ``get_analysis_data`` / ``dump_data`` / ``set_frame_range`` /
+``reset`` / ``run_analysis`` and the iterator protocol.
+
+What differs: ``__next__`` in the reference (:901-1031) unwraps, builds a COMFrame, assigns
+leaflets, optionally builds lipid grids and calls every plugin -- all in Python, one frame
+at a time.  Here all analysed frames are pushed through ``LipidReductionEngine`` (libpbk) in
+batches, the representations stay in HBM, the batched protocols run their kernels over all
+frames at once, and ``reps[...]`` are host views materialised per frame only for iterator
+users and for plain per-frame plugins.
+
+Trajectory input: an MDAnalysis Universe is built when ``structure`` / ``trajectory`` are
+file names (MDAnalysis must be importable); in-memory input is accepted as
+``structure=<topology>`` (attributes masses, names, resindex, resnames, resids) and
+``trajectory=<trajectory>`` (attributes positions f32 [F,M,3], dimensions f32 [F,6], times)
+or the tuple ``(positions, dimensions, times)``.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import analysis_protocols as ap
+from . import com_frame as cf
+from . import leaflet as lf
+from . import lipid_grid as lg
+from .engine import LipidReductionEngine, build_bead_layout
+
+default_analysis_commands = ['msd msd_1']
+
+
+class _HostFrame(object):
+    """What plugins see as ``reps['current_mda_frame']``: dimensions, time, frame, positions."""
+
+    def __init__(self, positions, dimensions, time, frame):
+        self._pos = positions
+        self.dimensions = dimensions
+        self.time = time
+        self.frame = frame
+
+    @property
+    def positions(self):
+        return self._pos
+
+
+class TrajectoryData(object):
+    """Equivalent of pybilt/bilayer_analyzer/mda_data.py:9-38 (``MDAData``): topology of the
+    selected atoms plus frame access."""
+
+    def __init__(self, structure, trajectory, sel_string):
+        self.psf_file = structure if isinstance(structure, str) else None
+        self.trajectory_file = trajectory if isinstance(trajectory, (str, list)) else None
+        self.bilayer_sel_string = sel_string
+        self.mda_universe = None
+        if isinstance(structure, str):
+            self._from_mdanalysis(structure, trajectory, sel_string)
+        else:
+            self._from_arrays(structure, trajectory, sel_string)
+        self.natoms = int(self.masses.shape[0])
+        self.n_residues = len(self.resnames)
+
+    # -- in-memory -------------------------------------------------------------------
+    def _from_arrays(self, top, traj, sel):
+        if isinstance(traj, (tuple, list)):
+            positions, dimensions, times = traj
+        else:
+            positions, dimensions, times = traj.positions, traj.dimensions, traj.times
+        resnames_all = list(top.resnames)
+        resindex = np.asarray(top.resindex, dtype=np.int64)
+        words = (sel or "all").split()
+        if words[0] == "all":
+            keep_res = np.ones(len(resnames_all), dtype=bool)
+        elif words[0] == "resname":
+            keep_res = np.isin(np.asarray(resnames_all, dtype=object), words[1:])
+        else:
+            raise RuntimeError("in-memory input supports the selections 'all' and "
+                               "'resname A B ...' (got %r)" % sel)
+        atom_keep = keep_res[resindex]
+        self.indices = np.nonzero(atom_keep)[0]
+        self.masses = np.asarray(top.masses, dtype=np.float64)[self.indices]
+        self.names = np.asarray(top.names, dtype=object)[self.indices]
+        new_index = np.cumsum(keep_res) - 1
+        self.resindex = new_index[resindex[self.indices]]
+        self.resnames = [r for r, k in zip(resnames_all, keep_res) if k]
+        self.resids = np.asarray(top.resids)[keep_res]
+        self._positions = positions
+        self._dimensions = np.asarray(dimensions, dtype=np.float32)
+        self._times = np.asarray(times, dtype=np.float64)
+        self.nframes = int(self._dimensions.shape[0])
+        self._all_atoms = bool(atom_keep.all())
+
+    def frames(self, frame_idx):
+        """float32 positions [f, M, 3] (selected atoms), dimensions [f, 6], times [f]."""
+        if self.mda_universe is not None:
+            return self._read_mda(frame_idx)
+        x = self._positions
+        contiguous = len(frame_idx) > 0 and (np.diff(frame_idx) == 1).all()
+        if torch.is_tensor(x):
+            sel = x[int(frame_idx[0]):int(frame_idx[-1]) + 1] if contiguous else x[torch.as_tensor(frame_idx)]
+            if not self._all_atoms:
+                sel = sel[:, torch.as_tensor(self.indices)]
+        else:
+            sel = x[int(frame_idx[0]):int(frame_idx[-1]) + 1] if contiguous else x[frame_idx]
+            if not self._all_atoms:
+                sel = sel[:, self.indices]
+        return sel, self._dimensions[frame_idx], self._times[frame_idx]
+
+    # -- MDAnalysis ------------------------------------------------------------------
+    def _from_mdanalysis(self, structure, trajectory, sel):
+        try:
+            import MDAnalysis as mda
+        except ImportError as exc:       # pragma: no cover - MDAnalysis absent in this image
+            raise RuntimeError("reading structure/trajectory files needs MDAnalysis, which is not "
+                               "installed; pass in-memory arrays instead") from exc
+        self.mda_universe = mda.Universe(structure, trajectory)
+        group = self.mda_universe.select_atoms(sel)
+        whole = group.residues.atoms
+        if len(whole) != len(group):
+            raise RuntimeError("the selection must cover whole residues")
+        self.indices = group.indices
+        self.masses = np.asarray(group.masses, dtype=np.float64)
+        self.names = np.asarray(group.names, dtype=object)
+        res = group.residues
+        ridx = group.resindices
+        remap = {r: i for i, r in enumerate(res.resindices)}
+        self.resindex = np.array([remap[r] for r in ridx], dtype=np.int64)
+        self.resnames = list(res.resnames)
+        self.resids = np.asarray(res.resids)
+        self.nframes = len(self.mda_universe.trajectory)
+
+    def _read_mda(self, frame_idx):      # pragma: no cover - MDAnalysis absent in this image
+        traj = self.mda_universe.trajectory
+        x = np.empty((len(frame_idx), len(self.indices), 3), dtype=np.float32)
+        d = np.empty((len(frame_idx), 6), dtype=np.float32)
+        t = np.empty(len(frame_idx))
+        for k, f in enumerate(frame_idx):
+            ts = traj[int(f)]
+            x[k] = ts.positions[self.indices]
+            d[k] = ts.dimensions
+            t[k] = ts.time
+        return x, d, t
+
+
+class GridBatch(object):
+    """Device lipid grids of all analysed frames + their host reductions."""
+
+    def __init__(self, grid_idx, grid_z, cells, thickness_host, apl_host, runs):
+        self.grid_idx, self.grid_z, self.cells = grid_idx, grid_z, cells
+        self.thickness_host, self.apl_host = thickness_host, apl_host
+        self.runs = runs          # [(frame slice, nx, ny, index into the lists above)]
+
+    def frame(self, f):
+        for k, (sl, _nx, _ny) in enumerate(self.runs):
+            if sl.start <= f < sl.stop:
+                j = f - sl.start
+                return (self.grid_idx[k][j].cpu().numpy(), self.grid_z[k][j].cpu().numpy(),
+                        self.cells[k][j].cpu().numpy())
+        raise IndexError(f)
+
+
+class ReductionBatch(object):
+    """What a batched protocol's ``run_batch`` receives: the engine holding the resident
+    representations, host metadata, and the leaflets of the first analysed frame."""
+
+    def __init__(self, analyzer, engine, times, box_host, first_leaflets):
+        self._analyzer = analyzer
+        self.engine = engine
+        self.n_frames = engine.n_done
+        self.times = times
+        self.box_host = box_host
+        self.types = engine.layout.types
+        self.resids = engine.layout.resids
+        names = []
+        for t in self.types:
+            if t not in names:
+                names.append(t)
+        self.type_names = names
+        codes = np.array([names.index(t) for t in self.types], dtype=np.int32)
+        self.type_code_host = codes
+        self.type_code_dev = torch.from_numpy(codes).to(engine.dev)
+        self.first_leaflets = first_leaflets
+        self._grids = None
+
+    def type_code_of(self, name):
+        if name == 'all':
+            return -1
+        return self.type_names.index(name) if name in self.type_names else -2
+
+    def lipid_grids(self) -> GridBatch:
+        if self._grids is None:
+            self._grids = self._analyzer._build_lipid_grids(self)
+        return self._grids
+
+
+class BilayerAnalyzer(object):
+    _valid_commands = ["structure", "trajectory", "analysis", "selection", "frames", "plot",
+                       "lipid_grid"]
+    _required_commands = ['structure', 'trajectory', 'selection']
+
+    def __init__(self, structure=None, trajectory=None, selection=None, input_file=None,
+                 input_dict=None, device=0):
+        self.next = self.__next__
+        self.settings = {'frame_range': [0, -1, 1], 'print_interval': 5, 'norm': 2,
+                         'lateral': [0, 1], 'lateral_dimension': "xy", 'normal_dimension': "z",
+                         'frame_index': 0}
+        self.reps = {'current_mda_frame': None, 'com_frame': None, 'leaflets': None,
+                     'lipid_grid': None, 'vector_frame': None, 'first_com_frame': None}
+        self.rep_settings = {
+            'com_frame': {'dump': False, 'dump_path': "./", 'name_dict': None, 'multi_bead': False,
+                          'rewrap': False, 'make_whole': False},
+            'leaflets': {'dump': False, 'dump_path': "./", 'update_interval': 1,
+                         'assign_method': 'avg_norm', 'orientation_atoms': None},
+            'lipid_grid': {'dump': False, 'dump_path': "./", 'n_xbins': 10, 'n_ybins': 10,
+                           'area_per_bin': None},
+            'vector_frame': {'dump': False, 'dump_path': "./", 'ref_atoms': None}}
+        self.device = device
+        self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
+        self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
+        self._frame_loop_count = 0
+        if input_file is not None:
+            self._commands = self.parse_input_script(self._input_script_name)
+            self._apply_frames_and_grid(self._commands, cast=lambda v: v)
+        elif structure is not None and trajectory is not None and selection is not None:
+            self._commands = {'structure': structure, 'trajectory': trajectory,
+                              'selection': selection}
+        elif input_dict is not None and isinstance(input_dict, dict):
+            for key in self._required_commands:
+                if key not in input_dict:
+                    raise RuntimeError("key '{}' needs to be included in the input "
+                                       "dictionary.".format(key))
+            self._commands = {k: v for k, v in input_dict.items() if k in self._valid_commands}
+            self._apply_frames_and_grid(self._commands, cast=int)
+        else:
+            raise RuntimeError('Must provide input_file or all three options for'
+                               '"structure", "trajectory", and "selection"')
+        self._analysis_protocol = ap.Analyses(self._commands.get('analysis',
+                                                                 default_analysis_commands))
+        self._plot_commands = self._commands.get('plot', [])
+        self._mda_data = TrajectoryData(self._commands['structure'], self._commands['trajectory'],
+                                        self._commands['selection'])
+        self._current_frame = self.settings['frame_range'][0]
+        self._last_frame = self.settings['frame_range'][1]
+        if self._last_frame < 0:
+            self._last_frame += self._mda_data.nframes
+        self._engine = None
+        self._batch = None
+        self._host = None
+        self._cursor = 0
+
+    def __repr__(self):
+        return 'BilayerAnalyzer'
+
+    # -- input script ---------------------------------------------------------------------
+    def _apply_frames_and_grid(self, commands, cast):
+        if 'frames' in commands:
+            f_args = commands['frames']
+            if isinstance(f_args, list) and len(f_args) == 1 and isinstance(f_args[0], str):
+                f_args = f_args[0].split()
+            for i in range(0, len(f_args) - 1, 2):
+                slot = {'first': 0, 'last': 1, 'interval': 2}.get(f_args[i])
+                if slot is not None:
+                    self.settings['frame_range'][slot] = int(f_args[i + 1])
+        if 'lipid_grid' in commands:
+            lg_args = commands['lipid_grid']
+            if isinstance(lg_args, list) and len(lg_args) == 1 and isinstance(lg_args[0], str):
+                lg_args = lg_args[0].split()
+            for i in range(0, len(lg_args) - 1, 2):
+                if lg_args[i] in ('n_xbins', 'n_ybins'):
+                    self.rep_settings['lipid_grid'][lg_args[i]] = int(lg_args[i + 1])
+
+    def parse_input_script(self, input_script_name):
+        """Line-oriented setup script (bilayer_analyzer.py:479-531)."""
+        commands = {}
+        with open(input_script_name) as ifile:
+            for line in ifile:
+                line = line.rstrip("\n")
+                words = line.split()
+                if len(words) <= 1 or words[0][0] == '#':
+                    continue
+                key = words[0]
+                if key in ('structure', 'trajectory', 'selection'):
+                    value = line.replace(key, '', 1).strip()
+                    if key == 'selection':
+                        value = ast.literal_eval(value)
+                    commands[key] = value
+                elif key in self._valid_commands:
+                    commands.setdefault(key, []).append(" ".join(words[1:]))
+                else:
+                    raise RuntimeError("invalid input command '{}'".format(key))
+        for required in self._required_commands:
+            if required not in commands:
+                raise RuntimeError("the {} needs to be specified in the input "
+                                   "script".format(required))
+        return commands
+
+    # -- analysis protocol ----------------------------------------------------------------
+    def print_analysis_protocol(self):
+        self._analysis_protocol.print_protocol()
+
+    def add_analysis(self, analysis_in):
+        self._analysis_protocol.add_analysis(analysis_in)
+
+    def remove_analysis(self, analysis_id):
+        self._analysis_protocol.remove_analysis(analysis_id)
+
+    def remove_all_analyses(self):
+        self._analysis_protocol.remove_all()
+
+    def get_analysis_ids(self):
+        return self._analysis_protocol.analysis_ids
+
+    def get_analysis_data(self, analysis_id):
+        return self._analysis_protocol.command_protocol[analysis_id].get_data()
+
+    def dump_data(self, path=None):
+        self._analysis_protocol.dump_data(path=path)
+
+    @staticmethod
+    def available_analysis():
+        return list(ap.command_protocols.keys())
+
+    @staticmethod
+    def print_available_analysis():
+        print(list(ap.command_protocols.keys()))
+
+    # -- settings -------------------------------------------------------------------------
+    def set_frame_range(self, first=0, last=-1, interval=1):
+        """bilayer_analyzer.py:716-747 (fractions in (0,1) scale with the trajectory length)."""
+        n = self._mda_data.nframes
+        if isinstance(first, (float, np.floating)):
+            first = int(first * n) if 0.0 < first < 1.0 else int(first)
+        if isinstance(last, (float, np.floating)):
+            last = int(last * n) if 0.0 < last < 1.0 else int(last)
+        if first != self.settings['frame_range'][0]:
+            self.settings['frame_range'][0] = first
+            self._current_frame = first
+        if last != self.settings['frame_range'][1]:
+            self.settings['frame_range'][1] = last
+            self._last_frame = last
+            if self._last_frame < 0:
+                self._last_frame += n
+        if interval != self.settings['frame_range'][2]:
+            self.settings['frame_range'][2] = interval
+        self._invalidate()
+
+    def adjust_rep_setting(self, rep_key, setting_key, setting_value):
+        self.rep_settings[rep_key][setting_key] = setting_value
+        self._invalidate()
+
+    def print_rep_settings(self):
+        for rep in self.rep_settings.keys():
+            print("represetation: {}".format(rep))
+            for setting in self.rep_settings[rep].keys():
+                print("  setting:value {}:{}".format(setting, self.rep_settings[rep][setting]))
+
+    def set_dump_com_frame(self, on=True, path="./"):
+        self.rep_settings['com_frame']['dump'] = on
+        self.rep_settings['com_frame']['dump_path'] = path
+
+    def set_dump_leaflet(self, on=True, path="./"):
+        self.rep_settings['leaflets']['dump'] = on
+        self.rep_settings['leaflets']['dump_path'] = path
+
+    def set_dump_lipid_grid(self, on=True, path="./"):
+        self.rep_settings['lipid_grid']['dump'] = on
+        self.rep_settings['lipid_grid']['dump_path'] = path
+
+    def turn_off_representation(self, rep_key):
+        self._analysis_protocol.use_objects[rep_key] = False
+
+    def turn_on_representation(self, rep_key):
+        self._analysis_protocol.use_objects[rep_key] = True
+
+    def reset(self):
+        """Clear analysis outputs and rewind the frame loop (bilayer_analyzer.py:761-774)."""
+        self.settings['frame_index'] = 0
+        self._current_frame = self.settings['frame_range'][0]
+        self._frame_loop_count = 0
+        self._analysis_protocol.reset()
+        self._invalidate()
+
+    def _invalidate(self):
+        self._engine = None
+        self._batch = None
+        self._host = None
+        self._cursor = 0
+
+    # -- the device pipeline ----------------------------------------------------------------
+    def analysed_frame_indices(self):
+        first, _last, interval = self.settings['frame_range']
+        return np.arange(first, self._last_frame + 1, interval)
+
+    def _reduce(self):
+        """Push every analysed frame through the engine (unwrap -> COMs -> leaflets)."""
+        if self._batch is not None:
+            return self._batch
+        lset = self.rep_settings['leaflets']
+        if lset['assign_method'] != 'avg_norm':
+            raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
+                               "(only 'avg_norm')" % lset['assign_method'])
+        if self.rep_settings['com_frame']['rewrap'] or self.rep_settings['com_frame']['make_whole']:
+            raise RuntimeError("com_frame:rewrap / make_whole are outside the accelerated path")
+        md = self._mda_data
+        cset = self.rep_settings['com_frame']
+        layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
+                                   cset['name_dict'], cset['multi_bead'])
+        fr = self.analysed_frame_indices()
+        self._frames = fr
+        eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
+                                   norm=self.settings['norm'],
+                                   leaflet_update_interval=int(lset['update_interval']))
+        # host -> device in engine-batch sized pieces, double-buffered on a copy stream
+        dev = eng.dev
+        copy_stream = torch.cuda.Stream(dev)
+        times = np.empty(len(fr))
+        dims_all = np.empty((len(fr), 6), dtype=np.float32)
+        B = eng.B
+        bufs = [torch.empty((B, md.natoms, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        boxes = [torch.empty((B, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream(dev)
+        for k, b0 in enumerate(range(0, len(fr), B)):
+            b1 = min(len(fr), b0 + B)
+            slot = k % 2
+            x, d, t = md.frames(fr[b0:b1])
+            times[b0:b1] = t
+            dims_all[b0:b1] = d
+            xh = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            bh = torch.from_numpy(np.ascontiguousarray(d[:, :3]))
+            with torch.cuda.stream(copy_stream):
+                if k >= 2:
+                    copy_stream.wait_event(consumed[slot])
+                bufs[slot][:b1 - b0].copy_(xh, non_blocking=True)
+                boxes[slot][:b1 - b0].copy_(bh, non_blocking=True)
+                ready[slot].record(copy_stream)
+            main.wait_event(ready[slot])
+            eng.push(bufs[slot][:b1 - b0], boxes[slot][:b1 - b0])
+            consumed[slot].record(main)
+        eng.check_status()
+        labels0 = eng.labels[0].cpu().numpy()
+        first_leaflets = lf.leaflets_from_labels(labels0, layout.types, layout.resids)
+        self._engine = eng
+        self._times = times
+        self._dims = dims_all
+        self._batch = ReductionBatch(self, eng, times, dims_all[:, :3].copy(), first_leaflets)
+        return self._batch
+
+    def _build_lipid_grids(self, batch):
+        gs = self.rep_settings['lipid_grid']
+        lat = self.settings['lateral']
+        F = batch.n_frames
+        if gs['area_per_bin'] is not None:
+            bins = [lg.fixed_resolution_bins(batch.box_host[f][lat[0]], batch.box_host[f][lat[1]],
+                                             gs['area_per_bin']) for f in range(F)]
+        else:
+            bins = [(int(gs['n_xbins']), int(gs['n_ybins']))] * F
+        runs, start = [], 0
+        for f in range(1, F + 1):
+            if f == F or bins[f] != bins[start]:
+                runs.append((slice(start, f), bins[start][0], bins[start][1]))
+                start = f
+        eng = batch.engine
+        gi_l, gz_l, cells_l = [], [], []
+        thick = np.empty((F, 2))
+        apl = np.empty((F, 1 + 2 * len(batch.type_names)))
+        for sl, nx, ny in runs:
+            gi, gz, _knn = eng.lipid_grid(nx, ny, self.grid_mode, lat, frames=sl)
+            cells, th, ap_ = eng.grid_reduce(gi, gz, batch.type_code_dev, len(batch.type_names), lat,
+                                             frames=sl)
+            gi_l.append(gi); gz_l.append(gz); cells_l.append(cells)
+            thick[sl] = th.cpu().numpy()
+            apl[sl] = ap_.cpu().numpy()
+        return GridBatch(gi_l, gz_l, cells_l, thick, apl, runs)
+
+    # -- iterator: per-frame host views -------------------------------------------------------
+    def __iter__(self):
+        return self
+
+    def _start(self):
+        batch = self._reduce()
+        for a_id in self._analysis_protocol.analysis_ids:
+            proto = self._analysis_protocol.command_protocol[a_id]
+            if getattr(proto, 'batched', False):
+                proto.run_batch(self.settings, batch, self._mda_data)
+        self._legacy = [self._analysis_protocol.command_protocol[a] for a in
+                        self._analysis_protocol.analysis_ids
+                        if not getattr(self._analysis_protocol.command_protocol[a], 'batched', False)]
+        self._started = True
+
+    def _host_arrays(self):
+        if self._host is None:
+            e = self._engine
+            self._host = {'com': e.com.cpu().numpy(), 'com_unwrap': e.com_unwrap.cpu().numpy(),
+                          'mem_com': e.mem_com.cpu().numpy(), 'labels': e.labels.cpu().numpy()}
+        return self._host
+
+    def frame_views(self, f, need_grid=None):
+        """Host views of analysed frame ``f``: the objects the reference rebuilds per frame."""
+        h = self._host_arrays()
+        e, lay = self._engine, self._engine.layout
+        g = int(f)
+        upd = int(self.rep_settings['leaflets']['update_interval'])
+        src = g - (g % upd)
+        names = None
+        if g == src:          # _update_com_frame_leaflet_positions only on rebuild frames (A.10)
+            names = np.where(h['labels'][g] == 1, 'upper', 'lower')
+        frame = cf.COMFrame(h['com'][g], h['com_unwrap'][g], lay.bead_mass, lay.types, lay.resids,
+                            self._dims[g, :3], self._times[g], int(self._frames[g]), h['mem_com'][g],
+                            names)
+        leaflets = lf.leaflets_from_labels(h['labels'][g], lay.types, lay.resids)
+        grid = None
+        if need_grid if need_grid is not None else self._analysis_protocol.use_objects['lipid_grid']:
+            gb = self._batch.lipid_grids()
+            gi, gz, cells = gb.frame(g)
+            grid = lg.LipidGrids(frame, leaflets, self.settings['lateral'], gi, gz,
+                                 gb.thickness_host[g], gb.apl_host[g], cells, self._batch.type_names)
+        return frame, leaflets, grid
+
+    def __next__(self):
+        if self._batch is None or not getattr(self, '_started', False):
+            if self._current_frame > self._last_frame:
+                raise StopIteration()
+            self._started = False
+            self._start()
+            self._cursor = 0
+        if self._cursor >= len(self._frames):
+            self._started = False
+            raise StopIteration()
+        g = self._cursor
+        self.settings['frame_index'] = int(self._frames[g])
+        need_views = bool(self._legacy) or self._iterating_for_user
+        if need_views:
+            frame, leaflets, grid = self.frame_views(g)
+            x, d, t = self._mda_data.frames(self._frames[g:g + 1])
+            self.reps['current_mda_frame'] = _HostFrame(np.asarray(x[0]), d[0], t[0], int(self._frames[g]))
+            self.reps['com_frame'] = frame
+            if g == 0:
+                self.reps['first_com_frame'] = frame
+            self.reps['leaflets'] = leaflets
+            self.reps['lipid_grid'] = grid
+            self._dump_reps(int(self._frames[g]))
+            for proto in self._legacy:
+                proto.run_analysis(self.settings, self.reps, self._mda_data)
+        self._cursor += 1
+        self._frame_loop_count += 1
+        self._current_frame = int(self._frames[g]) + self.settings['frame_range'][2]
+        return
+
+    _iterating_for_user = True
+
+    def run_analysis(self):
+        """Run every registered analysis over the analysed frames (bilayer_analyzer.py:777-790).
+        Batched run: no per-frame host views unless a plain per-frame plugin needs them."""
+        self._iterating_for_user = False
+        try:
+            for _frame in self:
+                pass
+        finally:
+            self._iterating_for_user = True
+
+    def _dump_reps(self, frame_number):
+        """Per-frame pickles of the representations (bilayer_analyzer.py:982-1003)."""
+        for rep, prefix in (('com_frame', 'com_frame_'), ('leaflets', 'leaflets_'),
+                            ('lipid_grid', 'lipid_grid_')):
+            if self.rep_settings[rep]['dump'] and self.reps[rep] is not None:
+                name = self.rep_settings[rep]['dump_path'] + prefix + str(frame_number) + ".pickle"
+                with open(name, 'wb') as ofile:
+                    pickle.dump(self.reps[rep], ofile)

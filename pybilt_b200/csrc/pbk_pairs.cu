@@ -13,7 +13,7 @@
 // class byte of a lipid in a frame: bit0 = leaflet label, bit1 = is type A, bit2 = is type B
 __device__ __forceinline__ unsigned pbk_cls(uint8_t label, int type, int ta, int tb)
 {
-    return (unsigned)(label & 1) | ((ta < 0 || type == ta) ? 2u : 0u) | ((tb < 0 || type == tb) ? 4u : 0u);
+    return (unsigned)(label & 1) | ((ta == -1 || type == ta) ? 2u : 0u) | ((tb == -1 || type == tb) ? 4u : 0u);
 }
 
 // counts[leaf][0..2] = (N_a, N_b, N_leaflet) of the frame; every thread gets the result

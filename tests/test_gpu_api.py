@@ -1,0 +1,137 @@
+"""The drop-in API (pybilt_b200.BilayerAnalyzer + the plugin registry) against the golden
+outputs of the literal reference: same analysis strings, same get_analysis_data shapes."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def close(a, b, rtol, atol=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    both_nan = np.isnan(a) & np.isnan(b)
+    ok = both_nan | (np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + atol)
+    assert ok.all(), float(np.nanmax(np.abs(a - b)))
+
+
+def make_analyzer(name):
+    from pybilt_b200 import BilayerAnalyzer
+    c = cases.CASES[name]
+    top, traj = cases.make_inputs(name)
+    ba = BilayerAnalyzer(structure=top, trajectory=traj, selection="all")
+    ba.remove_analysis("msd_1")
+    for a in c["analyses"]:
+        ba.add_analysis(a)
+    for rep, d in (c.get("rep_settings") or {}).items():
+        for k, v in d.items():
+            ba.rep_settings[rep][k] = v
+    if c.get("frame_range"):
+        ba.set_frame_range(*c["frame_range"])
+    return ba, c
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_api_outputs_match_reference(name):
+    gold = load(name)
+    ba, c = make_analyzer(name)
+    ba.run_analysis()
+    out = {a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()}
+    flat = cases.flatten_outputs(out)
+    keys = [k for k in gold if k.startswith("out/")]
+    assert sorted(keys) == sorted(flat)
+    for k in keys:
+        # msd / msd_multi / nnf / thickness / apl rows: 1e-9 relative (north_star);
+        # RDF: counts are exact, so the normalised g(r) agrees to rounding
+        close(flat[k], gold[k], 1e-9, atol=1e-300)
+
+
+def test_iterator_views_match_reference():
+    name = "tiny_all"
+    gold = load(name)
+    ba, c = make_analyzer(name)
+    n = 0
+    for _ in ba:
+        frame = ba.reps["com_frame"]
+        f = n
+        assert len(frame) == gold["rep/com"].shape[1]
+        got = np.array([l.com for l in frame.lipidcom])
+        assert np.array_equal(got, gold["rep/com"][f])
+        got_u = np.array([l.com_unwrap for l in frame.lipidcom])
+        assert np.array_equal(got_u, gold["rep/com_unwrap"][f])
+        assert np.array_equal(frame.mem_com, gold["rep/mem_com"][f])
+        up = ba.reps["leaflets"]["upper"].get_member_indices()
+        assert np.array_equal(np.nonzero(gold["rep/labels"][f] == 1)[0], up)
+        grid = ba.reps["lipid_grid"]
+        for leaf in ("upper", "lower"):
+            assert np.array_equal(grid.leaf_grid[leaf].lipid_grid, gold[f"rep/grid_{leaf}"][f])
+        th = grid.average_thickness()
+        close(np.array(th), gold["rep/thickness"][f], 1e-12)
+        avg, per_res, area = grid.area_per_lipid()
+        close(np.array([area[i] for i in sorted(area)]), gold["rep/apl_lipid"][f], 1e-12)
+        assert frame.time == gold["rep/time"][f]
+        n += 1
+    assert n == gold["rep/com"].shape[0]
+    # results are the same as a batched run
+    close(ba.get_analysis_data("msd_1"), gold["out/msd_1"], 1e-9)
+
+
+def test_plain_per_frame_plugin_still_works():
+    """A plugin written against the reference recipe (analysis_protocols.py:9-37)."""
+    from pybilt_b200 import analysis_protocols as ap
+
+    class ZSpread(ap.AnalysisProtocol):
+        analysis_key = "zspread"
+
+        def __init__(self, args):
+            self.analysis_id = "none"
+            self.settings = {"leaflet": "upper"}
+            self._valid_settings = list(self.settings)
+            self._parse_args(args)
+            self.save_file_name = self.analysis_id + ".pickle"
+            self.analysis_output = []
+
+        def run_analysis(self, ba_settings, ba_reps, ba_mda_data):
+            idx = ba_reps["leaflets"][self.settings["leaflet"]].get_member_indices()
+            z = [ba_reps["com_frame"].lipidcom[i].com_unwrap[ba_settings["norm"]] for i in idx]
+            self.analysis_output.append([ba_reps["com_frame"].time, float(np.std(z))])
+
+    ap.valid_analysis.append("zspread")
+    ap.analysis_obj_name_dict["zspread"] = "com_frame"
+    ap.command_protocols["zspread"] = ZSpread
+    try:
+        gold = load("tiny_all")
+        ba, c = make_analyzer("tiny_all")
+        ba.add_analysis("zspread zs leaflet lower")
+        ba.run_analysis()
+        got = ba.get_analysis_data("zs")
+        assert got.shape == (gold["rep/com"].shape[0], 2)
+        lab = gold["rep/labels"]
+        want = [np.std(gold["rep/com_unwrap"][f][lab[f] == 0][:, 2]) for f in range(len(lab))]
+        close(got[:, 1], np.array(want), 1e-12)
+    finally:
+        ap.valid_analysis.remove("zspread")
+        del ap.analysis_obj_name_dict["zspread"], ap.command_protocols["zspread"]
+
+
+def test_reset_and_rerun_and_frame_range():
+    ba, c = make_analyzer("c2_prefix")
+    ba.run_analysis()
+    first = ba.get_analysis_data("msd_1").copy()
+    ba.run_analysis()                      # exhausted iterator: nothing happens
+    assert np.array_equal(ba.get_analysis_data("msd_1"), first)
+    ba.reset()
+    ba.set_frame_range(10, 40, 3)
+    ba.run_analysis()
+    again = ba.get_analysis_data("msd_1")
+    assert again.shape == (11, 2)
+    assert again[0, 1] == 0.0 and again[0, 0] == 100.0
