@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- lipid-frames/s of the COM + MSD + lateral-RDF hot path on B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: every frame of the
+workload goes through unwrap -> membrane COM -> per-lipid COM -> leaflets, then single-origin
+MSD, multi-origin MSD (n_tau = n_sigma = 50) and the COM lateral RDF (reference defaults:
+25 bins, 0-25 A, both leaflets).  Workload at every N: BASELINE.json configs[1], the
+512-lipid POPC CG bilayer (12 beads/lipid), 5,000 frames PER GPU (frame shards, weak
+scaling; rank r holds frames r*5000 .. r*5000+4999 of one trajectory).
+
+value   lipid-frames/s with the frames already resident in HBM (CUDA events, max over ranks)
+e2e     the same through the public API (pybilt_b200.BilayerAnalyzer.run_analysis +
+        get_analysis_data) from PINNED HOST buffers, host<->device copies inside the timing
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+
+--impl reference times the CPU restatement of the reference (oracle/port.py; the reference
+itself is pure Python + MDAnalysis, which cannot run on the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LIPIDS, BEADS, FRAMES = 512, 12, 5000
+ANALYSES = ["msd msd_1", "msd_multi mm n_tau 50 n_sigma 50", "com_lateral_rdf rdf"]
+B_COM = 12 * BEADS + 48 + 1          # read f32 xyz of A atoms, write 2 f64 COMs + label
+B_MSD = 16
+B_RDF = 16 + 2
+B_PIPE = B_COM + B_MSD + B_RDF       # = 12*A + 83
+METRIC = "lipid-frames/s (COM+MSD+lateral RDF)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload(rank: int, frames: int):
+    from pybilt_b200 import synthetic as syn
+    spec, _ = syn.config_spec("C2")
+    return syn.generate(spec, frames, first_frame=rank * frames)
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_port_run(args):
+    """One shard of the CPU baseline: the oracle port over `frames` frames (own process)."""
+    rank, first, frames = args
+    from oracle import port
+    from pybilt_b200 import synthetic as syn
+    spec, _ = syn.config_spec("C2")
+    top, traj = syn.generate(spec, frames, first_frame=first)
+    t0 = time.perf_counter()
+    port.run(top, traj, ANALYSES)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(frames: int, procs: int):
+    """lipid-frames/s of oracle/port.py over `frames` frames split over `procs` processes
+    (each shard an independent frame range, like COMTraj.calc_msd_parallel's mp.Pool)."""
+    import multiprocessing as mp
+    from oracle import build as obuild
+    obuild.build()
+    per = max(50, frames // procs)
+    jobs = [(i, i * per, per) for i in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        cpu_port_run(jobs[0])
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(cpu_port_run, jobs)
+    wall = time.perf_counter() - t0
+    return N_LIPIDS * per * procs / wall, per * procs, wall
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    # spawn start-up (numpy import + generating the shard) is excluded by timing inside the
+    # workers; the line reports whole-job throughput over the slowest worker
+    import multiprocessing as mp
+    from oracle import build as obuild
+    obuild.build()
+    per = max(50, FRAMES // procs)
+    jobs = [(i, i * per, per) for i in range(procs)]
+    times = []
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for _ in range(a.warmup):
+            pool.map(cpu_port_run, jobs)
+        for _ in range(a.steps):
+            times.append(max(pool.map(cpu_port_run, jobs)))
+    ms = 1e3 * sum(times) / len(times)
+    value = N_LIPIDS * per * procs / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "lipid-frames/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C2: 512-lipid POPC CG bilayer (12 beads), %d frames per step; "
+                                   "COM + msd + msd_multi(50,50) + com_lateral_rdf(25 bins, 25 A)"
+                                   % (per * procs)},
+            "cpu_baseline": {"value": value, "unit": "lipid-frames/s", "cores": procs,
+                             "kind": "port",
+                             "sample": "%d frames in %d frame-range shards of %d (oracle/port.py, "
+                                       "one process per host core)" % (per * procs, procs, per)},
+            "e2e": {"value": value, "unit": "lipid-frames/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: config C2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pybilt_b200 import BilayerAnalyzer, engine as eng
+    from pybilt_b200.analysis_protocols import msd_multi_schedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = a.frames
+    top, traj = workload(rank, F)
+    M = top.n_atoms
+    layout = eng.build_bead_layout(top.masses, top.names, top.resindex, top.resnames, top.resids)
+    e = eng.LipidReductionEngine(top.masses, layout, F, device=local)
+
+    x_host = torch.from_numpy(traj.positions).pin_memory()
+    box_host = torch.from_numpy(np.ascontiguousarray(traj.dimensions[:, :3])).pin_memory()
+    x_dev = x_host.to(dev)
+    box_dev = box_host.to(dev)
+    codes = torch.zeros(layout.n_beads, dtype=torch.int32, device=dev)
+    edges = np.histogram([-1], bins=25, range=[0.0, 25.0])[1]
+    edges_dev = torch.from_numpy(edges).to(dev)
+    fin, _nb = msd_multi_schedule(F, 50, 50)
+    mm_o = torch.tensor([fin[b][0] for b in sorted(fin)], dtype=torch.int32, device=dev)
+    mm_e = torch.tensor([fin[b][1] for b in sorted(fin)], dtype=torch.int32, device=dev)
+    zeros = torch.zeros(F, dtype=torch.int32, device=dev)
+    arange = torch.arange(F, dtype=torch.int32, device=dev)
+
+    # index list of 'msd ... leaflet both resname all': upper members then lower (frame 0)
+    e.push(x_dev[:1], box_dev[:1])
+    lab0 = e.labels[0].cpu().numpy()
+    idx = torch.from_numpy(np.concatenate([np.nonzero(lab0 == 1)[0], np.nonzero(lab0 == 0)[0]])
+                           .astype(np.int32)).to(dev)
+
+    stage_names = ["reduce(unwrap+memCOM+lipidCOM+leaflets)", "msd", "msd_multi", "rdf"]
+
+    def step(events=None):
+        def mark(i):
+            if events is not None:
+                events[i].record()
+        e.reset()
+        mark(0)
+        e.push(x_dev, box_dev)
+        mark(1)
+        m1 = e.msd_pairs(idx, zeros, arange)
+        mark(2)
+        m2 = e.msd_pairs(idx, mm_o, mm_e)
+        mark(3)
+        cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev)
+        if world > 1:                       # partial histograms of the frame shards (NCCL, NVLink)
+            dist.all_reduce(cnt)
+        mark(4)
+        return m1, m2, cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    l0 = e.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = e.launches - l0
+    e.check_status()
+    # per-stage device time (same steps, instrumented) -> dominant kernel for the roofline
+    stage_ms = np.zeros(4)
+    reps = max(3, min(a.steps, 10))
+    for _ in range(reps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        step(evs)
+        torch.cuda.synchronize()
+        stage_ms += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(4)])
+    stage_ms /= reps
+
+    # ---- end to end through the public API, from pinned host memory ---------------------
+    ba = BilayerAnalyzer(structure=top, trajectory=(x_host, traj.dimensions, traj.times),
+                         selection="all", device=local)
+    ba.remove_analysis("msd_1")
+    for s in ANALYSES:
+        ba.add_analysis(s)
+    ba.batch_frames = 500
+
+    def api_step():
+        ba.reset()
+        ba.run_analysis()
+        return [ba.get_analysis_data(k) for k in ("msd_1", "mm", "rdf")]
+
+    for _ in range(max(1, a.warmup)):
+        res = api_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = api_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    d2h = F * layout.n_beads + F * 8 + len(mm_o) * 8 + 25 * 8 + F * 24 + 4   # labels0.., msd, mm, rdf count, frame counts, status
+    h2d = int(x_host.numel() * 4 + box_host.numel() * 4)
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / a.steps
+    total_lf = N_LIPIDS * F * world
+    value = total_lf / (ms_step * 1e-3)
+    e2e_val = total_lf / (e2e_ms / a.steps * 1e-3)
+
+    if rank == 0:
+        peak, which = peaks()
+        dom = int(np.argmax(stage_ms))
+        dom_bytes = [B_COM, B_MSD, B_MSD * len(mm_o) / F, B_RDF][dom] * N_LIPIDS * F
+        achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "lipid-frames/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 512-lipid POPC CG bilayer (12 beads/lipid), %d frames per GPU; "
+                                   "COM+unwrap+leaflets, msd, msd_multi(50,50), com_lateral_rdf(25 bins, "
+                                   "0-25 A, both leaflets)" % F,
+                       "frames_per_gpu": F, "lipids": N_LIPIDS, "atoms": M,
+                       "l2": "inputs larger than L2 (%.0f MB of positions per step)" % (h2d / 1e6),
+                       "sharding": "frames"},
+            "e2e": {"value": e2e_val, "unit": "lipid-frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved,
+                         "peak": peak, "peak_source": which, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "pipeline_achieved": B_PIPE * N_LIPIDS * F / (ms_step * 1e-3) / 1e9,
+                         "pipeline_frac": B_PIPE * N_LIPIDS * F / (ms_step * 1e-3) / 1e9 / peak},
+            "stages_ms": {n: float(v) for n, v in zip(stage_names, stage_ms)},
+        }
+        if not a.no_cpu_baseline and world == 1:
+            v, nfr, wall = cpu_baseline(FRAMES, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "lipid-frames/s", "cores": 1, "kind": "port",
+                                    "sample": "all %d frames of the workload, oracle/port.py in one "
+                                              "process (%.1f s)" % (nfr, wall)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -222,6 +222,7 @@ class BilayerAnalyzer(object):
                            'area_per_bin': None},
             'vector_frame': {'dump': False, 'dump_path': "./", 'ref_atoms': None}}
         self.device = device
+        self.batch_frames = None    # frames per host->device batch (None: sized from scratch memory)
         self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
         self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
         self._frame_loop_count = 0
@@ -416,7 +417,8 @@ class BilayerAnalyzer(object):
         self._frames = fr
         eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
                                    norm=self.settings['norm'],
-                                   leaflet_update_interval=int(lset['update_interval']))
+                                   leaflet_update_interval=int(lset['update_interval']),
+                                   batch_frames=self.batch_frames)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
         dev = eng.dev
         copy_stream = torch.cuda.Stream(dev)

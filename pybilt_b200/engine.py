@@ -181,9 +181,7 @@ class LipidReductionEngine:
     def msd_pairs(self, idx: np.ndarray, origins: Sequence[int], ends: Sequence[int],
                   lateral=(0, 1)) -> torch.Tensor:
         d = self.dev
-        d_idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=d)
-        d_o = torch.as_tensor(np.ascontiguousarray(origins, dtype=np.int32), device=d)
-        d_e = torch.as_tensor(np.ascontiguousarray(ends, dtype=np.int32), device=d)
+        d_idx, d_o, d_e = (self._i32(v) for v in (idx, origins, ends))
         out = torch.empty(len(d_o), dtype=torch.float64, device=d)
         self.ctx.call("pbk_msd_pairs", self.com_unwrap.data_ptr(), self.n_done, self.N,
                       d_idx.data_ptr(), int(d_idx.numel()), int(lateral[0]), int(lateral[1]),
@@ -191,13 +189,22 @@ class LipidReductionEngine:
         self.launches += 1
         return out
 
+    def _i32(self, v) -> torch.Tensor:
+        if torch.is_tensor(v):
+            assert v.is_cuda and v.dtype == torch.int32
+            return v
+        return torch.as_tensor(np.ascontiguousarray(v, dtype=np.int32), device=self.dev)
+
     def rdf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int,
-            edges: np.ndarray, lateral=(0, 1), frames: Optional[slice] = None):
+            edges, lateral=(0, 1), frames: Optional[slice] = None, edges_dev=None):
+        """``edges``: the float64 np.histogram edges (host); ``edges_dev`` an optional
+        device copy of them so that no host->device copy happens inside the call."""
         d = self.dev
         sl = frames or slice(0, self.n_done)
         F = sl.stop - sl.start
         nb = len(edges) - 1
-        d_edges = torch.as_tensor(np.ascontiguousarray(edges, dtype=np.float64), device=d)
+        d_edges = edges_dev if edges_dev is not None else torch.as_tensor(
+            np.ascontiguousarray(edges, dtype=np.float64), device=d)
         count = torch.zeros(nb, dtype=torch.int64, device=d)
         fc = torch.empty((F, 2, 3), dtype=torch.int32, device=d)
         self.ctx.call("pbk_rdf", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
