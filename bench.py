@@ -206,6 +206,7 @@ def main():
     codes = torch.zeros(layout.n_beads, dtype=torch.int32, device=dev)
     edges = np.histogram([-1], bins=25, range=[0.0, 25.0])[1]
     edges_dev = torch.from_numpy(edges).to(dev)
+    thr_dev = torch.from_numpy(eng.rdf_thresholds(edges)).to(dev)
     fin, _nb = msd_multi_schedule(F, 50, 50)
     mm_o = torch.tensor([fin[b][0] for b in sorted(fin)], dtype=torch.int32, device=dev)
     mm_e = torch.tensor([fin[b][1] for b in sorted(fin)], dtype=torch.int32, device=dev)
@@ -232,7 +233,7 @@ def main():
         mark(2)
         m2 = e.msd_pairs(idx, mm_o, mm_e)
         mark(3)
-        cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev)
+        cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev, thr_dev=thr_dev)
         if world > 1:                       # partial histograms of the frame shards (NCCL, NVLink)
             dist.all_reduce(cnt)
         mark(4)

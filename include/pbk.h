@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 1
+#define PBK_ABI_VERSION 2
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -112,13 +112,17 @@ int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
  * Per frame and per leaflet in leaflet_mask (bit0 upper, bit1 lower) that holds at least one
  * lipid of type_a and one of type_b (type -1 = 'all', any other negative = no lipid): every ordered pair i in A, j in B,
  * i != j, minimum-image lateral distance of the wrapped COMs, binned on edges[n_bins+1]
- * (the float64 linspace np.histogram builds).  count[n_bins] (uint64) is accumulated;
+ * (the float64 linspace np.histogram builds).  thr[n_bins+1] are the same edges expressed on
+ * d^2: thr[k] = min{t : sqrt_rn(t) >= edges[k]}, thr[n_bins] = min{t : sqrt_rn(t) > edges[n_bins]}
+ * (pybilt_b200/engine.py: rdf_thresholds), which lets the kernel bin without sqrt; thr == NULL
+ * selects the dense sqrt-based fallback kernel.  count[n_bins] (uint64) is accumulated;
  * frame_counts[F][2][3] int32 receives (N_a, N_b, N_leaflet) per frame and leaflet
  * (upper row 0, lower row 1), N_a = N_b = 0 where the leaflet was skipped. */
 int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
             const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
             int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
-            const double *edges, unsigned long long *count, int32_t *frame_counts, void *stream);
+            const double *edges, const double *thr, unsigned long long *count,
+            int32_t *frame_counts, void *stream);
 
 /* ---- D3  nearest-neighbour fraction -----------------------------------------------------
  * NNFProtocol.run_analysis             pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257

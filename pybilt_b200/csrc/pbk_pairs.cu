@@ -121,17 +121,13 @@ k_rdf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
     }
 }
 
-extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
-                       const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
-                       int lat1, int type_a, int type_b, int leaflet_mask, int32_t n_bins,
-                       double range_lo, double range_hi, const double *edges,
-                       unsigned long long *count, int32_t *frame_counts, void *stream)
+// dense O(N^2) fallback of pbk_rdf (pbk_rdf2.cu) for leaflets that do not fit in shared memory
+int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
+                  const double *edges, unsigned long long *count, int32_t *frame_counts,
+                  cudaStream_t stream)
 {
-    if (!ctx || !com || !labels || !type_code || !box || !edges || !count || !frame_counts ||
-        F < 0 || N <= 0 || n_bins <= 0 || !(range_hi > range_lo) || (leaflet_mask & ~3) ||
-        lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
-        return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: bad argument");
-    if (F == 0) return PBK_OK;
     int warps = PAIR_THREADS / 32;
     int copies = warps;
     auto smem_for = [&](int c) {

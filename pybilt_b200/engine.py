@@ -76,6 +76,39 @@ def build_bead_layout(masses, names, resindex, resnames, resids, name_dict=None,
     return BeadLayout(seg, gather, types, np.asarray(rid, dtype=np.int64), bead_mass)
 
 
+def rdf_thresholds(edges: np.ndarray) -> np.ndarray:
+    """Histogram edges expressed on d^2 so that binning needs no square root.
+
+    ``np.histogram`` puts r = sqrt(d2) (IEEE correctly rounded) into bin k iff
+    edges[k] <= r < edges[k+1] (last bin closed).  sqrt is monotone, so
+    thr[k] = min{t >= 0 : sqrt(t) >= edges[k]} and thr[n] = min{t : sqrt(t) > edges[n]} give
+    thr[k] <= d2 < thr[k+1]  <=>  r in bin k, exactly.
+    """
+    edges = np.asarray(edges, dtype=np.float64)
+    n = len(edges) - 1
+    thr = np.zeros(n + 1)
+
+    def least(e, strict):
+        ok = (lambda t: np.sqrt(t) > e) if strict else (lambda t: np.sqrt(t) >= e)
+        if e < 0 or (e == 0 and not strict):
+            return 0.0
+        t = np.float64(e) * np.float64(e)
+        while not ok(t):
+            t = np.nextafter(t, np.inf)
+        while t > 0:
+            prev = np.nextafter(t, -np.inf)
+            if ok(prev):
+                t = prev
+            else:
+                break
+        return float(t)
+
+    for k in range(n):
+        thr[k] = least(edges[k], False)
+    thr[n] = least(edges[n], True)
+    return thr
+
+
 class LipidReductionEngine:
     """Runs unwrap -> membrane COM -> lipid COM -> leaflets for batches of frames and keeps
     the results for all analysed frames resident on the device."""
@@ -196,22 +229,28 @@ class LipidReductionEngine:
         return torch.as_tensor(np.ascontiguousarray(v, dtype=np.int32), device=self.dev)
 
     def rdf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int,
-            edges, lateral=(0, 1), frames: Optional[slice] = None, edges_dev=None):
-        """``edges``: the float64 np.histogram edges (host); ``edges_dev`` an optional
-        device copy of them so that no host->device copy happens inside the call."""
+            edges, lateral=(0, 1), frames: Optional[slice] = None, edges_dev=None, thr_dev=None,
+            dense=False):
+        """``edges``: the float64 np.histogram edges (host); ``edges_dev`` / ``thr_dev``
+        optional device copies of the edges and of ``rdf_thresholds(edges)`` so that no
+        host->device copy happens inside the call.  ``dense`` forces the O(N^2) sqrt kernel."""
         d = self.dev
         sl = frames or slice(0, self.n_done)
         F = sl.stop - sl.start
         nb = len(edges) - 1
         d_edges = edges_dev if edges_dev is not None else torch.as_tensor(
             np.ascontiguousarray(edges, dtype=np.float64), device=d)
+        if dense:
+            thr_dev = None
+        elif thr_dev is None:
+            thr_dev = torch.as_tensor(rdf_thresholds(edges), device=d)
         count = torch.zeros(nb, dtype=torch.int64, device=d)
         fc = torch.empty((F, 2, 3), dtype=torch.int32, device=d)
         self.ctx.call("pbk_rdf", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
                       type_code.data_ptr(), self.box[sl.start:].data_ptr(), F, self.N,
                       int(lateral[0]), int(lateral[1]), int(type_a), int(type_b), int(leaflet_mask),
-                      nb, float(edges[0]), float(edges[-1]), d_edges.data_ptr(), count.data_ptr(),
-                      fc.data_ptr(), self.stream_ptr())
+                      nb, float(edges[0]), float(edges[-1]), d_edges.data_ptr(), _ptr(thr_dev),
+                      count.data_ptr(), fc.data_ptr(), self.stream_ptr())
         self.launches += 1
         return count, fc
 

@@ -126,6 +126,9 @@ def test_rdf_counts_match_port(name):
         count, fc = e.rdf(d_codes, ca, cb, mask, edges)
         got = count.cpu().numpy()
         assert np.array_equal(got, want), (name, ra, rb, mask, np.abs(got - want).max())
+        count_d, fc_d = e.rdf(d_codes, ca, cb, mask, edges, dense=True)     # dense fallback kernel
+        assert np.array_equal(count_d.cpu().numpy(), want)
+        assert np.array_equal(fc.cpu().numpy(), fc_d.cpu().numpy())
         assert want.sum() > 0 or name == "tiny_all"
 
 
