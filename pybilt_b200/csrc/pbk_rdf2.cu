@@ -7,19 +7,28 @@
 // but organised for the hardware:
 //   * one work item = (frame, leaflet); a persistent grid loops over the items;
 //   * the leaflet's lipids of type A or B are counting-sorted into a 2-D cell grid in shared
-//     memory (cell edge ~ range_outer/2), and every lipid sweeps only the forward half shell
-//     of neighbouring cells, so each UNORDERED pair {p,q} is evaluated once;
-//   * the reference evaluates ordered pairs dist(a=i in A, b=j in B).  Without a minimum-image
-//     wrap d^2(p->q) == d^2(q->p) bit for bit, so one evaluation serves both directions; with a
-//     wrap the two orders round differently ((L-|a'|)-|b'|) and both are evaluated;
-//   * histogram bins are found from d^2 against thresholds thr[k] = min{t : sqrt_rn(t) >= edge_k}
-//     (thr[n_bins] = min{t : sqrt_rn(t) > edge_last}), which is exactly np.histogram's
-//     half-open-bins-last-closed rule on r = sqrt_rn(d^2) without a device sqrt or division;
-//   * bins accumulate in warp-private shared histograms, flushed to global uint64 once per CTA.
+//     memory (cell edge ~ range_outer/2); every lipid p (8 lanes each) sweeps the forward half
+//     shell of neighbouring cells -- per cell row one or two contiguous slot ranges -- so each
+//     UNORDERED pair {p,q} is visited once;
+//   * phase 1 (all candidates, float32): minimum-image d^2 against (range_outer + 0.01)^2; the
+//     survivors (p,q) are compacted into a per-warp ring queue;
+//   * phase 2 (survivors, 32 lanes in lockstep, float64): the reference's exact arithmetic.
+//     It evaluates ordered pairs dist(a=i in A, b=j in B); without a minimum-image wrap
+//     d^2(p->q) == d^2(q->p) bit for bit, so one evaluation serves both directions; with a
+//     wrap the two orders round differently ((L-|a'|)-|b'|) and both are formed;
+//   * bins come from d^2 against thresholds thr[k] = min{t : sqrt_rn(t) >= edge_k}
+//     (thr[n_bins] = min{t : sqrt_rn(t) > edge_last}) -- exactly np.histogram's rule on
+//     r = sqrt_rn(d^2) without a device sqrt or division -- through a look-up table over
+//     d^2 cells of width 2^-m (index and cell edges exact in binary floating point, at most
+//     one threshold per cell);
+//   * counts accumulate in warp-private shared histograms, flushed to global uint64 once per CTA.
 #include "pbk_common.cuh"
 
 #define RDF2_THREADS 256
-#define RDF2_MAXCELLS 1024          // per dimension product cap (<= 32 x 32)
+#define RDF2_WARPS (RDF2_THREADS / 32)
+#define RDF2_MAXCELLS 1024          // cells per leaflet (<= 32 x 32)
+#define RDF2_MAXROWS 8              // my + 1
+#define RDF2_QCAP 128               // ring queue entries per warp
 
 struct Rdf2Params {
     const double *com;
@@ -28,35 +37,75 @@ struct Rdf2Params {
     const float *box;
     int64_t F, N;
     int lat0, lat1, ta, tb, leaflet_mask, nb;
-    float lo_f, inv_w_f;
     double range_hi;
+    float cut2_f;                   // (range_hi + margin)^2 for the float32 prefilter
     const double *thr;
     unsigned long long *count;
     int32_t *frame_counts;
     int cap;                        // capacity of the per-leaflet shared arrays
     int hist_copies;
     int lut_n;                      // entries of the d^2 -> bin look-up table
-    float lut_scale;                // lut index = (d2 - thr[0]) * lut_scale
-    float thr0_f;
+    double lut_scale;               // 2^m: lut index = floor(d2 * 2^m) - lut_c0
+    int lut_c0;
 };
 
-// bin of d2: look-up table on uniformly quantised d^2 gives a bin at most one off (every
-// table cell holds at most one threshold when lut_n > n_bins^2), corrected against thr[].
+// bin of d2 (or -1).  The table holds, per d^2 cell, the bin of the cell's lower edge; a cell
+// contains at most one threshold, so the bin is that or the next one.
 __device__ __forceinline__ int rdf2_bin(double d2, const double *s_thr, const unsigned char *s_lut,
                                         const Rdf2Params &P)
 {
     if (!(d2 >= s_thr[0]) || !(d2 < s_thr[P.nb])) return -1;
-    int c = (int)(((float)d2 - P.thr0_f) * P.lut_scale);
+    int c = __double2int_rd(d2 * P.lut_scale) - P.lut_c0;
     c = max(0, min(P.lut_n - 1, c));
     int k = s_lut[c];
-    while (d2 >= s_thr[k + 1]) k++;
-    while (d2 < s_thr[k]) k--;
+    k += (d2 >= s_thr[k + 1]) ? 1 : 0;
     return k;
 }
 
-struct Rdf2Params;
-__device__ __forceinline__ int rdf2_bin(double d2, const double *s_thr, const unsigned char *s_lut,
-                                        const Rdf2Params &P);
+template <bool SAME>
+__device__ __forceinline__ void rdf2_exact(unsigned entry, const double *s_bx, const double *s_by,
+                                           const unsigned char *s_flag, const double *s_thr,
+                                           const unsigned char *s_lut, unsigned *myhist,
+                                           const Rdf2Params &P, double Lx, double Ly, double hx,
+                                           double hy)
+{
+    const int p = entry & 0xFFFFu, q = entry >> 16;
+    int w1 = 1, w2 = 1;
+    if (!SAME) {
+        const unsigned fp = s_flag[p], fq = s_flag[q];
+        w1 = (fp & 1u) && (fq & 2u);            // ordered p -> q
+        w2 = (fq & 1u) && (fp & 2u);            // ordered q -> p
+        if (!(w1 | w2)) return;
+    }
+    const double apx = s_bx[p], apy = s_by[p], bqx = s_bx[q], bqy = s_by[q];
+    double dx = __dsub_rn(apx, bqx), dy = __dsub_rn(apy, bqy);
+    const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
+    if (!(wrx | wry)) {
+        const int k = rdf2_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, s_lut, P);
+        if (k >= 0) atomicAdd(&myhist[k], (unsigned)(w1 + w2));
+        return;
+    }
+    double dx2 = dx, dy2 = dy;                  // the q -> p evaluation
+    if (wrx) {
+        dx = __dsub_rn(__dsub_rn(Lx, fabs(apx)), fabs(bqx));
+        dx2 = __dsub_rn(__dsub_rn(Lx, fabs(bqx)), fabs(apx));
+    }
+    if (wry) {
+        dy = __dsub_rn(__dsub_rn(Ly, fabs(apy)), fabs(bqy));
+        dy2 = __dsub_rn(__dsub_rn(Ly, fabs(bqy)), fabs(apy));
+    }
+    const double d2a = fma(dy, dy, __dmul_rn(dx, dx));
+    const double d2b = fma(dy2, dy2, __dmul_rn(dx2, dx2));
+    const int ka = rdf2_bin(d2a, s_thr, s_lut, P);
+    int kb = ka;
+    if (d2b != d2a) kb = rdf2_bin(d2b, s_thr, s_lut, P);
+    if (ka == kb) {
+        if (ka >= 0) atomicAdd(&myhist[ka], (unsigned)(w1 + w2));
+    } else {
+        if (w1 && ka >= 0) atomicAdd(&myhist[ka], 1u);
+        if (w2 && kb >= 0) atomicAdd(&myhist[kb], 1u);
+    }
+}
 
 template <bool SAME>
 __global__ void __launch_bounds__(RDF2_THREADS)
@@ -67,27 +116,31 @@ k_rdf2(Rdf2Params P)
     double *s_thr = reinterpret_cast<double *>(smem_raw);                   // nb+1
     double *s_bx = s_thr + (nb + 1);                                        // cap   b' = x - hx
     double *s_by = s_bx + cap;                                              // cap
-    unsigned *s_hist = reinterpret_cast<unsigned *>(s_by + cap);            // copies*nb
+    float2 *s_fxy = reinterpret_cast<float2 *>(s_by + cap);                 // cap   float32 copy of b'
+    unsigned *s_hist = reinterpret_cast<unsigned *>(s_fxy + cap);           // copies*nb
     int *s_cell_start = reinterpret_cast<int *>(s_hist + (size_t)P.hist_copies * nb);  // MAXCELLS+1
     int *s_cell_fill = s_cell_start + (RDF2_MAXCELLS + 1);                  // MAXCELLS
-    unsigned short *s_cellid = reinterpret_cast<unsigned short *>(s_cell_fill + RDF2_MAXCELLS);  // N
+    unsigned *s_queue = reinterpret_cast<unsigned *>(s_cell_fill + RDF2_MAXCELLS);     // WARPS*QCAP
+    unsigned short *s_cellid = reinterpret_cast<unsigned short *>(s_queue + RDF2_WARPS * RDF2_QCAP);  // N
     unsigned short *s_scell = s_cellid + P.N;                               // cap (sorted): cell of slot
     unsigned char *s_flag = reinterpret_cast<unsigned char *>(s_scell + cap);    // cap (sorted)
     unsigned char *s_lut = s_flag + cap;                                    // lut_n
     __shared__ int s_cnt[3];
-    __shared__ int s_scan[RDF2_THREADS / 32];
+    __shared__ int s_scan[RDF2_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int q = tid; q <= nb; q += blockDim.x) s_thr[q] = P.thr[q];
     for (int q = tid; q < P.hist_copies * nb; q += blockDim.x) s_hist[q] = 0u;
-    // look-up table: bin of the lower edge of every d^2 cell
+    // look-up table: bin of the lower edge of every d^2 cell (edges c * 2^-m are exact)
     for (int c = tid; c < P.lut_n; c += blockDim.x) {
-        const double t = (double)P.thr0_f + (double)c / (double)P.lut_scale;
+        const double t = (double)(c + P.lut_c0) / P.lut_scale;
         int k = 0;
         while (k < nb - 1 && t >= P.thr[k + 1]) k++;
         s_lut[c] = (unsigned char)k;
     }
     unsigned *myhist = s_hist + (size_t)(warp % P.hist_copies) * nb;
+    unsigned *myq = s_queue + warp * RDF2_QCAP;
+    const unsigned lt_mask = (1u << lane) - 1u;
     __syncthreads();
 
     const int64_t n_items = P.F * 2;
@@ -109,34 +162,48 @@ k_rdf2(Rdf2Params P)
         const double wx = Lx / ncx, wy = Ly / ncy;
         int mx = (int)floor((P.range_hi + 1e-6) / wx) + 1, my = (int)floor((P.range_hi + 1e-6) / wy) + 1;
         if (2 * mx + 1 > ncx) { ncx = 1; mx = 0; }
-        if (2 * my + 1 > ncy) { ncy = 1; my = 0; }
-        const double iwx = ncx / Lx, iwy = ncy / Ly;
-        const int ncell = ncx * ncy;
-
-        if (tid < 3) s_cnt[tid] = 0;
-        for (int c = tid; c < ncell; c += blockDim.x) s_cell_fill[c] = 0;
-        __syncthreads();
-        // pass 1: classify, count, bin into cells
-        int cA = 0, cB = 0, cL = 0;
-        for (int64_t i = tid; i < P.N; i += blockDim.x) {
-            unsigned short cid = 0xFFFF;
-            if (lab[i] == want) {
-                int t = P.type_code[i];
-                bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
-                cL++; cA += a; cB += b;
-                if (a || b) {
-                    int cx = (int)(cf[i * 3 + P.lat0] * iwx), cy = (int)(cf[i * 3 + P.lat1] * iwy);
-                    cx = max(0, min(ncx - 1, cx));
-                    cy = max(0, min(ncy - 1, cy));
-                    cid = (unsigned short)(cy * ncx + cx);
-                    atomicAdd(&s_cell_fill[cid], 1);
+        if (2 * my + 1 > ncy || my + 1 > RDF2_MAXROWS) { ncy = 1; my = 0; }
+        double iwx = ncx / Lx, iwy = ncy / Ly;
+        int ncell = ncx * ncy;
+        // Cells and the float32 prefilter assume wrapped coordinates (0 <= x <= L).  If any
+        // member lies outside the box the item is redone as a single cell with the prefilter
+        // off, i.e. every pair goes through the exact path (reference formula for any input).
+        bool all_pairs = false;
+        for (;;) {
+            if (tid < 3) s_cnt[tid] = 0;
+            for (int c = tid; c < ncell; c += blockDim.x) s_cell_fill[c] = 0;
+            __syncthreads();
+            // pass 1: classify, count, bin into cells
+            int cA = 0, cB = 0, cL = 0, oob = 0;
+            for (int64_t i = tid; i < P.N; i += blockDim.x) {
+                unsigned short cid = 0xFFFF;
+                if (lab[i] == want) {
+                    int t = P.type_code[i];
+                    bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
+                    cL++; cA += a; cB += b;
+                    if (a || b) {
+                        const double x = cf[i * 3 + P.lat0], y = cf[i * 3 + P.lat1];
+                        oob |= !(x >= 0.0 && x <= Lx && y >= 0.0 && y <= Ly);
+                        int cx = (int)(x * iwx), cy = (int)(y * iwy);
+                        cx = max(0, min(ncx - 1, cx));
+                        cy = max(0, min(ncy - 1, cy));
+                        cid = (unsigned short)(cy * ncx + cx);
+                        atomicAdd(&s_cell_fill[cid], 1);
+                    }
                 }
+                s_cellid[i] = cid;
             }
-            s_cellid[i] = cid;
+            cA = pbk_warp_sum(cA); cB = pbk_warp_sum(cB); cL = pbk_warp_sum(cL);
+            if (lane == 0) { atomicAdd(&s_cnt[0], cA); atomicAdd(&s_cnt[1], cB); atomicAdd(&s_cnt[2], cL); }
+            const int any_oob = __syncthreads_or(oob);
+            if (any_oob && !all_pairs) {
+                all_pairs = true;
+                ncx = ncy = 1; mx = my = 0; ncell = 1;
+                iwx = 1.0 / Lx; iwy = 1.0 / Ly;
+                continue;
+            }
+            break;
         }
-        cA = pbk_warp_sum(cA); cB = pbk_warp_sum(cB); cL = pbk_warp_sum(cL);
-        if (lane == 0) { atomicAdd(&s_cnt[0], cA); atomicAdd(&s_cnt[1], cB); atomicAdd(&s_cnt[2], cL); }
-        __syncthreads();
         const bool on = selected && s_cnt[0] > 0 && s_cnt[1] > 0;
         if (tid < 3) {
             int v = s_cnt[tid];
@@ -167,35 +234,34 @@ k_rdf2(Rdf2Params P)
             if (cid == 0xFFFF) continue;
             int slot = atomicAdd(&s_cell_fill[cid], 1);
             int t = P.type_code[i];
-            s_bx[slot] = __dsub_rn(cf[i * 3 + P.lat0], hx);
-            s_by[slot] = __dsub_rn(cf[i * 3 + P.lat1], hy);
+            const double bx = __dsub_rn(cf[i * 3 + P.lat0], hx), by = __dsub_rn(cf[i * 3 + P.lat1], hy);
+            s_bx[slot] = bx;
+            s_by[slot] = by;
+            s_fxy[slot] = make_float2((float)bx, (float)by);
             s_flag[slot] = (unsigned char)(((P.ta == -1 || t == P.ta) ? 1 : 0) | ((P.tb == -1 || t == P.tb) ? 2 : 0));
             s_scell[slot] = cid;
         }
         __syncthreads();
-        // pair sweep: 8 lanes per sorted lipid p; per row of the forward half shell the
-        // candidate cells are one or two contiguous slot ranges (cells of a row are adjacent
-        // in the sorted order), swept by the 8 lanes in lockstep
+
+        // ---- pair sweep -------------------------------------------------------------------
         const int sub = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+        const unsigned gshift = (unsigned)(lane & ~7);          // first lane of my group
+        int qhead = 0, qtail = 0;                               // ring queue (warp uniform)
         for (int p0 = 0; p0 < n_u; p0 += ngrp) {
             const int p = p0 + grp;
             const bool pact = p < n_u;
-            double apx = 0, apy = 0, tpx = 0, tpy = 0;
-            unsigned fp = 0;
-            int pcx = 0, pcy = 0;
+            float fpx = 0.f, fpy = 0.f;
+            // lane `sub` of the group prepares the slot ranges of half-shell row oy = sub
+            int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
             if (pact) {
-                apx = s_bx[p]; apy = s_by[p];
-                fp = s_flag[p];
-                tpx = __dsub_rn(Lx, fabs(apx)); tpy = __dsub_rn(Ly, fabs(apy));
-                const int pc = s_scell[p];
-                pcy = pc / ncx; pcx = pc - pcy * ncx;
-            }
-            for (int oy = 0; oy <= my; oy++) {
-                int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
-                if (pact) {
-                    int cy = pcy + oy; if (cy >= ncy) cy -= ncy;
+                const float2 fp = s_fxy[p];
+                fpx = fp.x; fpy = fp.y;
+                if (sub <= my) {
+                    const int pc = s_scell[p];
+                    const int pcy = pc / ncx, pcx = pc - pcy * ncx;
+                    int cy = pcy + sub; if (cy >= ncy) cy -= ncy;
                     const int row = cy * ncx;
-                    int xlo = (oy == 0) ? pcx : pcx - mx, xhi = pcx + mx;
+                    int xlo = (sub == 0) ? pcx : pcx - mx, xhi = pcx + mx;
                     if (xlo < 0) {                      // wraps on the left
                         b2 = s_cell_start[row + xlo + ncx]; n2 = s_cell_start[row + ncx] - b2;
                         xlo = 0;
@@ -205,43 +271,48 @@ k_rdf2(Rdf2Params P)
                         xhi = ncx - 1;
                     }
                     b1 = s_cell_start[row + xlo]; n1 = s_cell_start[row + xhi + 1] - b1;
-                    if (oy == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }   // own cell: later entries only
+                    if (sub == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }   // own cell: later entries only
                 }
-                const int ntot = n1 + n2;
-                for (int t = sub; t < ntot; t += 8) {
-                    const int q = t < n1 ? b1 + t : b2 + (t - n1);
-                    int w = 2;
-                    int w1 = 1, w2 = 1;
-                    if (!SAME) {
-                        const unsigned fq = s_flag[q];
-                        w1 = (fp & 1u) && (fq & 2u);            // ordered p -> q
-                        w2 = (fq & 1u) && (fp & 2u);            // ordered q -> p
-                        w = w1 + w2;
-                        if (!w) continue;
+            }
+            for (int oy = 0; oy <= my; oy++) {
+                const int rb1 = __shfl_sync(0xffffffffu, b1, gshift + oy);
+                const int rn1 = __shfl_sync(0xffffffffu, n1, gshift + oy);
+                const int rb2 = __shfl_sync(0xffffffffu, b2, gshift + oy);
+                const int rn2 = __shfl_sync(0xffffffffu, n2, gshift + oy);
+                const int ntot = rn1 + rn2;
+                // all lanes of the warp iterate together (max trip count over the 4 groups)
+                int nmax = ntot;
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+                for (int t0 = 0; t0 < nmax; t0 += 8) {
+                    const int t = t0 + sub;
+                    bool hit = false;
+                    int q = 0;
+                    if (t < ntot) {
+                        q = t < rn1 ? rb1 + t : rb2 + (t - rn1);
+                        const float2 fq = s_fxy[q];
+                        float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
+                        dx = fminf(dx, bxf - dx);
+                        dy = fminf(dy, byf - dy);
+                        hit = all_pairs || fmaf(dy, dy, dx * dx) < P.cut2_f;
                     }
-                    const double bqx = s_bx[q], bqy = s_by[q];
-                    double dx = __dsub_rn(apx, bqx), dy = __dsub_rn(apy, bqy);
-                    const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
-                    if (!(wrx | wry)) {
-                        const double d2 = fma(dy, dy, __dmul_rn(dx, dx));
-                        const int k = rdf2_bin(d2, s_thr, s_lut, P);
-                        if (k >= 0) atomicAdd(&myhist[k], (unsigned)w);
-                    } else {
-                        double dx2 = dx, dy2 = dy;              // the q -> p evaluation
-                        if (wrx) { dx = __dsub_rn(tpx, fabs(bqx)); dx2 = __dsub_rn(__dsub_rn(Lx, fabs(bqx)), fabs(apx)); }
-                        if (wry) { dy = __dsub_rn(tpy, fabs(bqy)); dy2 = __dsub_rn(__dsub_rn(Ly, fabs(bqy)), fabs(apy)); }
-                        if (w1) {
-                            const int k = rdf2_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, s_lut, P);
-                            if (k >= 0) atomicAdd(&myhist[k], 1u);
-                        }
-                        if (w2) {
-                            const int k = rdf2_bin(fma(dy2, dy2, __dmul_rn(dx2, dx2)), s_thr, s_lut, P);
-                            if (k >= 0) atomicAdd(&myhist[k], 1u);
-                        }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) myq[(qtail + __popc(m & lt_mask)) & (RDF2_QCAP - 1)] = (unsigned)p | ((unsigned)q << 16);
+                    qtail += __popc(m);
+                    if (qtail - qhead >= 32) {
+                        __syncwarp();
+                        rdf2_exact<SAME>(myq[(qhead + lane) & (RDF2_QCAP - 1)], s_bx, s_by, s_flag, s_thr,
+                                         s_lut, myhist, P, Lx, Ly, hx, hy);
+                        qhead += 32;
+                        __syncwarp();
                     }
                 }
             }
         }
+        __syncwarp();
+        if (lane < qtail - qhead)
+            rdf2_exact<SAME>(myq[(qhead + lane) & (RDF2_QCAP - 1)], s_bx, s_by, s_flag, s_thr, s_lut,
+                             myhist, P, Lx, Ly, hx, hy);
         __syncthreads();
     }
     __syncthreads();
@@ -271,16 +342,28 @@ extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: bad argument");
     if (F == 0) return PBK_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int copies = RDF2_THREADS / 32;
-    int lut_n = n_bins * n_bins + n_bins + 16;
-    if (lut_n > 16384) lut_n = 16384;
+    // d^2 look-up table: cells of width 2^-m no wider than the narrowest threshold spacing,
+    // which for uniform bins of width w starting at lo >= 0 is (lo+w)^2 - lo^2 >= w^2
+    const double w = (range_hi - range_lo) / n_bins;
+    const double lo = range_lo > 0 ? range_lo : 0.0;
+    const double min_gap = 0.999 * ((lo + w) * (lo + w) - lo * lo);
+    int m = 0;
+    while (ldexp(1.0, -m) > min_gap && m < 40) m++;
+    while (m > -40 && ldexp(1.0, -(m - 1)) <= min_gap) m--;
+    const double scale = ldexp(1.0, m);
+    const double c0d = floor(lo * lo * scale) - 1.0, c1d = floor(range_hi * range_hi * scale) + 2.0;
+    const double lut_nd = c1d - c0d + 1.0;
+    int copies = RDF2_WARPS;
+    const bool lut_ok = lut_nd <= 32768.0 && fabs(c0d) < 1e9;
+    const int lut_n = lut_ok ? (int)lut_nd : 0;
     auto smem_for = [&](int c) {
-        return (size_t)(n_bins + 1) * 8 + (size_t)N * 16 + (size_t)c * n_bins * 4 +
-               (size_t)(2 * RDF2_MAXCELLS + 1) * 4 + (size_t)N * 4 + (size_t)N + (size_t)lut_n + 16;
+        return (size_t)(n_bins + 1) * 8 + (size_t)N * 24 + (size_t)c * n_bins * 4 +
+               (size_t)(2 * RDF2_MAXCELLS + 1) * 4 + (size_t)RDF2_WARPS * RDF2_QCAP * 4 +
+               (size_t)N * 4 + (size_t)N + (size_t)lut_n + 16;
     };
     while (copies > 1 && smem_for(copies) > 64 * 1024) copies >>= 1;
     size_t smem = smem_for(copies);
-    if (!thr || smem > 200 * 1024 || N >= 65535 || n_bins > 255)
+    if (!thr || !lut_ok || smem > 200 * 1024 || N >= 65535 || n_bins > 255 || range_lo < 0)
         return pbk_rdf_dense(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
                              leaflet_mask, n_bins, range_lo, range_hi, edges, count, frame_counts, st);
     const bool same = (type_a == type_b);
@@ -295,15 +378,11 @@ extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
     Rdf2Params P;
     P.com = com; P.labels = labels; P.type_code = type_code; P.box = box; P.F = F; P.N = N;
     P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
-    P.nb = n_bins; P.lo_f = (float)range_lo; P.inv_w_f = (float)((double)n_bins / (range_hi - range_lo));
-    P.range_hi = range_hi; P.thr = thr; P.count = count; P.frame_counts = frame_counts;
+    P.nb = n_bins; P.range_hi = range_hi;
+    P.cut2_f = (float)((range_hi + 0.01) * (range_hi + 0.01) * 1.0001);
+    P.thr = thr; P.count = count; P.frame_counts = frame_counts;
     P.cap = (int)N; P.hist_copies = copies;
-    P.lut_n = lut_n;
-    // thr[] lives on the device; the table is laid over [range_lo^2, range_hi^2] (thr[0] and
-    // thr[n] differ from those by rounding only, and the kernel corrects +-1 cell anyway)
-    double t0 = range_lo > 0 ? range_lo * range_lo : 0.0, t1 = range_hi * range_hi;
-    P.thr0_f = (float)t0;
-    P.lut_scale = (float)((double)lut_n / (t1 - t0));
+    P.lut_n = lut_n; P.lut_scale = scale; P.lut_c0 = (int)c0d;
     kern<<<(unsigned)grid, RDF2_THREADS, smem, st>>>(P);
     PBK_CHECK_LAUNCH(ctx, "k_rdf2");
     return PBK_OK;

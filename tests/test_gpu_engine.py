@@ -186,3 +186,26 @@ def test_lipid_grid_matches_port(name, nx, mode):
         for li, leaf in enumerate(("upper", "lower")):
             cnt_want += np.bincount(g[leaf][0].reshape(-1), minlength=len(cnt_want))
         assert np.array_equal(cells[f], cnt_want)
+
+
+def test_rdf_out_of_box_coordinates_follow_reference_formula():
+    """Lipid COMs outside [0, L] (unwrapped input fed as wrapped): the reference's
+    `box - |a'| - |b'|` branch gives odd values; the kernel must reproduce them, not the
+    geometric minimum image (the cell list / prefilter is bypassed for such frames)."""
+    e, top, traj, fr, layout = run_engine("c3_small")
+    reps = port_reps("c3_small")
+    names, codes = type_codes(layout.types)
+    d_codes = torch.from_numpy(codes).cuda()
+    com = reps["com"].copy()
+    L = float(reps["box"][0, 0])
+    com[1, ::7, 0] += L            # frame 1: every 7th lipid one image to the right
+    com[2, ::5, 1] -= 0.75 * L     # frame 2: some lipids below the box
+    e.com.copy_(torch.from_numpy(com).cuda())
+    for (na, ca, nbn, cb, mask, nb, lo, hi) in [("all", -1, "all", -1, 3, 25, 0.0, 25.0),
+                                                 (names[0], 0, names[1], 1, 3, 80, 0.0, 40.0)]:
+        leaflet = {3: "both", 1: "upper", 2: "lower"}[mask]
+        (g, bins), want = port.rdf(com, reps["labels"], reps["types"], reps["box"], leaflet,
+                                   na, nbn, nb, lo, hi)
+        edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
+        count, fc = e.rdf(d_codes, ca, cb, mask, edges)
+        assert np.array_equal(count.cpu().numpy(), want)
