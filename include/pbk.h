@@ -29,15 +29,20 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 2
+#define PBK_ABI_VERSION 3
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
 #define PBK_ECUDA (-2)  /* CUDA runtime error (launch, attribute ...) */
+#define PBK_EUNSUPPORTED (-3) /* shape outside this entry point's fast path: use the generic one */
 
 /* bits of the device-side status word */
 #define PBK_ST_IMAGE_OVERFLOW 1 /* |image count| > 32767 or non-positive box length */
 #define PBK_ST_LEAFLET_TIE 2    /* com_unwrap[norm] == zavg: reference raises KeyError('') */
+#define PBK_ST_UNWRAP_AMBIGUOUS 4 /* fused path: a jump within rounding distance of L/2; redo with
+                                     pbk_unwrap_images/pbk_membrane_com/pbk_lipid_com */
+#define PBK_ST_FUSED_RANGE 8    /* fused path: |image count| > 126; redo with the generic path */
+#define PBK_ST_INTERNAL 16      /* a bulk copy never completed (should not happen) */
 
 typedef struct pbk_ctx pbk_ctx;
 
@@ -82,6 +87,29 @@ int pbk_lipid_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t 
                   const double *mass, const double *mem_com, const int32_t *seg,
                   const int32_t *gather, const double *lipid_mass, int64_t F, int64_t M, int64_t N,
                   double *com, double *com_unwrap, void *stream);
+
+/* ---- A1-A4 + B1 fused  (small systems: one frame of positions fits in shared memory) -------
+ * Same results as pbk_unwrap_images + pbk_membrane_com + pbk_lipid_com (+ pbk_leaflets with
+ * update_interval 1 when do_labels != 0) with one reducing pass over the positions:
+ * a streaming pre-pass counts periodic images per frame chunk, a scan turns them into the
+ * image count at every chunk start, and one CTA per chunk then applies the exact reference
+ * recurrence frame by frame out of shared memory (frames arrive by TMA bulk copy).
+ * Returns PBK_EUNSUPPORTED when a frame does not fit (caller falls back to the calls above).
+ * The pre-pass decides image increments from consecutive raw frames; if any jump lies
+ * within rounding distance of half a box, PBK_ST_UNWRAP_AMBIGUOUS is raised in `status` and
+ * the outputs must be recomputed with the generic entry points.
+ * scratch: pbk_reduce_fused_scratch_bytes(F, M, sm_count) bytes of device memory. */
+int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
+                                   int32_t *n_chunks, int32_t *chunk);
+int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
+                     const int32_t *seg, const int32_t *gather, const double *lipid_mass,
+                     const int32_t *leaf_start, const int32_t *leaf_len, int32_t L,
+                     const int32_t *node_left, const int32_t *node_right, int32_t K,
+                     const int32_t *level_off, int32_t H, double total_mass, float *u_state,
+                     int first_frame, int64_t F, int64_t M, int64_t N, int norm, int do_labels,
+                     void *scratch, int64_t scratch_bytes, double *com, double *com_unwrap,
+                     double *mem_com, uint8_t *labels, int32_t *status, void *stream);
+int pbk_sm_count(const pbk_ctx *ctx);
 
 /* ---- B1  leaflet assignment -------------------------------------------------------------
  * BilayerAnalyzer._build_leaflets             pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847

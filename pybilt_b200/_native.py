@@ -15,6 +15,10 @@ SO_PATH = os.path.join(HERE, "_pbk.so")
 
 ST_IMAGE_OVERFLOW = 1
 ST_LEAFLET_TIE = 2
+ST_UNWRAP_AMBIGUOUS = 4
+ST_FUSED_RANGE = 8
+ST_INTERNAL = 16
+E_UNSUPPORTED = -3
 
 _SIGNATURES = {
     "pbk_abi_version": (c_int, []),
@@ -29,6 +33,14 @@ _SIGNATURES = {
     "pbk_lipid_com": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                               c_void_p]),
+    "pbk_sm_count": (c_int, [c_void_p]),
+    "pbk_reduce_fused_scratch_bytes": (c_int, [c_int64, c_int64, c_int, ctypes.POINTER(c_int64),
+                                               ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
+    "pbk_reduce_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                 c_int32, c_double, c_void_p, c_int, c_int64, c_int64, c_int64, c_int,
+                                 c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "pbk_leaflets": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
     "pbk_msd_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int, c_int,
@@ -64,7 +76,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.pbk_abi_version() != 2:
+        if lib.pbk_abi_version() != 3:
             raise RuntimeError("pybilt_b200: libpbk ABI version mismatch")
         _lib = lib
     return _lib
@@ -94,6 +106,19 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def try_call(self, name: str, *args) -> bool:
+        """Like call(), but returns False when the entry point answers PBK_EUNSUPPORTED."""
+        rc = getattr(self.lib, name)(self._h, *args)
+        if rc == E_UNSUPPORTED:
+            return False
+        if rc != 0:
+            msg = self.lib.pbk_last_error(self._h)
+            raise RuntimeError("libpbk %s failed (%d): %s" % (name, rc, (msg or b"").decode()))
+        return True
+
+    def sm_count(self) -> int:
+        return int(self.lib.pbk_sm_count(self._h))
 
     def call(self, name: str, *args):
         rc = getattr(self.lib, name)(self._h, *args)

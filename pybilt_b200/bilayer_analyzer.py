@@ -32,7 +32,7 @@ from . import analysis_protocols as ap
 from . import com_frame as cf
 from . import leaflet as lf
 from . import lipid_grid as lg
-from .engine import LipidReductionEngine, build_bead_layout
+from .engine import FusedPathRejected, LipidReductionEngine, build_bead_layout
 
 default_analysis_commands = ['msd msd_1']
 
@@ -403,6 +403,13 @@ class BilayerAnalyzer(object):
         """Push every analysed frame through the engine (unwrap -> COMs -> leaflets)."""
         if self._batch is not None:
             return self._batch
+        try:
+            return self._reduce_with(allow_fused=True)
+        except FusedPathRejected:
+            # a jump the chunked fast path cannot decide locally: sequential kernels instead
+            return self._reduce_with(allow_fused=False)
+
+    def _reduce_with(self, allow_fused):
         lset = self.rep_settings['leaflets']
         if lset['assign_method'] != 'avg_norm':
             raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
@@ -418,7 +425,7 @@ class BilayerAnalyzer(object):
         eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
                                    norm=self.settings['norm'],
                                    leaflet_update_interval=int(lset['update_interval']),
-                                   batch_frames=self.batch_frames)
+                                   batch_frames=self.batch_frames, allow_fused=allow_fused)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
         dev = eng.dev
         copy_stream = torch.cuda.Stream(dev)

@@ -38,3 +38,5 @@ extern "C" int pbk_ctx_create(int device, pbk_ctx **out)
 extern "C" void pbk_ctx_destroy(pbk_ctx *ctx) { delete ctx; }
 
 extern "C" const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int pbk_sm_count(const pbk_ctx *ctx) { return ctx ? ctx->sm_count : 0; }

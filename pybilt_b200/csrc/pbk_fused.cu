@@ -1,0 +1,471 @@
+// pbk_fused.cu -- fused frame reduction for small systems (one frame fits in shared memory):
+// unwrap + membrane COM + per-lipid COMs + leaflet labels with ONE pass over the positions
+// (plus a streaming pre-pass that only counts periodic images).
+//
+// Reference arithmetic restated (paths relative to the PyBILT tree), identical to pbk_com.cu:
+//   unwrap        pybilt/mda_tools/mda_unwrap_vectorized.py:12-93
+//   membrane COM  pybilt/bilayer_analyzer/com_frame.py:172-181 (NumPy pairwise order)
+//   lipid COM     pybilt/bilayer_analyzer/com_frame.py:43-96,163-185
+//   leaflets      pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847
+//
+// Why three kernels.  The unwrap is a recurrence over frames, but with only 3*M chains a small
+// system cannot fill the GPU chain-by-chain.  So the frames are cut into one contiguous chunk
+// per SM and
+//   k_fused_agg    streams the positions once and, per (chunk, chain), sums the image-count
+//                  increments delta_t, which depend on x_t and x_{t-1} only as long as the jump
+//                  is not within rounding distance of half a box (the "slack" it records);
+//   k_fused_scan   prefix-sums the chunk totals per chain -> image count at every chunk start,
+//                  and checks every recorded slack against the rounding bound that the now
+//                  known image counts imply; a violation raises PBK_ST_UNWRAP_AMBIGUOUS and
+//                  the host redoes the batch with the sequential kernels of pbk_com.cu;
+//   k_fused_frames one CTA per chunk walks its frames with the EXACT reference recurrence:
+//                  frame t+1 arrives by TMA bulk copy (cp.async.bulk + mbarrier) into one of two
+//                  shared-memory frame buffers while frame t is reduced out of the other:
+//                  image counts (int8, shared), NumPy-pairwise membrane COM (warp per leaf,
+//                  tree in shared memory), per-lipid wrapped / unwrapped COMs (one thread per
+//                  lipid and role, atoms in order), leaflet labels.
+// HBM traffic: positions twice (once per streaming pass), outputs once.
+#include "pbk_common.cuh"
+
+#define FUSED_THREADS 1024
+#define FUSED_UNR 8
+
+// ------------------------------------------------------------------------------------------
+// image shift of the reference rule for difference d (float32) and box length L; also returns
+// the distance of the shifted difference from the nearer window boundary +-L/2
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fused_shift(float d, float L, float *slack, int *bad)
+{
+    const float h = L * 0.5f;
+    int s = 0;
+    if (!(L > 0.0f)) { *bad = 1; *slack = 0.f; return 0; }
+    if (d > h) {
+        const double dd = (double)d, Ld = (double)L, hd = (double)h;
+        do { s -= 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) > hd && s > -32768);
+        *slack = (float)(hd - fabs(__dadd_rn(dd, __dmul_rn((double)s, Ld))));
+    } else if (d < -h) {
+        const double dd = (double)d, Ld = (double)L, hd = (double)h;
+        do { s += 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) < -hd && s < 32768);
+        *slack = (float)(hd - fabs(__dadd_rn(dd, __dmul_rn((double)s, Ld))));
+    } else {
+        *slack = h - fabsf(d);
+    }
+    if (s <= -32768 || s >= 32768) { *bad = 1; s = 0; }
+    return s;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS)
+k_fused_agg(const float *__restrict__ x, const float *__restrict__ box,
+            const float *__restrict__ u_state, int first_frame, int64_t F, int C3, int chunk,
+            int32_t *__restrict__ agg, int32_t *__restrict__ amax, float *__restrict__ slack_out,
+            float *__restrict__ chunk_box, int32_t *status)
+{
+    const int kc = blockIdx.x;
+    const int64_t f0 = (int64_t)kc * chunk, f1 = min(F, f0 + chunk);
+    int bad = 0;
+    if (threadIdx.x == 0) {                 // largest box edge and largest frame-to-frame change
+        float Lmax = 0.f, dL = 0.f;
+        for (int64_t t = f0; t < f1; t++)
+            for (int k = 0; k < 3; k++) {
+                float L = box[t * 3 + k];
+                Lmax = fmaxf(Lmax, L);
+                if (t > 0) dL = fmaxf(dL, fabsf(L - box[(t - 1) * 3 + k]));
+            }
+        chunk_box[kc * 2] = Lmax;
+        chunk_box[kc * 2 + 1] = dL;
+    }
+    for (int c = threadIdx.x; c < C3; c += blockDim.x) {
+        const int k = c % 3;
+        float prevx, smin = 3.0e38f;
+        int acc = 0, am = 0;
+        int64_t t = f0;
+        if (kc == 0) {
+            prevx = x[c];
+            if (!first_frame) {             // exact rule against the carried unwrapped state
+                float sl;
+                acc = fused_shift(__fsub_rn(prevx, u_state[c]), box[k], &sl, &bad);
+                am = abs(acc);
+            }
+            t = 1;
+        } else {
+            prevx = x[(f0 - 1) * C3 + c];
+        }
+        for (; t < f1; t += FUSED_UNR) {
+            float xv[FUSED_UNR], Lv[FUSED_UNR];
+#pragma unroll
+            for (int j = 0; j < FUSED_UNR; j++) {
+                const int64_t tt = min(t + j, f1 - 1);
+                xv[j] = __ldg(x + tt * C3 + c);
+                Lv[j] = __ldg(box + tt * 3 + k);
+            }
+#pragma unroll
+            for (int j = 0; j < FUSED_UNR; j++) {
+                if (t + j < f1) {
+                    float sl;
+                    acc += fused_shift(__fsub_rn(xv[j], prevx), Lv[j], &sl, &bad);
+                    smin = fminf(smin, sl);
+                    am = max(am, abs(acc));
+                    prevx = xv[j];
+                }
+            }
+        }
+        agg[(int64_t)kc * C3 + c] = acc;
+        amax[(int64_t)kc * C3 + c] = am;
+        slack_out[(int64_t)kc * C3 + c] = smin;
+    }
+    if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_scan(const int32_t *__restrict__ agg, const int32_t *__restrict__ amax,
+             const float *__restrict__ slack, const float *__restrict__ chunk_box, int C3, int n_chunks,
+             int32_t *__restrict__ sstart, int32_t *status)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C3) return;
+    int S = 0, flags = 0;
+    for (int kc = 0; kc < n_chunks; kc++) {
+        const int64_t o = (int64_t)kc * C3 + c;
+        sstart[o] = S;
+        const int smax = abs(S) + amax[o] + 1;
+        const float Lmax = chunk_box[kc * 2], dL = chunk_box[kc * 2 + 1];
+        // |true shifted difference - delta-form one| <= ulp32(u)/2 + ulp32(d)/2 + ulp32(d0)/2
+        //                                              + |s| * |L_t - L_{t-1}|
+        const float eps = (float)(smax + 2) * Lmax * 2.3841858e-7f + (float)smax * dL;
+        if (!(slack[o] > eps)) flags |= PBK_ST_UNWRAP_AMBIGUOUS;
+        if (smax > 126) flags |= PBK_ST_FUSED_RANGE;
+        S += agg[o];
+    }
+    if (flags) atomicOr(status, flags);
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: returns false if the phase never completed (reported, never spins forever)
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); it++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+struct FusedParams {
+    const float *x; const float *box; const double *mass; const int32_t *seg; const int32_t *gather;
+    const double *lipid_mass;
+    const int32_t *leaf_start, *leaf_len, *node_left, *node_right, *level_off;
+    int L, K, H;
+    double total_mass;
+    const float *u_state; float *u_out; int first_frame;
+    int64_t F; int M, N, norm, chunk, n_chunks, do_labels;
+    const int32_t *sstart;
+    double *com, *com_unwrap, *mem_com; uint8_t *labels; int32_t *status;
+    int use_tma, mass_in_smem;
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+k_fused_frames(FusedParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C3 = 3 * P.M;
+    const int C3pad = (C3 + 3) & ~3;
+    float *XA = reinterpret_cast<float *>(smem_raw);
+    float *XB = XA + C3pad;
+    double *s_leaf = reinterpret_cast<double *>(XB + C3pad);           // (L+K)*3
+    double *s_z = s_leaf + (size_t)(P.L + P.K) * 3;                     // N   com_unwrap[norm]
+    double *s_mass = s_z + P.N;                                         // M (optional)
+    signed char *S = reinterpret_cast<signed char *>(s_mass + (P.mass_in_smem ? P.M : 0));  // C3
+    __shared__ uint64_t bar[2];
+    __shared__ double s_mem[3];
+    __shared__ double red[32];
+    __shared__ float s_box[2][3];
+    __shared__ double s_zexact;
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int kc = blockIdx.x;
+    const int64_t f0 = (int64_t)kc * P.chunk, f1 = min(P.F, f0 + P.chunk);
+    if (f0 >= f1) return;
+    const double *mass = P.mass_in_smem ? s_mass : P.mass;
+    const uint32_t frame_bytes = (uint32_t)C3 * 4u;
+    int bad = 0;
+
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); s_flag = 0; }
+    if (P.mass_in_smem) for (int a = tid; a < P.M; a += blockDim.x) s_mass[a] = P.mass[a];
+    // image counts at the chunk start; "previous" frame buffer
+    //   chunk 0, first batch : prev = x_0 itself, counts 0  (u_0 = x_0)
+    //   chunk 0, later batch : prev = carried u_state, counts 0 (u_prev = prev + 0*L)
+    //   chunk k > 0          : prev = raw x_{f0-1}, counts from the scan
+    float *cur = XA, *prev = XB;
+    const float *prev_src = (kc == 0) ? (P.first_frame ? P.x : P.u_state) : P.x + (f0 - 1) * (int64_t)C3;
+    for (int c = tid; c < C3; c += blockDim.x) {
+        prev[c] = prev_src[c];
+        S[c] = (signed char)((kc == 0) ? 0 : P.sstart[(int64_t)kc * C3 + c]);
+    }
+    if (tid < 3) s_box[1][tid] = (kc == 0) ? P.box[tid] : P.box[(f0 - 1) * 3 + tid];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // prefetch the first frame of the chunk
+    uint32_t parbits = 0u;                      // bit b = parity to wait for on bar[b]
+    int cb = 0;                                 // barrier / buffer index of `cur`
+    if (P.use_tma) {
+        if (tid == 0) { mbar_expect_tx(&bar[0], frame_bytes); bulk_g2s(cur, P.x + f0 * (int64_t)C3, frame_bytes, &bar[0]); }
+    } else {
+        for (int c = tid; c < C3; c += blockDim.x) cur[c] = P.x[f0 * (int64_t)C3 + c];
+    }
+
+    for (int64_t t = f0; t < f1; t++) {
+        if (tid < 3) s_box[0][tid] = P.box[t * 3 + tid];
+        if (P.use_tma) {
+            if (!mbar_wait(&bar[cb], (parbits >> cb) & 1u)) bad = 2;
+            parbits ^= (1u << cb);
+        }
+        __syncthreads();
+        const float Lc0 = s_box[0][0], Lc1 = s_box[0][1], Lc2 = s_box[0][2];
+        const float Lp0 = s_box[1][0], Lp1 = s_box[1][1], Lp2 = s_box[1][2];
+        // ---- phase U: image counts of frame t (exact reference recurrence) -------------------
+        for (int c = tid; c < C3; c += blockDim.x) {
+            const int k = c % 3;
+            const float Lp = k == 0 ? Lp0 : (k == 1 ? Lp1 : Lp2), Lc = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2);
+            const float up = pbk_unwrapped(prev[c], (int)S[c], Lp);
+            const float xv = cur[c];
+            const float d = __fsub_rn(xv, up);
+            const float h = Lc * 0.5f;
+            int s = 0;
+            if (d > h || d < -h) { float sl; s = fused_shift(d, Lc, &sl, &bad); }
+            if (s > 127 || s < -127) { bad |= 4; s = 0; }
+            S[c] = (signed char)s;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `prev` before the async write
+        __syncthreads();
+        // the other buffer is free now: fetch frame t+1 into it while frame t is reduced
+        if (t + 1 < f1) {
+            if (P.use_tma) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bar[cb ^ 1], frame_bytes);
+                    bulk_g2s(prev, P.x + (t + 1) * (int64_t)C3, frame_bytes, &bar[cb ^ 1]);
+                }
+            }
+        }
+        // ---- phase L: NumPy-pairwise leaf sums of m*f64(u), one warp per leaf -----------------
+        for (int leaf = warp; leaf < P.L; leaf += nwarp) {
+            const int start = P.leaf_start[leaf], n = P.leaf_len[leaf];
+            const int j = lane / 3, k = lane % 3;
+            const bool act = lane < 24;
+            const float Lk = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2);
+            const float *xf = cur + (size_t)start * 3;
+            const signed char *sf = S + (size_t)start * 3;
+            const double *mf = mass + start;
+            double r = 0.0;
+            const int nfull = n - (n % 8);
+            if (n >= 8 && act) {
+                r = __dmul_rn(mf[j], (double)pbk_unwrapped(xf[j * 3 + k], sf[j * 3 + k], Lk));
+                for (int i = 8; i < nfull; i += 8) {
+                    const int a = i + j;
+                    r = __dadd_rn(r, __dmul_rn(mf[a], (double)pbk_unwrapped(xf[a * 3 + k], sf[a * 3 + k], Lk)));
+                }
+            }
+            const int src1 = ((j ^ 1) * 3 + k) & 31, src2 = ((j ^ 2) * 3 + k) & 31, src4 = ((j ^ 4) * 3 + k) & 31;
+            r = __dadd_rn(r, __shfl_sync(0xffffffffu, r, act ? src1 : lane));
+            r = __dadd_rn(r, __shfl_sync(0xffffffffu, r, act ? src2 : lane));
+            r = __dadd_rn(r, __shfl_sync(0xffffffffu, r, act ? src4 : lane));
+            if (lane < 3) {
+                int i0 = nfull;
+                if (n < 8) { r = 0.0; i0 = 0; }
+                for (int i = i0; i < n; i++)
+                    r = __dadd_rn(r, __dmul_rn(mf[i], (double)pbk_unwrapped(xf[i * 3 + k], sf[i * 3 + k], Lk)));
+                s_leaf[leaf * 3 + k] = r;
+            }
+        }
+        __syncthreads();
+        for (int h = 0; h < P.H; h++) {
+            const int a = P.level_off[h], b = P.level_off[h + 1];
+            for (int w = tid; w < (b - a) * 3; w += blockDim.x) {
+                const int node = a + w / 3, k = w % 3;
+                s_leaf[(P.L + node) * 3 + k] = __dadd_rn(s_leaf[P.node_left[node] * 3 + k], s_leaf[P.node_right[node] * 3 + k]);
+            }
+            __syncthreads();
+        }
+        if (tid < 3) {
+            const double mc = __ddiv_rn(s_leaf[(P.L + P.K - 1) * 3 + tid], P.total_mass);
+            s_mem[tid] = mc;
+            P.mem_com[t * 3 + tid] = mc;
+        }
+        __syncthreads();
+        // ---- phase C: per-lipid COMs; thread (i, role): role 0 wrapped, role 1 unwrapped -----
+        {
+            const double m0 = s_mem[0], m1 = s_mem[1], m2 = s_mem[2];
+            for (int w = tid; w < 2 * P.N; w += blockDim.x) {
+                const int role = w >= P.N, i = role ? w - P.N : w;
+                const int a0 = P.seg[i], a1 = P.seg[i + 1];
+                double c0 = 0, c1 = 0, c2 = 0;
+                for (int p = a0; p < a1; p++) {
+                    const int a = P.gather ? P.gather[p] : p;
+                    const double m = mass[a];
+                    float x0 = cur[a * 3], x1 = cur[a * 3 + 1], x2 = cur[a * 3 + 2];
+                    if (role) {
+                        x0 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x0, S[a * 3], Lc0), m0));
+                        x1 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x1, S[a * 3 + 1], Lc1), m1));
+                        x2 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x2, S[a * 3 + 2], Lc2), m2));
+                    }
+                    c0 = __dadd_rn(c0, __dmul_rn((double)x0, m));
+                    c1 = __dadd_rn(c1, __dmul_rn((double)x1, m));
+                    c2 = __dadd_rn(c2, __dmul_rn((double)x2, m));
+                }
+                const double lm = P.lipid_mass[i];
+                c0 = __ddiv_rn(c0, lm); c1 = __ddiv_rn(c1, lm); c2 = __ddiv_rn(c2, lm);
+                double *o = (role ? P.com_unwrap : P.com) + (t * (int64_t)P.N + i) * 3;
+                o[0] = c0; o[1] = c1; o[2] = c2;
+                if (role) s_z[i] = P.norm == 0 ? c0 : (P.norm == 1 ? c1 : c2);
+            }
+        }
+        __syncthreads();
+        // ---- phase Z: leaflet labels (tree mean decides unless a lipid is within the rounding
+        // bound of it; then thread 0 replays the sequential Welford mean) -------------------------
+        if (P.do_labels) {
+            double s = 0.0, mx = 0.0;
+            for (int i = tid; i < P.N; i += blockDim.x) { const double v = s_z[i]; s += v; mx = fmax(mx, fabs(v)); }
+            s = pbk_block_sum(s, red);
+            mx = pbk_block_max(mx, red);
+            double mean = s / (double)P.N;
+            const double tol = 64.0 * (double)P.N * 2.220446049250313e-16 * mx;
+            int close = 0;
+            for (int i = tid; i < P.N; i += blockDim.x) if (fabs(s_z[i] - mean) <= tol) close = 1;
+            if (__syncthreads_or(close)) {
+                if (tid == 0) {
+                    double m = 0.0;
+                    for (int i = 0; i < P.N; i++) {
+                        const double v = s_z[i];
+                        m = (i == 0) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)(i + 1)));
+                    }
+                    s_zexact = m;
+                }
+                __syncthreads();
+                mean = s_zexact;
+            }
+            uint8_t *out = P.labels + t * (int64_t)P.N;
+            for (int i = tid; i < P.N; i += blockDim.x) {
+                const double v = s_z[i];
+                if (v > mean) out[i] = 1;
+                else if (v < mean) out[i] = 0;
+                else { out[i] = 0; bad |= 8; }
+            }
+        }
+        // carried state for the next batch
+        if (t == P.F - 1) {
+            for (int c = tid; c < C3; c += blockDim.x) {
+                const int k = c % 3;
+                P.u_out[c] = pbk_unwrapped(cur[c], (int)S[c], k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2));
+            }
+        }
+        if (tid < 3) s_box[1][tid] = s_box[0][tid];
+        if (!P.use_tma && t + 1 < f1) {
+            __syncthreads();
+            for (int c = tid; c < C3; c += blockDim.x) prev[c] = P.x[(t + 1) * (int64_t)C3 + c];
+        }
+        // swap: the buffer being filled becomes `cur`, the frame just reduced becomes `prev`
+        float *tmp = cur; cur = prev; prev = tmp;
+        cb ^= 1;
+        __syncthreads();
+    }
+    if (bad) {
+        int st = 0;
+        if (bad & 1) st |= PBK_ST_IMAGE_OVERFLOW;
+        if (bad & 2) st |= PBK_ST_INTERNAL;
+        if (bad & 4) st |= PBK_ST_FUSED_RANGE;
+        if (bad & 8) st |= PBK_ST_LEAFLET_TIE;
+        atomicOr(P.status, st);
+    }
+}
+
+extern "C" int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
+                                             int32_t *n_chunks_out, int32_t *chunk_out)
+{
+    if (F <= 0 || M <= 0 || sm_count <= 0 || !bytes) return PBK_EINVAL;
+    int64_t chunk = (F + sm_count - 1) / sm_count;
+    if (chunk < 4) chunk = 4;
+    int64_t n_chunks = (F + chunk - 1) / chunk;
+    *bytes = n_chunks * 3 * M * 16 + n_chunks * 8 + 3 * M * 4 + 256;
+    if (n_chunks_out) *n_chunks_out = (int32_t)n_chunks;
+    if (chunk_out) *chunk_out = (int32_t)chunk;
+    return PBK_OK;
+}
+
+extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
+                                const int32_t *seg, const int32_t *gather, const double *lipid_mass,
+                                const int32_t *leaf_start, const int32_t *leaf_len, int32_t L,
+                                const int32_t *node_left, const int32_t *node_right, int32_t K,
+                                const int32_t *level_off, int32_t H, double total_mass, float *u_state,
+                                int first_frame, int64_t F, int64_t M, int64_t N, int norm,
+                                int do_labels, void *scratch, int64_t scratch_bytes, double *com,
+                                double *com_unwrap, double *mem_com, uint8_t *labels, int32_t *status,
+                                void *stream)
+{
+    if (!ctx || !x || !box || !mass || !seg || !lipid_mass || !leaf_start || !leaf_len || !u_state ||
+        !scratch || !com || !com_unwrap || !mem_com || !status || (do_labels && !labels) || F < 0 ||
+        M <= 0 || N <= 0 || L <= 0 || K < 0 || norm < 0 || norm > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: bad argument");
+    if (F == 0) return PBK_OK;
+    if (M > (1 << 20)) return PBK_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t need; int32_t n_chunks, chunk;
+    pbk_reduce_fused_scratch_bytes(F, M, ctx->sm_count, &need, &n_chunks, &chunk);
+    if (scratch_bytes < need) return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small");
+    const int C3 = (int)(3 * M), C3pad = (C3 + 3) & ~3;
+    size_t base = (size_t)C3pad * 8 + (size_t)(L + K) * 24 + (size_t)N * 8 + (size_t)C3 + 64;
+    int mass_in_smem = 1;
+    size_t smem = base + (size_t)M * 8;
+    const size_t limit = 227 * 1024 - 1024;      // static shared of the kernel is < 1 KB
+    if (smem > limit) { mass_in_smem = 0; smem = base; }
+    if (smem > limit) return PBK_EUNSUPPORTED;   // frame does not fit: caller uses pbk_com.cu path
+    // scratch layout
+    int32_t *agg = reinterpret_cast<int32_t *>(scratch);
+    int32_t *amax = agg + (int64_t)n_chunks * C3;
+    float *slack = reinterpret_cast<float *>(amax + (int64_t)n_chunks * C3);
+    int32_t *sstart = reinterpret_cast<int32_t *>(slack + (int64_t)n_chunks * C3);
+    float *chunk_box = reinterpret_cast<float *>(sstart + (int64_t)n_chunks * C3);
+    float *u_out = chunk_box + 2 * (int64_t)n_chunks;
+    k_fused_agg<<<n_chunks, FUSED_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk, agg,
+                                                    amax, slack, chunk_box, status);
+    PBK_CHECK_LAUNCH(ctx, "k_fused_agg");
+    k_fused_scan<<<(C3 + 255) / 256, 256, 0, st>>>(agg, amax, slack, chunk_box, C3, n_chunks, sstart, status);
+    PBK_CHECK_LAUNCH(ctx, "k_fused_scan");
+    FusedParams P;
+    P.x = x; P.box = box; P.mass = mass; P.seg = seg; P.gather = gather; P.lipid_mass = lipid_mass;
+    P.leaf_start = leaf_start; P.leaf_len = leaf_len; P.node_left = node_left; P.node_right = node_right;
+    P.level_off = level_off; P.L = L; P.K = K; P.H = H; P.total_mass = total_mass;
+    P.u_state = u_state; P.u_out = u_out; P.first_frame = first_frame; P.F = F; P.M = (int)M; P.N = (int)N; P.norm = norm;
+    P.chunk = chunk; P.n_chunks = n_chunks; P.do_labels = do_labels; P.sstart = sstart;
+    P.com = com; P.com_unwrap = com_unwrap; P.mem_com = mem_com; P.labels = labels; P.status = status;
+    P.use_tma = ((C3 * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) % 16) == 0);
+    P.mass_in_smem = mass_in_smem;
+    cudaError_t e = cudaFuncSetAttribute(k_fused_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_fused_frames smem attribute", e);
+    k_fused_frames<<<n_chunks, FUSED_THREADS, smem, st>>>(P);
+    PBK_CHECK_LAUNCH(ctx, "k_fused_frames");
+    // u_state is read by chunk 0 and replaced by the last chunk: the new state is produced in
+    // scratch and copied over once the kernel is done
+    e = cudaMemcpyAsync(u_state, u_out, (size_t)C3 * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "u_state copy", e);
+    return PBK_OK;
+}

@@ -109,13 +109,18 @@ def rdf_thresholds(edges: np.ndarray) -> np.ndarray:
     return thr
 
 
+class FusedPathRejected(RuntimeError):
+    """The fused small-system path met a jump it cannot decide chunk-locally (or an image
+    count outside int8); the caller re-runs the frames with ``allow_fused=False``."""
+
+
 class LipidReductionEngine:
     """Runs unwrap -> membrane COM -> lipid COM -> leaflets for batches of frames and keeps
     the results for all analysed frames resident on the device."""
 
     def __init__(self, masses, layout: BeadLayout, n_frames: int, device: int = 0, norm: int = 2,
                  leaflet_update_interval: int = 1, batch_frames: Optional[int] = None,
-                 scratch_bytes: int = 4 << 30):
+                 scratch_bytes: int = 4 << 30, allow_fused: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pybilt_b200: a CUDA device is required (no CPU fallback)")
         self.ctx = _native.Context(device)
@@ -157,6 +162,18 @@ class LipidReductionEngine:
         self.box = torch.empty((self.F, 3), dtype=torch.float32, device=d)
         self.n_done = 0
         self.launches = 0
+        self.allow_fused = bool(allow_fused)
+        self.used_fused = False
+        self._fused_scratch = None
+
+    def _fused_scratch_for(self, nb: int) -> torch.Tensor:
+        import ctypes
+        need = ctypes.c_int64(0)
+        self.ctx.lib.pbk_reduce_fused_scratch_bytes(nb, self.M, self.ctx.sm_count(), ctypes.byref(need),
+                                                    None, None)
+        if self._fused_scratch is None or self._fused_scratch.numel() < need.value:
+            self._fused_scratch = torch.empty(int(need.value), dtype=torch.uint8, device=self.dev)
+        return self._fused_scratch
 
     # ---------------------------------------------------------------------------------
     def reset(self):
@@ -182,9 +199,34 @@ class LipidReductionEngine:
             xb, bb = x[b0:b1], box[b0:b1]
             g0 = self.n_done
             self.box[g0:g0 + nb].copy_(bb)
+            p = self.plan
+            prev = self.labels[g0 - 1].data_ptr() if g0 > 0 else None
+            if self.allow_fused:
+                scratch = self._fused_scratch_for(nb)
+                do_labels = 1 if self.update_interval == 1 else 0
+                ok = c.try_call("pbk_reduce_fused", xb.data_ptr(), bb.data_ptr(), self.d_mass.data_ptr(),
+                                self.d_seg.data_ptr(), _ptr(self.d_gather), self.d_bead_mass.data_ptr(),
+                                self.d_leaf_start.data_ptr(), self.d_leaf_len.data_ptr(), p.n_leaves,
+                                self.d_node_left.data_ptr(), self.d_node_right.data_ptr(), p.n_nodes,
+                                self.d_level_off.data_ptr(), p.n_levels, self.total_mass,
+                                self.d_u_state.data_ptr(), 1 if g0 == 0 else 0, nb, self.M, self.N,
+                                self.norm, do_labels, scratch.data_ptr(), int(scratch.numel()),
+                                self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
+                                self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(),
+                                self.d_status.data_ptr(), st)
+                if ok:
+                    self.launches += 3
+                    self.used_fused = True
+                    if not do_labels:
+                        c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
+                               self.update_interval, prev, self.labels[g0:].data_ptr(),
+                               self.d_status.data_ptr(), st)
+                        self.launches += 1
+                    self.n_done += nb
+                    continue
+                self.allow_fused = False          # frame does not fit in shared memory
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
                    1 if g0 == 0 else 0, nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
-            p = self.plan
             c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
                    self.d_mass.data_ptr(), nb, self.M, self.d_leaf_start.data_ptr(),
                    self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(),
@@ -194,7 +236,6 @@ class LipidReductionEngine:
                    self.d_mass.data_ptr(), self.mem_com[g0:].data_ptr(), self.d_seg.data_ptr(),
                    _ptr(self.d_gather), self.d_bead_mass.data_ptr(), nb, self.M, self.N,
                    self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(), st)
-            prev = self.labels[g0 - 1].data_ptr() if g0 > 0 else None
             c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
                    self.update_interval, prev, self.labels[g0:].data_ptr(), self.d_status.data_ptr(), st)
             self.launches += 5
@@ -203,6 +244,10 @@ class LipidReductionEngine:
     def check_status(self):
         """Synchronises; raises like the reference does for data-dependent failures."""
         s = int(self.d_status.item())
+        if s & _native.ST_INTERNAL:
+            raise RuntimeError("libpbk: a bulk copy did not complete (internal error)")
+        if s & (_native.ST_UNWRAP_AMBIGUOUS | _native.ST_FUSED_RANGE):
+            raise FusedPathRejected("fused reduction rejected (status %d)" % s)
         if s & _native.ST_LEAFLET_TIE:
             raise KeyError("")      # bilayer_analyzer.py:838-845: pos stays '' -> leaflets['']
         if s & _native.ST_IMAGE_OVERFLOW:
