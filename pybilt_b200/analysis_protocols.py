@@ -286,7 +286,7 @@ class MSDProtocol(AnalysisProtocol):
         vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
                                       np.zeros(F, dtype=np.int32), np.arange(F, dtype=np.int32),
                                       ba_settings['lateral']).cpu().numpy()
-        self.analysis_output = [np.array([batch.times[f], vals[f]]) for f in range(F)]
+        self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
 
 def msd_multi_schedule(n_frames, n_tau, n_sigma):
@@ -409,8 +409,17 @@ class COMLateralRDFProtocol(AnalysisProtocol):
         self._N_b += int(fc[:, :, 1].sum())
         self._N += int(fc[:, :, 2].sum())
         lat = list(ba_settings['lateral'])
-        for f in range(batch.n_frames):
-            self._area_run.push(batch.box_host[f][lat].prod())      # float32 product (:5004)
+        # box[lateral].prod() per frame is a float32 product (:5004) pushed into a Welford mean
+        areas = batch.box_host[:, lat[0]] * batch.box_host[:, lat[1]]
+        if self._area_run.n == 0 and len(areas) and (areas == areas[0]).all():
+            # constant box: every Welford update adds exactly zero
+            self._area_run.push(areas[0])
+            self._area_run.n = len(areas)
+            if len(areas) > 1:
+                self._area_run._mean = self._area_run._mean + np.float64(0.0)   # float64 after push 2
+        else:
+            for a in areas:
+                self._area_run.push(a)
         self._n_frames += batch.n_frames
 
     def get_data(self):

@@ -389,6 +389,8 @@ class BilayerAnalyzer(object):
         self._invalidate()
 
     def _invalidate(self):
+        if getattr(self, '_engine', None) is not None:
+            self._engine_cache = (self._engine_key, self._engine)
         self._engine = None
         self._batch = None
         self._host = None
@@ -418,14 +420,32 @@ class BilayerAnalyzer(object):
             raise RuntimeError("com_frame:rewrap / make_whole are outside the accelerated path")
         md = self._mda_data
         cset = self.rep_settings['com_frame']
-        layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
-                                   cset['name_dict'], cset['multi_bead'])
+        layout = None
+        cached = getattr(self, '_engine_cache', None)
+        if cached is None or cached[0][:3] != (id(md), repr(cset['name_dict']), bool(cset['multi_bead'])):
+            layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
+                                       cset['name_dict'], cset['multi_bead'])
         fr = self.analysed_frame_indices()
         self._frames = fr
-        eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
-                                   norm=self.settings['norm'],
-                                   leaflet_update_interval=int(lset['update_interval']),
-                                   batch_frames=self.batch_frames, allow_fused=allow_fused)
+        # the engine (device buffers, summation plan, libpbk context) is reused across reset()
+        # as long as nothing that shapes it changed
+        key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), len(fr), self.device,
+               self.settings['norm'], int(lset['update_interval']), self.batch_frames)
+        cached = getattr(self, '_engine_cache', None)
+        if cached is not None and cached[0] == key:
+            eng = cached[1]
+            eng.reset()
+            eng.allow_fused = allow_fused and eng.fused_supported
+            layout = eng.layout
+        else:
+            if layout is None:
+                layout = cached[1].layout
+            eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
+                                       norm=self.settings['norm'],
+                                       leaflet_update_interval=int(lset['update_interval']),
+                                       batch_frames=self.batch_frames, allow_fused=allow_fused)
+        self._engine_key = key
+        self._engine_cache = None
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
         dev = eng.dev
         copy_stream = torch.cuda.Stream(dev)
@@ -569,10 +589,24 @@ class BilayerAnalyzer(object):
     def run_analysis(self):
         """Run every registered analysis over the analysed frames (bilayer_analyzer.py:777-790).
         Batched run: no per-frame host views unless a plain per-frame plugin needs them."""
+        if self._current_frame > self._last_frame and not getattr(self, '_started', False):
+            return
         self._iterating_for_user = False
         try:
-            for _frame in self:
-                pass
+            if not getattr(self, '_started', False):
+                self._started = False
+                self._start()
+                self._cursor = 0
+            if self._legacy:
+                for _frame in self:
+                    pass
+            else:                       # nothing needs per-frame host views: skip the frame loop
+                n = len(self._frames)
+                self._frame_loop_count += n - self._cursor
+                self._cursor = n
+                self.settings['frame_index'] = int(self._frames[-1])
+                self._current_frame = int(self._frames[-1]) + self.settings['frame_range'][2]
+                self._started = False
         finally:
             self._iterating_for_user = True
 

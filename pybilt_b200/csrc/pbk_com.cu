@@ -30,6 +30,17 @@ __device__ __forceinline__ int pbk_image_shift(float x, float uprev, float L, in
     return s;
 }
 
+// Chain state = (raw previous coordinate, its image count).  The common case -- the raw
+// jump is nowhere near half a box -- keeps the image count without touching float64
+// (pbk_same_image, pbk_common.cuh); otherwise the reference's loops run.
+__device__ __forceinline__ int pbk_next_image(float xv, float xprev, int s, float L, float Lprev, int *bad)
+{
+    const int as = s < 0 ? -s : s;
+    const float eps = (float)(as + 2) * fmaxf(L, Lprev) * 2.3841858e-7f + (float)as * fabsf(L - Lprev);
+    if (pbk_same_image(xv, xprev, L, eps) && L > 0.0f) return s;
+    return pbk_image_shift(xv, pbk_unwrapped(xprev, s, Lprev), L, bad);
+}
+
 __global__ void __launch_bounds__(128)
 k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, float *u_state,
                 int first_frame, int64_t F, int64_t C, int16_t *__restrict__ img, int32_t *status)
@@ -38,14 +49,17 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
     if (c >= C) return;
     int k = (int)(c % 3);
     int bad = 0;
-    float up;
+    float xprev, Lprev;
+    int s = 0;
     int64_t t = 0;
     if (first_frame) {
-        up = x[c];
+        xprev = x[c];
+        Lprev = box[k];
         img[c] = 0;
         t = 1;
     } else {
-        up = u_state[c];
+        xprev = u_state[c];            // an unwrapped coordinate is a raw one with image count 0
+        Lprev = box[k];
     }
     for (; t + UNR <= F; t += UNR) {
         float xv[UNR], Lv[UNR];
@@ -56,18 +70,20 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
         }
 #pragma unroll
         for (int j = 0; j < UNR; j++) {
-            int s = pbk_image_shift(xv[j], up, Lv[j], &bad);
-            up = pbk_unwrapped(xv[j], s, Lv[j]);
+            s = pbk_next_image(xv[j], xprev, s, Lv[j], Lprev, &bad);
+            xprev = xv[j];
+            Lprev = Lv[j];
             img[(t + j) * C + c] = (int16_t)s;
         }
     }
     for (; t < F; t++) {
         float xv = __ldg(x + t * C + c), L = __ldg(box + t * 3 + k);
-        int s = pbk_image_shift(xv, up, L, &bad);
-        up = pbk_unwrapped(xv, s, L);
+        s = pbk_next_image(xv, xprev, s, L, Lprev, &bad);
+        xprev = xv;
+        Lprev = L;
         img[t * C + c] = (int16_t)s;
     }
-    u_state[c] = up;
+    u_state[c] = pbk_unwrapped(xprev, s, Lprev);
     if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
 }
 

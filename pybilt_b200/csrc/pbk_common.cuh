@@ -21,7 +21,31 @@ struct pbk_ctx {
 __device__ __forceinline__ float pbk_unwrapped(float x, int s, float L)
 {
     // u = f32(f64(x) + s*L)      mda_unwrap_vectorized.py:49,70,92
-    return s == 0 ? x : __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)s, (double)L)));
+    if (s == 0) return x;
+    // s*L is exact in float64 and, for |s| <= 255, L < 2^13 and |x| >= 2^-8, so is f64(x) + s*L
+    // (all its bits lie between 2^21 and 2^-31): the only rounding is the final one to float32,
+    // which is what a single float32 FMA performs.  Outside that range: the float64 path.
+    if (s >= -255 && s <= 255 && L < 8192.0f && fabsf(x) >= 0.00390625f)
+        return __fmaf_rn((float)s, L, x);
+    return __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)s, (double)L)));
+}
+
+// Image count of frame t from the RAW previous frame.  The reference compares
+// d = f32(x_t - u_{t-1}) with +-L/2 where u_{t-1} = f32(x_{t-1} + s_{t-1} L_{t-1}); writing
+// d0 = f32(x_t - x_{t-1}), the shifted difference d + s_t L_t equals d0 + (s_t - s_{t-1}) L_t up to
+// ulp32(u)/2 + ulp32(d)/2 + ulp32(d0)/2 + |s| |L_t - L_{t-1}|.  So when d0 is further than that
+// bound (`eps`, supplied by the caller for |s| <= 127) from +-L/2 the image count cannot change.
+// Returns true and leaves *s untouched in that case; false = caller must run the exact rule.
+__device__ __forceinline__ bool pbk_same_image(float x, float xprev_raw, float L, float eps)
+{
+    const float d0 = __fsub_rn(x, xprev_raw);
+    return (L * 0.5f - fabsf(d0)) > eps;
+}
+
+__device__ __forceinline__ float pbk_image_eps(float Lc, float Lp)
+{
+    // (|s|+2) * L * 2^-22 + |s| * |dL| with |s| <= 127, L = max(Lc, Lp)
+    return 130.0f * fmaxf(Lc, Lp) * 2.3841858e-7f + 127.0f * fabsf(Lc - Lp);
 }
 
 // distance_euclidean_pbc(a, b, l_box, center='box_half') with a' = a - c, b' = b - c already

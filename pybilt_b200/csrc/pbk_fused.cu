@@ -54,7 +54,36 @@ __device__ __forceinline__ int fused_shift(float d, float L, float *slack, int *
     return s;
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS)
+// Out-of-line slow path: |d| > L/2.  The image count is found with float32 arithmetic and
+// confirmed with the reference's float64 comparisons (the loops then run 0 extra times unless
+// the estimate sits within rounding of a window boundary).
+__device__ __noinline__ int fused_shift_far(float d, float L, float *slack, int *bad)
+{
+    return fused_shift(d, L, slack, bad);
+}
+
+__device__ __forceinline__ int fused_step(float xv, float prevx, float L, float *smin, int *bad)
+{
+    const float d = __fsub_rn(xv, prevx);
+    const float h = L * 0.5f;
+    const float sl = h - fabsf(d);
+    if (sl < 0.0f || !(L > 0.0f)) {               // |d| > h  (rare): out of line
+        float s2;
+        const int s = fused_shift_far(d, L, &s2, bad);
+        *smin = fminf(*smin, s2);
+        return s;
+    }
+    *smin = fminf(*smin, sl);
+    return 0;
+}
+
+// k_fused_agg: per (chunk, chain) the sum of image-count increments, its running |max| and
+// the smallest slack.  VEC = 4: each thread owns 4 consecutive chains and streams them with
+// 128-bit loads (needs 3*M % 4 == 0); VEC = 1 is the generic variant.
+#define AGG_THREADS 512
+#define AGG_SPLIT 2                 // CTAs per chunk (each takes a slice of the chains)
+template <int VEC>
+__global__ void __launch_bounds__(AGG_THREADS, 2)
 k_fused_agg(const float *__restrict__ x, const float *__restrict__ box,
             const float *__restrict__ u_state, int first_frame, int64_t F, int C3, int chunk,
             int32_t *__restrict__ agg, int32_t *__restrict__ amax, float *__restrict__ slack_out,
@@ -63,7 +92,7 @@ k_fused_agg(const float *__restrict__ x, const float *__restrict__ box,
     const int kc = blockIdx.x;
     const int64_t f0 = (int64_t)kc * chunk, f1 = min(F, f0 + chunk);
     int bad = 0;
-    if (threadIdx.x == 0) {                 // largest box edge and largest frame-to-frame change
+    if (threadIdx.x == 0 && blockIdx.y == 0) {   // largest box edge and largest frame-to-frame change
         float Lmax = 0.f, dL = 0.f;
         for (int64_t t = f0; t < f1; t++)
             for (int k = 0; k < 3; k++) {
@@ -74,67 +103,112 @@ k_fused_agg(const float *__restrict__ x, const float *__restrict__ box,
         chunk_box[kc * 2] = Lmax;
         chunk_box[kc * 2 + 1] = dL;
     }
-    for (int c = threadIdx.x; c < C3; c += blockDim.x) {
-        const int k = c % 3;
-        float prevx, smin = 3.0e38f;
-        int acc = 0, am = 0;
+    const int nq = C3 / VEC;
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < nq; q += blockDim.x * gridDim.y) {
+        const int c0 = q * VEC;
+        int kk[VEC];
+        float prevx[VEC], smin[VEC];
+        int acc[VEC], am[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e++) { kk[e] = (c0 + e) % 3; smin[e] = 3.0e38f; acc[e] = 0; am[e] = 0; }
         int64_t t = f0;
         if (kc == 0) {
-            prevx = x[c];
-            if (!first_frame) {             // exact rule against the carried unwrapped state
-                float sl;
-                acc = fused_shift(__fsub_rn(prevx, u_state[c]), box[k], &sl, &bad);
-                am = abs(acc);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                prevx[e] = x[c0 + e];
+                if (!first_frame) {         // exact rule against the carried unwrapped state
+                    float sl;
+                    acc[e] = fused_shift(__fsub_rn(prevx[e], u_state[c0 + e]), box[kk[e]], &sl, &bad);
+                    am[e] = abs(acc[e]);
+                }
             }
             t = 1;
         } else {
-            prevx = x[(f0 - 1) * C3 + c];
-        }
-        for (; t < f1; t += FUSED_UNR) {
-            float xv[FUSED_UNR], Lv[FUSED_UNR];
 #pragma unroll
-            for (int j = 0; j < FUSED_UNR; j++) {
+            for (int e = 0; e < VEC; e++) prevx[e] = x[(f0 - 1) * C3 + c0 + e];
+        }
+        for (; t < f1; t += 4) {
+            float xv[4][VEC];
+            float Lb[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
                 const int64_t tt = min(t + j, f1 - 1);
-                xv[j] = __ldg(x + tt * C3 + c);
-                Lv[j] = __ldg(box + tt * 3 + k);
+                if (VEC == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(x + tt * C3 + c0));
+                    xv[j][0] = v.x; xv[j][1 % VEC] = v.y; xv[j][2 % VEC] = v.z; xv[j][3 % VEC] = v.w;
+                } else {
+                    xv[j][0] = __ldg(x + tt * C3 + c0);
+                }
+                Lb[j][0] = __ldg(box + tt * 3); Lb[j][1] = __ldg(box + tt * 3 + 1); Lb[j][2] = __ldg(box + tt * 3 + 2);
             }
 #pragma unroll
-            for (int j = 0; j < FUSED_UNR; j++) {
+            for (int j = 0; j < 4; j++) {
                 if (t + j < f1) {
-                    float sl;
-                    acc += fused_shift(__fsub_rn(xv[j], prevx), Lv[j], &sl, &bad);
-                    smin = fminf(smin, sl);
-                    am = max(am, abs(acc));
-                    prevx = xv[j];
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) {
+                        const float L = kk[e] == 0 ? Lb[j][0] : (kk[e] == 1 ? Lb[j][1] : Lb[j][2]);
+                        const int s = fused_step(xv[j][e], prevx[e], L, &smin[e], &bad);
+                        if (s) { acc[e] += s; am[e] = max(am[e], abs(acc[e])); }
+                        prevx[e] = xv[j][e];
+                    }
                 }
             }
         }
-        agg[(int64_t)kc * C3 + c] = acc;
-        amax[(int64_t)kc * C3 + c] = am;
-        slack_out[(int64_t)kc * C3 + c] = smin;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            agg[(int64_t)kc * C3 + c0 + e] = acc[e];
+            amax[(int64_t)kc * C3 + c0 + e] = am[e];
+            slack_out[(int64_t)kc * C3 + c0 + e] = smin[e];
+        }
     }
     if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
 }
 
+// k_fused_scan: per chain, exclusive prefix of the chunk totals (= image count at every chunk
+// start) and the slack check.  256 threads = 32 chains x 8 chunk groups, so the loads of one
+// chain's chunks are spread over 8 threads instead of serialised in one.
+#define SCAN_GROUPS 8
 __global__ void __launch_bounds__(256)
 k_fused_scan(const int32_t *__restrict__ agg, const int32_t *__restrict__ amax,
              const float *__restrict__ slack, const float *__restrict__ chunk_box, int C3, int n_chunks,
              int32_t *__restrict__ sstart, int32_t *status)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int tot[SCAN_GROUPS][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int cpg = (n_chunks + SCAN_GROUPS - 1) / SCAN_GROUPS;
+    const int k0 = g * cpg, k1 = min(n_chunks, k0 + cpg);
+    int sum = 0;
+    if (c < C3)
+        for (int kc = k0; kc < k1; kc++) sum += __ldg(agg + (int64_t)kc * C3 + c);
+    tot[g][cl] = sum;
+    __syncthreads();
     if (c >= C3) return;
     int S = 0, flags = 0;
-    for (int kc = 0; kc < n_chunks; kc++) {
-        const int64_t o = (int64_t)kc * C3 + c;
-        sstart[o] = S;
-        const int smax = abs(S) + amax[o] + 1;
-        const float Lmax = chunk_box[kc * 2], dL = chunk_box[kc * 2 + 1];
-        // |true shifted difference - delta-form one| <= ulp32(u)/2 + ulp32(d)/2 + ulp32(d0)/2
-        //                                              + |s| * |L_t - L_{t-1}|
-        const float eps = (float)(smax + 2) * Lmax * 2.3841858e-7f + (float)smax * dL;
-        if (!(slack[o] > eps)) flags |= PBK_ST_UNWRAP_AMBIGUOUS;
-        if (smax > 126) flags |= PBK_ST_FUSED_RANGE;
-        S += agg[o];
+    for (int gg = 0; gg < g; gg++) S += tot[gg][cl];
+    for (int kb = k0; kb < k1; kb += 4) {
+        int a[4], m[4];
+        float sl[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {              // independent loads first
+            const int64_t o = (int64_t)min(kb + j, k1 - 1) * C3 + c;
+            a[j] = __ldg(agg + o); m[j] = __ldg(amax + o); sl[j] = __ldg(slack + o);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kc = kb + j;
+            if (kc < k1) {
+                sstart[(int64_t)kc * C3 + c] = S;
+                const int smax = abs(S) + m[j] + 1;
+                const float Lmax = chunk_box[kc * 2], dL = chunk_box[kc * 2 + 1];
+                // |true shifted difference - delta-form one| <= ulp32(u)/2 + ulp32(d)/2 + ulp32(d0)/2
+                //                                              + |s| * |L_t - L_{t-1}|
+                const float eps = (float)(smax + 2) * Lmax * 2.3841858e-7f + (float)smax * dL;
+                if (!(sl[j] > eps)) flags |= PBK_ST_UNWRAP_AMBIGUOUS;
+                if (smax > 126) flags |= PBK_ST_FUSED_RANGE;
+                S += a[j];
+            }
+        }
     }
     if (flags) atomicOr(status, flags);
 }
@@ -198,6 +272,7 @@ k_fused_frames(FusedParams P)
     __shared__ uint64_t bar[2];
     __shared__ double s_mem[3];
     __shared__ double red[32];
+    __shared__ double s_pmax[32];
     __shared__ float s_box[2][3];
     __shared__ double s_zexact;
     __shared__ int s_flag;
@@ -243,47 +318,33 @@ k_fused_frames(FusedParams P)
         __syncthreads();
         const float Lc0 = s_box[0][0], Lc1 = s_box[0][1], Lc2 = s_box[0][2];
         const float Lp0 = s_box[1][0], Lp1 = s_box[1][1], Lp2 = s_box[1][2];
-        // ---- phase U: image counts of frame t (exact reference recurrence) -------------------
-        for (int c = tid; c < C3; c += blockDim.x) {
-            const int k = c % 3;
-            const float Lp = k == 0 ? Lp0 : (k == 1 ? Lp1 : Lp2), Lc = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2);
-            const float up = pbk_unwrapped(prev[c], (int)S[c], Lp);
-            const float xv = cur[c];
-            const float d = __fsub_rn(xv, up);
-            const float h = Lc * 0.5f;
-            int s = 0;
-            if (d > h || d < -h) { float sl; s = fused_shift(d, Lc, &sl, &bad); }
-            if (s > 127 || s < -127) { bad |= 4; s = 0; }
-            S[c] = (signed char)s;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `prev` before the async write
-        __syncthreads();
-        // the other buffer is free now: fetch frame t+1 into it while frame t is reduced
-        if (t + 1 < f1) {
-            if (P.use_tma) {
-                if (tid == 0) {
-                    mbar_expect_tx(&bar[cb ^ 1], frame_bytes);
-                    bulk_g2s(prev, P.x + (t + 1) * (int64_t)C3, frame_bytes, &bar[cb ^ 1]);
-                }
-            }
-        }
-        // ---- phase L: NumPy-pairwise leaf sums of m*f64(u), one warp per leaf -----------------
+        // ---- phase UL: per chain the exact reference recurrence (image count of frame t), and in
+        // the same sweep the NumPy-pairwise leaf sums of m*f64(u); one warp per leaf, lanes
+        // 0..23 = 8 accumulator lanes x 3 axes ------------------------------------------------------
         for (int leaf = warp; leaf < P.L; leaf += nwarp) {
             const int start = P.leaf_start[leaf], n = P.leaf_len[leaf];
             const int j = lane / 3, k = lane % 3;
             const bool act = lane < 24;
-            const float Lk = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2);
-            const float *xf = cur + (size_t)start * 3;
-            const signed char *sf = S + (size_t)start * 3;
+            const float Lc = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2), Lp = k == 0 ? Lp0 : (k == 1 ? Lp1 : Lp2);
+            const float eps = pbk_image_eps(Lc, Lp);
             const double *mf = mass + start;
+            auto elem = [&](int a) -> double {              // atom a of the leaf, axis k
+                const int idx = (start + a) * 3 + k;
+                const float xv = cur[idx], xp = prev[idx];
+                int s = (int)S[idx];
+                if (!pbk_same_image(xv, xp, Lc, eps) || !(Lc > 0.0f)) {     // rare: exact rule
+                    float sl;
+                    s = fused_shift_far(__fsub_rn(xv, pbk_unwrapped(xp, s, Lp)), Lc, &sl, &bad);
+                    if (s > 127 || s < -127) { bad |= 4; s = 0; }
+                    S[idx] = (signed char)s;
+                }
+                return __dmul_rn(mf[a], (double)pbk_unwrapped(xv, s, Lc));
+            };
             double r = 0.0;
             const int nfull = n - (n % 8);
             if (n >= 8 && act) {
-                r = __dmul_rn(mf[j], (double)pbk_unwrapped(xf[j * 3 + k], sf[j * 3 + k], Lk));
-                for (int i = 8; i < nfull; i += 8) {
-                    const int a = i + j;
-                    r = __dadd_rn(r, __dmul_rn(mf[a], (double)pbk_unwrapped(xf[a * 3 + k], sf[a * 3 + k], Lk)));
-                }
+                r = elem(j);
+                for (int i = 8; i < nfull; i += 8) r = __dadd_rn(r, elem(i + j));
             }
             const int src1 = ((j ^ 1) * 3 + k) & 31, src2 = ((j ^ 2) * 3 + k) & 31, src4 = ((j ^ 4) * 3 + k) & 31;
             r = __dadd_rn(r, __shfl_sync(0xffffffffu, r, act ? src1 : lane));
@@ -292,12 +353,17 @@ k_fused_frames(FusedParams P)
             if (lane < 3) {
                 int i0 = nfull;
                 if (n < 8) { r = 0.0; i0 = 0; }
-                for (int i = i0; i < n; i++)
-                    r = __dadd_rn(r, __dmul_rn(mf[i], (double)pbk_unwrapped(xf[i * 3 + k], sf[i * 3 + k], Lk)));
+                for (int i = i0; i < n; i++) r = __dadd_rn(r, elem(i));
                 s_leaf[leaf * 3 + k] = r;
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `prev` before the async write
         __syncthreads();
+        // the other buffer is free now: fetch frame t+1 into it while frame t is reduced
+        if (t + 1 < f1 && P.use_tma && tid == 0) {
+            mbar_expect_tx(&bar[cb ^ 1], frame_bytes);
+            bulk_g2s(prev, P.x + (t + 1) * (int64_t)C3, frame_bytes, &bar[cb ^ 1]);
+        }
         for (int h = 0; h < P.H; h++) {
             const int a = P.level_off[h], b = P.level_off[h + 1];
             for (int w = tid; w < (b - a) * 3; w += blockDim.x) {
@@ -315,39 +381,60 @@ k_fused_frames(FusedParams P)
         // ---- phase C: per-lipid COMs; thread (i, role): role 0 wrapped, role 1 unwrapped -----
         {
             const double m0 = s_mem[0], m1 = s_mem[1], m2 = s_mem[2];
-            for (int w = tid; w < 2 * P.N; w += blockDim.x) {
-                const int role = w >= P.N, i = role ? w - P.N : w;
-                const int a0 = P.seg[i], a1 = P.seg[i + 1];
-                double c0 = 0, c1 = 0, c2 = 0;
-                for (int p = a0; p < a1; p++) {
-                    const int a = P.gather ? P.gather[p] : p;
-                    const double m = mass[a];
-                    float x0 = cur[a * 3], x1 = cur[a * 3 + 1], x2 = cur[a * 3 + 2];
-                    if (role) {
-                        x0 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x0, S[a * 3], Lc0), m0));
-                        x1 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x1, S[a * 3 + 1], Lc1), m1));
-                        x2 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(x2, S[a * 3 + 2], Lc2), m2));
+            for (int w0 = 0; w0 < 2 * P.N; w0 += blockDim.x) {
+                const int w = w0 + tid;
+                double zv = 0.0;
+                bool zact = false;
+                if (w < 2 * P.N) {
+                    const int role = w >= P.N, i = role ? w - P.N : w;
+                    const int a0 = P.seg[i], a1 = P.seg[i + 1];
+                    double c0 = 0, c1 = 0, c2 = 0;
+                    if (!role) {
+                        for (int p = a0; p < a1; p++) {
+                            const int a = P.gather ? P.gather[p] : p;
+                            const double m = mass[a];
+                            c0 = __dadd_rn(c0, __dmul_rn((double)cur[a * 3], m));
+                            c1 = __dadd_rn(c1, __dmul_rn((double)cur[a * 3 + 1], m));
+                            c2 = __dadd_rn(c2, __dmul_rn((double)cur[a * 3 + 2], m));
+                        }
+                    } else {
+                        for (int p = a0; p < a1; p++) {
+                            const int a = P.gather ? P.gather[p] : p;
+                            const double m = mass[a];
+                            const float v0 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(cur[a * 3], S[a * 3], Lc0), m0));
+                            const float v1 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(cur[a * 3 + 1], S[a * 3 + 1], Lc1), m1));
+                            const float v2 = __double2float_rn(__dsub_rn((double)pbk_unwrapped(cur[a * 3 + 2], S[a * 3 + 2], Lc2), m2));
+                            c0 = __dadd_rn(c0, __dmul_rn((double)v0, m));
+                            c1 = __dadd_rn(c1, __dmul_rn((double)v1, m));
+                            c2 = __dadd_rn(c2, __dmul_rn((double)v2, m));
+                        }
                     }
-                    c0 = __dadd_rn(c0, __dmul_rn((double)x0, m));
-                    c1 = __dadd_rn(c1, __dmul_rn((double)x1, m));
-                    c2 = __dadd_rn(c2, __dmul_rn((double)x2, m));
+                    const double lm = P.lipid_mass[i];
+                    c0 = __ddiv_rn(c0, lm); c1 = __ddiv_rn(c1, lm); c2 = __ddiv_rn(c2, lm);
+                    double *o = (role ? P.com_unwrap : P.com) + (t * (int64_t)P.N + i) * 3;
+                    o[0] = c0; o[1] = c1; o[2] = c2;
+                    if (role) { zv = P.norm == 0 ? c0 : (P.norm == 1 ? c1 : c2); s_z[i] = zv; zact = true; }
                 }
-                const double lm = P.lipid_mass[i];
-                c0 = __ddiv_rn(c0, lm); c1 = __ddiv_rn(c1, lm); c2 = __ddiv_rn(c2, lm);
-                double *o = (role ? P.com_unwrap : P.com) + (t * (int64_t)P.N + i) * 3;
-                o[0] = c0; o[1] = c1; o[2] = c2;
-                if (role) s_z[i] = P.norm == 0 ? c0 : (P.norm == 1 ? c1 : c2);
             }
         }
         __syncthreads();
         // ---- phase Z: leaflet labels (tree mean decides unless a lipid is within the rounding
         // bound of it; then thread 0 replays the sequential Welford mean) -------------------------
         if (P.do_labels) {
-            double s = 0.0, mx = 0.0;
-            for (int i = tid; i < P.N; i += blockDim.x) { const double v = s_z[i]; s += v; mx = fmax(mx, fabs(v)); }
-            s = pbk_block_sum(s, red);
-            mx = pbk_block_max(mx, red);
-            double mean = s / (double)P.N;
+            // the first N threads hold the data; the other warps only take part in the barriers
+            double sm = 0.0, mx = 0.0;
+            for (int i = tid; i < P.N; i += blockDim.x) { const double v = s_z[i]; sm += v; mx = fmax(mx, fabs(v)); }
+            if (warp * 32 < P.N) {
+                sm = pbk_warp_sum(sm);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) { red[warp] = sm; s_pmax[warp] = mx; }
+            }
+            __syncthreads();
+            const int nw_data = min(nwarp, (P.N + 31) / 32);
+            sm = 0.0; mx = 0.0;
+            for (int w = 0; w < nw_data; w++) { sm += red[w]; mx = fmax(mx, s_pmax[w]); }
+            double mean = sm / (double)P.N;
             const double tol = 64.0 * (double)P.N * 2.220446049250313e-16 * mx;
             int close = 0;
             for (int i = tid; i < P.N; i += blockDim.x) if (fabs(s_z[i] - mean) <= tol) close = 1;
@@ -445,10 +532,14 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     int32_t *sstart = reinterpret_cast<int32_t *>(slack + (int64_t)n_chunks * C3);
     float *chunk_box = reinterpret_cast<float *>(sstart + (int64_t)n_chunks * C3);
     float *u_out = chunk_box + 2 * (int64_t)n_chunks;
-    k_fused_agg<<<n_chunks, FUSED_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk, agg,
-                                                    amax, slack, chunk_box, status);
+    if (C3 % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0)
+        k_fused_agg<4><<<dim3(n_chunks, AGG_SPLIT), AGG_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk, agg,
+                                                           amax, slack, chunk_box, status);
+    else
+        k_fused_agg<1><<<dim3(n_chunks, AGG_SPLIT), AGG_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk, agg,
+                                                           amax, slack, chunk_box, status);
     PBK_CHECK_LAUNCH(ctx, "k_fused_agg");
-    k_fused_scan<<<(C3 + 255) / 256, 256, 0, st>>>(agg, amax, slack, chunk_box, C3, n_chunks, sstart, status);
+    k_fused_scan<<<(C3 + 31) / 32, 256, 0, st>>>(agg, amax, slack, chunk_box, C3, n_chunks, sstart, status);
     PBK_CHECK_LAUNCH(ctx, "k_fused_scan");
     FusedParams P;
     P.x = x; P.box = box; P.mass = mass; P.seg = seg; P.gather = gather; P.lipid_mass = lipid_mass;

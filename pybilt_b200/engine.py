@@ -163,6 +163,7 @@ class LipidReductionEngine:
         self.n_done = 0
         self.launches = 0
         self.allow_fused = bool(allow_fused)
+        self.fused_supported = True       # cleared when libpbk answers PBK_EUNSUPPORTED
         self.used_fused = False
         self._fused_scratch = None
 
@@ -225,6 +226,7 @@ class LipidReductionEngine:
                     self.n_done += nb
                     continue
                 self.allow_fused = False          # frame does not fit in shared memory
+                self.fused_supported = False
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
                    1 if g0 == 0 else 0, nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
             c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
