@@ -30,6 +30,17 @@ __device__ __forceinline__ float pbk_unwrapped(float x, int s, float L)
     return __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)s, (double)L)));
 }
 
+// Branch-free variant for |s| <= 127 (int8 image counts) and L < 2^13: (float)s through the
+// 2^23 magic constant (no I2F), one FMA; the float64 route only for |x| < 2^-8 with s != 0.
+__device__ __forceinline__ float pbk_unwrapped_i8(float x, int s, float L)
+{
+    const float sf = __int_as_float(0x4B400000 + s) - 12582912.0f;
+    float u = __fmaf_rn(sf, L, x);
+    if (s != 0 && (fabsf(x) < 0.00390625f || !(L < 8192.0f)))
+        u = __double2float_rn(__dadd_rn((double)x, __dmul_rn((double)s, (double)L)));
+    return u;
+}
+
 // Image count of frame t from the RAW previous frame.  The reference compares
 // d = f32(x_t - u_{t-1}) with +-L/2 where u_{t-1} = f32(x_{t-1} + s_{t-1} L_{t-1}); writing
 // d0 = f32(x_t - x_{t-1}), the shifted difference d + s_t L_t equals d0 + (s_t - s_{t-1}) L_t up to
