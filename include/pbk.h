@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 3
+#define PBK_ABI_VERSION 4
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -57,10 +57,13 @@ const char *pbk_last_error(const pbk_ctx *ctx);
  * Per atom and axis: d = f32(x_t - u_{t-1}); image shift s_t from the strict >/< loops
  * evaluated in float64; u_t = f32(f64(x_t) + s_t*L_t).  Writes the integer image counts
  * img[F][M][3]; u_state[M][3] (float32) carries u of the last frame in and out so batches
- * chain.  first_frame != 0: frame 0 of the batch is its own reference (u_0 = x_0). */
+ * chain.  first_frame != 0: frame 0 of the batch is its own reference (u_0 = x_0).
+ * init_images (may be NULL; needs first_frame): frame 0 is a raw frame whose image counts
+ * [M][3] int32 are already known -- how a frame shard continues the ranks before it
+ * (pybilt_b200/distributed.py). */
 int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
-                      int first_frame, int64_t F, int64_t M, int16_t *img, int32_t *status,
-                      void *stream);
+                      int first_frame, const int32_t *init_images, int64_t F, int64_t M,
+                      int16_t *img, int32_t *status, void *stream);
 
 /* ---- A3  membrane centre of mass --------------------------------------------------------
  * mem_com_k = (f64(u[:,k]) * masses).sum() / masses.sum()   pybilt/bilayer_analyzer/com_frame.py:175-179
@@ -98,7 +101,11 @@ int pbk_lipid_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t 
  * The pre-pass decides image increments from consecutive raw frames; if any jump lies
  * within rounding distance of half a box, PBK_ST_UNWRAP_AMBIGUOUS is raised in `status` and
  * the outputs must be recomputed with the generic entry points.
- * scratch: pbk_reduce_fused_scratch_bytes(F, M, sm_count) bytes of device memory. */
+ * scratch: pbk_reduce_fused_scratch_bytes(F, M, sm_count) bytes of device memory.
+ * phase: 3 = everything; 1 = image-count pre-pass only (writes net_images[M][3], the net
+ * image-count change over the batch, when not NULL); 2 = finish from the pre-pass left in
+ * scratch, with init_images[M][3] (image counts of frame 0, may be NULL) added -- the two
+ * halves of a frame shard, around the exchange of net counts between ranks. */
 int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
                                    int32_t *n_chunks, int32_t *chunk);
 int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
@@ -107,6 +114,7 @@ int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const doubl
                      const int32_t *node_left, const int32_t *node_right, int32_t K,
                      const int32_t *level_off, int32_t H, double total_mass, float *u_state,
                      int first_frame, int64_t F, int64_t M, int64_t N, int norm, int do_labels,
+                     int phase, const int32_t *init_images, int32_t *net_images,
                      void *scratch, int64_t scratch_bytes, double *com, double *com_unwrap,
                      double *mem_com, uint8_t *labels, int32_t *status, void *stream);
 int pbk_sm_count(const pbk_ctx *ctx);

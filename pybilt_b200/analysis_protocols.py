@@ -282,10 +282,12 @@ class MSDProtocol(AnalysisProtocol):
     def run_batch(self, ba_settings, batch, ba_mda_data):
         self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
                                              self.settings['resname'])
-        F = batch.n_frames
-        vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
-                                      np.zeros(F, dtype=np.int32), np.arange(F, dtype=np.int32),
+        rows = batch.rows                    # engine rows of the frames this rank owns
+        ends = np.arange(rows.start, rows.stop, dtype=np.int32)
+        origins = np.full(len(ends), batch.ref_row, dtype=np.int32)   # frame 0 of the whole run
+        vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32), origins, ends,
                                       ba_settings['lateral']).cpu().numpy()
+        vals = batch.to_global(vals)
         self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
 
@@ -332,16 +334,19 @@ class MSDMultiProtocol(AnalysisProtocol):
         n_tau, n_sigma = self.settings['n_tau'], self.settings['n_sigma']
         F = batch.n_frames
         finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
-        out = [0.0] * n_blocks
-        if finished:
-            blocks = sorted(finished)
+        out = np.zeros(n_blocks)
+        shard = batch.shard
+        # a rank evaluates the blocks whose origin frame it owns (the end frame lies in its
+        # forward halo); row = engine row of an analysed frame
+        blocks = [b for b in sorted(finished) if shard is None or shard.lo <= finished[b][0] < shard.hi]
+        row = (lambda g: g) if shard is None else shard.local_of
+        if blocks:
             vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
-                                          [finished[b][0] for b in blocks],
-                                          [finished[b][1] for b in blocks],
+                                          [row(finished[b][0]) for b in blocks],
+                                          [row(finished[b][1]) for b in blocks],
                                           ba_settings['lateral']).cpu().numpy()
-            for b, v in zip(blocks, vals):
-                out[b] = v
-        self.analysis_output = out
+            out[blocks] = vals
+        self.analysis_output = list(batch.allreduce(out))
         self._tau = batch.times[n_tau - 1] - batch.times[0] if F >= n_tau else 0.0
 
     def _process_output(self, analysis_output):
@@ -402,12 +407,14 @@ class COMLateralRDFProtocol(AnalysisProtocol):
         self._n_leaf = float(len(do_leaflet))
         count, fc = batch.engine.rdf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                      batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
-                                     edges, ba_settings['lateral'])
+                                     edges, ba_settings['lateral'], frames=batch.rows)
         fc = fc.cpu().numpy().astype(np.int64)
-        self._count = count.cpu().numpy().astype(np.float64)
-        self._N_a += int(fc[:, :, 0].sum())
-        self._N_b += int(fc[:, :, 1].sum())
-        self._N += int(fc[:, :, 2].sum())
+        # frame shards: partial histograms and (N_a, N_b, N) sums are all-reduced
+        self._count = batch.allreduce(count.cpu().numpy()).astype(np.float64)
+        sums = batch.allreduce(np.array([fc[:, :, 0].sum(), fc[:, :, 1].sum(), fc[:, :, 2].sum()]))
+        self._N_a += int(sums[0])
+        self._N_b += int(sums[1])
+        self._N += int(sums[2])
         lat = list(ba_settings['lateral'])
         # box[lateral].prod() per frame is a float32 product (:5004) pushed into a Welford mean
         areas = batch.box_host[:, lat[0]] * batch.box_host[:, lat[1]]
@@ -473,9 +480,9 @@ class NNFProtocol(AnalysisProtocol):
         self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
         n_b, frac = batch.engine.nnf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                      batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
-                                     s['n_neighbors'], ba_settings['lateral'])
-        self.neighbor_counts = n_b            # device int32 [F, N]; -1 = not a reference lipid
-        rows, self.running = running_rows(batch.times, frac.cpu().numpy())
+                                     s['n_neighbors'], ba_settings['lateral'], frames=batch.rows)
+        self.neighbor_counts = n_b            # device int32 [owned frames, N]; -1 = not a reference lipid
+        rows, self.running = running_rows(batch.times, batch.to_global(frac.cpu().numpy()))
         self.analysis_output = [list(r) for r in rows]
 
 
@@ -495,7 +502,7 @@ class BTGridProtocol(AnalysisProtocol):
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
         grids = batch.lipid_grids()
-        rows, self.running = running_rows(batch.times, grids.thickness_host[:, 0])
+        rows, self.running = running_rows(batch.times, batch.to_global(grids.thickness_host[:, 0]))
         self.analysis_output = [r for r in rows]
 
     def reset(self):
@@ -520,7 +527,7 @@ class APLGridProtocol(AnalysisProtocol):
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
         grids = batch.lipid_grids()
-        apl = grids.apl_host
+        apl = batch.to_global(grids.apl_host)
         rows, self.running = running_rows(batch.times, apl[:, 0])
         out = {'composite': rows}
         # resnames in the order LipidGrids.area_per_lipid lists them at the first frame

@@ -32,6 +32,7 @@ from . import analysis_protocols as ap
 from . import com_frame as cf
 from . import leaflet as lf
 from . import lipid_grid as lg
+from . import distributed as pd
 from .engine import FusedPathRejected, LipidReductionEngine, build_bead_layout
 
 default_analysis_commands = ['msd msd_1']
@@ -170,10 +171,15 @@ class ReductionBatch(object):
     """What a batched protocol's ``run_batch`` receives: the engine holding the resident
     representations, host metadata, and the leaflets of the first analysed frame."""
 
-    def __init__(self, analyzer, engine, times, box_host, first_leaflets):
+    def __init__(self, analyzer, engine, times, box_host, first_leaflets, shard=None):
         self._analyzer = analyzer
         self.engine = engine
-        self.n_frames = engine.n_done
+        self.shard = shard                  # pybilt_b200.distributed.Shard or None
+        # n_frames / times / box_host describe ALL analysed frames; the engine rows of a
+        # shard are [back halo | owned | forward halo | reference row]
+        self.n_frames = len(times)
+        self.rows = shard.owned_local() if shard is not None else slice(0, engine.n_done)
+        self.ref_row = shard.n_local if shard is not None else 0     # frame 0 of the whole run
         self.times = times
         self.box_host = box_host
         self.types = engine.layout.types
@@ -188,6 +194,26 @@ class ReductionBatch(object):
         self.type_code_dev = torch.from_numpy(codes).to(engine.dev)
         self.first_leaflets = first_leaflets
         self._grids = None
+
+    def allreduce(self, values):
+        """Sum of a small host array over the ranks (identity when not sharded)."""
+        values = np.asarray(values)
+        if self.shard is None:
+            return values
+        dt = torch.int64 if values.dtype.kind in "iu" else torch.float64
+        t = torch.as_tensor(values, dtype=dt, device=self.engine.dev)
+        return pd.combine_slots(t).cpu().numpy()
+
+    def to_global(self, owned_values):
+        """Per-frame values of the owned frames -> values of all analysed frames (all ranks)."""
+        owned_values = np.asarray(owned_values)
+        if self.shard is None:
+            return owned_values
+        full = torch.zeros((self.n_frames,) + owned_values.shape[1:], dtype=torch.float64,
+                           device=self.engine.dev)
+        full[self.shard.lo:self.shard.hi] = torch.as_tensor(owned_values, dtype=torch.float64,
+                                                            device=self.engine.dev)
+        return pd.combine_slots(full).cpu().numpy()
 
     def type_code_of(self, name):
         if name == 'all':
@@ -206,8 +232,9 @@ class BilayerAnalyzer(object):
     _required_commands = ['structure', 'trajectory', 'selection']
 
     def __init__(self, structure=None, trajectory=None, selection=None, input_file=None,
-                 input_dict=None, device=0):
+                 input_dict=None, device=0, distributed=True):
         self.next = self.__next__
+        self.distributed = distributed      # shard frames across ranks when torch.distributed is up
         self.settings = {'frame_range': [0, -1, 1], 'print_interval': 5, 'norm': 2,
                          'lateral': [0, 1], 'lateral_dimension': "xy", 'normal_dimension': "z",
                          'frame_index': 0}
@@ -425,12 +452,30 @@ class BilayerAnalyzer(object):
         if cached is None or cached[0][:3] != (id(md), repr(cset['name_dict']), bool(cset['multi_bead'])):
             layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
                                        cset['name_dict'], cset['multi_bead'])
-        fr = self.analysed_frame_indices()
+        fr_all = self.analysed_frame_indices()
+        shard = None
+        if self.distributed and pd.is_distributed():
+            import torch.distributed as dist
+            fwd = 0
+            for a_id in self._analysis_protocol.analysis_ids:
+                proto = self._analysis_protocol.command_protocol[a_id]
+                if proto.analysis_key == 'msd_multi':
+                    fwd = max(fwd, int(proto.settings['n_tau']) - 1)
+            shard = pd.make_shard(len(fr_all), dist.get_world_size(), dist.get_rank(), fwd)
+            if shard.n_owned == 0:
+                raise RuntimeError("more ranks than analysed frames")
+            fr = fr_all[shard.first_local:shard.first_local + shard.n_local]
+        else:
+            fr = fr_all
         self._frames = fr
+        self._frames_all = fr_all
+        self._shard = shard
+        n_rows = len(fr) + (1 if shard is not None else 0)
         # the engine (device buffers, summation plan, libpbk context) is reused across reset()
         # as long as nothing that shapes it changed
-        key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), len(fr), self.device,
-               self.settings['norm'], int(lset['update_interval']), self.batch_frames)
+        batch_frames = self.batch_frames if shard is None else len(fr)
+        key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), n_rows, self.device,
+               self.settings['norm'], int(lset['update_interval']), batch_frames)
         cached = getattr(self, '_engine_cache', None)
         if cached is not None and cached[0] == key:
             eng = cached[1]
@@ -440,12 +485,14 @@ class BilayerAnalyzer(object):
         else:
             if layout is None:
                 layout = cached[1].layout
-            eng = LipidReductionEngine(md.masses, layout, len(fr), device=self.device,
+            eng = LipidReductionEngine(md.masses, layout, n_rows, device=self.device,
                                        norm=self.settings['norm'],
                                        leaflet_update_interval=int(lset['update_interval']),
-                                       batch_frames=self.batch_frames, allow_fused=allow_fused)
+                                       batch_frames=batch_frames, allow_fused=allow_fused)
         self._engine_key = key
         self._engine_cache = None
+        if shard is not None:
+            return self._reduce_sharded(eng, md, fr, fr_all, shard, layout)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
         dev = eng.dev
         copy_stream = torch.cuda.Stream(dev)
@@ -483,12 +530,52 @@ class BilayerAnalyzer(object):
         self._batch = ReductionBatch(self, eng, times, dims_all[:, :3].copy(), first_leaflets)
         return self._batch
 
+    def _reduce_sharded(self, eng, md, fr, fr_all, shard, layout):
+        """Frame-shard variant of the reduction (pybilt_b200/distributed.py)."""
+        dev = eng.dev
+        # metadata of ALL analysed frames (tiny) is known to every rank
+        dims_all = np.asarray(md._dimensions[fr_all], dtype=np.float32) if hasattr(md, '_dimensions') else None
+        times_all = np.asarray(md._times[fr_all], dtype=np.float64) if hasattr(md, '_times') else None
+        n_a = shard.back + shard.n_owned
+        x, d, t = md.frames(fr)
+        if dims_all is None:                 # MDAnalysis input: only the shard was read
+            raise RuntimeError("sharded runs need in-memory box/time arrays for all frames")
+        xh = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        xd = xh.to(dev, non_blocking=True)
+        bd = torch.from_numpy(np.ascontiguousarray(d[:, :3])).to(dev)
+        net = torch.zeros((md.natoms, 3), dtype=torch.int32, device=dev)
+        eng.push(xd[:n_a], bd[:n_a], phase=1, net_out=net)
+        off = pd.image_offsets(net)
+        eng.push(xd[:n_a], bd[:n_a], phase=2, init_images=off)
+        seen = eng.image_counts_last(xd[n_a - 1], bd[n_a - 1])
+        if not bool(torch.equal(seen, off + net)):
+            raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
+                               "makes the shard decomposition ambiguous; run on one rank")
+        if shard.fwd:
+            eng.push(xd[n_a:], bd[n_a:])
+        eng.check_status()
+        # frame 0 of the run: leaflets (index lists) and unwrapped COMs (MSD reference)
+        lab0 = eng.labels[0].clone()
+        pd.broadcast_from_first(lab0)
+        ref = eng.com_unwrap[0].clone()
+        pd.broadcast_from_first(ref)
+        eng.com_unwrap[shard.n_local].copy_(ref)
+        first_leaflets = lf.leaflets_from_labels(lab0.cpu().numpy(), layout.types, layout.resids)
+        self._engine = eng
+        self._times = times_all[shard.first_local:shard.first_local + shard.n_local]
+        self._dims = dims_all[shard.first_local:shard.first_local + shard.n_local]
+        self._batch = ReductionBatch(self, eng, times_all, dims_all[:, :3].copy(), first_leaflets, shard)
+        return self._batch
+
     def _build_lipid_grids(self, batch):
         gs = self.rep_settings['lipid_grid']
         lat = self.settings['lateral']
-        F = batch.n_frames
+        # grids are built for the owned frames; index 0 = first owned frame (engine row r0)
+        r0 = batch.rows.start
+        F = batch.rows.stop - batch.rows.start
+        g0 = batch.shard.lo if batch.shard is not None else 0
         if gs['area_per_bin'] is not None:
-            bins = [lg.fixed_resolution_bins(batch.box_host[f][lat[0]], batch.box_host[f][lat[1]],
+            bins = [lg.fixed_resolution_bins(batch.box_host[g0 + f][lat[0]], batch.box_host[g0 + f][lat[1]],
                                              gs['area_per_bin']) for f in range(F)]
         else:
             bins = [(int(gs['n_xbins']), int(gs['n_ybins']))] * F
@@ -502,9 +589,10 @@ class BilayerAnalyzer(object):
         thick = np.empty((F, 2))
         apl = np.empty((F, 1 + 2 * len(batch.type_names)))
         for sl, nx, ny in runs:
-            gi, gz, _knn = eng.lipid_grid(nx, ny, self.grid_mode, lat, frames=sl)
+            esl = slice(r0 + sl.start, r0 + sl.stop)            # engine rows of this run
+            gi, gz, _knn = eng.lipid_grid(nx, ny, self.grid_mode, lat, frames=esl)
             cells, th, ap_ = eng.grid_reduce(gi, gz, batch.type_code_dev, len(batch.type_names), lat,
-                                             frames=sl)
+                                             frames=esl)
             gi_l.append(gi); gz_l.append(gz); cells_l.append(cells)
             thick[sl] = th.cpu().numpy()
             apl[sl] = ap_.cpu().numpy()
@@ -549,9 +637,10 @@ class BilayerAnalyzer(object):
         grid = None
         if need_grid if need_grid is not None else self._analysis_protocol.use_objects['lipid_grid']:
             gb = self._batch.lipid_grids()
-            gi, gz, cells = gb.frame(g)
+            o = g - self._batch.rows.start          # grids are indexed by owned frame
+            gi, gz, cells = gb.frame(o)
             grid = lg.LipidGrids(frame, leaflets, self.settings['lateral'], gi, gz,
-                                 gb.thickness_host[g], gb.apl_host[g], cells, self._batch.type_names)
+                                 gb.thickness_host[o], gb.apl_host[o], cells, self._batch.type_names)
         return frame, leaflets, grid
 
     def __next__(self):
@@ -560,8 +649,8 @@ class BilayerAnalyzer(object):
                 raise StopIteration()
             self._started = False
             self._start()
-            self._cursor = 0
-        if self._cursor >= len(self._frames):
+            self._cursor = self._batch.rows.start
+        if self._cursor >= self._batch.rows.stop:
             self._started = False
             raise StopIteration()
         g = self._cursor
@@ -572,7 +661,7 @@ class BilayerAnalyzer(object):
             x, d, t = self._mda_data.frames(self._frames[g:g + 1])
             self.reps['current_mda_frame'] = _HostFrame(np.asarray(x[0]), d[0], t[0], int(self._frames[g]))
             self.reps['com_frame'] = frame
-            if g == 0:
+            if g == self._batch.rows.start:
                 self.reps['first_com_frame'] = frame
             self.reps['leaflets'] = leaflets
             self.reps['lipid_grid'] = grid
@@ -596,16 +685,16 @@ class BilayerAnalyzer(object):
             if not getattr(self, '_started', False):
                 self._started = False
                 self._start()
-                self._cursor = 0
+                self._cursor = self._batch.rows.start
             if self._legacy:
                 for _frame in self:
                     pass
             else:                       # nothing needs per-frame host views: skip the frame loop
-                n = len(self._frames)
+                n = self._batch.rows.stop
                 self._frame_loop_count += n - self._cursor
                 self._cursor = n
-                self.settings['frame_index'] = int(self._frames[-1])
-                self._current_frame = int(self._frames[-1]) + self.settings['frame_range'][2]
+                self.settings['frame_index'] = int(self._frames_all[-1])
+                self._current_frame = int(self._frames_all[-1]) + self.settings['frame_range'][2]
                 self._started = False
         finally:
             self._iterating_for_user = True

@@ -43,7 +43,8 @@ __device__ __forceinline__ int pbk_next_image(float xv, float xprev, int s, floa
 
 __global__ void __launch_bounds__(128)
 k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, float *u_state,
-                int first_frame, int64_t F, int64_t C, int16_t *__restrict__ img, int32_t *status)
+                int first_frame, const int32_t *__restrict__ init_images, int64_t F, int64_t C,
+                int16_t *__restrict__ img, int32_t *status)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -53,9 +54,13 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
     int s = 0;
     int64_t t = 0;
     if (first_frame) {
+        // frame 0 is its own reference; in a frame shard it is a raw halo frame whose image
+        // counts (init_images) are already known from the ranks before
         xprev = x[c];
         Lprev = box[k];
-        img[c] = 0;
+        s = init_images ? init_images[c] : 0;
+        if (s > 32767 || s < -32767) { bad = 1; s = 0; }
+        img[c] = (int16_t)s;
         t = 1;
     } else {
         xprev = u_state[c];            // an unwrapped coordinate is a raw one with image count 0
@@ -88,9 +93,11 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
 }
 
 extern "C" int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
-                                 int first_frame, int64_t F, int64_t M, int16_t *img,
-                                 int32_t *status, void *stream)
+                                 int first_frame, const int32_t *init_images, int64_t F, int64_t M,
+                                 int16_t *img, int32_t *status, void *stream)
 {
+    if (init_images && !first_frame)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_unwrap_images: init_images needs first_frame");
     if (!ctx || !x || !box || !u_state || !img || !status || F < 0 || M <= 0)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_unwrap_images: bad argument");
     if (F == 0) return PBK_OK;
@@ -98,7 +105,7 @@ extern "C" int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box,
     int threads = 128;
     int64_t blocks = (C + threads - 1) / threads;
     k_unwrap_images<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        x, box, u_state, first_frame, F, C, img, status);
+        x, box, u_state, first_frame, init_images, F, C, img, status);
     PBK_CHECK_LAUNCH(ctx, "k_unwrap_images");
     return PBK_OK;
 }

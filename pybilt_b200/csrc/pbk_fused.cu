@@ -267,7 +267,7 @@ k_fused_agg12(const float *__restrict__ x, const float *__restrict__ box,
 __global__ void __launch_bounds__(256)
 k_fused_scan(const int32_t *__restrict__ agg, const int32_t *__restrict__ amax,
              const float *__restrict__ slack, const float *__restrict__ chunk_box, int C3, int n_chunks,
-             int32_t *__restrict__ sstart, int32_t *status)
+             const int32_t *__restrict__ init_images, int32_t *__restrict__ sstart, int32_t *status)
 {
     __shared__ int tot[SCAN_GROUPS][32];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -280,7 +280,7 @@ k_fused_scan(const int32_t *__restrict__ agg, const int32_t *__restrict__ amax,
     tot[g][cl] = sum;
     __syncthreads();
     if (c >= C3) return;
-    int S = 0, flags = 0;
+    int S = init_images ? init_images[c] : 0, flags = 0;
     for (int gg = 0; gg < g; gg++) S += tot[gg][cl];
     for (int kb = k0; kb < k1; kb += 4) {
         int a[4], m[4];
@@ -307,6 +307,17 @@ k_fused_scan(const int32_t *__restrict__ agg, const int32_t *__restrict__ amax,
         }
     }
     if (flags) atomicOr(status, flags);
+}
+
+// net image-count change over the whole batch (sum of the sub-chunk totals): what a frame
+// shard hands to the ranks after it
+__global__ void k_fused_net(const int32_t *__restrict__ agg, int C3, int n_chunks, int32_t *__restrict__ net)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C3) return;
+    int s = 0;
+    for (int kc = 0; kc < n_chunks; kc++) s += __ldg(agg + (int64_t)kc * C3 + c);
+    net[c] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,6 +360,7 @@ struct FusedParams {
     const float *u_state; float *u_out; int first_frame;
     int64_t F; int M, N, norm, chunk, n_chunks, do_labels, sub;
     const int32_t *sstart;
+    const int32_t *init_images;
     double *com, *com_unwrap, *mem_com; uint8_t *labels; int32_t *status;
     int use_tma, mass_in_smem;
     int skip;                   // debug ablation mask (PBK_FUSED_SKIP): 1 U, 2 L, 4 C role0, 8 C role1, 16 Z, 32 stores
@@ -401,7 +413,9 @@ k_fused_frames(FusedParams P)
     const float *prev_src = (kc == 0) ? (P.first_frame ? P.x : P.u_state) : P.x + (f0 - 1) * (int64_t)C3;
     for (int c = tid; c < C3; c += blockDim.x) {
         prev[c] = prev_src[c];
-        S[c] = (signed char)((kc == 0) ? 0 : P.sstart[(int64_t)kc * P.sub * C3 + c]);
+        int s0 = (kc == 0) ? (P.init_images ? P.init_images[c] : 0) : P.sstart[(int64_t)kc * P.sub * C3 + c];
+        if (s0 > 127 || s0 < -127) { bad |= 4; s0 = 0; }
+        S[c] = (signed char)s0;
     }
     if (tid < 3) s_box[1][tid] = (kc == 0) ? P.box[tid] : P.box[(f0 - 1) * 3 + tid];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -678,10 +692,13 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
                                 const int32_t *node_left, const int32_t *node_right, int32_t K,
                                 const int32_t *level_off, int32_t H, double total_mass, float *u_state,
                                 int first_frame, int64_t F, int64_t M, int64_t N, int norm,
-                                int do_labels, void *scratch, int64_t scratch_bytes, double *com,
+                                int do_labels, int phase, const int32_t *init_images,
+                                int32_t *net_images, void *scratch, int64_t scratch_bytes, double *com,
                                 double *com_unwrap, double *mem_com, uint8_t *labels, int32_t *status,
                                 void *stream)
 {
+    if ((phase & ~3) || phase == 0 || (init_images && !first_frame))
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: bad phase / init_images needs first_frame");
     if (!ctx || !x || !box || !mass || !seg || !lipid_mass || !leaf_start || !leaf_len || !u_state ||
         !scratch || !com || !com_unwrap || !mem_com || !status || (do_labels && !labels) || F < 0 ||
         M <= 0 || N <= 0 || L <= 0 || K < 0 || norm < 0 || norm > 2)
@@ -712,6 +729,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     int32_t *sstart = reinterpret_cast<int32_t *>(slack + (int64_t)n_sub * C3);
     float *chunk_box = reinterpret_cast<float *>(sstart + (int64_t)n_sub * C3);
     float *u_out = chunk_box + 2 * (int64_t)n_sub;
+    if (phase & 1) {
     if (C3 % 12 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0)
         k_fused_agg12<<<dim3(n_sub, AGG_SPLIT), AGG_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk_sub,
                                                                      agg, amax, slack, chunk_box, status);
@@ -722,14 +740,20 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
         k_fused_agg<1><<<dim3(n_sub, AGG_SPLIT), AGG_THREADS, 0, st>>>(x, box, u_state, first_frame, F, C3, chunk_sub, agg,
                                                            amax, slack, chunk_box, status);
     PBK_CHECK_LAUNCH(ctx, "k_fused_agg");
-    k_fused_scan<<<(C3 + 31) / 32, 256, 0, st>>>(agg, amax, slack, chunk_box, C3, n_sub, sstart, status);
+    if (net_images) {
+        k_fused_net<<<(C3 + 255) / 256, 256, 0, st>>>(agg, C3, n_sub, net_images);
+        PBK_CHECK_LAUNCH(ctx, "k_fused_net");
+    }
+    }
+    if (!(phase & 2)) return PBK_OK;
+    k_fused_scan<<<(C3 + 31) / 32, 256, 0, st>>>(agg, amax, slack, chunk_box, C3, n_sub, init_images, sstart, status);
     PBK_CHECK_LAUNCH(ctx, "k_fused_scan");
     FusedParams P;
     P.x = x; P.box = box; P.mass = mass; P.seg = seg; P.gather = gather; P.lipid_mass = lipid_mass;
     P.leaf_start = leaf_start; P.leaf_len = leaf_len; P.node_left = node_left; P.node_right = node_right;
     P.level_off = level_off; P.L = L; P.K = K; P.H = H; P.total_mass = total_mass;
     P.u_state = u_state; P.u_out = u_out; P.first_frame = first_frame; P.F = F; P.M = (int)M; P.N = (int)N; P.norm = norm;
-    P.sub = sub; P.chunk = chunk; P.n_chunks = n_chunks; P.do_labels = do_labels; P.sstart = sstart;
+    P.sub = sub; P.chunk = chunk; P.n_chunks = n_chunks; P.init_images = init_images; P.do_labels = do_labels; P.sstart = sstart;
     P.com = com; P.com_unwrap = com_unwrap; P.mem_com = mem_com; P.labels = labels; P.status = status;
     P.use_tma = ((C3 * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(x) % 16) == 0);
     P.mass_in_smem = mass_in_smem;

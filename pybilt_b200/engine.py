@@ -184,14 +184,22 @@ class LipidReductionEngine:
     def stream_ptr(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def push(self, x: torch.Tensor, box: torch.Tensor):
+    def push(self, x: torch.Tensor, box: torch.Tensor, phase: int = 3,
+             init_images: Optional[torch.Tensor] = None, net_out: Optional[torch.Tensor] = None):
         """Process the next ``x.shape[0]`` analysed frames.  ``x`` float32 [f, M, 3] and ``box``
-        float32 [f, 3] are device tensors (any f; split into scratch-sized batches here)."""
+        float32 [f, 3] are device tensors (any f; split into scratch-sized batches here).
+
+        Frame shards (pybilt_b200/distributed.py) call this twice for their first push:
+        ``phase=1`` only counts periodic images and writes the net change over the frames into
+        ``net_out`` (int32 [M, 3]); after the ranks exchanged those, ``phase=2`` finishes the
+        same frames with ``init_images`` (int32 [M, 3]), the image counts of frame 0."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         assert box.is_cuda and box.dtype == torch.float32 and box.is_contiguous()
         f_total = int(x.shape[0])
         if self.n_done + f_total > self.F:
             raise RuntimeError("more frames pushed than the engine was sized for")
+        if (phase != 3 or init_images is not None) and (f_total > self.B or self.n_done != 0):
+            raise RuntimeError("sharded pushes must be the first push and fit one engine batch")
         st = self.stream_ptr()
         c = self.ctx
         for b0 in range(0, f_total, self.B):
@@ -199,7 +207,8 @@ class LipidReductionEngine:
             nb = b1 - b0
             xb, bb = x[b0:b1], box[b0:b1]
             g0 = self.n_done
-            self.box[g0:g0 + nb].copy_(bb)
+            if phase & 2:
+                self.box[g0:g0 + nb].copy_(bb)
             p = self.plan
             prev = self.labels[g0 - 1].data_ptr() if g0 > 0 else None
             if self.allow_fused:
@@ -211,13 +220,16 @@ class LipidReductionEngine:
                                 self.d_node_left.data_ptr(), self.d_node_right.data_ptr(), p.n_nodes,
                                 self.d_level_off.data_ptr(), p.n_levels, self.total_mass,
                                 self.d_u_state.data_ptr(), 1 if g0 == 0 else 0, nb, self.M, self.N,
-                                self.norm, do_labels, scratch.data_ptr(), int(scratch.numel()),
+                                self.norm, do_labels, int(phase), _ptr(init_images), _ptr(net_out),
+                                scratch.data_ptr(), int(scratch.numel()),
                                 self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
                                 self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(),
                                 self.d_status.data_ptr(), st)
                 if ok:
-                    self.launches += 3
+                    self.launches += 3 if phase == 3 else (2 if phase == 1 else 2)
                     self.used_fused = True
+                    if not (phase & 2):
+                        continue
                     if not do_labels:
                         c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
                                self.update_interval, prev, self.labels[g0:].data_ptr(),
@@ -227,8 +239,17 @@ class LipidReductionEngine:
                     continue
                 self.allow_fused = False          # frame does not fit in shared memory
                 self.fused_supported = False
+            if phase == 1:
+                # generic path: a plain unwrap of the shard; its last row is the net change
+                c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(), 1, None,
+                       nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+                self.launches += 1
+                if net_out is not None:
+                    net_out.copy_(self.d_img[nb - 1].to(torch.int32))
+                continue
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
-                   1 if g0 == 0 else 0, nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+                   1 if g0 == 0 else 0, _ptr(init_images), nb, self.M, self.d_img.data_ptr(),
+                   self.d_status.data_ptr(), st)
             c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
                    self.d_mass.data_ptr(), nb, self.M, self.d_leaf_start.data_ptr(),
                    self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(),
@@ -242,6 +263,11 @@ class LipidReductionEngine:
                    self.update_interval, prev, self.labels[g0:].data_ptr(), self.d_status.data_ptr(), st)
             self.launches += 5
             self.n_done += nb
+
+    def image_counts_last(self, x_last: torch.Tensor, box_last: torch.Tensor) -> torch.Tensor:
+        """int32 [M, 3] image counts of the last pushed frame, recovered from the carried
+        unwrapped state: u = f32(x + s*L)  =>  s = rint((u - x) / L)."""
+        return torch.round((self.d_u_state.double() - x_last.double()) / box_last.double()[None, :]).to(torch.int32)
 
     def check_status(self):
         """Synchronises; raises like the reference does for data-dependent failures."""
@@ -302,13 +328,15 @@ class LipidReductionEngine:
         return count, fc
 
     def nnf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int, k: int,
-            lateral=(0, 1)):
+            lateral=(0, 1), frames: Optional[slice] = None):
         d = self.dev
-        F = self.n_done
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        s0 = sl.start
         n_b = torch.empty((F, self.N), dtype=torch.int32, device=d)
         frac = torch.empty(F, dtype=torch.float64, device=d)
-        self.ctx.call("pbk_nnf", self.com.data_ptr(), self.labels.data_ptr(), type_code.data_ptr(),
-                      self.box.data_ptr(), F, self.N, int(lateral[0]), int(lateral[1]), int(type_a),
+        self.ctx.call("pbk_nnf", self.com[s0:].data_ptr(), self.labels[s0:].data_ptr(), type_code.data_ptr(),
+                      self.box[s0:].data_ptr(), F, self.N, int(lateral[0]), int(lateral[1]), int(type_a),
                       int(type_b), int(leaflet_mask), int(k), n_b.data_ptr(), frac.data_ptr(),
                       self.stream_ptr())
         self.launches += 2
