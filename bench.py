@@ -194,10 +194,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     F = a.frames
-    top, traj = workload(rank, F)
+    from pybilt_b200 import distributed as pd
+    from pybilt_b200 import synthetic as syn
+    from pybilt_b200.bilayer_analyzer import FrameWindow
+    spec, _ = syn.config_spec("C2")
+    F_total = F * world
+    # frame shard of one F*world-frame trajectory: [1-frame back halo | F owned | 49-frame
+    # forward halo for msd_multi(50,50)]; at N = 1 this is just the F frames
+    sh = pd.make_shard(F_total, world, rank, forward_halo=49) if world > 1 else None
+    first_local = sh.first_local if sh else 0
+    n_local = sh.n_local if sh else F
+    top, traj = syn.generate(spec, n_local, first_frame=first_local)
     M = top.n_atoms
     layout = eng.build_bead_layout(top.masses, top.names, top.resindex, top.resnames, top.resids)
-    e = eng.LipidReductionEngine(top.masses, layout, F, device=local)
+    e = eng.LipidReductionEngine(top.masses, layout, n_local + 1, device=local, batch_frames=n_local)
 
     x_host = torch.from_numpy(traj.positions).pin_memory()
     box_host = torch.from_numpy(np.ascontiguousarray(traj.dimensions[:, :3])).pin_memory()
@@ -207,15 +217,38 @@ def main():
     edges = np.histogram([-1], bins=25, range=[0.0, 25.0])[1]
     edges_dev = torch.from_numpy(edges).to(dev)
     thr_dev = torch.from_numpy(eng.rdf_thresholds(edges)).to(dev)
-    fin, _nb = msd_multi_schedule(F, 50, 50)
-    mm_o = torch.tensor([fin[b][0] for b in sorted(fin)], dtype=torch.int32, device=dev)
-    mm_e = torch.tensor([fin[b][1] for b in sorted(fin)], dtype=torch.int32, device=dev)
-    zeros = torch.zeros(F, dtype=torch.int32, device=dev)
-    arange = torch.arange(F, dtype=torch.int32, device=dev)
+    fin, _nb = msd_multi_schedule(F_total, 50, 50)
+    row = sh.local_of if sh else (lambda g: g)
+    mine = [b for b in sorted(fin) if sh is None or sh.lo <= fin[b][0] < sh.hi]
+    mm_o = torch.tensor([row(fin[b][0]) for b in mine], dtype=torch.int32, device=dev)
+    mm_e = torch.tensor([row(fin[b][1]) for b in mine], dtype=torch.int32, device=dev)
+    owned = sh.owned_local() if sh else slice(0, F)
+    ref_row = n_local if sh else 0
+    origins = torch.full((F,), ref_row, dtype=torch.int32, device=dev)
+    ends = torch.arange(owned.start, owned.stop, dtype=torch.int32, device=dev)
+    net = torch.zeros((M, 3), dtype=torch.int32, device=dev)
+    n_a = (sh.back + sh.n_owned) if sh else F
 
-    # index list of 'msd ... leaflet both resname all': upper members then lower (frame 0)
-    e.push(x_dev[:1], box_dev[:1])
-    lab0 = e.labels[0].cpu().numpy()
+    def reduce_all():
+        e.reset()
+        if sh is None:
+            e.push(x_dev, box_dev)
+            return
+        e.push(x_dev[:n_a], box_dev[:n_a], phase=1, net_out=net)      # count periodic images
+        off = pd.image_offsets(net)                                   # NCCL all-gather + prefix
+        e.push(x_dev[:n_a], box_dev[:n_a], phase=2, init_images=off)  # finish from the true counts
+        if sh.fwd:
+            e.push(x_dev[n_a:], box_dev[n_a:])
+        ref = e.com_unwrap[0].clone()
+        pd.broadcast_from_first(ref)                                  # frame 0 of the whole run
+        e.com_unwrap[n_local].copy_(ref)
+
+    # index list of 'msd ... leaflet both resname all': upper members then lower (frame 0 of the run)
+    reduce_all()
+    lab0 = e.labels[0].clone()
+    if sh is not None:
+        pd.broadcast_from_first(lab0)
+    lab0 = lab0.cpu().numpy()
     idx = torch.from_numpy(np.concatenate([np.nonzero(lab0 == 1)[0], np.nonzero(lab0 == 0)[0]])
                            .astype(np.int32)).to(dev)
 
@@ -225,15 +258,14 @@ def main():
         def mark(i):
             if events is not None:
                 events[i].record()
-        e.reset()
         mark(0)
-        e.push(x_dev, box_dev)
+        reduce_all()
         mark(1)
-        m1 = e.msd_pairs(idx, zeros, arange)
+        m1 = e.msd_pairs(idx, origins, ends)
         mark(2)
-        m2 = e.msd_pairs(idx, mm_o, mm_e)
+        m2 = e.msd_pairs(idx, mm_o, mm_e) if len(mm_o) else None
         mark(3)
-        cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev, thr_dev=thr_dev)
+        cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev, thr_dev=thr_dev, frames=owned)
         if world > 1:                       # partial histograms of the frame shards (NCCL, NVLink)
             dist.all_reduce(cnt)
         mark(4)
@@ -272,12 +304,13 @@ def main():
     stage_ms /= reps
 
     # ---- end to end through the public API, from pinned host memory ---------------------
-    ba = BilayerAnalyzer(structure=top, trajectory=(x_host, traj.dimensions, traj.times),
-                         selection="all", device=local)
+    dims_all = syn.box_at(spec, np.arange(F_total))
+    times_all = np.arange(F_total) * spec.dt
+    ba = BilayerAnalyzer(structure=top, trajectory=(FrameWindow(x_host, first_local, F_total), dims_all,
+                                                    times_all), selection="all", device=local)
     ba.remove_analysis("msd_1")
     for s in ANALYSES:
         ba.add_analysis(s)
-    ba.batch_frames = 500
 
     def api_step():
         ba.reset()
@@ -293,7 +326,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    d2h = F * layout.n_beads + F * 8 + len(mm_o) * 8 + 25 * 8 + F * 24 + 4   # labels0.., msd, mm, rdf count, frame counts, status
+    d2h = layout.n_beads + F * 8 + len(mm_o) * 8 + 25 * 8 + F * 24 + 4   # labels[0], msd, mm, rdf count, frame counts, status
     h2d = int(x_host.numel() * 4 + box_host.numel() * 4)
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -308,7 +341,7 @@ def main():
     if rank == 0:
         peak, which = peaks()
         dom = int(np.argmax(stage_ms))
-        dom_bytes = [B_COM, B_MSD, B_MSD * len(mm_o) / F, B_RDF][dom] * N_LIPIDS * F
+        dom_bytes = [B_COM, B_MSD, B_MSD * max(len(mm_o), 1) / F, B_RDF][dom] * N_LIPIDS * F
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "lipid-frames/s", "n_gpus": world,

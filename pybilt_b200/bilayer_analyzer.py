@@ -52,6 +52,25 @@ class _HostFrame(object):
         return self._pos
 
 
+class FrameWindow(object):
+    """Positions of a contiguous window of a longer trajectory: ``window[g0:g1]`` with GLOBAL
+    frame indices returns the rows held locally.  Lets a frame shard keep only its own frames
+    (+ halos) in host memory while box / time arrays describe the whole run."""
+
+    def __init__(self, positions_local, first_global, n_global):
+        self.local = positions_local
+        self.first = int(first_global)
+        self.n_global = int(n_global)
+
+    def __getitem__(self, item):
+        if not isinstance(item, slice):
+            raise TypeError("FrameWindow supports contiguous slices of global frame indices")
+        lo, hi, step = item.indices(self.n_global)
+        if step != 1 or lo < self.first or hi > self.first + self.local.shape[0]:
+            raise IndexError("frames %d:%d are outside this rank's window" % (lo, hi))
+        return self.local[lo - self.first:hi - self.first]
+
+
 class TrajectoryData(object):
     """Equivalent of pybilt/bilayer_analyzer/mda_data.py:9-38 (``MDAData``): topology of the
     selected atoms plus frame access."""
@@ -104,7 +123,13 @@ class TrajectoryData(object):
             return self._read_mda(frame_idx)
         x = self._positions
         contiguous = len(frame_idx) > 0 and (np.diff(frame_idx) == 1).all()
-        if torch.is_tensor(x):
+        if isinstance(x, FrameWindow):
+            if not contiguous:
+                raise RuntimeError("a FrameWindow trajectory needs a contiguous frame range")
+            sel = x[int(frame_idx[0]):int(frame_idx[-1]) + 1]
+            if not self._all_atoms:
+                sel = sel[:, torch.as_tensor(self.indices)] if torch.is_tensor(sel) else sel[:, self.indices]
+        elif torch.is_tensor(x):
             sel = x[int(frame_idx[0]):int(frame_idx[-1]) + 1] if contiguous else x[torch.as_tensor(frame_idx)]
             if not self._all_atoms:
                 sel = sel[:, torch.as_tensor(self.indices)]
