@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 4
+#define PBK_ABI_VERSION 5
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -61,8 +61,10 @@ const char *pbk_last_error(const pbk_ctx *ctx);
  * init_images (may be NULL; needs first_frame): frame 0 is a raw frame whose image counts
  * [M][3] int32 are already known -- how a frame shard continues the ranks before it
  * (pybilt_b200/distributed.py). */
+#define PBK_UNWRAP_SCALAR_F32 1 /* flags: the scalar unwrap of pybilt/mda_tools/mda_unwrap.py:12-85
+                                  (what COMTraj calls): `dz + shift*C` evaluated in float32 */
 int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
-                      int first_frame, const int32_t *init_images, int64_t F, int64_t M,
+                      int first_frame, const int32_t *init_images, int flags, int64_t F, int64_t M,
                       int16_t *img, int32_t *status, void *stream);
 
 /* ---- A3  membrane centre of mass --------------------------------------------------------
@@ -78,6 +80,13 @@ int pbk_membrane_com(pbk_ctx *ctx, const float *x, const float *box, const int16
                      const int32_t *leaf_len, int32_t L, const int32_t *node_left,
                      const int32_t *node_right, int32_t K, const int32_t *level_off, int32_t H,
                      double total_mass, double *node_vals, double *mem_com, void *stream);
+
+/* ---- T1  membrane centre of mass as COMTraj forms it -------------------------------------
+ * mem_sel.center_of_mass()                       pybilt/com_trajectory/COMTraj.py:1084
+ * = (pos.astype(f64) * m[:,None]).sum(axis=0) / m.sum(): rows accumulated in atom order. */
+int pbk_membrane_com_seq(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                         const double *mass, int64_t F, int64_t M, double total_mass,
+                         double *mem_com, void *stream);
 
 /* ---- A2 + A4  per-lipid centres of mass -------------------------------------------------
  * LipidCOM.extract wrapped / unwrapped passes  pybilt/bilayer_analyzer/com_frame.py:43-96,163-185

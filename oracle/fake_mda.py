@@ -57,6 +57,10 @@ class _Trajectory:
     def __len__(self):
         return int(self._X.shape[0])
 
+    @property
+    def time(self):
+        return self.ts.time
+
     def __iter__(self):
         for f in range(len(self)):
             yield self._load(f)
@@ -123,6 +127,10 @@ class AtomGroup:
     def residues(self):
         ridx = np.unique(self.universe._resindex[self._ix])
         return [Residue(self.universe, r) for r in ridx]
+
+    @property
+    def n_residues(self):
+        return len(np.unique(self.universe._resindex[self._ix]))
 
     def __len__(self):
         return int(self._ix.shape[0])

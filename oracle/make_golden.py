@@ -79,8 +79,26 @@ def make(name: str) -> str:
     return path
 
 
+COMTRAJ_CASES = ["big_steps", "name_dict", "c2_prefix"]
+
+
+def make_comtraj(name: str) -> str:
+    """pybilt.com_trajectory.COMTraj.COMTraj (literal) on the inputs of case `name`."""
+    top, traj = cases.make_inputs(name)
+    ref = rh.run_comtraj_reference(top, traj)
+    flat = {"com": ref["com"], "com_unwrap": ref["com_unwrap"],
+            "labels0": np.array([1 if l == "upper" else 0 for l in ref["com_leaflet"]], dtype=np.uint8),
+            "msd_both": ref["msd_both"], "msd_upper": ref["msd_upper"],
+            "msd_lower_first": ref["msd_lower_first"], "first_group": np.array(ref["first_group"]),
+            "upper_all": np.array(ref["upper_all"]),
+            "meta/input_sha256": np.array(cases.input_digest(traj))}
+    path = os.path.join(GOLDEN, "comtraj_" + name + ".npz")
+    np.savez_compressed(path, **flat)
+    return path
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(cases.CASES)
+    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES])
     for n in names:
-        p = make(n)
+        p = make_comtraj(n.split(":", 1)[1]) if n.startswith("comtraj:") else make(n)
         print(n, "->", p, os.path.getsize(p), "bytes")

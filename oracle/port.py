@@ -533,6 +533,82 @@ def grid_apl(grid, label_f, types):
 
 
 # --------------------------------------------------------------------------------------
+# T1: COMTraj               pybilt/com_trajectory/COMTraj.py:916-1117, 1142-1240
+# --------------------------------------------------------------------------------------
+def unwrap_frame_scalar(x, u_prev, abc):
+    """pybilt/mda_tools/mda_unwrap.py:12-85: like unwrap_frame, but `dz + shift*C` is formed
+    from NumPy float32 scalars, i.e. the loop conditions are evaluated in float32."""
+    u = x.copy()
+    for k in range(3):
+        L = abc[k]
+        h = L / 2.0
+        d = x[:, k] - u_prev[:, k]
+        s = np.zeros(x.shape[0])
+        for i in np.nonzero((d > h) | (d < -h))[0]:
+            di, shift = d[i], 0
+            if di > h:
+                shift -= 1
+                while (di + shift * L) > h:
+                    shift -= 1
+            else:
+                shift += 1
+                while (di + shift * L) < -h:
+                    shift += 1
+            s[i] = shift
+        u[:, k] = (x[:, k].astype(np.float64) + s * L).astype(np.float32)
+    return u
+
+
+def comtraj(top, traj, plane=(0, 1), norm=2, frames=None):
+    """COMTraj.__init__: wrapped COMs, scalar unwrap, membrane COM = center_of_mass() of the
+    selection (rows accumulated in atom order), unwrapped COMs, leaflets from frame 0."""
+    fr = np.arange(traj.positions.shape[0]) if frames is None else np.asarray(frames)
+    X = traj.positions[fr]
+    box = np.array(traj.dimensions[fr][:, :3])
+    for f in range(1, len(box)):
+        if (box[f] == 0).any():
+            box[f] = box[f - 1]
+    gather, seg, types, _resids = build_beads(top)
+    m = top.masses
+    total = m.sum()
+    F = X.shape[0]
+    comu = np.empty((F, len(types), 3))
+    prev = None
+    for f in range(F):
+        u = X[f] if prev is None else unwrap_frame_scalar(X[f], prev, box[f])
+        prev = u
+        mem = (u.astype(np.float64) * m[:, None]).sum(axis=0) / total
+        v = (u.astype(np.float64) - mem).astype(np.float32)
+        comu[f] = lipid_coms(v[None], m, gather, seg)[0]
+    com = lipid_coms(X, m, gather, seg)
+    labels0 = leaflet_labels(comu[:1], norm)[0]
+    return {"com": com, "com_unwrap": comu, "labels0": labels0, "types": types,
+            "times": np.asarray(traj.times)[fr]}
+
+
+def comtraj_group_indices(labels0, types, leaflet, group):
+    """COMTraj Leaflet.get_group_indices (:525-554): 'all' concatenates group by group."""
+    out = []
+    for lab in ([1, 0] if leaflet == "both" else [1 if leaflet == "upper" else 0]):
+        members = np.nonzero(labels0 == lab)[0]
+        names = []
+        for i in members:
+            if types[i] not in names:
+                names.append(types[i])
+        pick = [group] if (group != "all" and group in names) else names
+        for g in pick:
+            out += [int(i) for i in members if types[i] == g]
+    return np.asarray(out, dtype=np.int64)
+
+
+def comtraj_msd(ct, leaflet="both", group="all", plane=(0, 1)):
+    idx = comtraj_group_indices(ct["labels0"], ct["types"], leaflet, group)
+    res = msd(ct["com_unwrap"], ct["times"], idx, plane)
+    res[0] = 0.0                                    # row 0 is never written (COMTraj.py:1203-1236)
+    return res
+
+
+# --------------------------------------------------------------------------------------
 # driver: the BilayerAnalyzer frame loop over arrays (bilayer_analyzer.py:901-1031)
 # --------------------------------------------------------------------------------------
 def parse_analysis(s: str):

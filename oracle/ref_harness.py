@@ -164,3 +164,28 @@ def run_reference(top, traj, analyses=(), selection="all", rep_settings=None,
             frames.append(rec)
         out = {a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()}
     return out, frames, ba
+
+
+def run_comtraj_reference(top, traj, plane="xy", fstart=0, fend=-1, fskip=1):
+    """The literal ``pybilt.com_trajectory.COMTraj.COMTraj`` over (top, traj) arrays."""
+    install()
+    import tempfile
+    from . import fake_mda
+    with quiet():
+        from pybilt.com_trajectory import COMTraj as ct
+        u = fake_mda.Universe(top, (traj.positions, traj.dimensions, traj.times))
+        sel = u.select_atoms("all")
+        tmp = tempfile.mkdtemp(prefix="comtraj_") + "/"
+        obj = ct.COMTraj(u.trajectory, sel, plane=plane, fstart=fstart, fend=fend, fskip=fskip,
+                         frame_path=tmp)
+        n = obj.nframes
+        com = np.array([[l.com for l in obj.frame[f].lipidcom] for f in range(n)])
+        comu = np.array([[l.com_unwrap for l in obj.frame[f].lipidcom] for f in range(n)])
+        out = {"com": com, "com_unwrap": comu, "com_leaflet": list(obj.com_leaflet),
+               "msd_both": obj.calc_msd(), "msd_upper": obj.calc_msd(leaflet="upper"),
+               "upper_all": obj.leaflets["upper"].get_group_indices("all"),
+               "n_groups": len(obj.leaflets["upper"].groups)}
+        first = obj.leaflets["upper"].get_group_names()[0]
+        out["msd_lower_first"] = obj.calc_msd(leaflet="lower", group=first)
+        out["first_group"] = first
+    return out

@@ -25,8 +25,10 @@ _SIGNATURES = {
     "pbk_ctx_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "pbk_ctx_destroy": (None, [c_void_p]),
     "pbk_last_error": (ctypes.c_char_p, [c_void_p]),
-    "pbk_unwrap_images": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+    "pbk_unwrap_images": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64,
                                   c_int64, c_void_p, c_void_p, c_void_p]),
+    "pbk_membrane_com_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                     c_double, c_void_p, c_void_p]),
     "pbk_membrane_com": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                  c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                  c_int32, c_double, c_void_p, c_void_p, c_void_p]),
@@ -76,7 +78,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.pbk_abi_version() != 4:
+        if lib.pbk_abi_version() != 5:
             raise RuntimeError("pybilt_b200: libpbk ABI version mismatch")
         _lib = lib
     return _lib

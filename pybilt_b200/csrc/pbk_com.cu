@@ -30,20 +30,39 @@ __device__ __forceinline__ int pbk_image_shift(float x, float uprev, float L, in
     return s;
 }
 
+// mda_unwrap.py:12-85 (the scalar unwrap COMTraj uses, pybilt/com_trajectory/COMTraj.py:1067-1081):
+// same rule, but `dz + shift*C` is evaluated on NumPy float32 scalars, i.e. in float32.
+__device__ __forceinline__ int pbk_image_shift_f32(float x, float uprev, float L, int *bad)
+{
+    float d = __fsub_rn(x, uprev);
+    float h = L * 0.5f;
+    int s = 0;
+    if (!(L > 0.0f)) { *bad = 1; return 0; }
+    if (d > h) {
+        do { s -= 1; } while (__fadd_rn(d, __fmul_rn((float)s, L)) > h && s > -32768);
+    } else if (d < -h) {
+        do { s += 1; } while (__fadd_rn(d, __fmul_rn((float)s, L)) < -h && s < 32768);
+    }
+    if (s <= -32768 || s >= 32768) { *bad = 1; s = 0; }
+    return s;
+}
+
 // Chain state = (raw previous coordinate, its image count).  The common case -- the raw
 // jump is nowhere near half a box -- keeps the image count without touching float64
 // (pbk_same_image, pbk_common.cuh); otherwise the reference's loops run.
-__device__ __forceinline__ int pbk_next_image(float xv, float xprev, int s, float L, float Lprev, int *bad)
+__device__ __forceinline__ int pbk_next_image(float xv, float xprev, int s, float L, float Lprev, int flags,
+                                              int *bad)
 {
     const int as = s < 0 ? -s : s;
     const float eps = (float)(as + 2) * fmaxf(L, Lprev) * 2.3841858e-7f + (float)as * fabsf(L - Lprev);
     if (pbk_same_image(xv, xprev, L, eps) && L > 0.0f) return s;
-    return pbk_image_shift(xv, pbk_unwrapped(xprev, s, Lprev), L, bad);
+    const float up = pbk_unwrapped(xprev, s, Lprev);
+    return (flags & PBK_UNWRAP_SCALAR_F32) ? pbk_image_shift_f32(xv, up, L, bad) : pbk_image_shift(xv, up, L, bad);
 }
 
 __global__ void __launch_bounds__(128)
 k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, float *u_state,
-                int first_frame, const int32_t *__restrict__ init_images, int64_t F, int64_t C,
+                int first_frame, const int32_t *__restrict__ init_images, int flags, int64_t F, int64_t C,
                 int16_t *__restrict__ img, int32_t *status)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,7 +94,7 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
         }
 #pragma unroll
         for (int j = 0; j < UNR; j++) {
-            s = pbk_next_image(xv[j], xprev, s, Lv[j], Lprev, &bad);
+            s = pbk_next_image(xv[j], xprev, s, Lv[j], Lprev, flags, &bad);
             xprev = xv[j];
             Lprev = Lv[j];
             img[(t + j) * C + c] = (int16_t)s;
@@ -83,7 +102,7 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
     }
     for (; t < F; t++) {
         float xv = __ldg(x + t * C + c), L = __ldg(box + t * 3 + k);
-        s = pbk_next_image(xv, xprev, s, L, Lprev, &bad);
+        s = pbk_next_image(xv, xprev, s, L, Lprev, flags, &bad);
         xprev = xv;
         Lprev = L;
         img[t * C + c] = (int16_t)s;
@@ -93,8 +112,8 @@ k_unwrap_images(const float *__restrict__ x, const float *__restrict__ box, floa
 }
 
 extern "C" int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box, float *u_state,
-                                 int first_frame, const int32_t *init_images, int64_t F, int64_t M,
-                                 int16_t *img, int32_t *status, void *stream)
+                                 int first_frame, const int32_t *init_images, int flags, int64_t F,
+                                 int64_t M, int16_t *img, int32_t *status, void *stream)
 {
     if (init_images && !first_frame)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_unwrap_images: init_images needs first_frame");
@@ -105,7 +124,7 @@ extern "C" int pbk_unwrap_images(pbk_ctx *ctx, const float *x, const float *box,
     int threads = 128;
     int64_t blocks = (C + threads - 1) / threads;
     k_unwrap_images<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        x, box, u_state, first_frame, init_images, F, C, img, status);
+        x, box, u_state, first_frame, init_images, flags, F, C, img, status);
     PBK_CHECK_LAUNCH(ctx, "k_unwrap_images");
     return PBK_OK;
 }
@@ -209,6 +228,49 @@ extern "C" int pbk_membrane_com(pbk_ctx *ctx, const float *x, const float *box, 
     k_mem_tree<<<(unsigned)F, 256, 0, st>>>(node_left, node_right, level_off, H, L, K, total_mass,
                                             node_vals, mem_com);
     PBK_CHECK_LAUNCH(ctx, "k_mem_tree");
+    return PBK_OK;
+}
+
+// K2c  membrane COM the way COMTraj forms it: mem_sel.center_of_mass()
+// (pybilt/com_trajectory/COMTraj.py:1084) = (pos.astype(f64) * m[:,None]).sum(axis=0) / m.sum(),
+// whose axis-0 sum accumulates the rows one after the other.  One thread per (frame, axis).
+__global__ void __launch_bounds__(128)
+k_mem_seq(const float *__restrict__ x, const float *__restrict__ box, const int16_t *__restrict__ img,
+          const double *__restrict__ mass, int64_t F, int64_t M, double total_mass,
+          double *__restrict__ mem_com)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= F * 3) return;
+    int64_t f = g / 3;
+    int k = (int)(g % 3);
+    const float *xf = x + f * M * 3 + k;
+    const int16_t *sf = img + f * M * 3 + k;
+    float L = box[f * 3 + k];
+    double acc = 0.0;
+    int64_t a = 0;
+    for (; a + 4 <= M; a += 4) {
+        double p[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            p[j] = __dmul_rn((double)pbk_unwrapped(xf[(a + j) * 3], sf[(a + j) * 3], L), mass[a + j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc = __dadd_rn(acc, p[j]);
+    }
+    for (; a < M; a++)
+        acc = __dadd_rn(acc, __dmul_rn((double)pbk_unwrapped(xf[a * 3], sf[a * 3], L), mass[a]));
+    mem_com[g] = __ddiv_rn(acc, total_mass);
+}
+
+extern "C" int pbk_membrane_com_seq(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
+                                    const double *mass, int64_t F, int64_t M, double total_mass,
+                                    double *mem_com, void *stream)
+{
+    if (!ctx || !x || !box || !img || !mass || !mem_com || F < 0 || M <= 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_membrane_com_seq: bad argument");
+    if (F == 0) return PBK_OK;
+    k_mem_seq<<<(unsigned)((F * 3 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, box, img, mass, F, M,
+                                                                                total_mass, mem_com);
+    PBK_CHECK_LAUNCH(ctx, "k_mem_seq");
     return PBK_OK;
 }
 

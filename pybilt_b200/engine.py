@@ -120,7 +120,7 @@ class LipidReductionEngine:
 
     def __init__(self, masses, layout: BeadLayout, n_frames: int, device: int = 0, norm: int = 2,
                  leaflet_update_interval: int = 1, batch_frames: Optional[int] = None,
-                 scratch_bytes: int = 4 << 30, allow_fused: bool = True):
+                 scratch_bytes: int = 4 << 30, allow_fused: bool = True, comtraj_rules: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("pybilt_b200: a CUDA device is required (no CPU fallback)")
         self.ctx = _native.Context(device)
@@ -162,7 +162,10 @@ class LipidReductionEngine:
         self.box = torch.empty((self.F, 3), dtype=torch.float32, device=d)
         self.n_done = 0
         self.launches = 0
-        self.allow_fused = bool(allow_fused)
+        # COMTraj arithmetic (pybilt/com_trajectory/COMTraj.py:1067-1085): scalar float32 unwrap
+        # rule and membrane COM accumulated atom by atom; only the generic kernels implement it
+        self.comtraj_rules = bool(comtraj_rules)
+        self.allow_fused = bool(allow_fused) and not self.comtraj_rules
         self.fused_supported = True       # cleared when libpbk answers PBK_EUNSUPPORTED
         self.used_fused = False
         self._fused_scratch = None
@@ -242,19 +245,24 @@ class LipidReductionEngine:
             if phase == 1:
                 # generic path: a plain unwrap of the shard; its last row is the net change
                 c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(), 1, None,
-                       nb, self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+                       1 if self.comtraj_rules else 0, nb, self.M, self.d_img.data_ptr(),
+                       self.d_status.data_ptr(), st)
                 self.launches += 1
                 if net_out is not None:
                     net_out.copy_(self.d_img[nb - 1].to(torch.int32))
                 continue
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
-                   1 if g0 == 0 else 0, _ptr(init_images), nb, self.M, self.d_img.data_ptr(),
-                   self.d_status.data_ptr(), st)
-            c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
-                   self.d_mass.data_ptr(), nb, self.M, self.d_leaf_start.data_ptr(),
-                   self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(),
-                   self.d_node_right.data_ptr(), p.n_nodes, self.d_level_off.data_ptr(), p.n_levels,
-                   self.total_mass, self.d_nodes.data_ptr(), self.mem_com[g0:].data_ptr(), st)
+                   1 if g0 == 0 else 0, _ptr(init_images), 1 if self.comtraj_rules else 0, nb, self.M,
+                   self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+            if self.comtraj_rules:
+                c.call("pbk_membrane_com_seq", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
+                       self.d_mass.data_ptr(), nb, self.M, self.total_mass, self.mem_com[g0:].data_ptr(), st)
+            else:
+                c.call("pbk_membrane_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
+                       self.d_mass.data_ptr(), nb, self.M, self.d_leaf_start.data_ptr(),
+                       self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(),
+                       self.d_node_right.data_ptr(), p.n_nodes, self.d_level_off.data_ptr(), p.n_levels,
+                       self.total_mass, self.d_nodes.data_ptr(), self.mem_com[g0:].data_ptr(), st)
             c.call("pbk_lipid_com", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
                    self.d_mass.data_ptr(), self.mem_com[g0:].data_ptr(), self.d_seg.data_ptr(),
                    _ptr(self.d_gather), self.d_bead_mass.data_ptr(), nb, self.M, self.N,

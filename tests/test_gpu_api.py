@@ -135,3 +135,27 @@ def test_reset_and_rerun_and_frame_range():
     again = ba.get_analysis_data("msd_1")
     assert again.shape == (11, 2)
     assert again[0, 1] == 0.0 and again[0, 0] == 100.0
+
+
+@pytest.mark.parametrize("name", ["big_steps", "name_dict", "c2_prefix"])
+def test_comtraj_matches_reference(name):
+    """pybilt_b200.com_trajectory.COMTraj against the literal COMTraj (com_trajectory objects
+    of the north star): COMs bit-identical, leaflets exact, calc_msd within 1e-9."""
+    from pybilt_b200.com_trajectory import COMTraj
+    gold = load("comtraj_" + name)
+    top, traj = cases.make_inputs(name)
+    ct = COMTraj(traj, top)
+    assert ct.nframes == gold["com"].shape[0] and ct.nlipids == gold["com"].shape[1]
+    e = ct._engine
+    assert np.array_equal(e.com.cpu().numpy(), gold["com"])
+    assert np.array_equal(e.com_unwrap.cpu().numpy(), gold["com_unwrap"])
+    lab = np.array([1 if l == "upper" else 0 for l in ct.com_leaflet], dtype=np.uint8)
+    assert np.array_equal(lab, gold["labels0"])
+    assert ct.leaflets["upper"].get_group_indices("all") == list(gold["upper_all"])
+    close(ct.calc_msd(), gold["msd_both"], 1e-9)
+    close(ct.calc_msd(leaflet="upper"), gold["msd_upper"], 1e-9)
+    close(ct.calc_msd(leaflet="lower", group=str(gold["first_group"])), gold["msd_lower_first"], 1e-9)
+    close(ct.calc_msd_parallel(nprocs=4), gold["msd_both"], 1e-9)
+    fr = ct.frame[3]
+    assert np.array_equal(np.array([l.com_unwrap for l in fr.lipidcom]), gold["com_unwrap"][3])
+    assert fr.lipidcom[0].type == top.resnames[0] and len(ct.frame) == ct.nframes

@@ -114,3 +114,21 @@ def test_histogram_rule_is_numpy():
     seen = np.abs((pos[ib, 0] - float(centre)) - (0.0 - float(centre)))
     want = np.histogram(seen, bins=nb, range=[lo, hi])[0]
     assert np.array_equal(count, want)
+
+
+@pytest.mark.parametrize("name", ["big_steps", "name_dict", "c2_prefix"])
+def test_port_comtraj_matches_reference(name):
+    """oracle.port.comtraj against the literal pybilt.com_trajectory.COMTraj (scalar float32
+    unwrap, sequential membrane COM, leaflets from frame 0)."""
+    gold = load("comtraj_" + name)
+    top, traj = cases.make_inputs(name)
+    assert cases.input_digest(traj) == str(gold["meta/input_sha256"])
+    ct = port.comtraj(top, traj)
+    close(ct["com"], gold["com"])
+    close(ct["com_unwrap"], gold["com_unwrap"])
+    assert np.array_equal(ct["labels0"], gold["labels0"])
+    close(port.comtraj_msd(ct), gold["msd_both"])
+    close(port.comtraj_msd(ct, "upper"), gold["msd_upper"])
+    close(port.comtraj_msd(ct, "lower", str(gold["first_group"])), gold["msd_lower_first"])
+    assert np.array_equal(port.comtraj_group_indices(ct["labels0"], ct["types"], "upper", "all"),
+                          gold["upper_all"])
