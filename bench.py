@@ -51,10 +51,17 @@ def peaks():
         return 6650.0, "fallback"
 
 
-def workload(rank: int, frames: int):
-    from pybilt_b200 import synthetic as syn
-    spec, _ = syn.config_spec("C2")
-    return syn.generate(spec, frames, first_frame=rank * frames)
+def ncu_traffic(stage: str):
+    """dram read+write bytes per step of a stage, from the committed ncu capture
+    (profiles/traffic.json: per-launch bytes of each kernel); None if not captured."""
+    kernels = {"reduce(unwrap+memCOM+lipidCOM+leaflets)": ["k_fused_agg12", "k_fused_scan", "k_fused_frames<1>"],
+               "rdf": ["k_rdf2<1>"], "msd": ["k_msd_pairs"], "msd_multi": ["k_msd_pairs"]}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            per = json.load(fh)["bytes_per_launch"]
+        return float(sum(per[k] for k in kernels[stage]))
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -359,7 +366,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved,
                          "peak": peak, "peak_source": which, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic(stage_names[dom]) if (world == 1 and F == FRAMES) else None,
+                         "algorithmic_bytes": dom_bytes,
                          "pipeline_achieved": B_PIPE * N_LIPIDS * F / (ms_step * 1e-3) / 1e9,
                          "pipeline_frac": B_PIPE * N_LIPIDS * F / (ms_step * 1e-3) / 1e9 / peak},
             "stages_ms": {n: float(v) for n, v in zip(stage_names, stage_ms)},

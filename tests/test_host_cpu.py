@@ -1,0 +1,170 @@
+"""CPU-only checks: the C ABI loads and exports what include/pbk.h declares, the host mirror of
+the plugin interface behaves like the reference's, and the product refuses to run without a
+CUDA device (no CPU fallback)."""
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pbk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pybilt_b200 import _native
+    lib = _native.load()                      # dlopen only, no CUDA call
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_native.EXPORTS) == syms    # the ctypes stub binds exactly the header
+    assert lib.pbk_abi_version() == 5
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pybilt_b200 import BilayerAnalyzer
+    from tests import cases
+    top, traj = cases.make_inputs("tiny_all")
+    ba = BilayerAnalyzer(structure=top, trajectory=traj, selection="all")
+    with pytest.raises(RuntimeError):
+        ba.run_analysis()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pybilt_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_registry_and_argument_parsing():
+    from pybilt_b200 import analysis_protocols as ap
+    assert set(ap.valid_analysis) == {"msd", "msd_multi", "com_lateral_rdf", "nnf", "apl_grid",
+                                      "thickness_grid"}
+    assert ap.analysis_obj_name_dict["apl_grid"] == "lipid_grid"
+    a = ap.Analyses(["msd msd_1", "com_lateral_rdf r n_bins 80 range_outer 40.0 leaflet upper"])
+    assert a.analysis_ids == ["msd_1", "r"] and not a.use_objects["lipid_grid"]
+    r = a["r"]
+    assert r.settings["n_bins"] == 80 and r.settings["range_outer"] == 40.0
+    assert r.settings["resname_1"] == "first" and r.save_file_name == "r.pickle"
+    a.add_analysis(["nnf", "n1", {"n_neighbors": 6}])
+    a.add_analysis({"analysis_key": "thickness_grid", "analysis_id": "bt", "analysis_settings": {}})
+    assert a.use_objects["lipid_grid"] and len(a) == 4
+    with pytest.raises(RuntimeError):
+        a.add_analysis("msd msd_1")                       # duplicate id
+    with pytest.raises(RuntimeError):
+        a.add_analysis("not_an_analysis x")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        a.add_analysis("msd m2 bogus_key 3")
+        assert any("invalid argument key" in str(x.message) for x in w)
+    a.remove_analysis("m2")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        a.remove_analysis("m2")
+        assert w
+    a.remove_all()
+    assert len(a) == 0
+
+
+def test_input_script_and_frame_range(tmp_path):
+    from pybilt_b200 import BilayerAnalyzer
+    from tests import cases
+    top, traj = cases.make_inputs("tiny_all")
+    ba = BilayerAnalyzer(input_dict={"structure": top, "trajectory": traj, "selection": "all",
+                                     "analysis": ["msd m", "nnf n n_neighbors 4"],
+                                     "frames": ["first", 2, "last", -3, "interval", 2],
+                                     "lipid_grid": ["n_xbins", 12, "n_ybins", 12]})
+    assert ba.settings["frame_range"] == [2, -3, 2]
+    assert ba.rep_settings["lipid_grid"]["n_xbins"] == 12
+    assert list(ba.analysed_frame_indices()) == [2, 4, 6, 8]
+    assert ba.get_analysis_ids() == ["m", "n"]
+    ba.set_frame_range(0.25, -1, 1)
+    assert ba.settings["frame_range"][0] == 3
+    with pytest.raises(RuntimeError):
+        BilayerAnalyzer(input_dict={"structure": top})
+    with pytest.raises(RuntimeError):
+        BilayerAnalyzer()
+    script = tmp_path / "setup.in"
+    script.write_text("# comment\nstructure a.psf\ntrajectory b.dcd\nselection 'resname POPC'\n"
+                      "analysis msd msd_1\nanalysis nnf n1 n_neighbors 3\nframes first 1 last 5\n")
+    cmds = BilayerAnalyzer.parse_input_script(BilayerAnalyzer.__new__(BilayerAnalyzer), str(script))
+    assert cmds["selection"] == "resname POPC" and cmds["analysis"] == ["msd msd_1", "nnf n1 n_neighbors 3"]
+    bad = tmp_path / "bad.in"
+    bad.write_text("structure a\ntrajectory b\nselection 'all'\nbogus x y\n")
+    with pytest.raises(RuntimeError):
+        BilayerAnalyzer.parse_input_script(BilayerAnalyzer.__new__(BilayerAnalyzer), str(bad))
+
+
+def test_selection_of_whole_residues():
+    from pybilt_b200.bilayer_analyzer import TrajectoryData
+    from tests import cases
+    top, traj = cases.make_inputs("tiny_all")
+    md = TrajectoryData(top, traj, "resname POPC DOPE")
+    keep = [r for r in top.resnames if r in ("POPC", "DOPE")]
+    assert md.resnames == keep and md.n_residues == len(keep)
+    x, d, t = md.frames(np.array([0, 1, 2]))
+    assert x.shape == (3, md.natoms, 3) and md.natoms < top.n_atoms
+    assert np.array_equal(x[1], traj.positions[1][md.indices])
+
+
+def test_msd_multi_schedule_matches_the_oracle():
+    from oracle import port
+    from pybilt_b200.analysis_protocols import msd_multi_schedule
+    for (F, nt, ns) in [(20, 3, 3), (12, 4, 2), (97, 10, 4), (5000, 50, 50), (30, 50, 50), (9, 1, 1)]:
+        fin, nb = msd_multi_schedule(F, nt, ns)
+        pairs, n_orig = port.msd_multi_blocks(F, nt, ns)
+        assert [fin[b] for b in sorted(fin)] == pairs and nb == n_orig
+
+
+def test_running_stats_float32_promotion():
+    """pybilt/common/running_stats.py: the first push keeps float32 (RDF area, APL)."""
+    from oracle.port import Welford
+    from pybilt_b200.running_stats import RunningStats
+    rng = np.random.default_rng(3)
+    vals = (rng.uniform(60, 70, 50).astype(np.float32))
+    a, b = RunningStats(), Welford()
+    for v in vals:
+        a.push(v); b.push(v)
+        assert a.mean() == b.mean() and a.deviation() == b.deviation()
+    assert RunningStats().mean() == 0.0
+
+
+def test_bead_layout_matches_the_oracle():
+    from oracle import port
+    from pybilt_b200.engine import build_bead_layout
+    from tests import cases
+    top, _ = cases.make_inputs("name_dict")
+    nd = cases.CASES["name_dict"]["rep_settings"]["com_frame"]["name_dict"]
+    for multi in (False, True):
+        lay = build_bead_layout(top.masses, top.names, top.resindex, top.resnames, top.resids, nd, multi)
+        g, seg, types, resids = port.build_beads(top, nd, multi)
+        assert np.array_equal(lay.gather, g) and np.array_equal(lay.seg, seg) and lay.types == types
+        assert np.array_equal(lay.bead_mass, port.bead_masses(top.masses, g, seg))
+
+
+def test_diffusion_estimators():
+    """tests/test_diffusion_coefficent_estimation.py of the reference: MSD = 4 D t + noise."""
+    from pybilt_b200 import diffusion as dc
+    t = np.linspace(0.0, 100.0, 400)
+    rng = np.random.default_rng(0)
+    msd = 4.0 * 2.0 * t + rng.normal(0, 0.05, t.size)
+    assert abs(dc.diffusion_coefficient_Einstein(t, msd) - 2.0) < 0.01
+    d, err = dc.diffusion_coefficient_linear_fit(t, msd)
+    assert abs(d - 2.0) < 0.01 and err < 0.01
+    p = dc.diffusion_coefficient_anomalous_fit(t[1:], msd[1:] - msd[1] + 4.0 * 2.0 * 0.0)
+    assert abs(p[1] - 1.0) < 0.05
+    t0 = t.copy()
+    dc.diffusion_coefficient_anomalous_fit(t0[1:], msd[1:])
+    assert np.array_equal(t0, t)              # unlike the reference, the input is left alone
