@@ -673,7 +673,7 @@ k_fused_frames(FusedParams P)
     }
 }
 
-extern "C" int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
+static int fused_v1_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
                                              int32_t *n_chunks_out, int32_t *chunk_out)
 {
     if (F <= 0 || M <= 0 || sm_count <= 0 || !bytes) return PBK_EINVAL;
@@ -686,7 +686,7 @@ extern "C" int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count
     return PBK_OK;
 }
 
-extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
+int pbk_reduce_fused_v1(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
                                 const int32_t *seg, const int32_t *gather, const double *lipid_mass,
                                 const int32_t *leaf_start, const int32_t *leaf_len, int32_t L,
                                 const int32_t *node_left, const int32_t *node_right, int32_t K,
@@ -707,7 +707,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     if (M > (1 << 20) || 2 * (int64_t)L + 2 * (int64_t)K + H + 1 > FUSED_TAB) return PBK_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t need; int32_t n_chunks, chunk;
-    pbk_reduce_fused_scratch_bytes(F, M, ctx->sm_count, &need, &n_chunks, &chunk);
+    fused_v1_scratch_bytes(F, M, ctx->sm_count, &need, &n_chunks, &chunk);
     if (scratch_bytes < need) return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small");
     const int C3 = (int)(3 * M), C3pad = (C3 + 3) & ~3;
     size_t base = (size_t)C3pad * 8 + (size_t)(L + K) * 24 + (size_t)N * 8 + (size_t)C3 + 64;

@@ -25,9 +25,11 @@ ev1.record(); torch.cuda.synchronize()
 print("SKIP=%s reduce ms/step: %.3f" % (os.environ.get("PBK_FUSED_SKIP", "0"), ev0.elapsed_time(ev1) / 5))
 off = ((need.value + 63) // 64) * 64
 prof = e._fused_scratch[off:off + 64 * nch.value].view(torch.int64).reshape(nch.value, 8).cpu().numpy()
-names = ["wait_frame", "phaseU", "phaseL(sync)", "tree", "phaseC", "phaseZ", "tail", "phaseL(own)"]
+names = ["wait_frame", "leaf phase", "tree(+labels t-1)", "lipid phase", "final labels", "-", "-", "-"]
+if os.environ.get("PBK_FUSED_V1"):
+    names = ["wait_frame", "phaseU", "phaseL(sync)", "tree", "phaseC", "phaseZ", "tail", "phaseL(own)"]
 tot = prof.sum(axis=1)
 print("chunks", nch.value, "frames/chunk", ch.value, "cycles per frame (mean over chunks):")
 for i, n in enumerate(names):
-    print(f"  {n:10s} {prof[:, i].mean() / ch.value:10.0f}  ({100 * prof[:, i].sum() / tot.sum():5.1f}%)")
+    print(f"  {n:18s} {prof[:, i].mean() / ch.value:10.0f}  ({100 * prof[:, i].sum() / tot.sum():5.1f}%)")
 print("  total      %10.0f" % (tot.mean() / ch.value))
