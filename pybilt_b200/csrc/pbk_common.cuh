@@ -10,10 +10,13 @@
 
 #include "pbk.h"
 
+#define PBK_WORK_SLOTS 64
 struct pbk_ctx {
     int device;
     int sm_count;
     char err[512];
+    int *work;                  // device: PBK_WORK_SLOTS work counters of persistent kernels (may be NULL)
+    unsigned work_next;
 };
 
 #define PBK_WARP 32

@@ -31,11 +31,24 @@ extern "C" int pbk_ctx_create(int device, pbk_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->err[0] = 0;
+    c->work = nullptr;
+    c->work_next = 0;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess) {
+        if (cur != device) cudaSetDevice(device);
+        if (cudaMalloc(&c->work, PBK_WORK_SLOTS * sizeof(int)) != cudaSuccess) { c->work = nullptr; cudaGetLastError(); }
+        if (cur != device) cudaSetDevice(cur);
+    }
     *out = c;
     return PBK_OK;
 }
 
-extern "C" void pbk_ctx_destroy(pbk_ctx *ctx) { delete ctx; }
+extern "C" void pbk_ctx_destroy(pbk_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->work) cudaFree(ctx->work);
+    delete ctx;
+}
 
 extern "C" const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 
