@@ -11,12 +11,15 @@
 #include "pbk.h"
 
 #define PBK_WORK_SLOTS 64
+#define PBK_LUT_SLOTS 4
+#define PBK_LUT_ENTRIES 8192
 struct pbk_ctx {
     int device;
     int sm_count;
     char err[512];
     int *work;                  // device: PBK_WORK_SLOTS work counters of persistent kernels (may be NULL)
     unsigned work_next;
+    unsigned short *lut;        // device: PBK_LUT_SLOTS d^2 -> bin tables of PBK_LUT_ENTRIES entries (may be NULL)
 };
 
 #define PBK_WARP 32

@@ -33,10 +33,12 @@ extern "C" int pbk_ctx_create(int device, pbk_ctx **out)
     c->err[0] = 0;
     c->work = nullptr;
     c->work_next = 0;
+    c->lut = nullptr;
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != device) cudaSetDevice(device);
         if (cudaMalloc(&c->work, PBK_WORK_SLOTS * sizeof(int)) != cudaSuccess) { c->work = nullptr; cudaGetLastError(); }
+        if (cudaMalloc(&c->lut, (size_t)PBK_LUT_SLOTS * PBK_LUT_ENTRIES * sizeof(unsigned short)) != cudaSuccess) { c->lut = nullptr; cudaGetLastError(); }
         if (cur != device) cudaSetDevice(cur);
     }
     *out = c;
@@ -47,6 +49,7 @@ extern "C" void pbk_ctx_destroy(pbk_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->work) cudaFree(ctx->work);
+    if (ctx->lut) cudaFree(ctx->lut);
     delete ctx;
 }
 

@@ -336,6 +336,12 @@ int pbk_rdf3_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
                     int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *thr,
                     unsigned long long *count, int32_t *frame_counts, cudaStream_t st);
 
+// defined in pbk_rdf5.cu: CTA-per-leaflet kernel with a Verlet pair list over frame chunks
+int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                    const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                    int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *thr,
+                    unsigned long long *count, int32_t *frame_counts, cudaStream_t st);
+
 extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
                        const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
                        int lat1, int type_a, int type_b, int leaflet_mask, int32_t n_bins,
@@ -348,6 +354,11 @@ extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: bad argument");
     if (F == 0) return PBK_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = pbk_rdf5_launch(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
+                                       leaflet_mask, n_bins, range_lo, range_hi, thr, count, frame_counts, st);
+        if (rc != PBK_EUNSUPPORTED) return rc;
+    }
     {
         const int rc = pbk_rdf3_launch(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
                                        leaflet_mask, n_bins, range_lo, range_hi, thr, count, frame_counts, st);

@@ -141,6 +141,27 @@ def test_rdf_counts_match_port(name):
         assert want.sum() > 0 or name == "tiny_all"
 
 
+@pytest.mark.parametrize("name,chunk,skin", [("c2_prefix", 16, 4.0), ("c2_prefix", 16, 0.7), ("c2_prefix", 7, 2.0),
+                                             ("c2_prefix", 64, 8.0), ("c3_small", 4, 4.0), ("c3_small", 3, 0.5),
+                                             ("tiny_all", 12, 4.0)])
+def test_rdf_pair_list_reuse_matches_dense(name, chunk, skin, monkeypatch):
+    """k_rdf4 keeps a Verlet pair list over `chunk` frames (rebuilt when a lipid moved skin/2):
+    counts must equal the dense sqrt kernel (itself pinned to the port) for any chunk / skin."""
+    monkeypatch.setenv("PBK_RDF_CHUNK", str(chunk))
+    monkeypatch.setenv("PBK_RDF_SKIN", str(skin))
+    e, top, traj, fr, layout = run_engine(name)
+    names, codes = type_codes(layout.types)
+    d_codes = torch.from_numpy(codes).cuda()
+    for (ra, rb, mask, nb, lo, hi) in RDF_SETTINGS:
+        ca = -1 if ra == "all" else int(ra[1:]) % len(names)
+        cb = -1 if rb == "all" else int(rb[1:]) % len(names)
+        edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
+        count, fc = e.rdf(d_codes, ca, cb, mask, edges)
+        count_d, fc_d = e.rdf(d_codes, ca, cb, mask, edges, dense=True)
+        assert np.array_equal(count.cpu().numpy(), count_d.cpu().numpy()), (name, chunk, skin, ra, rb)
+        assert np.array_equal(fc.cpu().numpy(), fc_d.cpu().numpy())
+
+
 @pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
 def test_nnf_counts_match_port(name):
     e, top, traj, fr, layout = run_engine(name)
