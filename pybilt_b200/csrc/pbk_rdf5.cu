@@ -1,26 +1,34 @@
-// pbk_rdf5.cu -- COM lateral RDF for small leaflets with a Verlet pair list per CTA.
+// pbk_rdf5.cu -- COM lateral RDF for small leaflets: one pair list per leaflet and frame chunk.
 //
-// Same arithmetic contract as k_rdf3 (pbk_rdf3.cu), restating
+// Same arithmetic contract as k_rdf3 / k_rdf2 / k_rdf, restating
 //   pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006  (COMLateralRDFProtocol)
 //   pybilt/common/distance_cutoff_clustering.py:27-71        (distance_euclidean_pbc)
+//   numpy/lib/_histograms_impl.py                            (np.histogram on uniform bins)
 // One 256-thread CTA owns one leaflet over a CHUNK of consecutive frames (about 30 KB of shared
-// memory, so seven CTAs share an SM).  Lipids move a fraction of an Angstrom per frame, so the
-// cell sort and the half-shell sweep -- two thirds of k_rdf3's instructions -- are not repeated
-// every frame: the CTA sweeps once with the cutoff widened by a skin, keeps the unordered pairs
-// it found as a flat list in shared memory (two 8-bit slots per pair), and for the following
-// frames only refreshes the float32 coordinates and walks the list, four independent pairs per
-// thread per iteration.  The list stays valid for every lipid that has not moved further than
-// skin/2 (minimum image) from where it was when the list was built.  The few that have --
-// mostly lipids whose WRAPPED centre of mass jumps because one of their beads crossed the box
-// edge (com_frame.py:71 averages the raw wrapped atoms) -- are taken out of the list walk by
-// poisoning their float32 slot and are paired with every other member directly.  The list is
-// rebuilt when more than 32 lipids have left their skin, when the box differs by a bit or when
-// the leaflet's member set changes.  Anything the list cannot hold (more than 256 members,
-// overflow, coordinates outside the box) is binned by the direct sweep of k_rdf3, so every
-// input gives the reference's counts.
-// A pair's bin comes from its float32 d^2 through the same look-up table with per-entry
-// distance to the nearest threshold; pairs within the float32 rounding bound of a threshold
-// are evaluated with the exact float64 formulas in both orders (see pbk_rdf3.cu).
+// memory, four CTAs per SM).  Lipids move a fraction of an Angstrom per frame, so the cell sort
+// and the half-shell sweep -- two thirds of the per-frame kernels' instructions -- are done
+// once per chunk instead of once per frame:
+//   scan    the CTA reads the chunk's frames once and records, per lipid, the bounding box of
+//           its (minimum-image) positions over the run of frames with an identical member set
+//           and a bit-identical box;
+//   build   lipids are cell-sorted by box centre; a pair enters the list iff the gap between
+//           the two bounding boxes is within range_outer (+ margin), i.e. iff the pair can be
+//           within range in SOME frame of the run.  The half-shell sweep covers lipids whose
+//           half-extent is <= 3 A; the few with larger boxes -- lipids whose WRAPPED centre of
+//           mass jumps because a bead crossed the box edge (com_frame.py:71 averages the raw
+//           wrapped atoms) -- are paired with every member directly;
+//   walk    per frame: refresh the float32 coordinates, walk the flat list (two 8-bit slots
+//           per pair), four independent pairs per thread per iteration.
+// A pair's bin comes from its FLOAT32 minimum-image d^2 through a look-up table over d^2 cells
+// of width 2^-m; each entry holds the bin of the whole cell and the distance (in cells) to the
+// nearest bin threshold.  When that distance exceeds the rounding bound of the float32 d^2 the
+// float64 reference arithmetic provably lands in the same bin; the ~1 % of pairs that are
+// closer to a threshold are queued and evaluated with the reference's exact float64 formulas
+// from the original coordinates, in both orders when the minimum image wrapped ((L-|a'|)-|b'|
+// is not symmetric in rounding).  Thresholds on d^2 (thr[k] = min{t : sqrt_rn(t) >= edge_k})
+// replace the square root exactly as in pbk_rdf2.cu.
+// Frames that cannot join a run (member outside the box, leaflet without both groups, more than
+// 256 members, list overflow) are binned one by one by the direct sweep of k_rdf3.
 #include <stdlib.h>
 
 #include "pbk_common.cuh"
@@ -31,7 +39,9 @@
 #define R5_MAXCELLS (R5_MAXDIM * R5_MAXDIM)
 #define R5_MAXROWS 8
 #define R5_QCAP 64
-#define R5_MAXN 640
+#define R5_MAXN 512
+#define R5_LPT ((R5_MAXN + R5_THREADS - 1) / R5_THREADS)   // lipids per thread in the scan
+#define R5_MAXW 64                  // lipids with large boxes per run
 
 struct Rdf5Params {
     const double *com;
@@ -41,32 +51,52 @@ struct Rdf5Params {
     int64_t F, N;
     int lat0, lat1, ta, tb, leaflet_mask, nb;
     double range_hi;
-    float skin;                     // list radius = range_hi + skin (+ margin)
+    float ecap;                     // half-extent up to which a lipid takes part in the cell sweep
     const double *thr;
     unsigned long long *count;
     int32_t *frame_counts;
     int lut_n, lut_m;
     int chunk;                      // frames per work item
-    int list_cap;                   // pair-list entries per warp
+    int list_cap;                   // pair-list entries
     int *work;
     const unsigned short *lut;      // [lut_n] global (L1-resident): bin | distance-to-threshold << 8
 };
 
-#define R5_MAXJ 32                  // lipids handled outside the list per frame
 struct R5Sh {                       // the CTA's shared memory
-    float2 *fxy;                    // N (sorted): float32 b' = x - box/2 of the current frame
-    float2 *ref;                    // N (sorted): the same when the list was built
+    float2 *fxy;                    // N (sorted): float32 b' = x - box/2 of the current frame / box centres
+    float2 *ext;                    // N (sorted): half-extents of the bounding boxes
     unsigned short *list;           // list_cap: p | q << 8
     unsigned *hist;                 // this warp's nb counters
     unsigned *q;                    // this warp's R5_QCAP exact-path queue
     int *cell_start, *cell_fill;    // R5_MAXCELLS + 1 each
     unsigned short *idx;            // N (sorted): lipid of the slot
-    unsigned short *cid;            // N (by lipid): cell at build time, 0xFFFF = not a member
-    unsigned char *flag;            // N (sorted): bit0 type A, bit1 type B
-    unsigned short *jslot;          // R5_MAXJ slots out of their skin this frame
-    float2 *jxy;                    // R5_MAXJ their float32 coordinates
-    int *cnt;                       // 8 counters: cA, cB, cL, n_jump, n_list, item, n_u, -
+    unsigned short *cid;            // N (by lipid): cell, 0xFFFF = not a member
+    unsigned char *flag;            // N (sorted): bit0 type A, bit1 type B, bit2 large box
+    unsigned short *wslot;          // R5_MAXW slots with large boxes
+    int *cnt;                       // 8 counters: cA, cB, cL, n_wild, n_list, item, -, -
 };
+
+struct R5Frame {                    // per-frame constants
+    const double *cf;
+    float bxf, byf;
+    double Lx, Ly, hx, hy;
+    int tolc;
+    bool all_exact;
+};
+
+__device__ __forceinline__ void r5_frame(R5Frame &Fr, const Rdf5Params &P, int64_t f, float lut_scale)
+{
+    Fr.cf = P.com + f * P.N * 3;
+    Fr.bxf = __ldg(P.box + f * 3 + P.lat0); Fr.byf = __ldg(P.box + f * 3 + P.lat1);
+    const float cxf = Fr.bxf * 0.5f, cyf = Fr.byf * 0.5f;
+    Fr.Lx = (double)Fr.bxf; Fr.Ly = (double)Fr.byf; Fr.hx = (double)cxf; Fr.hy = (double)cyf;
+    // rounding bound of the float32 d^2 near the thresholds, in table cells (+1 cell of slack):
+    // |d2_f32 - d2_exact| <= 2^-23 (r+1) (8 L + 4 (r+1))  with r = range_hi, L = larger box edge
+    const float Lm = fmaxf(Fr.bxf, Fr.byf), rr = (float)P.range_hi + 1.0f;
+    const float tol = 1.1920929e-7f * rr * (8.0f * Lm + 4.0f * rr);
+    Fr.tolc = (int)ceilf(tol * lut_scale) + 1;
+    Fr.all_exact = !(tol * lut_scale < 200.0f) || !(Fr.bxf > 0.0f) || !(Fr.byf > 0.0f);
+}
 
 __device__ __forceinline__ int r5_bin_exact(double d2, const double *s_thr, int nb)
 {
@@ -79,14 +109,13 @@ __device__ __forceinline__ int r5_bin_exact(double d2, const double *s_thr, int 
     return lo;
 }
 
-// the reference's float64 arithmetic for the unordered pair of sorted slots (p, q)
+// the reference's float64 arithmetic for the unordered pair of sorted slots (p, q) of frame cf
 template <bool SAME>
-__device__ __noinline__ void r5_exact(unsigned entry, const double *cf, int lat0, int lat1,
+__device__ __noinline__ void r5_exact(int p, int q, const double *cf, int lat0, int lat1,
                                       const unsigned short *s_idx, const unsigned char *s_flag,
                                       const double *s_thr, int nb, unsigned *myhist, double Lx, double Ly,
                                       double hx, double hy)
 {
-    const int p = entry & 0xFFFFu, q = entry >> 16;
     int w1 = 1, w2 = 1;
     if (!SAME) {
         const unsigned fp = s_flag[p], fq = s_flag[q];
@@ -126,27 +155,31 @@ __device__ __noinline__ void r5_exact(unsigned entry, const double *cf, int lat0
     }
 }
 
-// per-frame constants of the float32 fast path
-struct R5Frame {
-    const double *cf;
-    float bxf, byf;
-    double Lx, Ly, hx, hy;
-    int tolc;
-    bool all_exact;
-};
-
-// queue the pairs flagged `amb` for the exact evaluation (all 32 lanes call this together)
+// Exact-path queue of a warp.  Entries: p | q << 10 | frame-in-run << 20.  `base` = first frame
+// of the run; box constants are those of the run (bit-identical in all its frames).
 template <bool SAME>
-__device__ __forceinline__ void r5_push(bool amb, int p, int q, int &qn, int lane, const R5Sh &W,
-                                        const R5Frame &Fr, const Rdf5Params &P, const double *s_thr)
+__device__ __forceinline__ void r5_drain(int n, int lane, const R5Sh &W, const R5Frame &Fr, const Rdf5Params &P,
+                                         const double *s_thr, int64_t base)
+{
+    if (lane < n) {
+        const unsigned e = W.q[lane];
+        r5_exact<SAME>((int)(e & 0x3FFu), (int)((e >> 10) & 0x3FFu), P.com + (base + (e >> 20)) * P.N * 3, P.lat0, P.lat1,
+                       W.idx, W.flag, s_thr, P.nb, W.hist, Fr.Lx, Fr.Ly, Fr.hx, Fr.hy);
+    }
+}
+
+// queue the pairs flagged `amb` (all 32 lanes call this together)
+template <bool SAME>
+__device__ __forceinline__ void r5_push(bool amb, int p, int q, unsigned df, int &qn, int lane, const R5Sh &W,
+                                        const R5Frame &Fr, const Rdf5Params &P, const double *s_thr, int64_t base)
 {
     const unsigned m = __ballot_sync(0xffffffffu, amb);
     if (!m) return;
-    if (amb) W.q[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned)p | ((unsigned)q << 16);
+    if (amb) W.q[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned)p | ((unsigned)q << 10) | (df << 20);
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32) {
-        r5_exact<SAME>(W.q[lane], Fr.cf, P.lat0, P.lat1, W.idx, W.flag, s_thr, P.nb, W.hist, Fr.Lx, Fr.Ly, Fr.hx, Fr.hy);
+        r5_drain<SAME>(32, lane, W, Fr, P, s_thr, base);
         __syncwarp();
         const unsigned moved = lane + 32 < qn ? W.q[lane + 32] : 0u;
         __syncwarp();
@@ -156,19 +189,25 @@ __device__ __forceinline__ void r5_push(bool amb, int p, int q, int &qn, int lan
     }
 }
 
-// float32 minimum-image d^2 of two slots and its table entry
-__device__ __forceinline__ unsigned r5_lookup(float2 fp, float2 fq, const R5Frame &Fr, float lut_scale, int lut_last,
-                                              const unsigned short *s_lut, float *d2_out)
+// float32 minimum-image d^2 of two slots
+__device__ __forceinline__ float r5_d2(float2 fp, float2 fq, float bxf, float byf)
 {
     float dx = fabsf(fp.x - fq.x), dy = fabsf(fp.y - fq.y);
-    dx = fminf(dx, Fr.bxf - dx);
-    dy = fminf(dy, Fr.byf - dy);
-    const float d2 = fmaf(dy, dy, dx * dx);
-    *d2_out = d2;
-    const int c = min(__float2int_rd(d2 * lut_scale), lut_last);
-    return __ldg(s_lut + c);
+    dx = fminf(dx, bxf - dx);
+    dy = fminf(dy, byf - dy);
+    return fmaf(dy, dy, dx * dx);
 }
 
+// smallest possible squared distance between the bounding boxes (centre c, half-extent e)
+__device__ __forceinline__ float r5_gap2(float2 cp, float2 ep, float2 cq, float2 eq, float bxf, float byf)
+{
+    float dx = fabsf(cp.x - cq.x), dy = fabsf(cp.y - cq.y);
+    dx = fminf(dx, bxf - dx);
+    dy = fminf(dy, byf - dy);
+    dx = fmaxf(0.0f, dx - (ep.x + eq.x));
+    dy = fmaxf(0.0f, dy - (ep.y + eq.y));
+    return fmaf(dy, dy, dx * dx);
+}
 
 // look-up table over d^2 cells [c, c+1) * 2^-m: low byte = bin of the cell (0xFF outside the
 // range), high byte = distance in cells to the nearest threshold (saturated at 255; 0 when a
@@ -194,14 +233,14 @@ __global__ void k_rdf5_lut(const double *__restrict__ thr, int nb, int lut_n, in
     lut[c] = (unsigned short)(bin | (dc << 8));
 }
 
-// one candidate pair in direct / jumper mode: count it or queue it for the exact path
+// one candidate pair: count it, or queue it for the exact path
 template <bool SAME>
-__device__ __forceinline__ void r5_pair(bool act, int p, int q, float2 fp, float2 fq, unsigned fpflag, int &qn, int lane,
-                                        const R5Sh &W, const R5Frame &Fr, const Rdf5Params &P, const double *s_thr,
-                                        float lut_scale, int lut_last)
+__device__ __forceinline__ void r5_pair(bool act, int p, int q, float2 fp, float2 fq, unsigned fpflag, unsigned df, int &qn,
+                                        int lane, const R5Sh &W, const R5Frame &Fr, const Rdf5Params &P,
+                                        const double *s_thr, float lut_scale, int lut_last, int64_t base)
 {
-    float d2;
-    const unsigned e = r5_lookup(fp, fq, Fr, lut_scale, lut_last, P.lut, &d2);
+    const float d2 = r5_d2(fp, fq, Fr.bxf, Fr.byf);
+    const unsigned e = __ldg(P.lut + min(__float2int_rd(d2 * lut_scale), lut_last));
     unsigned w = 2u;
     if (!SAME) {
         const unsigned fqf = W.flag[q];
@@ -209,7 +248,7 @@ __device__ __forceinline__ void r5_pair(bool act, int p, int q, float2 fp, float
     }
     const bool sure = (int)(e >> 8) >= Fr.tolc && !Fr.all_exact;
     if (act && sure && (e & 0xFFu) != 0xFFu && w) atomicAdd(&W.hist[e & 0xFFu], w);
-    r5_push<SAME>(act && !sure && w, p, q, qn, lane, W, Fr, P, s_thr);
+    r5_push<SAME>(act && !sure && w, p, q, df, qn, lane, W, Fr, P, s_thr, base);
 }
 
 template <bool SAME>
@@ -224,8 +263,7 @@ k_rdf5(Rdf5Params P)
     double *s_thr = reinterpret_cast<double *>(wb);                        wb += (((size_t)(nb + 1) * 8) + 15) & ~(size_t)15;
     R5Sh W;
     W.fxy = reinterpret_cast<float2 *>(wb);                                wb += npad * 8;
-    W.ref = reinterpret_cast<float2 *>(wb);                                wb += npad * 8;
-    W.jxy = reinterpret_cast<float2 *>(wb);                                wb += (size_t)R5_MAXJ * 8;
+    W.ext = reinterpret_cast<float2 *>(wb);                                wb += npad * 8;
     W.list = reinterpret_cast<unsigned short *>(wb);                       wb += ((size_t)P.list_cap * 2 + 15) & ~(size_t)15;
     unsigned *hist_all = reinterpret_cast<unsigned *>(wb);                 wb += (((size_t)R5_WARPS * nb * 4) + 15) & ~(size_t)15;
     W.hist = hist_all + (size_t)warp * nb;
@@ -235,7 +273,7 @@ k_rdf5(Rdf5Params P)
     W.cnt = reinterpret_cast<int *>(wb);                                   wb += 8 * 4;
     W.idx = reinterpret_cast<unsigned short *>(wb);                        wb += npad * 2;
     W.cid = reinterpret_cast<unsigned short *>(wb);                        wb += npad * 2;
-    W.jslot = reinterpret_cast<unsigned short *>(wb);                      wb += (size_t)R5_MAXJ * 2;
+    W.wslot = reinterpret_cast<unsigned short *>(wb);                      wb += (size_t)R5_MAXW * 2;
     W.flag = reinterpret_cast<unsigned char *>(wb);
 
     for (int q = tid; q <= nb; q += R5_THREADS) s_thr[q] = P.thr[q];
@@ -246,11 +284,12 @@ k_rdf5(Rdf5Params P)
     const int lut_last = P.lut_n - 1;
     const int64_t chunks = (P.F + P.chunk - 1) / P.chunk;
     const int64_t n_items = chunks * 2;
-    const float Rb = (float)P.range_hi + P.skin + 0.05f;          // list radius
-    const float Rb2 = Rb * Rb;
-    const float lim2 = 0.25f * P.skin * P.skin * 0.98f;           // (skin/2)^2 with a little slack
+    const float Rc = (float)P.range_hi + 0.05f;                   // pair criterion on the box gap
+    const float Rc2 = Rc * Rc;
+    const float Rb = Rc + 2.0f * P.ecap;                          // reach of the cell sweep (box centres)
 
     for (;;) {
+        __syncthreads();
         if (tid == 0) W.cnt[5] = atomicAdd(P.work, 1);
         __syncthreads();
         const long long item = W.cnt[5];
@@ -259,84 +298,82 @@ k_rdf5(Rdf5Params P)
         const int64_t fa = (item >> 1) * P.chunk, fb = min(P.F, fa + (int64_t)P.chunk);
         const unsigned want = leaf == 0 ? 1u : 0u;
         const bool selected = (P.leaflet_mask >> leaf) & 1;
-        bool have_list = false;                      // CTA uniform, like everything that steers the flow below
-        int n_list = 0, n_u = 0;
-        float bx0 = 0.f, by0 = 0.f;
-        int ncx = 1, ncy = 1, mx = 0, my = 0, ncell = 1;
 
-        for (int64_t f = fa; f < fb; f++) {
+        int64_t f0 = fa;
+        while (f0 < fb) {
+            // ================= scan: the run [f0, fe) of frames that share member set and box ========
             R5Frame Fr;
-            Fr.cf = P.com + f * P.N * 3;
-            const uint8_t *lab = P.labels + f * P.N;
-            Fr.bxf = __ldg(P.box + f * 3 + P.lat0); Fr.byf = __ldg(P.box + f * 3 + P.lat1);
-            const float cxf = Fr.bxf * 0.5f, cyf = Fr.byf * 0.5f;
-            Fr.Lx = (double)Fr.bxf; Fr.Ly = (double)Fr.byf; Fr.hx = (double)cxf; Fr.hy = (double)cyf;
-            // rounding bound of the float32 d^2 near the thresholds, in table cells (+1 cell of slack):
-            // |d2_f32 - d2_exact| <= 2^-23 (r+1) (8 L + 4 (r+1))  with r = range_hi, L = larger box edge
-            const float Lm = fmaxf(Fr.bxf, Fr.byf), rr = (float)P.range_hi + 1.0f;
-            const float tol = 1.1920929e-7f * rr * (8.0f * Lm + 4.0f * rr);
-            Fr.tolc = (int)ceilf(tol * lut_scale) + 1;
-            Fr.all_exact = !(tol * lut_scale < 200.0f) || !(Fr.bxf > 0.0f) || !(Fr.byf > 0.0f);
-            int qn = 0;                                           // this warp's queued exact pairs
-
-            // ---- member set and counts of the frame ----------------------------------------------
+            r5_frame(Fr, P, f0, lut_scale);
+            float c0x[R5_LPT], c0y[R5_LPT], lox[R5_LPT], hix[R5_LPT], loy[R5_LPT], hiy[R5_LPT];
+            bool in0[R5_LPT], mem0[R5_LPT];                      // in the leaflet / of type A or B as well
+            int cA = 0, cB = 0, cL = 0, oob0 = 0;
             if (tid < 5) W.cnt[tid] = 0;
             __syncthreads();
-            int cA = 0, cB = 0, cL = 0, changed = 0;
-            for (int i = tid; i < N; i += R5_THREADS) {
-                bool m2 = false;
-                if (lab[i] == want) {
+#pragma unroll
+            for (int u = 0; u < R5_LPT; u++) {
+                const int i = tid + u * R5_THREADS;
+                in0[u] = mem0[u] = false; c0x[u] = c0y[u] = 0.f; lox[u] = hix[u] = loy[u] = hiy[u] = 0.f;
+                if (i < N && P.labels[f0 * P.N + i] == want) {
                     const int t = __ldg(P.type_code + i);
                     const bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
+                    in0[u] = true;
                     cL++; cA += a; cB += b;
-                    m2 = a || b;
+                    if (a || b) {
+                        mem0[u] = true;
+                        const double x = Fr.cf[i * 3 + P.lat0], y = Fr.cf[i * 3 + P.lat1];
+                        oob0 |= !(x >= 0.0 && x <= Fr.Lx && y >= 0.0 && y <= Fr.Ly);
+                        c0x[u] = (float)__dsub_rn(x, Fr.hx); c0y[u] = (float)__dsub_rn(y, Fr.hy);
+                    }
                 }
-                if (have_list) changed |= (m2 != (W.cid[i] != 0xFFFF));
             }
             cA = pbk_warp_sum(cA); cB = pbk_warp_sum(cB); cL = pbk_warp_sum(cL);
             if (lane == 0) { atomicAdd(&W.cnt[0], cA); atomicAdd(&W.cnt[1], cB); atomicAdd(&W.cnt[2], cL); }
-            const int any_changed = __syncthreads_or(changed);
+            const int any_oob0 = __syncthreads_or(oob0);
             cA = W.cnt[0]; cB = W.cnt[1]; cL = W.cnt[2];
             const bool on = selected && cA > 0 && cB > 0;
-            if (tid < 3) {
-                int v = tid == 0 ? cA : (tid == 1 ? cB : cL);
-                if (tid < 2 && !on) v = 0;
-                if (tid == 2 && !selected) v = 0;
-                P.frame_counts[f * 6 + leaf * 3 + tid] = v;
-            }
-            if (!on) { have_list = false; __syncthreads(); continue; }
-            if (have_list && (any_changed || Fr.bxf != bx0 || Fr.byf != by0 || Fr.all_exact)) have_list = false;
-
-            // ---- list still valid?  refresh the coordinates; lipids out of their skin leave the list ----
-            int nj = 0;
-            if (have_list) {
-                int oob = 0;
-                for (int s = tid; s < n_u; s += R5_THREADS) {
-                    const int i = W.idx[s];
-                    const double x = Fr.cf[i * 3 + P.lat0], y = Fr.cf[i * 3 + P.lat1];
-                    oob |= !(x >= 0.0 && x <= Fr.Lx && y >= 0.0 && y <= Fr.Ly);
-                    float2 c = make_float2((float)__dsub_rn(x, Fr.hx), (float)__dsub_rn(y, Fr.hy));
-                    const float2 r = W.ref[s];
-                    float dx = fabsf(c.x - r.x), dy = fabsf(c.y - r.y);
-                    dx = fminf(dx, Fr.bxf - dx);
-                    dy = fminf(dy, Fr.byf - dy);
-                    if (!(fmaf(dy, dy, dx * dx) < lim2)) {
-                        const int k = atomicAdd(&W.cnt[3], 1);
-                        if (k < R5_MAXJ) { W.jslot[k] = (unsigned short)s; W.jxy[k] = c; }
-                        // poisoned slot: every list pair that touches it lands beyond the table
-                        c = make_float2(1.0e30f * (float)(s + 1), 1.0e30f * (float)(s + 1));
+            const int vA = on ? cA : 0, vB = on ? cB : 0, vL = selected ? cL : 0;
+            int64_t fe = f0 + 1;
+            if (any_oob0) Fr.all_exact = true;                     // a member outside the box: exact formulas only
+            const bool single = !on || Fr.all_exact;                // frame f0 cannot start a run
+            if (!single) {
+                for (; fe < fb; fe++) {
+                    const float bxe = __ldg(P.box + fe * 3 + P.lat0), bye = __ldg(P.box + fe * 3 + P.lat1);
+                    int stop = (bxe != Fr.bxf) || (bye != Fr.byf);
+                    const double *cfe = P.com + fe * P.N * 3;
+                    float nlx[R5_LPT], nhx[R5_LPT], nly[R5_LPT], nhy[R5_LPT];
+#pragma unroll
+                    for (int u = 0; u < R5_LPT; u++) {
+                        const int i = tid + u * R5_THREADS;
+                        nlx[u] = lox[u]; nhx[u] = hix[u]; nly[u] = loy[u]; nhy[u] = hiy[u];
+                        if (i < N) {
+                            // the leaflet (hence N_a, N_b, N_leaflet and the member set) must not change
+                            stop |= ((P.labels[fe * P.N + i] == want) != in0[u]);
+                            if (mem0[u]) {
+                                const double x = cfe[i * 3 + P.lat0], y = cfe[i * 3 + P.lat1];
+                                stop |= !(x >= 0.0 && x <= Fr.Lx && y >= 0.0 && y <= Fr.Ly);
+                                float dx = (float)__dsub_rn(x, Fr.hx) - c0x[u], dy = (float)__dsub_rn(y, Fr.hy) - c0y[u];
+                                if (dx > 0.5f * Fr.bxf) dx -= Fr.bxf; else if (dx < -0.5f * Fr.bxf) dx += Fr.bxf;
+                                if (dy > 0.5f * Fr.byf) dy -= Fr.byf; else if (dy < -0.5f * Fr.byf) dy += Fr.byf;
+                                nlx[u] = fminf(nlx[u], dx); nhx[u] = fmaxf(nhx[u], dx);
+                                nly[u] = fminf(nly[u], dy); nhy[u] = fmaxf(nhy[u], dy);
+                            }
+                        }
                     }
-                    W.fxy[s] = c;
+                    if (__syncthreads_or(stop)) break;              // frame fe starts the next run
+#pragma unroll
+                    for (int u = 0; u < R5_LPT; u++) { lox[u] = nlx[u]; hix[u] = nhx[u]; loy[u] = nly[u]; hiy[u] = nhy[u]; }
                 }
-                const int any_oob = __syncthreads_or(oob);
-                nj = W.cnt[3];
-                if (any_oob || nj > R5_MAXJ) { have_list = false; nj = 0; }
             }
+            for (int64_t f = f0 + tid / 3; f < fe; f += R5_THREADS / 3) {      // (N_a, N_b, N_leaflet) of every frame
+                const int k = tid % 3;
+                if (tid < (R5_THREADS / 3) * 3) P.frame_counts[f * 6 + leaf * 3 + k] = k == 0 ? vA : (k == 1 ? vB : vL);
+            }
+            if (!on) { f0 = fe; continue; }
 
-            // ---- (re)build: cell sort of the current frame, then one half-shell sweep that either
-            // fills the pair list (radius Rb) or, when a list is not possible, bins directly --------
-            if (!have_list) {
-                // cell grid: edge >= 0.51 * Rb so that the half shell reaches 2 cells
+            // ================= build: cell sort by box centre, pair list ===========================
+            // cell grid: edge >= 0.51 * Rb so that the half shell reaches 2 cells
+            int ncx, ncy, mx, my;
+            {
                 const double wmin = 0.51 * (double)Rb + 1e-6;
                 ncx = (int)floor(Fr.Lx / wmin); ncy = (int)floor(Fr.Ly / wmin);
                 ncx = max(1, min(R5_MAXDIM, ncx));
@@ -345,193 +382,208 @@ k_rdf5(Rdf5Params P)
                 mx = (int)floor(((double)Rb + 1e-6) / wx) + 1; my = (int)floor(((double)Rb + 1e-6) / wy) + 1;
                 if (2 * mx + 1 > ncx) { ncx = 1; mx = 0; }
                 if (2 * my + 1 > ncy || my + 1 > R5_MAXROWS) { ncy = 1; my = 0; }
-                const double iwx = ncx / Fr.Lx, iwy = ncy / Fr.Ly;
-                ncell = ncx * ncy;
-                int oob = 0;
-                for (int c = tid; c <= R5_MAXCELLS; c += R5_THREADS) W.cell_fill[c] = 0;
-                for (int i = tid; i < N; i += R5_THREADS) {
+                if (single) { ncx = ncy = 1; mx = my = 0; }         // (no sweep: one cell)
+            }
+            const int ncell = ncx * ncy;
+            const float iwx = (float)ncx / Fr.bxf, iwy = (float)ncy / Fr.byf;
+            for (int c = tid; c <= R5_MAXCELLS; c += R5_THREADS) W.cell_fill[c] = 0;
+            float cmx[R5_LPT], cmy[R5_LPT], ehx[R5_LPT], ehy[R5_LPT];
+#pragma unroll
+            for (int u = 0; u < R5_LPT; u++) {
+                const int i = tid + u * R5_THREADS;
+                cmx[u] = c0x[u] + 0.5f * (lox[u] + hix[u]); cmy[u] = c0y[u] + 0.5f * (loy[u] + hiy[u]);
+                // half-extent + the float32 rounding of the box bookkeeping
+                ehx[u] = 0.5f * (hix[u] - lox[u]) + 1.0e-5f * Fr.bxf; ehy[u] = 0.5f * (hiy[u] - loy[u]) + 1.0e-5f * Fr.byf;
+                if (i < N) {
                     unsigned short cid = 0xFFFF;
-                    if (lab[i] == want) {
-                        const int t = __ldg(P.type_code + i);
-                        const bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
-                        if (a || b) {
-                            const double x = Fr.cf[i * 3 + P.lat0], y = Fr.cf[i * 3 + P.lat1];
-                            oob |= !(x >= 0.0 && x <= Fr.Lx && y >= 0.0 && y <= Fr.Ly);
-                            int cx = (int)(x * iwx), cy = (int)(y * iwy);
-                            cx = max(0, min(ncx - 1, cx));
-                            cy = max(0, min(ncy - 1, cy));
-                            cid = (unsigned short)(cy * ncx + cx);
-                        }
+                    if (mem0[u]) {
+                        float gx = cmx[u] + 0.5f * Fr.bxf, gy = cmy[u] + 0.5f * Fr.byf;   // back to [0, L) for the cell index
+                        if (gx < 0.0f) gx += Fr.bxf; else if (gx >= Fr.bxf) gx -= Fr.bxf;
+                        if (gy < 0.0f) gy += Fr.byf; else if (gy >= Fr.byf) gy -= Fr.byf;
+                        int cx = (int)(gx * iwx), cy = (int)(gy * iwy);
+                        cx = max(0, min(ncx - 1, cx));
+                        cy = max(0, min(ncy - 1, cy));
+                        cid = (unsigned short)(cy * ncx + cx);
                     }
                     W.cid[i] = cid;
                 }
-                bool direct = Fr.all_exact;
-                if (__syncthreads_or(oob)) {
-                    // a member outside the box: one cell, every pair through the exact formulas
-                    Fr.all_exact = true;
-                    direct = true;
-                    ncx = ncy = 1; mx = my = 0; ncell = 1;
-                    for (int i = tid; i < N; i += R5_THREADS) if (W.cid[i] != 0xFFFF) W.cid[i] = 0;
-                    __syncthreads();
-                }
-                for (int i = tid; i < N; i += R5_THREADS) {
-                    const unsigned short cid = W.cid[i];
-                    if (cid != 0xFFFF) atomicAdd(&W.cell_fill[cid], 1);
-                }
-                __syncthreads();
-                if (warp == 0) {   // exclusive scan of the cell counts (<= 256 cells: 8 per lane)
-                    int v[8], s = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) { const int c = lane * 8 + q; v[q] = c < ncell ? W.cell_fill[c] : 0; s += v[q]; }
-                    int incl = s;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                    int excl = incl - s;
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int c = lane * 8 + q;
-                        if (c < ncell) { W.cell_start[c] = excl; W.cell_fill[c] = excl; }
-                        excl += v[q];
-                    }
-                    if (lane == 31) W.cell_start[ncell] = excl;
-                }
-                __syncthreads();
-                n_u = W.cell_start[ncell];
-                for (int i = tid; i < N; i += R5_THREADS) {
-                    const unsigned short cid = W.cid[i];
-                    if (cid == 0xFFFF) continue;
-                    const int slot = atomicAdd(&W.cell_fill[cid], 1);
-                    const float2 c = make_float2((float)__dsub_rn(Fr.cf[i * 3 + P.lat0], Fr.hx),
-                                                 (float)__dsub_rn(Fr.cf[i * 3 + P.lat1], Fr.hy));
-                    W.fxy[slot] = c;
-                    W.ref[slot] = c;
-                    W.idx[slot] = (unsigned short)i;
-                    if (!SAME) {
-                        const int t = __ldg(P.type_code + i);
-                        W.flag[slot] = (unsigned char)(((P.ta == -1 || t == P.ta) ? 1 : 0) | ((P.tb == -1 || t == P.tb) ? 2 : 0));
-                    }
-                }
-                __syncthreads();
-                if (n_u > 256) direct = true;               // slots do not fit the 8-bit list entries
-
-                // the sweep: thread = lipid p, forward half shell of cells.  emit = fill the list.
-                for (int attempt = 0; attempt < 2; attempt++) {
-                    const bool emit = !direct;
-                    for (int p0 = warp * 32; p0 < n_u; p0 += R5_THREADS) {
-                        const int p = p0 + lane;
-                        const bool pact = p < n_u;
-                        float2 fp = make_float2(0.f, 0.f);
-                        int pcx = 0, pcy = 0;
-                        unsigned fpflag = 3u;
-                        if (pact) {
-                            fp = W.fxy[p];
-                            const int pc = W.cid[W.idx[p]];
-                            pcy = pc / ncx; pcx = pc - pcy * ncx;
-                            if (!SAME) fpflag = W.flag[p];
-                        }
-                        for (int oy = 0; oy <= my; oy++) {
-                            int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
-                            if (pact) {
-                                int cy = pcy + oy; if (cy >= ncy) cy -= ncy;
-                                const int row = cy * ncx;
-                                int xlo = (oy == 0) ? pcx : pcx - mx, xhi = pcx + mx;
-                                if (xlo < 0) {                      // wraps on the left
-                                    b2 = W.cell_start[row + xlo + ncx]; n2 = W.cell_start[row + ncx] - b2;
-                                    xlo = 0;
-                                }
-                                if (xhi >= ncx) {                   // wraps on the right
-                                    b2 = W.cell_start[row]; n2 = W.cell_start[row + xhi - ncx + 1] - b2;
-                                    xhi = ncx - 1;
-                                }
-                                b1 = W.cell_start[row + xlo]; n1 = W.cell_start[row + xhi + 1] - b1;
-                                if (oy == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }   // own cell: later entries only
-                            }
-                            const int ntot = n1 + n2;
-                            for (int t = 0; __any_sync(0xffffffffu, t < ntot); t++) {
-                                const bool act = t < ntot;
-                                const int q = act ? (t < n1 ? b1 + t : b2 + (t - n1)) : 0;
-                                if (emit) {
-                                    float d2;
-                                    r5_lookup(fp, W.fxy[q], Fr, lut_scale, 0, P.lut, &d2);
-                                    const bool hit = act && d2 < Rb2;
-                                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                                    if (m) {
-                                        int base = 0;
-                                        if (lane == 0) base = atomicAdd(&W.cnt[4], __popc(m));
-                                        base = __shfl_sync(0xffffffffu, base, 0);
-                                        const int pos = base + __popc(m & lt_mask);
-                                        if (hit && pos < P.list_cap) W.list[pos] = (unsigned short)(p | (q << 8));
-                                    }
-                                } else {
-                                    r5_pair<SAME>(act, p, q, fp, W.fxy[q], fpflag, qn, lane, W, Fr, P, s_thr, lut_scale, lut_last);
-                                }
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    n_list = W.cnt[4];
-                    const bool overflow = emit && n_list > P.list_cap;
-                    if (emit && !overflow) { have_list = true; bx0 = Fr.bxf; by0 = Fr.byf; }
-                    if (!overflow) break;
-                    direct = true;                              // list too small: bin this frame directly
-                }
             }
-
-            if (have_list) {
-                // ---- bin the frame from the pair list: four independent pairs per thread per iteration ----
-                for (int e0 = 0; e0 < n_list; e0 += 4 * R5_THREADS) {
-                    int pp[4], qq[4];
-                    bool amb[4];
+            __syncthreads();
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int k = e0 + R5_THREADS * j + tid;
-                        const bool act = k < n_list;
-                        const unsigned ent = act ? W.list[k] : 0u;
-                        pp[j] = ent & 0xFFu; qq[j] = ent >> 8;
-                        float d2;
-                        const unsigned e = r5_lookup(W.fxy[pp[j]], W.fxy[qq[j]], Fr, lut_scale, lut_last, P.lut, &d2);
-                        unsigned w = 2u;
-                        if (!SAME) {
-                            const unsigned fpf = W.flag[pp[j]], fqf = W.flag[qq[j]];
-                            w = ((fpf & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((fpf >> 1) & 1u));
-                        }
-                        const bool sure = (int)(e >> 8) >= Fr.tolc;
-                        if (act && sure && (e & 0xFFu) != 0xFFu && w) atomicAdd(&W.hist[e & 0xFFu], w);
-                        amb[j] = act && !sure && w;
+            for (int u = 0; u < R5_LPT; u++) if (mem0[u]) atomicAdd(&W.cell_fill[W.cid[tid + u * R5_THREADS]], 1);
+            __syncthreads();
+            if (warp == 0) {   // exclusive scan of the cell counts (<= 256 cells: 8 per lane)
+                int v[8], s = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const int c = lane * 8 + q; v[q] = c < ncell ? W.cell_fill[c] : 0; s += v[q]; }
+                int incl = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                int excl = incl - s;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int c = lane * 8 + q;
+                    if (c < ncell) { W.cell_start[c] = excl; W.cell_fill[c] = excl; }
+                    excl += v[q];
+                }
+                if (lane == 31) W.cell_start[ncell] = excl;
+            }
+            __syncthreads();
+            const int n_u = W.cell_start[ncell];
+#pragma unroll
+            for (int u = 0; u < R5_LPT; u++) {
+                if (!mem0[u]) continue;
+                const int i = tid + u * R5_THREADS;
+                const int slot = atomicAdd(&W.cell_fill[W.cid[i]], 1);
+                const bool wild = !(ehx[u] <= P.ecap && ehy[u] <= P.ecap);
+                W.fxy[slot] = make_float2(cmx[u], cmy[u]);
+                W.ext[slot] = make_float2(ehx[u], ehy[u]);
+                W.idx[slot] = (unsigned short)i;
+                const int t = __ldg(P.type_code + i);
+                W.flag[slot] = (unsigned char)(((P.ta == -1 || t == P.ta) ? 1 : 0) | ((P.tb == -1 || t == P.tb) ? 2 : 0) | (wild ? 4 : 0));
+                if (wild) { const int k = atomicAdd(&W.cnt[3], 1); if (k < R5_MAXW) W.wslot[k] = (unsigned short)slot; }
+            }
+            __syncthreads();
+            const int nw = W.cnt[3];
+            // a list needs 8-bit slots, every large box listed, and a frame that may start a run
+            bool use_list = !single && n_u <= 256 && nw <= R5_MAXW;
+            int qn = 0;                                           // this warp's queued exact pairs
+            int n_list = 0;
+            if (use_list) {
+                // the sweep: thread = lipid p, forward half shell of cells
+                for (int p0 = warp * 32; p0 < n_u; p0 += R5_THREADS) {
+                    const int p = p0 + lane;
+                    const bool pact = p < n_u;
+                    float2 fp = make_float2(0.f, 0.f), ep = make_float2(0.f, 0.f);
+                    int pcx = 0, pcy = 0;
+                    bool pwild = true;
+                    if (pact) {
+                        fp = W.fxy[p]; ep = W.ext[p];
+                        const int pc = W.cid[W.idx[p]];
+                        pcy = pc / ncx; pcx = pc - pcy * ncx;
+                        pwild = (W.flag[p] & 4u) != 0u;
                     }
-                    if (__any_sync(0xffffffffu, amb[0] | amb[1] | amb[2] | amb[3])) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) r5_push<SAME>(amb[j], pp[j], qq[j], qn, lane, W, Fr, P, s_thr);
+                    for (int oy = 0; oy <= my; oy++) {
+                        int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
+                        if (!pwild) {
+                            int cy = pcy + oy; if (cy >= ncy) cy -= ncy;
+                            const int row = cy * ncx;
+                            int xlo = (oy == 0) ? pcx : pcx - mx, xhi = pcx + mx;
+                            if (xlo < 0) {                      // wraps on the left
+                                b2 = W.cell_start[row + xlo + ncx]; n2 = W.cell_start[row + ncx] - b2;
+                                xlo = 0;
+                            }
+                            if (xhi >= ncx) {                   // wraps on the right
+                                b2 = W.cell_start[row]; n2 = W.cell_start[row + xhi - ncx + 1] - b2;
+                                xhi = ncx - 1;
+                            }
+                            b1 = W.cell_start[row + xlo]; n1 = W.cell_start[row + xhi + 1] - b1;
+                            if (oy == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }   // own cell: later entries only
+                        }
+                        const int ntot = n1 + n2;
+                        for (int t = 0; __any_sync(0xffffffffu, t < ntot); t++) {
+                            const bool act = t < ntot;
+                            const int q = act ? (t < n1 ? b1 + t : b2 + (t - n1)) : 0;
+                            const bool hit = act && !(W.flag[q] & 4u) &&
+                                             r5_gap2(fp, ep, W.fxy[q], W.ext[q], Fr.bxf, Fr.byf) < Rc2;
+                            const unsigned m = __ballot_sync(0xffffffffu, hit);
+                            if (m) {
+                                int base = 0;
+                                if (lane == 0) base = atomicAdd(&W.cnt[4], __popc(m));
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                const int pos = base + __popc(m & lt_mask);
+                                if (hit && pos < P.list_cap) W.list[pos] = (unsigned short)(p | (q << 8));
+                            }
+                        }
                     }
                 }
-                // ---- lipids out of their skin: paired with every other member directly (their slots
-                // are poisoned, so two of them never meet here) and with each other below --------------
-                for (int jj = 0; jj < nj; jj++) {
-                    const int sj = W.jslot[jj];
-                    const float2 cj = W.jxy[jj];
-                    unsigned fjflag = 3u;
-                    if (!SAME) fjflag = W.flag[sj];
+                // lipids with large boxes: against every other member (two of them meet once, by slot order)
+                for (int jw = 0; jw < nw; jw++) {
+                    const int sw = W.wslot[jw];
+                    const float2 cw = W.fxy[sw], ew = W.ext[sw];
                     for (int s0 = warp * 32; s0 < n_u; s0 += R5_THREADS) {
                         const int s = s0 + lane;
-                        const bool act = s < n_u && s != sj;
-                        r5_pair<SAME>(act, sj, act ? s : 0, cj, W.fxy[act ? s : 0], fjflag, qn, lane, W, Fr, P, s_thr, lut_scale, lut_last);
+                        bool hit = false;
+                        if (s < n_u && s != sw && !((W.flag[s] & 4u) && s < sw))
+                            hit = r5_gap2(cw, ew, W.fxy[s], W.ext[s], Fr.bxf, Fr.byf) < Rc2;
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&W.cnt[4], __popc(m));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            const int pos = base + __popc(m & lt_mask);
+                            if (hit && pos < P.list_cap) W.list[pos] = (unsigned short)(sw | (s << 8));
+                        }
                     }
                 }
-                for (int t0 = warp * 32; t0 < nj * nj; t0 += R5_THREADS) {
-                    const int t = t0 + lane;
-                    const int a = t / max(nj, 1), b = t - a * max(nj, 1);
-                    const bool act = t < nj * nj && a < b;
-                    const int sa = W.jslot[act ? a : 0], sb = W.jslot[act ? b : 0];
-                    unsigned faflag = 3u;
-                    if (!SAME) faflag = W.flag[sa];
-                    r5_pair<SAME>(act, sa, sb, W.jxy[act ? a : 0], W.jxy[act ? b : 0], faflag, qn, lane, W, Fr, P, s_thr, lut_scale, lut_last);
+                __syncthreads();
+                n_list = W.cnt[4];
+                if (n_list > P.list_cap) use_list = false;          // list too small
+            }
+
+            if (use_list) {
+                // ================= walk: per frame of the run, refresh the coordinates, bin the list ======
+                for (int64_t f = f0; f < fe; f++) {
+                    const double *cf = P.com + f * P.N * 3;
+                    __syncthreads();                               // (the list is complete / the previous walk is done)
+                    for (int s = tid; s < n_u; s += R5_THREADS) {
+                        const int i = W.idx[s];
+                        W.fxy[s] = make_float2((float)__dsub_rn(cf[i * 3 + P.lat0], Fr.hx), (float)__dsub_rn(cf[i * 3 + P.lat1], Fr.hy));
+                    }
+                    __syncthreads();
+                    const unsigned df = (unsigned)(f - f0);
+                    for (int e0 = 0; e0 < n_list; e0 += 4 * R5_THREADS) {
+                        int pp[4], qq[4];
+                        bool amb[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int k = e0 + R5_THREADS * j + tid;
+                            const bool act = k < n_list;
+                            const unsigned ent = act ? W.list[k] : 0u;
+                            pp[j] = ent & 0xFFu; qq[j] = ent >> 8;
+                            const float d2 = r5_d2(W.fxy[pp[j]], W.fxy[qq[j]], Fr.bxf, Fr.byf);
+                            const unsigned e = __ldg(P.lut + min(__float2int_rd(d2 * lut_scale), lut_last));
+                            unsigned w = 2u;
+                            if (!SAME) {
+                                const unsigned fpf = W.flag[pp[j]], fqf = W.flag[qq[j]];
+                                w = ((fpf & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((fpf >> 1) & 1u));
+                            }
+                            const bool sure = (int)(e >> 8) >= Fr.tolc;
+                            if (act && sure && (e & 0xFFu) != 0xFFu && w) atomicAdd(&W.hist[e & 0xFFu], w);
+                            amb[j] = act && !sure && w;
+                        }
+                        if (__any_sync(0xffffffffu, amb[0] | amb[1] | amb[2] | amb[3])) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) r5_push<SAME>(amb[j], pp[j], qq[j], df, qn, lane, W, Fr, P, s_thr, f0);
+                        }
+                    }
+                }
+            } else {
+                // ================= no list: frame f0 alone, every pair of members straight from its
+                // coordinates (out-of-box members, > 256 members, overflow); the run is cut to f0 ========
+                fe = f0 + 1;
+                __syncthreads();
+                for (int s = tid; s < n_u; s += R5_THREADS) {
+                    const int i = W.idx[s];
+                    W.fxy[s] = make_float2((float)__dsub_rn(Fr.cf[i * 3 + P.lat0], Fr.hx), (float)__dsub_rn(Fr.cf[i * 3 + P.lat1], Fr.hy));
+                }
+                __syncthreads();
+                for (int p = 0; p < n_u; p++) {
+                    const float2 fp = W.fxy[p];
+                    const unsigned fpflag = W.flag[p];
+                    for (int s0 = warp * 32; s0 < n_u; s0 += R5_THREADS) {
+                        if (s0 + 31 <= p) continue;
+                        const int s = s0 + lane;
+                        const bool act = s > p && s < n_u;
+                        r5_pair<SAME>(act, p, act ? s : 0, fp, W.fxy[act ? s : 0], fpflag, 0u, qn, lane, W, Fr, P, s_thr, lut_scale, lut_last, f0);
+                    }
                 }
             }
             __syncwarp();
-            if (lane < qn)
-                r5_exact<SAME>(W.q[lane], Fr.cf, P.lat0, P.lat1, W.idx, W.flag, s_thr, nb, W.hist, Fr.Lx, Fr.Ly, Fr.hx, Fr.hy);
+            r5_drain<SAME>(qn, lane, W, Fr, P, s_thr, f0);
             __syncthreads();
+            f0 = fe;
         }
     }
     __syncthreads();
@@ -545,9 +597,9 @@ k_rdf5(Rdf5Params P)
 static size_t r5_smem(int64_t N, int nb, int list_cap)
 {
     const size_t npad = ((size_t)N + 15) & ~(size_t)15;
-    return ((((size_t)(nb + 1) * 8) + 15) & ~(size_t)15) + npad * 16 + (size_t)R5_MAXJ * 8 + (((size_t)list_cap * 2 + 15) & ~(size_t)15) +
+    return ((((size_t)(nb + 1) * 8) + 15) & ~(size_t)15) + npad * 16 + (((size_t)list_cap * 2 + 15) & ~(size_t)15) +
            ((((size_t)R5_WARPS * nb * 4) + 15) & ~(size_t)15) + (size_t)R5_WARPS * R5_QCAP * 4 + (size_t)(2 * R5_MAXCELLS + 2) * 4 + 32 +
-           npad * 4 + (size_t)R5_MAXJ * 2 + npad + 16;
+           npad * 4 + (size_t)R5_MAXW * 2 + npad + 16;
 }
 
 // Returns PBK_EUNSUPPORTED when the shape belongs to another RDF kernel.
@@ -571,10 +623,10 @@ int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
     const double lut_nd = floor((range_hi * range_hi + 1.0) * ldexp(1.0, m)) + 516.0;
     if (lut_nd > (double)PBK_LUT_ENTRIES || lut_nd < 8.0) return PBK_EUNSUPPORTED;
     const int lut_n = (int)lut_nd;
-    float skin = 4.0f;
-    if (const char *ev = getenv("PBK_RDF_SKIN")) { const float v = (float)atof(ev); if (v > 0.0f && v < 100.0f) skin = v; }
-    // pair list: room for a leaflet of 256 lipids at 64 A^2 each within range_hi + skin, plus a third
-    const double rb = range_hi + skin + 0.05;
+    float ecap = 3.0f;
+    if (const char *ev = getenv("PBK_RDF_SKIN")) { const float v = (float)atof(ev); if (v > 0.0f && v < 100.0f) ecap = 0.5f * v; }
+    // pair list: room for a leaflet of 256 lipids at 64 A^2 each within range_hi + 2 ecap, plus a third
+    const double rb = range_hi + 2.0 * ecap + 0.05;
     double want_cap = 128.0 * 3.14159 * rb * rb / 64.0 * 1.33 + 256.0;
     if (want_cap > 32760.0) want_cap = 32760.0;
     int list_cap = ((int)want_cap + 7) & ~7;
@@ -594,7 +646,7 @@ int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
     int64_t chunk = (2 * F + ctas - 1) / ctas;
     if (chunk < 1) chunk = 1;
     if (chunk > 64) chunk = 64;
-    if (const char *ev = getenv("PBK_RDF_CHUNK")) { const int v = atoi(ev); if (v >= 1 && v <= 4096) chunk = v; }   // tests
+    if (const char *ev = getenv("PBK_RDF_CHUNK")) { const int v = atoi(ev); if (v >= 1 && v <= 1024) chunk = v; }   // tests
     const int64_t n_items = 2 * ((F + chunk - 1) / chunk);
     int64_t grid = ctas < n_items ? ctas : n_items;
     const unsigned slot = ctx->work_next++;
@@ -607,7 +659,7 @@ int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
     Rdf5Params P;
     P.com = com; P.labels = labels; P.type_code = type_code; P.box = box; P.F = F; P.N = N;
     P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
-    P.nb = n_bins; P.range_hi = range_hi; P.skin = skin; P.thr = thr; P.count = count;
+    P.nb = n_bins; P.range_hi = range_hi; P.ecap = ecap; P.thr = thr; P.count = count;
     P.frame_counts = frame_counts; P.lut_n = lut_n; P.lut_m = m; P.chunk = (int)chunk; P.list_cap = list_cap;
     P.work = work; P.lut = lut;
     kern<<<(unsigned)grid, R5_THREADS, smem, st>>>(P);
