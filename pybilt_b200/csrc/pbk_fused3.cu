@@ -85,25 +85,72 @@ struct __align__(16) ImgCol {
 
 #define IMG_THREADS 128
 #define IMG_UNR 8
+#define IMG_MAXF 512                // frames of box rows staged in shared memory per chunk
+
+// one frame of one column: same-image test of the 4 chains at once; the exact rule only when
+// one of them fails (rare)
+static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], const float he[4], const float Le[4],
+                                                 int acc[4], int &am, float &smin, int &bad)
+{
+    const float xv[4] = {v.x, v.y, v.z, v.w};
+    float sl[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) sl[e] = he[e] - fabsf(__fsub_rn(xv[e], pv[e]));
+    const float m = fminf(fminf(sl[0], sl[1]), fminf(sl[2], sl[3]));
+    if (!(m > 0.0f) || !(sl[0] > 0.0f) || !(sl[1] > 0.0f) || !(sl[2] > 0.0f) || !(sl[3] > 0.0f)) {   // (the second form catches NaN)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (!(sl[e] > 0.0f)) {                          // |jump| >= L/2 (or bad box)
+                float s2;
+                acc[e] += f3_shift_far(__fsub_rn(xv[e], pv[e]), Le[e], &s2, &bad);
+                am = max(am, abs(acc[e]));
+                smin = fminf(smin, s2);
+            } else {
+                smin = fminf(smin, sl[e]);
+            }
+        }
+    } else {
+        smin = fminf(smin, m);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) pv[e] = xv[e];
+}
 
 __global__ void __launch_bounds__(IMG_THREADS)
 k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float4 *__restrict__ u4,
        int first_frame, int64_t F, int C3q, int chunk, ImgCol *__restrict__ cols,
        float *__restrict__ chunk_box, int32_t *status)
 {
+    __shared__ float s_L[IMG_MAXF * 3];
+    __shared__ int s_red[3];                     // Lmax bits, dL bits, "box differs" flag
     const int kc = blockIdx.y;                   // column blocks vary fastest: neighbouring CTAs read one frame
     const int64_t f0 = (int64_t)kc * chunk, f1 = min(F, f0 + (int64_t)chunk);
-    if (threadIdx.x == 0 && blockIdx.x == 0) {   // largest box edge and largest frame-to-frame change
+    const int nf = (int)(f1 - f0);
+    const bool staged = nf <= IMG_MAXF;
+    if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
+    __syncthreads();
+    {   // box rows of the chunk: largest edge, largest frame-to-frame change, constant or not
         float Lmax = 0.f, dL = 0.f;
-        for (int64_t t = f0; t < f1; t++)
-            for (int k = 0; k < 3; k++) {
-                const float L = box[t * 3 + k];
-                Lmax = fmaxf(Lmax, L);
-                if (t > 0) dL = fmaxf(dL, fabsf(L - box[(t - 1) * 3 + k]));
-            }
-        chunk_box[kc * 2] = Lmax;
-        chunk_box[kc * 2 + 1] = dL;
+        int diff = 0;
+        for (int r = threadIdx.x; r < nf * 3; r += IMG_THREADS) {
+            const int64_t t = f0 + r / 3;
+            const int k = r % 3;
+            const float L = box[t * 3 + k];
+            if (staged) s_L[r] = L;
+            Lmax = fmaxf(Lmax, L);
+            if (t > 0) dL = fmaxf(dL, fabsf(L - box[(t - 1) * 3 + k]));
+            diff |= (L != box[f0 * 3 + k]);
+        }
+        atomicMax(&s_red[0], __float_as_int(Lmax));      // (non-negative floats order like their bits; NaN/negative
+        atomicMax(&s_red[1], __float_as_int(dL));        //  boxes are caught by the L > 0 tests below)
+        if (diff) atomicOr(&s_red[2], 1);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        chunk_box[kc * 2] = __int_as_float(s_red[0]);
+        chunk_box[kc * 2 + 1] = __int_as_float(s_red[1]);
+    }
+    const bool cbox = s_red[2] == 0;
     const int q4 = blockIdx.x * IMG_THREADS + threadIdx.x;
     if (q4 >= C3q) return;
     const int k0 = (4 * q4) % 3;                 // axis of the column's first chain
@@ -131,31 +178,45 @@ k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float
         const float4 p = x4[(f0 - 1) * C3q + q4];
         pv[0] = p.x; pv[1] = p.y; pv[2] = p.z; pv[3] = p.w;
     }
-    for (; t < f1; t += IMG_UNR) {
-        float4 v[IMG_UNR];
+    const float4 *ptr = x4 + t * C3q + q4;
+    if (cbox) {
+        // constant box over the chunk (NVT runs): half edges in registers
+        float he[4], Le[4];
 #pragma unroll
-        for (int j = 0; j < IMG_UNR; j++) v[j] = __ldg(x4 + min(t + j, f1 - 1) * C3q + q4);
+        for (int e = 0; e < 4; e++) {
+            Le[e] = box[f0 * 3 + (k0 + e) % 3];
+            he[e] = Le[e] > 0.0f ? Le[e] * 0.5f : -1.0f;    // bad box: every test fails
+        }
+        for (; t + IMG_UNR <= f1; t += IMG_UNR) {
+            float4 v[IMG_UNR];
 #pragma unroll
-        for (int j = 0; j < IMG_UNR; j++) {
-            if (t + j < f1) {
-                const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                // (the box rows are L1 hits: every thread of the CTA reads the same three words)
-                const float Lb0 = __ldg(box + (t + j) * 3), Lb1 = __ldg(box + (t + j) * 3 + 1), Lb2 = __ldg(box + (t + j) * 3 + 2);
+            for (int j = 0; j < IMG_UNR; j++) v[j] = __ldg(ptr + (int64_t)j * C3q);
+            ptr += (int64_t)IMG_UNR * C3q;
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int k = (k0 + e) % 3;
-                    const float L = k == 0 ? Lb0 : (k == 1 ? Lb1 : Lb2);
-                    const float d = __fsub_rn(xv[e], pv[e]);
-                    const float sl = L * 0.5f - fabsf(d);
-                    if (!(sl > 0.0f)) {                     // rare: |jump| >= L/2 (or bad box)
-                        float s2;
-                        acc[e] += f3_shift_far(d, L, &s2, &bad);
-                        am = max(am, abs(acc[e]));
-                        smin = fminf(smin, s2);
-                    } else {
-                        smin = fminf(smin, sl);
+            for (int j = 0; j < IMG_UNR; j++) img3_step(v[j], pv, he, Le, acc, am, smin, bad);
+        }
+        for (; t < f1; t++) {
+            const float4 v = __ldg(ptr);
+            ptr += C3q;
+            img3_step(v, pv, he, Le, acc, am, smin, bad);
+        }
+    } else {
+        for (; t < f1; t += IMG_UNR) {
+            float4 v[IMG_UNR];
+#pragma unroll
+            for (int j = 0; j < IMG_UNR; j++) v[j] = __ldg(ptr + (int64_t)min((int64_t)j, f1 - 1 - t) * C3q);
+            ptr += (int64_t)IMG_UNR * C3q;
+#pragma unroll
+            for (int j = 0; j < IMG_UNR; j++) {
+                if (t + j < f1) {
+                    float he[4], Le[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int k = (k0 + e) % 3;
+                        Le[e] = staged ? s_L[(int)(t + j - f0) * 3 + k] : __ldg(box + (t + j) * 3 + k);
+                        he[e] = Le[e] > 0.0f ? Le[e] * 0.5f : -1.0f;
                     }
-                    pv[e] = xv[e];
+                    img3_step(v[j], pv, he, Le, acc, am, smin, bad);
                 }
             }
         }

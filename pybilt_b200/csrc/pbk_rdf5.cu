@@ -27,8 +27,8 @@
 // from the original coordinates, in both orders when the minimum image wrapped ((L-|a'|)-|b'|
 // is not symmetric in rounding).  Thresholds on d^2 (thr[k] = min{t : sqrt_rn(t) >= edge_k})
 // replace the square root exactly as in pbk_rdf2.cu.
-// Frames that cannot join a run (member outside the box, leaflet without both groups, more than
-// 256 members, list overflow) are binned one by one by the direct sweep of k_rdf3.
+// Frames that cannot join a run (member outside the box, more than 256 members, list overflow)
+// are binned one by one from all pairs of members with the same fast path / exact path split.
 #include <stdlib.h>
 
 #include "pbk_common.cuh"
@@ -536,14 +536,25 @@ k_rdf5(Rdf5Params P)
                     for (int e0 = 0; e0 < n_list; e0 += 4 * R5_THREADS) {
                         int pp[4], qq[4];
                         bool amb[4];
+                        unsigned ent[4], ee[4];
+                        float d2[4];
+                        // four independent chains first (list entry -> coordinates -> d^2 -> table), then the counts
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const int k = e0 + R5_THREADS * j + tid;
-                            const bool act = k < n_list;
-                            const unsigned ent = act ? W.list[k] : 0u;
-                            pp[j] = ent & 0xFFu; qq[j] = ent >> 8;
-                            const float d2 = r5_d2(W.fxy[pp[j]], W.fxy[qq[j]], Fr.bxf, Fr.byf);
-                            const unsigned e = __ldg(P.lut + min(__float2int_rd(d2 * lut_scale), lut_last));
+                            ent[j] = k < n_list ? (unsigned)W.list[k] : 0u;        // (slot 0 with itself, never counted)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            pp[j] = ent[j] & 0xFFu; qq[j] = ent[j] >> 8;
+                            d2[j] = r5_d2(W.fxy[pp[j]], W.fxy[qq[j]], Fr.bxf, Fr.byf);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) ee[j] = __ldg(P.lut + min(__float2int_rd(d2[j] * lut_scale), lut_last));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const bool act = e0 + R5_THREADS * j + tid < n_list;
+                            const unsigned e = ee[j];
                             unsigned w = 2u;
                             if (!SAME) {
                                 const unsigned fpf = W.flag[pp[j]], fqf = W.flag[qq[j]];
