@@ -18,6 +18,7 @@ analyzer feeds it host views frame by frame.
 from __future__ import annotations
 
 import pickle
+import functools
 import warnings
 
 import numpy as np
@@ -293,7 +294,14 @@ class MSDProtocol(AnalysisProtocol):
 
 def msd_multi_schedule(n_frames, n_tau, n_sigma):
     """Replay of the block counters of MSDMultiProtocol.run_analysis
-    (analysis_protocols.py:833-888): returns ({block: (origin, end frame)}, n_blocks)."""
+    (analysis_protocols.py:833-888): returns ({block: (origin, end frame)}, n_blocks).
+    A pure function of its arguments, memoised (an O(n_frames) Python loop)."""
+    finished, n_blocks = _msd_multi_schedule(int(n_frames), int(n_tau), int(n_sigma))
+    return dict(finished), n_blocks
+
+
+@functools.lru_cache(maxsize=64)
+def _msd_multi_schedule(n_frames, n_tau, n_sigma):
     finished = {}
     origins, counters = [0], [0]
     tau_counter = sigma_counter = 0

@@ -274,7 +274,7 @@ class BilayerAnalyzer(object):
                            'area_per_bin': None},
             'vector_frame': {'dump': False, 'dump_path': "./", 'ref_atoms': None}}
         self.device = device
-        self.batch_frames = None    # frames per host->device batch (None: sized from scratch memory)
+        self.batch_frames = None    # frames per host->device batch (None: about 48 MB of positions)
         self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
         self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
         self._frame_loop_count = 0
@@ -499,6 +499,10 @@ class BilayerAnalyzer(object):
         # the engine (device buffers, summation plan, libpbk context) is reused across reset()
         # as long as nothing that shapes it changed
         batch_frames = self.batch_frames if shard is None else len(fr)
+        if batch_frames is None:
+            # ~48 MB of positions per host->device batch: the copy of batch k+1 overlaps the
+            # reduction of batch k, and only the last batch's kernels are exposed
+            batch_frames = int(max(64, min(len(fr), (48 << 20) // max(1, md.natoms * 12))))
         key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), n_rows, self.device,
                self.settings['norm'], int(lset['update_interval']), batch_frames)
         cached = getattr(self, '_engine_cache', None)

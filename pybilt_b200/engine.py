@@ -169,6 +169,7 @@ class LipidReductionEngine:
         self.fused_supported = True       # cleared when libpbk answers PBK_EUNSUPPORTED
         self.used_fused = False
         self._fused_scratch = None
+        self._rdf_tables = {}
 
     def _fused_scratch_for(self, nb: int) -> torch.Tensor:
         import ctypes
@@ -319,12 +320,19 @@ class LipidReductionEngine:
         sl = frames or slice(0, self.n_done)
         F = sl.stop - sl.start
         nb = len(edges) - 1
-        d_edges = edges_dev if edges_dev is not None else torch.as_tensor(
-            np.ascontiguousarray(edges, dtype=np.float64), device=d)
+        if edges_dev is None or (thr_dev is None and not dense):
+            # bin edges and their d^2 thresholds are pure functions of the edges: kept per engine
+            key = np.ascontiguousarray(edges, dtype=np.float64).tobytes()
+            cached = self._rdf_tables.get(key)
+            if cached is None:
+                cached = (torch.as_tensor(np.ascontiguousarray(edges, dtype=np.float64), device=d),
+                          torch.as_tensor(rdf_thresholds(edges), device=d))
+                self._rdf_tables[key] = cached
+            edges_dev = edges_dev if edges_dev is not None else cached[0]
+            thr_dev = thr_dev if thr_dev is not None else cached[1]
+        d_edges = edges_dev
         if dense:
             thr_dev = None
-        elif thr_dev is None:
-            thr_dev = torch.as_tensor(rdf_thresholds(edges), device=d)
         count = torch.zeros(nb, dtype=torch.int64, device=d)
         fc = torch.empty((F, 2, 3), dtype=torch.int32, device=d)
         self.ctx.call("pbk_rdf", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
@@ -332,7 +340,7 @@ class LipidReductionEngine:
                       int(lateral[0]), int(lateral[1]), int(type_a), int(type_b), int(leaflet_mask),
                       nb, float(edges[0]), float(edges[-1]), d_edges.data_ptr(), _ptr(thr_dev),
                       count.data_ptr(), fc.data_ptr(), self.stream_ptr())
-        self.launches += 1
+        self.launches += 2 if (self.N <= 512 and not dense) else 1      # (k_rdf5_lut + k_rdf5 for small systems)
         return count, fc
 
     def nnf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int, k: int,
