@@ -1,0 +1,755 @@
+// pbk_cells.cu -- minimum-image pair work for LARGE leaflets on global-memory cell lists:
+// the COM lateral RDF, the k nearest neighbours of every lipid (nearest-neighbour fraction,
+// the 24-neighbour table of the heuristic lipid grid).
+//
+// Same arithmetic contract as the small-system kernels (pbk_rdf2.cu / pbk_pairs.cu /
+// pbk_grid.cu), restating
+//   pybilt/common/distance_cutoff_clustering.py:27-71            (distance_euclidean_pbc)
+//   pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006      (COMLateralRDFProtocol)
+//   pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257      (NNFProtocol)
+//   pybilt/lipid_grid/lipid_grid_opt.py:435-468                  (_knn, 24 neighbours)
+// but for leaflets of 10^3 .. 10^6 lipids, where neither a leaflet in shared memory nor an
+// O(N^2) sweep is an option (BASELINE configs C3, C4, C5).
+//
+// Data flow per chunk of frames (scratch from the context's arena, ~33 B per lipid-frame):
+//   k_cl_count    every member lipid -> its (leaflet, cell); cell populations by atomics;
+//                 per-frame class counts (N_a, N_b, N_leaflet) and the out-of-box flag
+//   k_cl_scan     exclusive scan of the cell populations per frame
+//   k_cl_scatter  lipids into cell order: b' = x - box/2 as float64 (exact phase) and as
+//                 float32 (prefilter), original index, class flags, cell id
+//   k_rdf_cl      8 lanes per lipid sweep the forward half shell of cells (every unordered
+//                 pair once); float32 prefilter -> per-warp ring queue -> the reference's
+//                 float64 formulas; d^2 -> bin through the exact threshold table
+//   k_knn_cl      thread per lipid, rings of cells of growing radius until the k-th best
+//                 distance is inside the searched radius; exact float64 distances, ties in
+//                 ascending lipid index (Python's stable sort)
+// Cells assume wrapped coordinates (0 <= x <= L).  A frame with a member outside the box is
+// flagged and handed to the dense kernels, which evaluate the reference formula for any input.
+#include <math.h>
+#include <stdlib.h>
+
+#include "pbk_common.cuh"
+
+#define CL_THREADS 256
+#define CL_QCAP 128
+
+struct ClGeom {
+    int ncx, ncy, ncell, mx, my;
+    double iwx, iwy, wx, wy;
+};
+
+// cell geometry of a frame: a pure function of the box, so every kernel derives the same one.
+//   wmin > 0 : RDF, cell edge >= wmin (= 0.51 range_hi: the half shell reaches two cells)
+//   wmin <= 0: kNN, about `occ` lipids per cell
+__device__ __forceinline__ ClGeom cl_geom(double Lx, double Ly, double wmin, double range_hi,
+                                          double occ, int64_t N, int ncap)
+{
+    ClGeom g;
+    double w = wmin;
+    if (!(w > 0.0)) w = sqrt(occ * Lx * Ly / fmax(1.0, 0.5 * (double)N));
+    int ncx = 1, ncy = 1;
+    if (Lx > 0.0 && Ly > 0.0 && w > 0.0) {
+        const double fx = floor(Lx / w), fy = floor(Ly / w);
+        ncx = fx < (double)ncap ? (int)fx : ncap;
+        ncy = fy < (double)ncap ? (int)fy : ncap;
+        ncx = max(1, ncx);
+        ncy = max(1, ncy);
+    }
+    g.mx = g.my = 0;
+    if (wmin > 0.0) {
+        g.mx = (int)floor((range_hi + 1e-6) / (Lx / ncx)) + 1;
+        g.my = (int)floor((range_hi + 1e-6) / (Ly / ncy)) + 1;
+        if (2 * g.mx + 1 > ncx) { ncx = 1; g.mx = 0; }
+        if (2 * g.my + 1 > ncy || g.my > 7) { ncy = 1; g.my = 0; }
+    }
+    g.ncx = ncx; g.ncy = ncy; g.ncell = ncx * ncy;
+    g.wx = Lx / ncx; g.wy = Ly / ncy;
+    g.iwx = ncx / Lx; g.iwy = ncy / Ly;
+    return g;
+}
+
+struct ClParams {
+    const double *com;
+    const uint8_t *labels;
+    const int32_t *type_code;
+    const float *box;
+    int64_t F, N;
+    int lat0, lat1, ta, tb, leaflet_mask;
+    int members_all;                // 1: every leaflet member is listed; 0: only type A or B
+    double wmin, range_hi, occ;
+    int ncap;
+    int64_t cstride;                // 2*ncap*ncap + 1 ints of cell data per frame
+    int *cell_fill;                 // [F][cstride] populations, then running fill pointers
+    int *cell_start;                // [F][cstride]
+    int *fcounts;                   // [F][8]: (N_a, N_b, N_leaf) upper, lower; out-of-box; listed
+    double *sx, *sy;                // [F][N] b' = x - box/2 in cell order
+    float2 *sf;                     // [F][N] float32 copy
+    int *sidx;                      // [F][N] original lipid index
+    int *scell;                     // [F][N] leaf*ncell + cell
+    unsigned char *sflag;           // [F][N] bit0 type A, bit1 type B
+    int32_t *frame_counts;          // RDF output [F][2][3] (may be NULL)
+};
+
+struct ClFrame {
+    double Lx, Ly, hx, hy;
+    float bxf, byf;
+    ClGeom g;
+};
+
+__device__ __forceinline__ ClFrame cl_frame(const ClParams &P, int64_t f)
+{
+    ClFrame fr;
+    fr.bxf = P.box[f * 3 + P.lat0];
+    fr.byf = P.box[f * 3 + P.lat1];
+    const float cxf = fr.bxf * 0.5f, cyf = fr.byf * 0.5f;
+    fr.Lx = (double)fr.bxf; fr.Ly = (double)fr.byf; fr.hx = (double)cxf; fr.hy = (double)cyf;
+    fr.g = cl_geom(fr.Lx, fr.Ly, P.wmin, P.range_hi, P.occ, P.N, P.ncap);
+    return fr;
+}
+
+// (leaflet row, flags, listed?) of lipid i; leaflet row 0 = upper (label 1), 1 = lower
+__device__ __forceinline__ bool cl_classify(const ClParams &P, const uint8_t *lab, int64_t i, int *leaf,
+                                            unsigned *flag)
+{
+    const int t = (P.ta == -1 && P.tb == -1) ? 0 : P.type_code[i];
+    const bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
+    *leaf = lab[i] ? 0 : 1;
+    *flag = (a ? 1u : 0u) | (b ? 2u : 0u);
+    return P.members_all || a || b;
+}
+
+__device__ __forceinline__ int cl_cell(const ClFrame &fr, double x, double y)
+{
+    int cx = (int)(x * fr.g.iwx), cy = (int)(y * fr.g.iwy);
+    cx = max(0, min(fr.g.ncx - 1, cx));
+    cy = max(0, min(fr.g.ncy - 1, cy));
+    return cy * fr.g.ncx + cx;
+}
+
+__global__ void __launch_bounds__(CL_THREADS)
+k_cl_count(ClParams P)
+{
+    const int64_t f = blockIdx.y;
+    const ClFrame fr = cl_frame(P, f);
+    const double *cf = P.com + f * P.N * 3;
+    const uint8_t *lab = P.labels + f * P.N;
+    int *fill = P.cell_fill + f * P.cstride;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (i < P.N) {
+        int leaf;
+        unsigned flag;
+        const bool listed = cl_classify(P, lab, i, &leaf, &flag);
+        c[leaf * 3 + 0] = flag & 1u;
+        c[leaf * 3 + 1] = (flag >> 1) & 1u;
+        c[leaf * 3 + 2] = 1;
+        if (listed) {
+            const double x = cf[i * 3 + P.lat0], y = cf[i * 3 + P.lat1];
+            c[6] = !(x >= 0.0 && x <= fr.Lx && y >= 0.0 && y <= fr.Ly);
+            atomicAdd(&fill[leaf * fr.g.ncell + cl_cell(fr, x, y)], 1);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        const int v = pbk_warp_sum(c[q]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.fcounts[f * 8 + q], v);
+    }
+}
+
+// one CTA per frame: exclusive scan of the 2*ncell populations; fill pointers = starts
+__global__ void __launch_bounds__(1024)
+k_cl_scan(ClParams P)
+{
+    __shared__ int s_warp[32];
+    const int64_t f = blockIdx.x;
+    const ClFrame fr = cl_frame(P, f);
+    const int n = 2 * fr.g.ncell;
+    int *fill = P.cell_fill + f * P.cstride;
+    int *start = P.cell_start + f * P.cstride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int c = lo; c < hi; c++) s += fill[c];
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp[lane], t = v;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+        s_warp[lane] = t - v;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + incl - s;
+    for (int c = lo; c < hi; c++) {
+        const int v = fill[c];
+        start[c] = run;
+        fill[c] = run;
+        run += v;
+    }
+    if (hi == n && lo < n || (n == 0 && tid == 0)) start[n] = run;
+    if (tid == 0) {
+        if (P.frame_counts && !P.fcounts[f * 8 + 6]) {
+            for (int l = 0; l < 2; l++) {
+                const bool sel = (P.leaflet_mask >> l) & 1;
+                const int ca = P.fcounts[f * 8 + l * 3], cb = P.fcounts[f * 8 + l * 3 + 1];
+                const bool on = sel && ca > 0 && cb > 0;
+                P.frame_counts[f * 6 + l * 3 + 0] = on ? ca : 0;
+                P.frame_counts[f * 6 + l * 3 + 1] = on ? cb : 0;
+                P.frame_counts[f * 6 + l * 3 + 2] = sel ? P.fcounts[f * 8 + l * 3 + 2] : 0;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CL_THREADS)
+k_cl_scatter(ClParams P)
+{
+    const int64_t f = blockIdx.y;
+    if (P.fcounts[f * 8 + 6]) return;            // out-of-box frame: dense kernels take it
+    const ClFrame fr = cl_frame(P, f);
+    const double *cf = P.com + f * P.N * 3;
+    const uint8_t *lab = P.labels + f * P.N;
+    int *fill = P.cell_fill + f * P.cstride;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    int leaf;
+    unsigned flag;
+    if (!cl_classify(P, lab, i, &leaf, &flag)) return;
+    const double x = cf[i * 3 + P.lat0], y = cf[i * 3 + P.lat1];
+    const int cell = leaf * fr.g.ncell + cl_cell(fr, x, y);
+    const int64_t slot = f * P.N + atomicAdd(&fill[cell], 1);
+    const double bx = __dsub_rn(x, fr.hx), by = __dsub_rn(y, fr.hy);
+    P.sx[slot] = bx;
+    P.sy[slot] = by;
+    P.sf[slot] = make_float2((float)bx, (float)by);
+    P.sidx[slot] = (int)i;
+    P.scell[slot] = cell;
+    P.sflag[slot] = (unsigned char)flag;
+}
+
+// ---------------------------------------------------------------------------------------
+// RDF sweep
+// ---------------------------------------------------------------------------------------
+struct ClRdf {
+    int nb, hist_copies, lut_n, lut_c0;
+    double lut_scale;
+    const double *thr;
+    unsigned long long *count;
+    int *work;                      // dynamic work counter
+    int chunk;                      // slots per work item
+};
+
+__device__ __forceinline__ int cl_bin(double d2, const double *s_thr, const unsigned char *s_lut,
+                                      const ClRdf &R)
+{
+    if (!(d2 >= s_thr[0]) || !(d2 < s_thr[R.nb])) return -1;
+    int c = __double2int_rd(d2 * R.lut_scale) - R.lut_c0;
+    c = max(0, min(R.lut_n - 1, c));
+    int k = s_lut[c];
+    k += (d2 >= s_thr[k + 1]) ? 1 : 0;
+    return k;
+}
+
+template <bool SAME>
+__device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double *gy,
+                                         const unsigned char *gflag, const double *s_thr,
+                                         const unsigned char *s_lut, unsigned *myhist, const ClRdf &R,
+                                         double Lx, double Ly, double hx, double hy)
+{
+    const int p = (int)e.x, q = (int)e.y;
+    int w1 = 1, w2 = 1;
+    if (!SAME) {
+        const unsigned fp = gflag[p], fq = gflag[q];
+        w1 = (fp & 1u) && (fq & 2u);            // ordered p -> q
+        w2 = (fq & 1u) && (fp & 2u);            // ordered q -> p
+        if (!(w1 | w2)) return;
+    }
+    const double apx = gx[p], apy = gy[p], bqx = gx[q], bqy = gy[q];
+    double dx = __dsub_rn(apx, bqx), dy = __dsub_rn(apy, bqy);
+    const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
+    if (!(wrx | wry)) {
+        const int k = cl_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, s_lut, R);
+        if (k >= 0) atomicAdd(&myhist[k], (unsigned)(w1 + w2));
+        return;
+    }
+    double dx2 = dx, dy2 = dy;                  // the q -> p evaluation
+    if (wrx) {
+        dx = __dsub_rn(__dsub_rn(Lx, fabs(apx)), fabs(bqx));
+        dx2 = __dsub_rn(__dsub_rn(Lx, fabs(bqx)), fabs(apx));
+    }
+    if (wry) {
+        dy = __dsub_rn(__dsub_rn(Ly, fabs(apy)), fabs(bqy));
+        dy2 = __dsub_rn(__dsub_rn(Ly, fabs(bqy)), fabs(apy));
+    }
+    const double d2a = fma(dy, dy, __dmul_rn(dx, dx));
+    const double d2b = fma(dy2, dy2, __dmul_rn(dx2, dx2));
+    const int ka = cl_bin(d2a, s_thr, s_lut, R);
+    int kb = ka;
+    if (d2b != d2a) kb = cl_bin(d2b, s_thr, s_lut, R);
+    if (ka == kb) {
+        if (ka >= 0) atomicAdd(&myhist[ka], (unsigned)(w1 + w2));
+    } else {
+        if (w1 && ka >= 0) atomicAdd(&myhist[ka], 1u);
+        if (w2 && kb >= 0) atomicAdd(&myhist[kb], 1u);
+    }
+}
+
+template <bool SAME>
+__global__ void __launch_bounds__(CL_THREADS)
+k_rdf_cl(ClParams P, ClRdf R)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int nb = R.nb;
+    double *s_thr = reinterpret_cast<double *>(smem_raw);                              // nb+1
+    uint2 *s_queue = reinterpret_cast<uint2 *>(s_thr + (nb + 1));                      // warps*QCAP
+    unsigned *s_hist = reinterpret_cast<unsigned *>(s_queue + (CL_THREADS / 32) * CL_QCAP);   // copies*nb
+    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_hist + (size_t)R.hist_copies * nb);
+    __shared__ int s_item;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q <= nb; q += blockDim.x) s_thr[q] = R.thr[q];
+    for (int q = tid; q < R.hist_copies * nb; q += blockDim.x) s_hist[q] = 0u;
+    for (int c = tid; c < R.lut_n; c += blockDim.x) {
+        const double t = (double)(c + R.lut_c0) / R.lut_scale;
+        int k = 0;
+        while (k < nb - 1 && t >= R.thr[k + 1]) k++;
+        s_lut[c] = (unsigned char)k;
+    }
+    unsigned *myhist = s_hist + (size_t)(warp % R.hist_copies) * nb;
+    uint2 *myq = s_queue + warp * CL_QCAP;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int sub = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
+    const unsigned gshift = (unsigned)(lane & ~7);
+    const int64_t per_frame = (P.N + R.chunk - 1) / R.chunk;
+    const int64_t n_items = P.F * per_frame;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(R.work, 1);
+        __syncthreads();
+        const int64_t item = s_item;
+        __syncthreads();
+        if (item >= n_items) break;
+        const int64_t f = item / per_frame;
+        const int p_lo = (int)(item - f * per_frame) * R.chunk;
+        const int *fc = P.fcounts + f * 8;
+        if (fc[6]) continue;                                     // out-of-box frame
+        const ClFrame fr = cl_frame(P, f);
+        const ClGeom &g = fr.g;
+        const int *cstart = P.cell_start + f * P.cstride;
+        const int n_u = cstart[2 * g.ncell];
+        if (p_lo >= n_u) continue;
+        const int p_hi = min(n_u, p_lo + R.chunk);
+        bool on[2];
+        for (int l = 0; l < 2; l++) on[l] = ((P.leaflet_mask >> l) & 1) && fc[l * 3] > 0 && fc[l * 3 + 1] > 0;
+        const double *gx = P.sx + f * P.N, *gy = P.sy + f * P.N;
+        const float2 *gf = P.sf + f * P.N;
+        const int *gcell = P.scell + f * P.N;
+        const unsigned char *gflag = P.sflag + f * P.N;
+        const float bxf = fr.bxf, byf = fr.byf;
+        const float marg = 0.01f + 4e-7f * fmaxf(bxf, byf);
+        const float cut = (float)P.range_hi + marg;
+        const float cut2_f = cut * cut * 1.0001f;
+        const int mx = g.mx, my = g.my, ncx = g.ncx, ncy = g.ncy;
+
+        int qhead = 0, qtail = 0;
+        for (int p0 = p_lo; p0 < p_hi; p0 += ngrp) {
+            const int p = p0 + grp;
+            bool pact = p < p_hi;
+            float fpx = 0.f, fpy = 0.f;
+            int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
+            if (pact) {
+                int pc = gcell[p];
+                const int leaf = pc >= g.ncell;
+                pact = on[leaf];
+                if (pact) {
+                    const float2 fp = gf[p];
+                    fpx = fp.x; fpy = fp.y;
+                    if (sub <= my) {
+                        const int cbase = leaf * g.ncell;
+                        pc -= cbase;
+                        const int pcy = pc / ncx, pcx = pc - pcy * ncx;
+                        int cy = pcy + sub; if (cy >= ncy) cy -= ncy;
+                        const int row = cbase + cy * ncx;
+                        int xlo = (sub == 0) ? pcx : pcx - mx, xhi = pcx + mx;
+                        if (xlo < 0) {
+                            b2 = cstart[row + xlo + ncx]; n2 = cstart[row + ncx] - b2;
+                            xlo = 0;
+                        }
+                        if (xhi >= ncx) {
+                            b2 = cstart[row]; n2 = cstart[row + xhi - ncx + 1] - b2;
+                            xhi = ncx - 1;
+                        }
+                        b1 = cstart[row + xlo]; n1 = cstart[row + xhi + 1] - b1;
+                        if (sub == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }
+                    }
+                }
+            }
+            for (int oy = 0; oy <= my; oy++) {
+                const int rb1 = __shfl_sync(0xffffffffu, b1, gshift + oy);
+                const int rn1 = __shfl_sync(0xffffffffu, n1, gshift + oy);
+                const int rb2 = __shfl_sync(0xffffffffu, b2, gshift + oy);
+                const int rn2 = __shfl_sync(0xffffffffu, n2, gshift + oy);
+                const int ntot = rn1 + rn2;
+                int nmax = ntot;
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
+                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+                for (int t0 = 0; t0 < nmax; t0 += 8) {
+                    const int t = t0 + sub;
+                    bool hit = false;
+                    int q = 0;
+                    if (t < ntot) {
+                        q = t < rn1 ? rb1 + t : rb2 + (t - rn1);
+                        const float2 fq = gf[q];
+                        float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
+                        dx = fminf(dx, bxf - dx);
+                        dy = fminf(dy, byf - dy);
+                        hit = fmaf(dy, dy, dx * dx) < cut2_f;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) myq[(qtail + __popc(m & lt_mask)) & (CL_QCAP - 1)] = make_uint2((unsigned)p, (unsigned)q);
+                    qtail += __popc(m);
+                    if (qtail - qhead >= 32) {
+                        __syncwarp();
+                        cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, s_lut,
+                                       myhist, R, fr.Lx, fr.Ly, fr.hx, fr.hy);
+                        qhead += 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < qtail - qhead)
+            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, s_lut, myhist, R,
+                           fr.Lx, fr.Ly, fr.hx, fr.hy);
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int q = tid; q < nb; q += blockDim.x) {
+        unsigned long long t = 0;
+        for (int c = 0; c < R.hist_copies; c++) t += s_hist[(size_t)c * nb + q];
+        if (t) atomicAdd(&R.count[q], t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k nearest leaflet members of every lipid
+// ---------------------------------------------------------------------------------------
+struct ClKnn {
+    int k;
+    int32_t *n_b;                   // NNF: [F][N] count of type-B lipids among the k nearest (-1: not a reference lipid)
+    int32_t *knn;                   // grid: [F][N][24] neighbour indices, -1 padded
+};
+
+// GRID: the reference's _knn evaluates each unordered pair once as dist(lower index, higher
+// index) (lipid_grid_opt.py:452-459); NNF: dist(reference lipid, other) (:2204).
+template <int KMAX, bool GRID>
+__global__ void __launch_bounds__(128)
+k_knn_cl(ClParams P, ClKnn K)
+{
+    const int64_t f = blockIdx.y;
+    const int *fc = P.fcounts + f * 8;
+    if (fc[6]) return;                                           // out-of-box frame
+    const ClFrame fr = cl_frame(P, f);
+    const ClGeom &g = fr.g;
+    const int *cstart = P.cell_start + f * P.cstride;
+    const int n_u = cstart[2 * g.ncell];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_u) return;
+    const double *gx = P.sx + f * P.N, *gy = P.sy + f * P.N;
+    const int *gidx = P.sidx + f * P.N;
+    const int i = gidx[p];
+    int pc = P.scell[f * P.N + p];
+    const int leaf = pc >= g.ncell;
+    const int cbase = leaf * g.ncell;
+    pc -= cbase;
+    if (!GRID) {
+        const bool on = ((P.leaflet_mask >> leaf) & 1) && fc[leaf * 3] > 0 && fc[leaf * 3 + 1] > 0;
+        if (!on || !(P.sflag[f * P.N + p] & 1u)) {
+            K.n_b[f * P.N + i] = -1;
+            return;
+        }
+    }
+    const int k = K.k;
+    const double apx = gx[p], apy = gy[p];
+    const int ncx = g.ncx, ncy = g.ncy;
+    const int pcy = pc / ncx, pcx = pc - pcy * ncx;
+    const int lox = (ncx - 1) / 2, hix = ncx / 2, loy = (ncy - 1) / 2, hiy = ncy / 2;
+    const int Rmax = max(hix, hiy);
+    double best[KMAX];
+    int bj[KMAX];
+    int nbest = 0;
+
+    auto visit = [&](int s0, int s1) {
+        for (int q = s0; q < s1; q++) {
+            if (q == p) continue;
+            const int j = gidx[q];
+            const double qx = gx[q], qy = gy[q];
+            const double d2 = (!GRID || j > i) ? pbk_pbc_dist2(apx, apy, qx, qy, fr.Lx, fr.Ly, fr.hx, fr.hy)
+                                               : pbk_pbc_dist2(qx, qy, apx, apy, fr.Lx, fr.Ly, fr.hx, fr.hy);
+            const double r = sqrt(d2);
+            if (nbest == k) {
+                const double rl = best[k - 1];
+                if (!(r < rl || (r == rl && j < bj[k - 1]))) continue;
+            }
+            int pos = nbest < k ? nbest : k - 1;
+            const int last = pos;
+            while (pos > 0 && (best[pos - 1] > r || (best[pos - 1] == r && bj[pos - 1] > j))) pos--;
+            for (int t = last; t > pos; t--) { best[t] = best[t - 1]; bj[t] = bj[t - 1]; }
+            best[pos] = r;
+            bj[pos] = j;
+            if (nbest < k) nbest++;
+        }
+    };
+    // cells [c0, c1] (offsets from pcx, c1 - c0 + 1 <= ncx) of row `row`
+    auto visit_row = [&](int row, int c0, int c1) {
+        int a = pcx + c0, b = pcx + c1;
+        if (a < 0) {
+            if (b < 0) { a += ncx; b += ncx; }
+            else { visit(cstart[row + a + ncx], cstart[row + ncx]); a = 0; }
+        }
+        if (b >= ncx) {
+            if (a >= ncx) { a -= ncx; b -= ncx; }
+            else { visit(cstart[row], cstart[row + b - ncx + 1]); b = ncx - 1; }
+        }
+        visit(cstart[row + a], cstart[row + b + 1]);
+    };
+
+    for (int R = 0; R <= Rmax; R++) {
+        const int dy0 = -min(R, loy), dy1 = min(R, hiy);
+        for (int dy = dy0; dy <= dy1; dy++) {
+            int cy = pcy + dy;
+            if (cy < 0) cy += ncy;
+            if (cy >= ncy) cy -= ncy;
+            const int row = cbase + cy * ncx;
+            if (dy == -R || dy == R) {
+                visit_row(row, -min(R, lox), min(R, hix));
+            } else {
+                if (R <= lox) visit_row(row, -R, -R);
+                if (R <= hix) visit_row(row, R, R);
+            }
+        }
+        if (nbest == k) {
+            const double bx = (R >= hix) ? 1e300 : R * g.wx, by = (R >= hiy) ? 1e300 : R * g.wy;
+            const double bound = fmin(bx, by);
+            if (best[k - 1] < bound * (1.0 - 1e-9) - 1e-9) break;
+        }
+    }
+    if (GRID) {
+        int32_t *o = K.knn + (f * P.N + i) * 24;
+        for (int t = 0; t < 24; t++) o[t] = t < nbest ? bj[t] : -1;
+    } else {
+        int c = 0;
+        for (int t = 0; t < nbest; t++) {
+            const int tj = P.type_code[bj[t]];
+            c += (P.tb == -1 || tj == P.tb) ? 1 : 0;
+        }
+        K.n_b[f * P.N + i] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct ClPlan {
+    int ncap;
+    int64_t cstride, per_frame_bytes, Fc;
+};
+
+static ClPlan cl_plan(int64_t F, int64_t N)
+{
+    ClPlan pl;
+    double s = sqrt(0.5 * (double)N) + 2.0;
+    if (s > 1024.0) s = 1024.0;
+    pl.ncap = (int)s;
+    pl.cstride = 2 * (int64_t)pl.ncap * pl.ncap + 1;
+    pl.per_frame_bytes = 2 * pl.cstride * 4 + 64 + N * 40;      // 8+8+8+4+4+1 rounded up for alignment
+    const int64_t budget = (int64_t)768 << 20;
+    pl.Fc = budget / pl.per_frame_bytes;
+    if (pl.Fc < 1) pl.Fc = 1;
+    if (pl.Fc > F) pl.Fc = F;
+    if (pl.Fc > 65535) pl.Fc = 65535;                            // gridDim.y
+    return pl;
+}
+
+static bool cl_carve(pbk_ctx *ctx, const ClPlan &pl, int64_t N, ClParams &P)
+{
+    const int64_t Fc = pl.Fc;
+    auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+    const int64_t b_cells = up(Fc * pl.cstride * 4), b_fc = up(Fc * 8 * 4), b_d = up(Fc * N * 8),
+                  b_i = up(Fc * N * 4), b_c = up(Fc * N);
+    const int64_t total = 2 * b_cells + b_fc + 3 * b_d + 2 * b_i + b_c;
+    unsigned char *a = (unsigned char *)pbk_arena(ctx, (size_t)total);
+    if (!a) return false;
+    P.cell_fill = (int *)a; a += b_cells;
+    P.fcounts = (int *)a; a += b_fc;                             // zeroed together with cell_fill
+    P.cell_start = (int *)a; a += b_cells;
+    P.sx = (double *)a; a += b_d;
+    P.sy = (double *)a; a += b_d;
+    P.sf = (float2 *)a; a += b_d;
+    P.sidx = (int *)a; a += b_i;
+    P.scell = (int *)a; a += b_i;
+    P.sflag = a;
+    return true;
+}
+
+// zero the counters, count, scan, scatter for frames [0, P.F) of the chunk
+static int cl_build(pbk_ctx *ctx, const ClPlan &pl, ClParams &P, cudaStream_t st)
+{
+    const size_t zero_bytes = (size_t)((unsigned char *)P.cell_start - (unsigned char *)P.cell_fill);
+    cudaError_t e = cudaMemsetAsync(P.cell_fill, 0, zero_bytes, st);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "cell list memset", e);
+    dim3 g((unsigned)((P.N + CL_THREADS - 1) / CL_THREADS), (unsigned)P.F);
+    k_cl_count<<<g, CL_THREADS, 0, st>>>(P);
+    PBK_CHECK_LAUNCH(ctx, "k_cl_count");
+    k_cl_scan<<<(unsigned)P.F, 1024, 0, st>>>(P);
+    PBK_CHECK_LAUNCH(ctx, "k_cl_scan");
+    k_cl_scatter<<<g, CL_THREADS, 0, st>>>(P);
+    PBK_CHECK_LAUNCH(ctx, "k_cl_scatter");
+    return PBK_OK;
+}
+
+// defined in pbk_pairs.cu / pbk_grid.cu: dense kernels restricted to flagged frames
+int pbk_rdf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
+                          const double *edges, unsigned long long *count, int32_t *frame_counts,
+                          const int *frame_flag, int flag_stride, cudaStream_t stream);
+int pbk_nnf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int k, int32_t *n_b, const int *frame_flag, int flag_stride,
+                          cudaStream_t stream);
+int pbk_grid_knn_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const float *box,
+                               int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, const int *frame_flag,
+                               int flag_stride, cudaStream_t stream);
+
+int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                  const double *thr, unsigned long long *count, int32_t *frame_counts, cudaStream_t st)
+{
+    if (!thr || !ctx->work || n_bins > 255 || range_lo < 0 || N > 0x7fffff00LL) return PBK_EUNSUPPORTED;
+    // d^2 look-up table (as in pbk_rdf2.cu): cells of width 2^-m no wider than the narrowest
+    // threshold spacing
+    const double w = (range_hi - range_lo) / n_bins;
+    const double lo = range_lo > 0 ? range_lo : 0.0;
+    const double min_gap = 0.999 * ((lo + w) * (lo + w) - lo * lo);
+    int m = 0;
+    while (ldexp(1.0, -m) > min_gap && m < 40) m++;
+    while (m > -40 && ldexp(1.0, -(m - 1)) <= min_gap) m--;
+    const double scale = ldexp(1.0, m);
+    const double c0d = floor(lo * lo * scale) - 1.0, c1d = floor(range_hi * range_hi * scale) + 2.0;
+    const double lut_nd = c1d - c0d + 1.0;
+    if (!(lut_nd <= 32768.0) || !(fabs(c0d) < 1e9)) return PBK_EUNSUPPORTED;
+    ClRdf R;
+    R.nb = n_bins; R.lut_n = (int)lut_nd; R.lut_c0 = (int)c0d; R.lut_scale = scale; R.thr = thr;
+    R.count = count; R.chunk = 256;
+    R.hist_copies = CL_THREADS / 32;
+    auto smem_for = [&](int c) {
+        return (size_t)(n_bins + 1) * 8 + (size_t)(CL_THREADS / 32) * CL_QCAP * 8 + (size_t)c * n_bins * 4 +
+               (size_t)R.lut_n + 16;
+    };
+    while (R.hist_copies > 1 && smem_for(R.hist_copies) > 48 * 1024) R.hist_copies >>= 1;
+    const size_t smem = smem_for(R.hist_copies);
+    const bool same = (type_a == type_b);
+    auto kern = same ? k_rdf_cl<true> : k_rdf_cl<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_rdf_cl smem attribute", e);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CL_THREADS, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+
+    ClPlan pl = cl_plan(F, N);
+    ClParams P;
+    P.N = N; P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
+    P.members_all = 0; P.wmin = 0.51 * range_hi + 1e-6; P.range_hi = range_hi; P.occ = 0.0;
+    P.ncap = pl.ncap; P.cstride = pl.cstride; P.type_code = type_code;
+    if (!cl_carve(ctx, pl, N, P)) return pbk_fail(ctx, PBK_ECUDA, "pbk_rdf: scratch arena");
+    for (int64_t f0 = 0; f0 < F; f0 += pl.Fc) {
+        const int64_t Fc = (F - f0 < pl.Fc) ? F - f0 : pl.Fc;
+        P.F = Fc;
+        P.com = com + f0 * N * 3; P.labels = labels + f0 * N; P.box = box + f0 * 3;
+        P.frame_counts = frame_counts + f0 * 6;
+        int rc = cl_build(ctx, pl, P, st);
+        if (rc) return rc;
+        R.work = ctx->work + (ctx->work_next++ % PBK_WORK_SLOTS);
+        e = cudaMemsetAsync(R.work, 0, sizeof(int), st);
+        if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_rdf_cl work counter", e);
+        const int64_t items = Fc * ((N + R.chunk - 1) / R.chunk);
+        int64_t grid = (int64_t)ctx->sm_count * per_sm;
+        if (grid > items) grid = items;
+        kern<<<(unsigned)grid, CL_THREADS, smem, st>>>(P, R);
+        PBK_CHECK_LAUNCH(ctx, "k_rdf_cl");
+        rc = pbk_rdf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, type_a, type_b,
+                                   leaflet_mask, n_bins, range_lo, range_hi, edges, count, P.frame_counts,
+                                   P.fcounts + 6, 8, st);
+        if (rc) return rc;
+    }
+    return PBK_OK;
+}
+
+template <bool GRID>
+static int cl_knn_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                      const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                      int leaflet_mask, int k, int32_t *n_b, int32_t *knn, cudaStream_t st)
+{
+    if (N > 0x7fffff00LL) return PBK_EUNSUPPORTED;
+    ClPlan pl = cl_plan(F, N);
+    ClParams P;
+    P.N = N; P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
+    P.members_all = 1; P.wmin = 0.0; P.range_hi = 0.0; P.occ = 4.0;
+    P.ncap = pl.ncap; P.cstride = pl.cstride; P.type_code = type_code; P.frame_counts = nullptr;
+    if (!cl_carve(ctx, pl, N, P)) return pbk_fail(ctx, PBK_ECUDA, "pbk knn: scratch arena");
+    ClKnn K;
+    K.k = k;
+    for (int64_t f0 = 0; f0 < F; f0 += pl.Fc) {
+        const int64_t Fc = (F - f0 < pl.Fc) ? F - f0 : pl.Fc;
+        P.F = Fc;
+        P.com = com + f0 * N * 3; P.labels = labels + f0 * N; P.box = box + f0 * 3;
+        K.n_b = n_b ? n_b + f0 * N : nullptr;
+        K.knn = knn ? knn + f0 * N * 24 : nullptr;
+        int rc = cl_build(ctx, pl, P, st);
+        if (rc) return rc;
+        dim3 g((unsigned)((N + 127) / 128), (unsigned)Fc);
+        if (GRID) k_knn_cl<24, true><<<g, 128, 0, st>>>(P, K);
+        else if (k <= 8) k_knn_cl<8, false><<<g, 128, 0, st>>>(P, K);
+        else if (k <= 24) k_knn_cl<24, false><<<g, 128, 0, st>>>(P, K);
+        else k_knn_cl<64, false><<<g, 128, 0, st>>>(P, K);
+        PBK_CHECK_LAUNCH(ctx, "k_knn_cl");
+        if (GRID)
+            rc = pbk_grid_knn_dense_flagged(ctx, P.com, P.labels, P.box, Fc, N, lat0, lat1, K.knn,
+                                            P.fcounts + 6, 8, st);
+        else
+            rc = pbk_nnf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, type_a,
+                                       type_b, leaflet_mask, k, K.n_b, P.fcounts + 6, 8, st);
+        if (rc) return rc;
+    }
+    return PBK_OK;
+}
+
+int pbk_nnf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int k, int32_t *n_b, cudaStream_t st)
+{
+    return cl_knn_run<false>(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b, leaflet_mask,
+                             k, n_b, nullptr, st);
+}
+
+int pbk_grid_knn_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code_or_null,
+                       const float *box, int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, cudaStream_t st)
+{
+    (void)type_code_or_null;
+    return cl_knn_run<true>(ctx, com, labels, nullptr, box, F, N, lat0, lat1, -1, -1, 3, 24, nullptr, knn, st);
+}
+
+// which systems take the cell-list kernels: N above the entry point's threshold, or every
+// system when PBK_FORCE_CELLS is set (tests), none when PBK_NO_CELLS is set.
+bool pbk_use_cells(int64_t N, int64_t threshold)
+{
+    if (getenv("PBK_NO_CELLS")) return false;
+    if (getenv("PBK_FORCE_CELLS")) return true;
+    return N > threshold;
+}

@@ -20,7 +20,13 @@ struct pbk_ctx {
     int *work;                  // device: PBK_WORK_SLOTS work counters of persistent kernels (may be NULL)
     unsigned work_next;
     unsigned short *lut;        // device: PBK_LUT_SLOTS d^2 -> bin tables of PBK_LUT_ENTRIES entries (may be NULL)
+    void *arena;                // device scratch of the cell-list kernels (pbk_cells.cu), grown on demand
+    size_t arena_bytes;
 };
+
+// scratch owned by the context; grows with cudaMalloc (which synchronises the device, so no kernel
+// still reads the block that is freed).  NULL when the allocation fails.
+void *pbk_arena(pbk_ctx *ctx, size_t bytes);
 
 #define PBK_WARP 32
 

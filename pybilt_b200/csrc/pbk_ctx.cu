@@ -34,6 +34,8 @@ extern "C" int pbk_ctx_create(int device, pbk_ctx **out)
     c->work = nullptr;
     c->work_next = 0;
     c->lut = nullptr;
+    c->arena = nullptr;
+    c->arena_bytes = 0;
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != device) cudaSetDevice(device);
@@ -50,9 +52,27 @@ extern "C" void pbk_ctx_destroy(pbk_ctx *ctx)
     if (!ctx) return;
     if (ctx->work) cudaFree(ctx->work);
     if (ctx->lut) cudaFree(ctx->lut);
+    if (ctx->arena) cudaFree(ctx->arena);
     delete ctx;
 }
 
 extern "C" const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 
 extern "C" int pbk_sm_count(const pbk_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+void *pbk_arena(pbk_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    if (bytes <= ctx->arena_bytes) return ctx->arena;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != ctx->device) cudaSetDevice(ctx->device);
+    if (ctx->arena) { cudaDeviceSynchronize(); cudaFree(ctx->arena); }
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) == cudaSuccess) { ctx->arena = p; ctx->arena_bytes = bytes; }
+    else cudaGetLastError();
+    if (cur != ctx->device && cur >= 0) cudaSetDevice(cur);
+    return ctx->arena;
+}

@@ -34,8 +34,10 @@ __device__ __forceinline__ double pbk_cell_dist(double cx, double cy, double xi,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_grid_knn(const double *__restrict__ com, const uint8_t *__restrict__ labels,
-           const float *__restrict__ box, int64_t N, int lat0, int lat1, int32_t *__restrict__ knn)
+           const float *__restrict__ box, int64_t N, int lat0, int lat1, int32_t *__restrict__ knn,
+           const int *__restrict__ frame_flag, int flag_stride)
 {
+    if (frame_flag && !frame_flag[(int64_t)blockIdx.x * flag_stride]) return;   // only flagged frames
     __shared__ double s_px[GRID_TJ], s_py[GRID_TJ];
     __shared__ unsigned char s_lab[GRID_TJ];
     int64_t f = blockIdx.x;
@@ -200,6 +202,21 @@ k_grid_assign(const double *__restrict__ com, const double *__restrict__ com_unw
     for (int c = threadIdx.x; c < nx * ny; c += blockDim.x) gz[c] = cu[(int64_t)gi[c] * 3 + norm];
 }
 
+int pbk_grid_knn_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const float *box,
+                               int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, const int *frame_flag,
+                               int flag_stride, cudaStream_t stream)
+{
+    dim3 g((unsigned)F, (unsigned)((N + 255) / 256));
+    k_grid_knn<<<g, 256, 0, stream>>>(com, labels, box, N, lat0, lat1, knn, frame_flag, flag_stride);
+    PBK_CHECK_LAUNCH(ctx, "k_grid_knn");
+    return PBK_OK;
+}
+
+// defined in pbk_cells.cu: cell-list search for large systems
+int pbk_grid_knn_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code_or_null,
+                       const float *box, int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, cudaStream_t st);
+bool pbk_use_cells(int64_t N, int64_t threshold);
+
 extern "C" int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com_unwrap,
                               const uint8_t *labels, const float *box, int64_t F, int64_t N,
                               int lat0, int lat1, int norm, int nx, int ny, int mode,
@@ -212,9 +229,12 @@ extern "C" int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com
     if (F == 0) return PBK_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 1) {
-        dim3 g((unsigned)F, (unsigned)((N + 255) / 256));
-        k_grid_knn<<<g, 256, 0, st>>>(com, labels, box, N, lat0, lat1, knn_scratch);
-        PBK_CHECK_LAUNCH(ctx, "k_grid_knn");
+        int rc = PBK_EUNSUPPORTED;
+        if (pbk_use_cells(N, 1024))
+            rc = pbk_grid_knn_cells(ctx, com, labels, nullptr, box, F, N, lat0, lat1, knn_scratch, st);
+        if (rc == PBK_EUNSUPPORTED)
+            rc = pbk_grid_knn_dense_flagged(ctx, com, labels, box, F, N, lat0, lat1, knn_scratch, nullptr, 0, st);
+        if (rc) return rc;
     }
     dim3 g2((unsigned)F, 2);
     k_grid_assign<<<g2, 128, 0, st>>>(com, com_unwrap, labels, box, N, lat0, lat1, norm, nx, ny,

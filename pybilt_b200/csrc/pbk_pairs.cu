@@ -47,8 +47,10 @@ k_rdf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
       const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N, int lat0,
       int lat1, int ta, int tb, int leaflet_mask, int nb, double lo, double hi,
       const double *__restrict__ edges, unsigned long long *__restrict__ count,
-      int32_t *__restrict__ frame_counts, int hist_copies)
+      int32_t *__restrict__ frame_counts, int hist_copies, const int *__restrict__ frame_flag,
+      int flag_stride)
 {
+    if (frame_flag && !frame_flag[(int64_t)blockIdx.x * flag_stride]) return;   // only flagged frames
     extern __shared__ unsigned char smem_raw[];
     double *s_edges = reinterpret_cast<double *>(smem_raw);                 // nb+1
     double *s_px = s_edges + (nb + 1);                                      // PAIR_TJ
@@ -122,11 +124,11 @@ k_rdf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
 }
 
 // dense O(N^2) fallback of pbk_rdf (pbk_rdf2.cu) for leaflets that do not fit in shared memory
-int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
-                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
-                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
-                  const double *edges, unsigned long long *count, int32_t *frame_counts,
-                  cudaStream_t stream)
+int pbk_rdf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
+                          const double *edges, unsigned long long *count, int32_t *frame_counts,
+                          const int *frame_flag, int flag_stride, cudaStream_t stream)
 {
     int warps = PAIR_THREADS / 32;
     int copies = warps;
@@ -141,9 +143,20 @@ int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
     dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
     k_rdf<<<grid, PAIR_THREADS, smem, (cudaStream_t)stream>>>(
         com, labels, type_code, box, N, lat0, lat1, type_a, type_b, leaflet_mask, n_bins, range_lo,
-        range_hi, edges, count, frame_counts, copies);
+        range_hi, edges, count, frame_counts, copies, frame_flag, flag_stride);
     PBK_CHECK_LAUNCH(ctx, "k_rdf");
     return PBK_OK;
+}
+
+int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
+                  const double *edges, unsigned long long *count, int32_t *frame_counts,
+                  cudaStream_t stream)
+{
+    return pbk_rdf_dense_flagged(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
+                                 leaflet_mask, n_bins, range_lo, range_hi, edges, count, frame_counts,
+                                 nullptr, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -157,8 +170,10 @@ int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
 __global__ void __launch_bounds__(PAIR_THREADS)
 k_nnf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
       const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N, int lat0,
-      int lat1, int ta, int tb, int leaflet_mask, int k, int32_t *__restrict__ n_b)
+      int lat1, int ta, int tb, int leaflet_mask, int k, int32_t *__restrict__ n_b,
+      const int *__restrict__ frame_flag, int flag_stride)
 {
+    if (frame_flag && !frame_flag[(int64_t)blockIdx.x * flag_stride]) return;   // only flagged frames
     __shared__ double s_px[PAIR_TJ], s_py[PAIR_TJ];
     __shared__ unsigned char s_cls[PAIR_TJ];
     __shared__ int sh_counts[6];
@@ -242,6 +257,24 @@ __global__ void k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t 
     frac[f] = m;
 }
 
+int pbk_nnf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int k, int32_t *n_b, const int *frame_flag, int flag_stride,
+                          cudaStream_t stream)
+{
+    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
+    k_nnf<<<grid, PAIR_THREADS, 0, stream>>>(com, labels, type_code, box, N, lat0, lat1, type_a, type_b,
+                                             leaflet_mask, k, n_b, frame_flag, flag_stride);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf");
+    return PBK_OK;
+}
+
+// defined in pbk_cells.cu: cell-list search for large systems
+int pbk_nnf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int k, int32_t *n_b, cudaStream_t st);
+bool pbk_use_cells(int64_t N, int64_t threshold);
+
 extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
                        const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
                        int lat1, int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b,
@@ -251,10 +284,14 @@ extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         k < 1 || k > NNF_KMAX || (leaflet_mask & ~3) || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_nnf: bad argument (1 <= k <= 64)");
     if (F == 0) return PBK_OK;
-    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
-    k_nnf<<<grid, PAIR_THREADS, 0, (cudaStream_t)stream>>>(com, labels, type_code, box, N, lat0,
-                                                           lat1, type_a, type_b, leaflet_mask, k, n_b);
-    PBK_CHECK_LAUNCH(ctx, "k_nnf");
+    int rc = PBK_EUNSUPPORTED;
+    if (pbk_use_cells(N, 1024))
+        rc = pbk_nnf_cells(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b, leaflet_mask,
+                           k, n_b, (cudaStream_t)stream);
+    if (rc == PBK_EUNSUPPORTED)
+        rc = pbk_nnf_dense_flagged(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
+                                   leaflet_mask, k, n_b, nullptr, 0, (cudaStream_t)stream);
+    if (rc) return rc;
     k_nnf_frame_mean<<<(unsigned)((F + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N,
                                                                                   k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");

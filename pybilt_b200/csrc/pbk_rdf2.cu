@@ -342,6 +342,13 @@ int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
                     int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *thr,
                     unsigned long long *count, int32_t *frame_counts, cudaStream_t st);
 
+// defined in pbk_cells.cu: global-memory cell lists for large leaflets
+int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                  const double *thr, unsigned long long *count, int32_t *frame_counts, cudaStream_t st);
+bool pbk_use_cells(int64_t N, int64_t threshold);
+
 extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
                        const int32_t *type_code, const float *box, int64_t F, int64_t N, int lat0,
                        int lat1, int type_a, int type_b, int leaflet_mask, int32_t n_bins,
@@ -354,6 +361,11 @@ extern "C" int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf: bad argument");
     if (F == 0) return PBK_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (thr && pbk_use_cells(N, 4096)) {
+        const int rc = pbk_rdf_cells(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
+                                     leaflet_mask, n_bins, range_lo, range_hi, edges, thr, count, frame_counts, st);
+        if (rc != PBK_EUNSUPPORTED) return rc;
+    }
     {
         const int rc = pbk_rdf5_launch(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
                                        leaflet_mask, n_bins, range_lo, range_hi, thr, count, frame_counts, st);

@@ -1,0 +1,107 @@
+"""Cell-list kernels for large leaflets (pbk_cells.cu: k_rdf_cl, k_knn_cl) against the golden
+fixtures / oracle port (forced onto the small parity cases) and against the dense kernels
+(themselves pinned to the port) on mid-size systems where the port would take minutes."""
+import numpy as np
+import pytest
+import torch
+
+from pybilt_b200 import synthetic as syn
+from tests import cases
+from tests import test_gpu_engine as tge
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def force_cells(monkeypatch):
+    monkeypatch.setenv("PBK_FORCE_CELLS", "1")
+
+
+@pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
+def test_cells_rdf_matches_port(name, force_cells):
+    tge.test_rdf_counts_match_port(name)
+
+
+@pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
+def test_cells_nnf_matches_port(name, force_cells):
+    tge.test_nnf_counts_match_port(name)
+
+
+@pytest.mark.parametrize("name,nx", [("tiny_all", 8), ("grid_dense", 16), ("grid_sparse", 8), ("c3_small", 32)])
+def test_cells_grid_knn_matches_port(name, nx, force_cells):
+    tge.test_lipid_grid_matches_port(name, nx, "opt")
+
+
+def test_cells_rdf_out_of_box_frames_go_dense(force_cells):
+    tge.test_rdf_out_of_box_coordinates_follow_reference_formula()
+
+
+def _mid_engine(n_lipids, n_frames, seed, npt=1e-3, jitter=None):
+    from pybilt_b200 import engine as eng
+    kw = dict(seed=seed, npt=npt)
+    if jitter is not None:
+        kw["lattice_jitter"] = jitter
+    spec = syn.BilayerSpec(n_lipids, cases.CG3, **kw)
+    top, traj = syn.generate(spec, n_frames)
+    layout = eng.build_bead_layout(top.masses, top.names, top.resindex, top.resnames, top.resids)
+    e = eng.LipidReductionEngine(top.masses, layout, n_frames)
+    e.push(torch.from_numpy(traj.positions).cuda(),
+           torch.from_numpy(np.ascontiguousarray(traj.dimensions[:, :3])).cuda())
+    e.check_status()
+    names, codes = tge.type_codes(layout.types)
+    return e, names, torch.from_numpy(codes).cuda()
+
+
+@pytest.mark.parametrize("n_lipids,seed,jitter", [(2048, 21, None), (6000, 22, 0.49), (10000, 23, None)])
+def test_cells_match_dense_kernels_mid_size(n_lipids, seed, jitter, monkeypatch):
+    e, names, codes = _mid_engine(n_lipids, 3, seed, jitter=jitter)
+    settings = [(-1, -1, 3, 25, 0.0, 25.0), (0, 0, 1, 80, 0.0, 40.0), (0, 1, 3, 30, 2.0, 32.0),
+                (-1, 2, 2, 25, 0.0, 25.0), (1, -1, 3, 200, 0.0, 60.0)]
+    knn_k = [(0, 1, 3, 5), (1, 0, 1, 6), (2, 2, 2, 30)]
+
+    def run_all():
+        out = []
+        for (ca, cb, mask, nb, lo, hi) in settings:
+            edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
+            cnt, fc = e.rdf(codes, ca, cb, mask, edges)
+            out += [cnt.cpu().numpy(), fc.cpu().numpy()]
+        for (ia, ib, mask, k) in knn_k:
+            n_b, frac = e.nnf(codes, ia, ib, mask, k)
+            out += [n_b.cpu().numpy(), frac.cpu().numpy()]
+        gi, gz, knn = e.lipid_grid(64, 64, "opt")
+        out += [knn.cpu().numpy(), gi.cpu().numpy(), gz.cpu().numpy()]
+        return out
+
+    monkeypatch.setenv("PBK_FORCE_CELLS", "1")
+    got = run_all()
+    monkeypatch.delenv("PBK_FORCE_CELLS")
+    monkeypatch.setenv("PBK_NO_CELLS", "1")
+    want = run_all()
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), (n_lipids, i)
+    assert got[0].sum() > 0
+
+
+def test_cells_out_of_box_frames_nnf_and_grid(monkeypatch):
+    e, names, codes = _mid_engine(2048, 3, 31)
+    L = float(e.box[0, 0])
+    com = e.com.clone()
+    com[1, ::7, 0] += L
+    com[2, ::5, 1] -= 0.75 * L
+    e.com.copy_(com)
+
+    def run_all():
+        n_b, frac = e.nnf(codes, 0, 1, 3, 5)
+        gi, gz, knn = e.lipid_grid(32, 32, "opt")
+        edges = np.histogram([-1], bins=25, range=[0.0, 25.0])[1]
+        cnt, fc = e.rdf(codes, -1, -1, 3, edges)
+        return [n_b.cpu().numpy(), frac.cpu().numpy(), knn.cpu().numpy(), gi.cpu().numpy(),
+                cnt.cpu().numpy(), fc.cpu().numpy()]
+
+    monkeypatch.setenv("PBK_FORCE_CELLS", "1")
+    got = run_all()
+    monkeypatch.delenv("PBK_FORCE_CELLS")
+    monkeypatch.setenv("PBK_NO_CELLS", "1")
+    want = run_all()
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), i
