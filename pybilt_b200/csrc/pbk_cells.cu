@@ -78,7 +78,7 @@ struct ClParams {
     int members_all;                // 1: every leaflet member is listed; 0: only type A or B
     double wmin, range_hi, occ;
     int ncap;
-    int64_t cstride;                // 2*ncap*ncap + 1 ints of cell data per frame
+    int64_t cstride;                // >= 2*ncap*ncap + 1 ints of cell data per frame, multiple of 4
     int *cell_fill;                 // [F][cstride] populations, then running fill pointers
     int *cell_start;                // [F][cstride]
     int *fcounts;                   // [F][8]: (N_a, N_b, N_leaf) upper, lower; out-of-box; listed
@@ -149,47 +149,73 @@ k_cl_count(ClParams P)
             atomicAdd(&fill[leaf * fr.g.ncell + cl_cell(fr, x, y)], 1);
         }
     }
+    // class counts: warp sums -> shared -> one global atomic per counter and CTA
+    __shared__ int s_c[7];
+    if (threadIdx.x < 7) s_c[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < 7; q++) {
         const int v = pbk_warp_sum(c[q]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.fcounts[f * 8 + q], v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[q], v);
     }
+    __syncthreads();
+    if (threadIdx.x < 7 && s_c[threadIdx.x]) atomicAdd(&P.fcounts[f * 8 + threadIdx.x], s_c[threadIdx.x]);
 }
 
-// one CTA per frame: exclusive scan of the 2*ncell populations; fill pointers = starts
+// one CTA per frame: exclusive scan of the 2*ncell populations (tiles of 4096 entries, 128-bit
+// loads; the per-frame stride is a multiple of 4 ints); fill pointers = starts
 __global__ void __launch_bounds__(1024)
 k_cl_scan(ClParams P)
 {
     __shared__ int s_warp[32];
+    __shared__ int s_carry;
     const int64_t f = blockIdx.x;
     const ClFrame fr = cl_frame(P, f);
     const int n = 2 * fr.g.ncell;
     int *fill = P.cell_fill + f * P.cstride;
     int *start = P.cell_start + f * P.cstride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int s = 0;
-    for (int c = lo; c < hi; c++) s += fill[c];
-    int incl = s;
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    if (lane == 31) s_warp[warp] = incl;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (warp == 0) {
-        int v = s_warp[lane], t = v;
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
-        s_warp[lane] = t - v;
+    for (int base = 0; base < n; base += 4096) {
+        const int c0 = base + tid * 4;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (c0 + 3 < n) v = *reinterpret_cast<const int4 *>(fill + c0);
+        else {
+            if (c0 < n) v.x = fill[c0];
+            if (c0 + 1 < n) v.y = fill[c0 + 1];
+            if (c0 + 2 < n) v.z = fill[c0 + 2];
+        }
+        const int s = v.x + v.y + v.z + v.w;
+        int incl = s;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_warp[lane];
+            int t = w;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            s_warp[lane] = t - w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int4 e;
+        e.x = carry + s_warp[warp] + incl - s;
+        e.y = e.x + v.x; e.z = e.y + v.y; e.w = e.z + v.z;
+        if (c0 + 3 < n) {
+            *reinterpret_cast<int4 *>(start + c0) = e;
+            *reinterpret_cast<int4 *>(fill + c0) = e;
+        } else {
+            if (c0 < n) { start[c0] = e.x; fill[c0] = e.x; }
+            if (c0 + 1 < n) { start[c0 + 1] = e.y; fill[c0 + 1] = e.y; }
+            if (c0 + 2 < n) { start[c0 + 2] = e.z; fill[c0 + 2] = e.z; }
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = e.w + v.w;
+        __syncthreads();
     }
-    __syncthreads();
-    int run = s_warp[warp] + incl - s;
-    for (int c = lo; c < hi; c++) {
-        const int v = fill[c];
-        start[c] = run;
-        fill[c] = run;
-        run += v;
-    }
-    if (hi == n && lo < n || (n == 0 && tid == 0)) start[n] = run;
     if (tid == 0) {
+        start[n] = s_carry;
         if (P.frame_counts && !P.fcounts[f * 8 + 6]) {
             for (int l = 0; l < 2; l++) {
                 const bool sel = (P.leaflet_mask >> l) & 1;
@@ -233,30 +259,30 @@ k_cl_scatter(ClParams P)
 // RDF sweep
 // ---------------------------------------------------------------------------------------
 struct ClRdf {
-    int nb, hist_copies, lut_n, lut_c0;
-    double lut_scale;
+    int nb, hist_copies, lut_n, lut_m;
     const double *thr;
+    const unsigned short *lut;      // d^2 cell -> bin | distance to the nearest threshold << 8 (k_rdf5_lut)
     unsigned long long *count;
     int *work;                      // dynamic work counter
     int chunk;                      // slots per work item
 };
 
-__device__ __forceinline__ int cl_bin(double d2, const double *s_thr, const unsigned char *s_lut,
-                                      const ClRdf &R)
+__device__ __forceinline__ int cl_bin(double d2, const double *s_thr, int nb)
 {
-    if (!(d2 >= s_thr[0]) || !(d2 < s_thr[R.nb])) return -1;
-    int c = __double2int_rd(d2 * R.lut_scale) - R.lut_c0;
-    c = max(0, min(R.lut_n - 1, c));
-    int k = s_lut[c];
-    k += (d2 >= s_thr[k + 1]) ? 1 : 0;
-    return k;
+    if (!(d2 >= s_thr[0]) || !(d2 < s_thr[nb])) return -1;
+    int lo = 0, hi = nb;            // invariant: thr[lo] <= d2 < thr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (d2 >= s_thr[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
+// the reference's float64 arithmetic for the unordered pair of sorted slots (p, q)
 template <bool SAME>
 __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double *gy,
-                                         const unsigned char *gflag, const double *s_thr,
-                                         const unsigned char *s_lut, unsigned *myhist, const ClRdf &R,
-                                         double Lx, double Ly, double hx, double hy)
+                                         const unsigned char *gflag, const double *s_thr, unsigned *myhist,
+                                         int nb, double Lx, double Ly, double hx, double hy)
 {
     const int p = (int)e.x, q = (int)e.y;
     int w1 = 1, w2 = 1;
@@ -270,7 +296,7 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
     double dx = __dsub_rn(apx, bqx), dy = __dsub_rn(apy, bqy);
     const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
     if (!(wrx | wry)) {
-        const int k = cl_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, s_lut, R);
+        const int k = cl_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, nb);
         if (k >= 0) atomicAdd(&myhist[k], (unsigned)(w1 + w2));
         return;
     }
@@ -285,9 +311,9 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
     }
     const double d2a = fma(dy, dy, __dmul_rn(dx, dx));
     const double d2b = fma(dy2, dy2, __dmul_rn(dx2, dx2));
-    const int ka = cl_bin(d2a, s_thr, s_lut, R);
+    const int ka = cl_bin(d2a, s_thr, nb);
     int kb = ka;
-    if (d2b != d2a) kb = cl_bin(d2b, s_thr, s_lut, R);
+    if (d2b != d2a) kb = cl_bin(d2b, s_thr, nb);
     if (ka == kb) {
         if (ka >= 0) atomicAdd(&myhist[ka], (unsigned)(w1 + w2));
     } else {
@@ -296,6 +322,10 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
     }
 }
 
+// A candidate's bin comes from its float32 minimum-image d^2 through the 16-bit table; the
+// table entry also says how many table cells separate the d^2 cell from the nearest bin
+// threshold, and a pair closer to a threshold than the float32 rounding bound (`tolc` cells,
+// see DESIGN.md "Why the RDF fast path is exact") goes to the exact float64 queue instead.
 template <bool SAME>
 __global__ void __launch_bounds__(CL_THREADS)
 k_rdf_cl(ClParams P, ClRdf R)
@@ -305,18 +335,13 @@ k_rdf_cl(ClParams P, ClRdf R)
     double *s_thr = reinterpret_cast<double *>(smem_raw);                              // nb+1
     uint2 *s_queue = reinterpret_cast<uint2 *>(s_thr + (nb + 1));                      // warps*QCAP
     unsigned *s_hist = reinterpret_cast<unsigned *>(s_queue + (CL_THREADS / 32) * CL_QCAP);   // copies*nb
-    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_hist + (size_t)R.hist_copies * nb);
+    unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_hist + (size_t)R.hist_copies * nb);
     __shared__ int s_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int q = tid; q <= nb; q += blockDim.x) s_thr[q] = R.thr[q];
     for (int q = tid; q < R.hist_copies * nb; q += blockDim.x) s_hist[q] = 0u;
-    for (int c = tid; c < R.lut_n; c += blockDim.x) {
-        const double t = (double)(c + R.lut_c0) / R.lut_scale;
-        int k = 0;
-        while (k < nb - 1 && t >= R.thr[k + 1]) k++;
-        s_lut[c] = (unsigned char)k;
-    }
+    for (int c = tid; c < R.lut_n; c += blockDim.x) s_lut[c] = R.lut[c];
     unsigned *myhist = s_hist + (size_t)(warp % R.hist_copies) * nb;
     uint2 *myq = s_queue + warp * CL_QCAP;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -324,6 +349,8 @@ k_rdf_cl(ClParams P, ClRdf R)
     const unsigned gshift = (unsigned)(lane & ~7);
     const int64_t per_frame = (P.N + R.chunk - 1) / R.chunk;
     const int64_t n_items = P.F * per_frame;
+    const float lut_scale = ldexpf(1.0f, R.lut_m);
+    const int lut_last = R.lut_n - 1;
     __syncthreads();
 
     for (;;) {
@@ -349,9 +376,14 @@ k_rdf_cl(ClParams P, ClRdf R)
         const int *gcell = P.scell + f * P.N;
         const unsigned char *gflag = P.sflag + f * P.N;
         const float bxf = fr.bxf, byf = fr.byf;
-        const float marg = 0.01f + 4e-7f * fmaxf(bxf, byf);
-        const float cut = (float)P.range_hi + marg;
-        const float cut2_f = cut * cut * 1.0001f;
+        // rounding bound of the float32 d^2 near the thresholds, in table cells (+1 of slack):
+        // |d2_f32 - d2_exact| <= 2^-23 (r+1) (8 L + 4 (r+1)), r = range_hi, L = larger box edge
+        const float Lm = fmaxf(bxf, byf), rr = (float)P.range_hi + 1.0f;
+        const float tol = 1.1920929e-7f * rr * (8.0f * Lm + 4.0f * rr);
+        const int tolc = (int)ceilf(tol * lut_scale) + 1;
+        const bool all_exact = !(tol * lut_scale < 200.0f);
+        const float cut = rr + 0.5f * tol;
+        const float cut2_f = cut * cut;                          // all_exact frames: plain cut-off
         const int mx = g.mx, my = g.my, ncx = g.ncx, ncy = g.ncy;
 
         int qhead = 0, qtail = 0;
@@ -359,6 +391,7 @@ k_rdf_cl(ClParams P, ClRdf R)
             const int p = p0 + grp;
             bool pact = p < p_hi;
             float fpx = 0.f, fpy = 0.f;
+            unsigned pflag = 3u;
             int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
             if (pact) {
                 int pc = gcell[p];
@@ -367,6 +400,7 @@ k_rdf_cl(ClParams P, ClRdf R)
                 if (pact) {
                     const float2 fp = gf[p];
                     fpx = fp.x; fpy = fp.y;
+                    if (!SAME) pflag = gflag[p];
                     if (sub <= my) {
                         const int cbase = leaf * g.ncell;
                         pc -= cbase;
@@ -406,25 +440,45 @@ k_rdf_cl(ClParams P, ClRdf R)
                         float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
                         dx = fminf(dx, bxf - dx);
                         dy = fminf(dy, byf - dy);
-                        hit = fmaf(dy, dy, dx * dx) < cut2_f;
+                        const float d2 = fmaf(dy, dy, dx * dx);
+                        if (all_exact) {
+                            hit = d2 < cut2_f;
+                        } else {
+                            const unsigned e = s_lut[min(__float2int_rd(d2 * lut_scale), lut_last)];
+                            const unsigned bin = e & 0xFFu;
+                            if ((int)(e >> 8) >= tolc) {
+                                if (bin != 0xFFu) {
+                                    unsigned w = 2u;
+                                    if (!SAME) {
+                                        const unsigned fqf = gflag[q];
+                                        w = ((pflag & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((pflag >> 1) & 1u));
+                                    }
+                                    if (w) atomicAdd(&myhist[bin], w);
+                                }
+                            } else {
+                                hit = true;
+                            }
+                        }
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit) myq[(qtail + __popc(m & lt_mask)) & (CL_QCAP - 1)] = make_uint2((unsigned)p, (unsigned)q);
-                    qtail += __popc(m);
-                    if (qtail - qhead >= 32) {
-                        __syncwarp();
-                        cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, s_lut,
-                                       myhist, R, fr.Lx, fr.Ly, fr.hx, fr.hy);
-                        qhead += 32;
-                        __syncwarp();
+                    if (m) {
+                        if (hit) myq[(qtail + __popc(m & lt_mask)) & (CL_QCAP - 1)] = make_uint2((unsigned)p, (unsigned)q);
+                        qtail += __popc(m);
+                        if (qtail - qhead >= 32) {
+                            __syncwarp();
+                            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
+                                           fr.Lx, fr.Ly, fr.hx, fr.hy);
+                            qhead += 32;
+                            __syncwarp();
+                        }
                     }
                 }
             }
         }
         __syncwarp();
         if (lane < qtail - qhead)
-            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, s_lut, myhist, R,
-                           fr.Lx, fr.Ly, fr.hx, fr.hy);
+            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb, fr.Lx, fr.Ly,
+                           fr.hx, fr.hy);
         __syncwarp();
     }
     __syncthreads();
@@ -565,7 +619,7 @@ static ClPlan cl_plan(int64_t F, int64_t N)
     double s = sqrt(0.5 * (double)N) + 2.0;
     if (s > 1024.0) s = 1024.0;
     pl.ncap = (int)s;
-    pl.cstride = 2 * (int64_t)pl.ncap * pl.ncap + 1;
+    pl.cstride = (2 * (int64_t)pl.ncap * pl.ncap + 1 + 3) & ~(int64_t)3;     // 16-byte aligned frames
     pl.per_frame_bytes = 2 * pl.cstride * 4 + 64 + N * 40;      // 8+8+8+4+4+1 rounded up for alignment
     const int64_t budget = (int64_t)768 << 20;
     pl.Fc = budget / pl.per_frame_bytes;
@@ -612,6 +666,11 @@ static int cl_build(pbk_ctx *ctx, const ClPlan &pl, ClParams &P, cudaStream_t st
     return PBK_OK;
 }
 
+// defined in pbk_rdf5.cu: the 16-bit d^2 -> (bin, distance to threshold) table
+bool pbk_rdf_lut16_shape(int32_t n_bins, double range_lo, double range_hi, int *m_out, int *lut_n_out);
+int pbk_rdf_lut16_build(pbk_ctx *ctx, const double *thr, int nb, int lut_n, int lut_m, unsigned short *lut,
+                        cudaStream_t st);
+
 // defined in pbk_pairs.cu / pbk_grid.cu: dense kernels restricted to flagged frames
 int pbk_rdf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
                           const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
@@ -632,25 +691,21 @@ int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
                   const double *thr, unsigned long long *count, int32_t *frame_counts, cudaStream_t st)
 {
     if (!thr || !ctx->work || n_bins > 255 || range_lo < 0 || N > 0x7fffff00LL) return PBK_EUNSUPPORTED;
-    // d^2 look-up table (as in pbk_rdf2.cu): cells of width 2^-m no wider than the narrowest
-    // threshold spacing
-    const double w = (range_hi - range_lo) / n_bins;
-    const double lo = range_lo > 0 ? range_lo : 0.0;
-    const double min_gap = 0.999 * ((lo + w) * (lo + w) - lo * lo);
-    int m = 0;
-    while (ldexp(1.0, -m) > min_gap && m < 40) m++;
-    while (m > -40 && ldexp(1.0, -(m - 1)) <= min_gap) m--;
-    const double scale = ldexp(1.0, m);
-    const double c0d = floor(lo * lo * scale) - 1.0, c1d = floor(range_hi * range_hi * scale) + 2.0;
-    const double lut_nd = c1d - c0d + 1.0;
-    if (!(lut_nd <= 32768.0) || !(fabs(c0d) < 1e9)) return PBK_EUNSUPPORTED;
+    int m = 0, lut_n = 0;
+    if (!ctx->lut || n_bins > 254 || !pbk_rdf_lut16_shape(n_bins, range_lo, range_hi, &m, &lut_n)) return PBK_EUNSUPPORTED;
+    const unsigned lslot = ctx->work_next++;
+    unsigned short *lut = ctx->lut + (size_t)(lslot % PBK_LUT_SLOTS) * PBK_LUT_ENTRIES;
+    {
+        const int rc = pbk_rdf_lut16_build(ctx, thr, n_bins, lut_n, m, lut, st);
+        if (rc) return rc;
+    }
     ClRdf R;
-    R.nb = n_bins; R.lut_n = (int)lut_nd; R.lut_c0 = (int)c0d; R.lut_scale = scale; R.thr = thr;
+    R.nb = n_bins; R.lut_n = lut_n; R.lut_m = m; R.thr = thr; R.lut = lut;
     R.count = count; R.chunk = 256;
     R.hist_copies = CL_THREADS / 32;
     auto smem_for = [&](int c) {
         return (size_t)(n_bins + 1) * 8 + (size_t)(CL_THREADS / 32) * CL_QCAP * 8 + (size_t)c * n_bins * 4 +
-               (size_t)R.lut_n + 16;
+               (size_t)lut_n * 2 + 16;
     };
     while (R.hist_copies > 1 && smem_for(R.hist_copies) > 48 * 1024) R.hist_copies >>= 1;
     const size_t smem = smem_for(R.hist_copies);

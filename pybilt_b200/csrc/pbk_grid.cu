@@ -244,18 +244,18 @@ extern "C" int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com
 }
 
 // ---------------------------------------------------------------------------------------
-// K9  reductions.  One CTA per frame: cells per lipid, thickness mean / population std,
-// then thread 0 replays the reference's Welford pushes (float32 areas, first push keeps
-// float32; pybilt/common/running_stats.py:34-52) over upper then lower members.
+// K9  reductions.  k_grid_reduce, one CTA per frame: cells per lipid, thickness mean /
+// population std.  k_grid_apl, one thread per (frame, Welford state): replays the reference's
+// pushes (float32 areas, first push keeps float32; pybilt/common/running_stats.py:34-52) over
+// upper then lower members -- state 0 is the composite mean, state 1+t the lipids of type t.
+// The recurrence is sequential by nature; one thread per state keeps it in registers and
+// lets all frames' replays run side by side.
 // ---------------------------------------------------------------------------------------
 #define GRID_MAX_TYPES 16
 
 __global__ void __launch_bounds__(256)
 k_grid_reduce(const int32_t *__restrict__ grid_idx, const double *__restrict__ grid_z,
-              const uint8_t *__restrict__ labels, const int32_t *__restrict__ type_code,
-              const float *__restrict__ box, int64_t N, int lat0, int lat1, int nx, int ny,
-              int n_types, int32_t *__restrict__ cells, double *__restrict__ thickness,
-              double *__restrict__ apl)
+              int64_t N, int nx, int ny, int32_t *__restrict__ cells, double *__restrict__ thickness)
 {
     __shared__ double red[32];
     int64_t f = blockIdx.x;
@@ -263,7 +263,6 @@ k_grid_reduce(const int32_t *__restrict__ grid_idx, const double *__restrict__ g
     const int32_t *gu = grid_idx + f * 2 * nc, *gl = gu + nc;
     const double *zu = grid_z + f * 2 * nc, *zl = zu + nc;
     int32_t *cnt = cells + f * N;
-    const uint8_t *lab = labels + f * N;
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
     double s = 0.0;
@@ -280,42 +279,51 @@ k_grid_reduce(const int32_t *__restrict__ grid_idx, const double *__restrict__ g
         q += d * d;
     }
     q = pbk_block_sum(q, red);
-    __syncthreads();          // all cell counts landed
     if (threadIdx.x != 0) return;
     thickness[f * 2] = mean;
     thickness[f * 2 + 1] = sqrt(q / (double)nc);
+}
 
-    float stepx = __fdiv_rn(box[f * 3 + lat0], (float)nx), stepy = __fdiv_rn(box[f * 3 + lat1], (float)ny);
-    float apb = __fmul_rn(stepx, stepy);                        // x_incr*y_incr, float32
-    // Welford states: slot 0 composite, 1..n_types per type
-    double M[GRID_MAX_TYPES + 1], S[GRID_MAX_TYPES + 1];
-    float M32[GRID_MAX_TYPES + 1];
-    long long n[GRID_MAX_TYPES + 1];
-    for (int t = 0; t <= n_types; t++) { M[t] = 0; S[t] = 0; M32[t] = 0; n[t] = 0; }
+__global__ void __launch_bounds__(64)
+k_grid_apl(const int32_t *__restrict__ cells, const uint8_t *__restrict__ labels,
+           const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t F, int64_t N,
+           int lat0, int lat1, int nx, int ny, int n_types, double *__restrict__ apl)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_states = n_types + 1;
+    if (gid >= F * n_states) return;
+    // consecutive threads = consecutive frames of one state (no divergence on the state test)
+    const int t = (int)(gid / F);
+    const int64_t f = gid - (int64_t)t * F;
+    const int32_t *cnt = cells + f * N;
+    const uint8_t *lab = labels + f * N;
+    const float stepx = __fdiv_rn(box[f * 3 + lat0], (float)nx), stepy = __fdiv_rn(box[f * 3 + lat1], (float)ny);
+    const float apb = __fmul_rn(stepx, stepy);                  // x_incr*y_incr, float32
+    double M = 0.0, S = 0.0;
+    float M32 = 0.0f;
+    long long n = 0;
     for (int pass = 1; pass >= 0; pass--) {
         for (int64_t i = 0; i < N; i++) {
             if (lab[i] != pass) continue;
-            float a = __fmul_rn(apb, (float)cnt[i]);            // area_per_bin*nlocs, float32
-            int slots[2] = {0, 1 + type_code[i]};
-            for (int w = 0; w < 2; w++) {
-                int t = slots[w];
-                n[t]++;
-                if (n[t] == 1) {
-                    M32[t] = a; M[t] = (double)a; S[t] = 0.0;
-                } else {
-                    double diff = (n[t] == 2) ? (double)__fsub_rn(a, M32[t]) : __dsub_rn((double)a, M[t]);
-                    double mn = __dadd_rn(M[t], __ddiv_rn(diff, (double)n[t]));
-                    S[t] = __dadd_rn(S[t], __dmul_rn(diff, __dsub_rn((double)a, mn)));
-                    M[t] = mn;
-                }
+            if (t > 0 && type_code[i] != t - 1) continue;
+            const float a = __fmul_rn(apb, (float)cnt[i]);      // area_per_bin*nlocs, float32
+            n++;
+            if (n == 1) {
+                M32 = a; M = (double)a; S = 0.0;
+            } else {
+                const double diff = (n == 2) ? (double)__fsub_rn(a, M32) : __dsub_rn((double)a, M);
+                const double mn = __dadd_rn(M, __ddiv_rn(diff, (double)n));
+                S = __dadd_rn(S, __dmul_rn(diff, __dsub_rn((double)a, mn)));
+                M = mn;
             }
         }
     }
     double *o = apl + f * (1 + 2 * n_types);
-    o[0] = n[0] ? M[0] : 0.0;
-    for (int t = 1; t <= n_types; t++) {
-        o[2 * t - 1] = n[t] ? M[t] : nan("");
-        o[2 * t] = n[t] > 1 ? sqrt(__ddiv_rn(S[t], (double)(n[t] - 1))) : (n[t] ? 0.0 : nan(""));
+    if (t == 0) {
+        o[0] = n ? M : 0.0;
+    } else {
+        o[2 * t - 1] = n ? M : nan("");
+        o[2 * t] = n > 1 ? sqrt(__ddiv_rn(S, (double)(n - 1))) : (n ? 0.0 : nan(""));
     }
 }
 
@@ -329,9 +337,12 @@ extern "C" int pbk_grid_reduce(pbk_ctx *ctx, const int32_t *grid_idx, const doub
         n_types > GRID_MAX_TYPES)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_grid_reduce: bad argument (n_types <= 16)");
     if (F == 0) return PBK_OK;
-    k_grid_reduce<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(grid_idx, grid_z, labels, type_code,
-                                                                box, N, lat0, lat1, nx, ny, n_types,
-                                                                cells_per_lipid, thickness, apl);
+    k_grid_reduce<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(grid_idx, grid_z, N, nx, ny,
+                                                                cells_per_lipid, thickness);
     PBK_CHECK_LAUNCH(ctx, "k_grid_reduce");
+    const int64_t n_thr = F * (n_types + 1);
+    k_grid_apl<<<(unsigned)((n_thr + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+        cells_per_lipid, labels, type_code, box, F, N, lat0, lat1, nx, ny, n_types, apl);
+    PBK_CHECK_LAUNCH(ctx, "k_grid_apl");
     return PBK_OK;
 }

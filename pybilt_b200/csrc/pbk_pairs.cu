@@ -236,25 +236,36 @@ k_nnf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
 }
 
 // Welford mean of n_b/k over the reference lipids of a frame, upper members first
-// (analysis_protocols.py:2219-2250); one thread per frame.
-__global__ void k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels,
-                                 int64_t F, int64_t N, int k, double *__restrict__ frac)
+// (analysis_protocols.py:2219-2250).  One warp per frame: coalesced loads, a ballot picks the
+// reference lipids, and every lane replays the sequential recurrence on the broadcast values
+// (the recurrence itself cannot be reordered without changing the rounding).
+__global__ void __launch_bounds__(128)
+k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels,
+                 int64_t F, int64_t N, int k, double *__restrict__ frac)
 {
-    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (f >= F) return;
     const int32_t *c = n_b + f * N;
     const uint8_t *lab = labels + f * N;
     double m = 0.0;
     int64_t n = 0;
     for (int pass = 1; pass >= 0; pass--) {
-        for (int64_t i = 0; i < N; i++) {
-            if (lab[i] != pass || c[i] < 0) continue;
-            double v = __ddiv_rn((double)c[i], (double)k);
-            n++;
-            m = (n == 1) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)n));
+        for (int64_t base = 0; base < N; base += 32) {
+            const int64_t i = base + lane;
+            int ci = -1;
+            if (i < N && lab[i] == pass) ci = c[i];
+            unsigned mask = __ballot_sync(0xffffffffu, ci >= 0);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double v = __ddiv_rn((double)__shfl_sync(0xffffffffu, ci, src), (double)k);
+                n++;
+                m = (n == 1) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)n));
+            }
         }
     }
-    frac[f] = m;
+    if (lane == 0) frac[f] = m;
 }
 
 int pbk_nnf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
@@ -292,7 +303,7 @@ extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         rc = pbk_nnf_dense_flagged(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
                                    leaflet_mask, k, n_b, nullptr, 0, (cudaStream_t)stream);
     if (rc) return rc;
-    k_nnf_frame_mean<<<(unsigned)((F + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N,
+    k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N,
                                                                                   k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;

@@ -613,6 +613,32 @@ static size_t r5_smem(int64_t N, int nb, int list_cap)
            npad * 4 + (size_t)R5_MAXW * 2 + npad + 16;
 }
 
+// d^2 table: cells of width 2^-m, up to 8 per narrowest threshold gap (w^2 for uniform bins of
+// width w starting at lo >= 0), capped at PBK_LUT_ENTRIES (a cell wider than a gap is still
+// handled correctly -- it is marked ambiguous).  Shared with pbk_cells.cu.
+bool pbk_rdf_lut16_shape(int32_t n_bins, double range_lo, double range_hi, int *m_out, int *lut_n_out)
+{
+    const double w = (range_hi - range_lo) / n_bins;
+    const double lo = range_lo > 0 ? range_lo : 0.0;
+    const double min_gap = (lo + w) * (lo + w) - lo * lo;
+    int m = 0;
+    while (ldexp(1.0, -m) > min_gap / 8.0 && m < 30) m++;
+    while (m > -20 && (range_hi * range_hi + 2.0) * ldexp(1.0, m) + 520.0 > (double)PBK_LUT_ENTRIES) m--;
+    const double lut_nd = floor((range_hi * range_hi + 1.0) * ldexp(1.0, m)) + 516.0;
+    if (lut_nd > (double)PBK_LUT_ENTRIES || lut_nd < 8.0) return false;
+    *m_out = m;
+    *lut_n_out = (int)lut_nd;
+    return true;
+}
+
+int pbk_rdf_lut16_build(pbk_ctx *ctx, const double *thr, int nb, int lut_n, int lut_m, unsigned short *lut,
+                        cudaStream_t st)
+{
+    k_rdf5_lut<<<(lut_n + 255) / 256, 256, 0, st>>>(thr, nb, lut_n, lut_m, lut);
+    PBK_CHECK_LAUNCH(ctx, "k_rdf5_lut");
+    return PBK_OK;
+}
+
 // Returns PBK_EUNSUPPORTED when the shape belongs to another RDF kernel.
 int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
                     const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
@@ -622,18 +648,8 @@ int pbk_rdf5_launch(pbk_ctx *ctx, const double *com, const uint8_t *labels, cons
     if (!thr || N > R5_MAXN || n_bins > 254 || range_lo < 0 || !ctx->work || !ctx->lut || getenv("PBK_RDF_NOLIST") ||
         getenv("PBK_RDF_V2"))
         return PBK_EUNSUPPORTED;
-    // d^2 table: cells of width 2^-m, up to 8 per narrowest threshold gap (w^2 for uniform bins of
-    // width w starting at lo >= 0), capped at PBK_LUT_ENTRIES (a cell wider than a gap is still
-    // handled correctly -- it is marked ambiguous)
-    const double w = (range_hi - range_lo) / n_bins;
-    const double lo = range_lo > 0 ? range_lo : 0.0;
-    const double min_gap = (lo + w) * (lo + w) - lo * lo;
-    int m = 0;
-    while (ldexp(1.0, -m) > min_gap / 8.0 && m < 30) m++;
-    while (m > -20 && (range_hi * range_hi + 2.0) * ldexp(1.0, m) + 520.0 > (double)PBK_LUT_ENTRIES) m--;
-    const double lut_nd = floor((range_hi * range_hi + 1.0) * ldexp(1.0, m)) + 516.0;
-    if (lut_nd > (double)PBK_LUT_ENTRIES || lut_nd < 8.0) return PBK_EUNSUPPORTED;
-    const int lut_n = (int)lut_nd;
+    int m = 0, lut_n = 0;
+    if (!pbk_rdf_lut16_shape(n_bins, range_lo, range_hi, &m, &lut_n)) return PBK_EUNSUPPORTED;
     float ecap = 3.0f;
     if (const char *ev = getenv("PBK_RDF_SKIN")) { const float v = (float)atof(ev); if (v > 0.0f && v < 100.0f) ecap = 0.5f * v; }
     // pair list: room for a leaflet of 256 lipids at 64 A^2 each within range_hi + 2 ecap, plus a third

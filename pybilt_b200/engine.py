@@ -390,5 +390,5 @@ class LipidReductionEngine:
                       type_code.data_ptr(), self.box[s:].data_ptr(), F, self.N, int(lateral[0]),
                       int(lateral[1]), nx, ny, int(n_types), cells.data_ptr(), thick.data_ptr(),
                       apl.data_ptr(), self.stream_ptr())
-        self.launches += 1
+        self.launches += 2
         return cells, thick, apl

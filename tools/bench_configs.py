@@ -40,7 +40,7 @@ def type_codes(types):
     return names, np.array([names.index(t) for t in types], dtype=np.int32)
 
 
-def run(cfg: str, F: int, reps: int, dense_check: bool):
+def run(cfg: str, F: int, reps: int, dense_check: bool, tile: int = 1):
     import torch
     from pybilt_b200 import engine as eng, synthetic as syn
     spec, f_full = syn.config_spec(cfg)
@@ -48,9 +48,15 @@ def run(cfg: str, F: int, reps: int, dense_check: bool):
     layout = eng.build_bead_layout(top.masses, top.names, top.resindex, top.resnames, top.resids)
     N, M = layout.n_beads, top.n_atoms
     A = M / N
-    e = eng.LipidReductionEngine(top.masses, layout, F, batch_frames=F)
     x = torch.from_numpy(traj.positions).cuda()
     box = torch.from_numpy(np.ascontiguousarray(traj.dimensions[:, :3])).cuda()
+    if tile > 1:
+        # the generated frames repeated along time: same per-frame work, enough frames to fill the
+        # GPU for the kernels that run one CTA (or thread) per frame
+        x = x.repeat(tile, 1, 1).contiguous()
+        box = box.repeat(tile, 1).contiguous()
+        F = F * tile
+    e = eng.LipidReductionEngine(top.masses, layout, F, batch_frames=F)
     names, codes_h = type_codes(layout.types)
     codes = torch.from_numpy(codes_h).cuda()
     out = {"config": cfg, "lipids": N, "atoms": M, "frames": F, "frames_full": f_full, "stages": {}}
@@ -109,12 +115,14 @@ def run(cfg: str, F: int, reps: int, dense_check: bool):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C3,C4,C5")
-    ap.add_argument("--frames", default="32,4,16")
+    ap.add_argument("--frames", default="256,32,48")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--dense-check", action="store_true")
+    ap.add_argument("--tile", default="1,1,1", help="repeat the generated frames this many times per config")
     a = ap.parse_args()
-    for cfg, f in zip(a.configs.split(","), a.frames.split(",")):
-        run(cfg, int(f), a.reps, a.dense_check)
+    tiles = a.tile.split(",")
+    for i, (cfg, f) in enumerate(zip(a.configs.split(","), a.frames.split(","))):
+        run(cfg, int(f), a.reps, a.dense_check, int(tiles[i]) if i < len(tiles) else 1)
 
 
 if __name__ == "__main__":
