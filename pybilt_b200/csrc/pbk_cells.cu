@@ -17,7 +17,7 @@
 //   k_cl_scan     exclusive scan of the cell populations per frame
 //   k_cl_scatter  lipids into cell order: b' = x - box/2 as float64 (exact phase) and as
 //                 float32 (prefilter), original index, class flags, cell id
-//   k_rdf_cl      8 lanes per lipid sweep the forward half shell of cells (every unordered
+//   k_rdf_cl      thread per lipid, sweeps the forward half shell of cells (every unordered
 //                 pair once); float32 prefilter -> per-warp ring queue -> the reference's
 //                 float64 formulas; d^2 -> bin through the exact threshold table
 //   k_knn_cl      thread per lipid, rings of cells of growing radius until the k-th best
@@ -327,7 +327,7 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
 // threshold, and a pair closer to a threshold than the float32 rounding bound (`tolc` cells,
 // see DESIGN.md "Why the RDF fast path is exact") goes to the exact float64 queue instead.
 template <bool SAME>
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 4)
 k_rdf_cl(ClParams P, ClRdf R)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -345,8 +345,6 @@ k_rdf_cl(ClParams P, ClRdf R)
     unsigned *myhist = s_hist + (size_t)(warp % R.hist_copies) * nb;
     uint2 *myq = s_queue + warp * CL_QCAP;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int sub = tid & 7, grp = tid >> 3, ngrp = blockDim.x >> 3;
-    const unsigned gshift = (unsigned)(lane & ~7);
     const int64_t per_frame = (P.N + R.chunk - 1) / R.chunk;
     const int64_t n_items = P.F * per_frame;
     const float lut_scale = ldexpf(1.0f, R.lut_m);
@@ -386,90 +384,84 @@ k_rdf_cl(ClParams P, ClRdf R)
         const float cut2_f = cut * cut;                          // all_exact frames: plain cut-off
         const int mx = g.mx, my = g.my, ncx = g.ncx, ncy = g.ncy;
 
+        // one lipid per thread; the warp walks the half-shell rows in lockstep, per row first the
+        // main slot range of every lane, then the (rare) range beyond the periodic edge
         int qhead = 0, qtail = 0;
-        for (int p0 = p_lo; p0 < p_hi; p0 += ngrp) {
-            const int p = p0 + grp;
+        const unsigned sure_min = all_exact ? 0xFFFFFFFFu : ((unsigned)tolc << 8);
+        for (int p0 = p_lo; p0 < p_hi; p0 += blockDim.x) {
+            const int p = p0 + tid;
             bool pact = p < p_hi;
             float fpx = 0.f, fpy = 0.f;
             unsigned pflag = 3u;
-            int b1 = 0, n1 = 0, b2 = 0, n2 = 0;
+            int cbase = 0, pcx = 0, pcy = 0;
             if (pact) {
                 int pc = gcell[p];
                 const int leaf = pc >= g.ncell;
                 pact = on[leaf];
-                if (pact) {
-                    const float2 fp = gf[p];
-                    fpx = fp.x; fpy = fp.y;
-                    if (!SAME) pflag = gflag[p];
-                    if (sub <= my) {
-                        const int cbase = leaf * g.ncell;
-                        pc -= cbase;
-                        const int pcy = pc / ncx, pcx = pc - pcy * ncx;
-                        int cy = pcy + sub; if (cy >= ncy) cy -= ncy;
-                        const int row = cbase + cy * ncx;
-                        int xlo = (sub == 0) ? pcx : pcx - mx, xhi = pcx + mx;
-                        if (xlo < 0) {
-                            b2 = cstart[row + xlo + ncx]; n2 = cstart[row + ncx] - b2;
-                            xlo = 0;
-                        }
-                        if (xhi >= ncx) {
-                            b2 = cstart[row]; n2 = cstart[row + xhi - ncx + 1] - b2;
-                            xhi = ncx - 1;
-                        }
-                        b1 = cstart[row + xlo]; n1 = cstart[row + xhi + 1] - b1;
-                        if (sub == 0) { n1 -= (p + 1 - b1); b1 = p + 1; }
-                    }
-                }
+                const float2 fp = gf[p];
+                fpx = fp.x; fpy = fp.y;
+                if (!SAME) pflag = gflag[p];
+                cbase = leaf * g.ncell;
+                pc -= cbase;
+                pcy = pc / ncx;
+                pcx = pc - pcy * ncx;
             }
             for (int oy = 0; oy <= my; oy++) {
-                const int rb1 = __shfl_sync(0xffffffffu, b1, gshift + oy);
-                const int rn1 = __shfl_sync(0xffffffffu, n1, gshift + oy);
-                const int rb2 = __shfl_sync(0xffffffffu, b2, gshift + oy);
-                const int rn2 = __shfl_sync(0xffffffffu, n2, gshift + oy);
-                const int ntot = rn1 + rn2;
-                int nmax = ntot;
-                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
-                nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-                for (int t0 = 0; t0 < nmax; t0 += 8) {
-                    const int t = t0 + sub;
-                    bool hit = false;
-                    int q = 0;
-                    if (t < ntot) {
-                        q = t < rn1 ? rb1 + t : rb2 + (t - rn1);
-                        const float2 fq = gf[q];
-                        float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
-                        dx = fminf(dx, bxf - dx);
-                        dy = fminf(dy, byf - dy);
-                        const float d2 = fmaf(dy, dy, dx * dx);
-                        if (all_exact) {
-                            hit = d2 < cut2_f;
-                        } else {
+                int seg_b[2] = {0, 0}, seg_n[2] = {0, 0};
+                if (pact) {
+                    int cy = pcy + oy; if (cy >= ncy) cy -= ncy;
+                    const int row = cbase + cy * ncx;
+                    int xlo = (oy == 0) ? pcx : pcx - mx, xhi = pcx + mx;
+                    if (xlo < 0) {
+                        seg_b[1] = cstart[row + xlo + ncx]; seg_n[1] = cstart[row + ncx] - seg_b[1];
+                        xlo = 0;
+                    }
+                    if (xhi >= ncx) {
+                        seg_b[1] = cstart[row]; seg_n[1] = cstart[row + xhi - ncx + 1] - seg_b[1];
+                        xhi = ncx - 1;
+                    }
+                    seg_b[0] = cstart[row + xlo]; seg_n[0] = cstart[row + xhi + 1] - seg_b[0];
+                    if (oy == 0) { seg_n[0] -= (p + 1 - seg_b[0]); seg_b[0] = p + 1; }   // own cell: later entries only
+                }
+#pragma unroll
+                for (int sg = 0; sg < 2; sg++) {
+                    const int n = seg_n[sg], b = seg_b[sg];
+                    const int nmax = __reduce_max_sync(0xffffffffu, n);
+                    const float2 *gp = gf + b;
+                    for (int t = 0; t < nmax; t++) {
+                        bool hit = false;
+                        if (t < n) {
+                            const float2 fq = gp[t];
+                            float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
+                            dx = fminf(dx, bxf - dx);
+                            dy = fminf(dy, byf - dy);
+                            const float d2 = fmaf(dy, dy, dx * dx);
                             const unsigned e = s_lut[min(__float2int_rd(d2 * lut_scale), lut_last)];
                             const unsigned bin = e & 0xFFu;
-                            if ((int)(e >> 8) >= tolc) {
+                            if (e >= sure_min) {
                                 if (bin != 0xFFu) {
                                     unsigned w = 2u;
                                     if (!SAME) {
-                                        const unsigned fqf = gflag[q];
+                                        const unsigned fqf = gflag[b + t];
                                         w = ((pflag & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((pflag >> 1) & 1u));
                                     }
                                     if (w) atomicAdd(&myhist[bin], w);
                                 }
                             } else {
-                                hit = true;
+                                hit = !all_exact || d2 < cut2_f;
                             }
                         }
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m) {
-                        if (hit) myq[(qtail + __popc(m & lt_mask)) & (CL_QCAP - 1)] = make_uint2((unsigned)p, (unsigned)q);
-                        qtail += __popc(m);
-                        if (qtail - qhead >= 32) {
-                            __syncwarp();
-                            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
-                                           fr.Lx, fr.Ly, fr.hx, fr.hy);
-                            qhead += 32;
-                            __syncwarp();
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m) {
+                            if (hit) myq[(qtail + __popc(m & lt_mask)) & (CL_QCAP - 1)] = make_uint2((unsigned)p, (unsigned)(b + t));
+                            qtail += __popc(m);
+                            if (qtail - qhead >= 32) {
+                                __syncwarp();
+                                cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
+                                               fr.Lx, fr.Ly, fr.hx, fr.hy);
+                                qhead += 32;
+                                __syncwarp();
+                            }
                         }
                     }
                 }
@@ -701,7 +693,7 @@ int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
     }
     ClRdf R;
     R.nb = n_bins; R.lut_n = lut_n; R.lut_m = m; R.thr = thr; R.lut = lut;
-    R.count = count; R.chunk = 256;
+    R.count = count; R.chunk = 2048;
     R.hist_copies = CL_THREADS / 32;
     auto smem_for = [&](int c) {
         return (size_t)(n_bins + 1) * 8 + (size_t)(CL_THREADS / 32) * CL_QCAP * 8 + (size_t)c * n_bins * 4 +

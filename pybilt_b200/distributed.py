@@ -93,16 +93,25 @@ def _wire(t: torch.Tensor, group=None) -> torch.Tensor:
     return t.contiguous()
 
 
+_gather_cache = {}
+
+
 def image_offsets(net: torch.Tensor, group=None) -> torch.Tensor:
-    """Exclusive prefix over ranks of the net image counts (int32 tensor of any shape)."""
+    """Exclusive prefix over ranks of the net image counts (int32 tensor of any shape).
+    One all-gather into a reused [world, ...] buffer and one reduction over the ranks before
+    this one (nothing is allocated per call after the first)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     w = _wire(net, group)
-    gathered = [torch.empty_like(w) for _ in range(world)]
-    dist.all_gather(gathered, w, group=group)
-    off = torch.zeros_like(w)
-    for q in range(rank):
-        off += gathered[q]
+    key = (w.device, w.dtype, tuple(w.shape), world)
+    buf = _gather_cache.get(key)
+    if buf is None:
+        buf = torch.empty(world * w.numel(), dtype=w.dtype, device=w.device)
+        _gather_cache.clear()
+        _gather_cache[key] = buf
+    dist.all_gather_into_tensor(buf, w.reshape(-1), group=group)     # rank-major concatenation
+    off = (buf.view(world, -1)[:rank].sum(dim=0, dtype=w.dtype).view(w.shape) if rank > 0
+           else torch.zeros_like(w))
     return off.to(net.device)
 
 
