@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 5
+#define PBK_ABI_VERSION 6
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -168,6 +168,21 @@ int pbk_rdf(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_
             int leaflet_mask, int32_t n_bins, double range_lo, double range_hi,
             const double *edges, const double *thr, unsigned long long *count,
             int32_t *frame_counts, void *stream);
+
+/* ---- D2, many analyses at once ----------------------------------------------------------
+ * The prefab drivers request one com_lateral_rdf per ordered resname pair and leaflet with the
+ * same bins (pybilt/bilayer_analyzer/prefab_analysis_protocols.py:1508-1521: 18 analyses for
+ * three lipid types).  pbk_rdf_multi makes ONE pair sweep per frame and leaflet and bins every
+ * ordered pair (i, j) into the table of (leaflet, type_i, type_j):
+ * count[2][n_types][n_types][n_bins] uint64 (accumulated; leaflet row 0 = upper);
+ * type_counts[F][2][n_types] int32 = lipids per frame, leaflet and type (overwritten).
+ * Any (resname_1, resname_2, leaflet) analysis -- 'all' included -- is a sum of table entries,
+ * its (N_a, N_b, N_leaflet) sums follow from type_counts (pybilt_b200/analysis_protocols.py).
+ * Returns PBK_EUNSUPPORTED for more than 8 types or tables that do not fit in shared memory. */
+int pbk_rdf_multi(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int n_types,
+                  int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                  const double *thr, unsigned long long *count, int32_t *type_counts, void *stream);
 
 /* ---- D3  nearest-neighbour fraction -----------------------------------------------------
  * NNFProtocol.run_analysis             pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257

@@ -50,6 +50,9 @@ _SIGNATURES = {
     "pbk_rdf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_int, c_int, c_int, c_int, c_int32, c_double, c_double, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p]),
+    "pbk_rdf_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                              c_int, c_int, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
     "pbk_nnf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_lipid_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
@@ -78,7 +81,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.pbk_abi_version() != 5:
+        if lib.pbk_abi_version() != 6:
             raise RuntimeError("pybilt_b200: libpbk ABI version mismatch")
         _lib = lib
     return _lib

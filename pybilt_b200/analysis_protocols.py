@@ -281,14 +281,20 @@ class MSDProtocol(AnalysisProtocol):
         self._setup({'leaflet': 'both', 'resname': 'all'}, args)
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
-        self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
-                                             self.settings['resname'])
+        """One window of analysed frames (all of them in a resident run)."""
+        if batch.first_window:
+            self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
+                                                 self.settings['resname'])
+            self._vals = np.zeros(batch.n_frames)
         rows = batch.rows                    # engine rows of the frames this rank owns
         ends = np.arange(rows.start, rows.stop, dtype=np.int32)
         origins = np.full(len(ends), batch.ref_row, dtype=np.int32)   # frame 0 of the whole run
         vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32), origins, ends,
                                       ba_settings['lateral']).cpu().numpy()
-        vals = batch.to_global(vals)
+        self._vals[batch.gframes] = vals
+
+    def finish(self, batch):
+        vals = batch.allreduce(self._vals)       # every frame has exactly one owner: x + 0 = x
         self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
 
@@ -337,25 +343,36 @@ class MSDMultiProtocol(AnalysisProtocol):
         self._setup({'leaflet': 'both', 'resname': 'all', 'n_tau': 50, 'n_sigma': 50}, args)
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
-        self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
-                                             self.settings['resname'])
         n_tau, n_sigma = self.settings['n_tau'], self.settings['n_sigma']
         F = batch.n_frames
-        finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
-        out = np.zeros(n_blocks)
+        if batch.first_window:
+            self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
+                                                 self.settings['resname'])
+            self._finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
+            self._out = np.zeros(n_blocks)
+        finished = self._finished
         shard = batch.shard
-        # a rank evaluates the blocks whose origin frame it owns (the end frame lies in its
-        # forward halo); row = engine row of an analysed frame
-        blocks = [b for b in sorted(finished) if shard is None or shard.lo <= finished[b][0] < shard.hi]
-        row = (lambda g: g) if shard is None else shard.local_of
+        if batch.windowed:
+            # streamed run: a window evaluates the blocks that END in it; the origin frame lies at
+            # most n_tau - 1 frames back, i.e. in the window or in the context rows kept before it
+            g = batch.gframes
+            blocks = [b for b in sorted(finished) if g.start <= finished[b][1] < g.stop]
+        else:
+            # resident run: a rank evaluates the blocks whose origin frame it owns (the end frame
+            # lies in its forward halo)
+            blocks = [b for b in sorted(finished) if shard is None or shard.lo <= finished[b][0] < shard.hi]
+        row = batch.row_of_global
         if blocks:
             vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
                                           [row(finished[b][0]) for b in blocks],
                                           [row(finished[b][1]) for b in blocks],
                                           ba_settings['lateral']).cpu().numpy()
-            out[blocks] = vals
-        self.analysis_output = list(batch.allreduce(out))
-        self._tau = batch.times[n_tau - 1] - batch.times[0] if F >= n_tau else 0.0
+            self._out[blocks] = vals
+
+    def finish(self, batch):
+        n_tau = self.settings['n_tau']
+        self.analysis_output = list(batch.allreduce(self._out))
+        self._tau = batch.times[n_tau - 1] - batch.times[0] if batch.n_frames >= n_tau else 0.0
 
     def _process_output(self, analysis_output):
         vals = np.array([v for v in analysis_output if v > 0.0])
@@ -400,30 +417,57 @@ class COMLateralRDFProtocol(AnalysisProtocol):
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
         s = self.settings
-        do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
-        rdf_range = [s['range_inner'], s['range_outer']]
-        # same call the reference uses to lay out the bins (:4909-4916)
-        _c, edges = np.histogram([-1], bins=s['n_bins'], range=rdf_range)
-        self._edges = edges
-        self._bins = 0.5 * (edges[:-1] + edges[1:])
-        lipid_types, _n = _lipid_types_in(batch.first_leaflets, do_leaflet)
-        if s['resname_1'] == 'first':
-            s['resname_1'] = lipid_types[0]
-        if s['resname_2'] == 'first':
-            s['resname_2'] = lipid_types[0]
-        self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
-        self._n_leaf = float(len(do_leaflet))
+        if batch.first_window:
+            do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
+            rdf_range = [s['range_inner'], s['range_outer']]
+            # same call the reference uses to lay out the bins (:4909-4916)
+            _c, edges = np.histogram([-1], bins=s['n_bins'], range=rdf_range)
+            self._edges = edges
+            self._bins = 0.5 * (edges[:-1] + edges[1:])
+            lipid_types, _n = _lipid_types_in(batch.first_leaflets, do_leaflet)
+            if s['resname_1'] == 'first':
+                s['resname_1'] = lipid_types[0]
+            if s['resname_2'] == 'first':
+                s['resname_2'] = lipid_types[0]
+            self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
+            self._n_leaf = float(len(do_leaflet))
+            self._count_acc = np.zeros(s['n_bins'], dtype=np.int64)
+            self._sums_acc = np.zeros(3, dtype=np.int64)
+        shared = batch.rdf_shared(self._edges, ba_settings['lateral'])
+        if shared is not None:
+            # one sweep binned every (leaflet, type_i, type_j) table; this analysis is a sum of tables
+            table, tc = shared                       # [2, T, T, n_bins], [F, 2, T]
+            T = table.shape[1]
+            ca, cb = batch.type_code_of(s['resname_1']), batch.type_code_of(s['resname_2'])
+            A = list(range(T)) if ca == -1 else ([ca] if 0 <= ca < T else [])
+            B = list(range(T)) if cb == -1 else ([cb] if 0 <= cb < T else [])
+            mask = _leaflet_mask(s['leaflet'])
+            for l in range(2):
+                if not (mask >> l) & 1:
+                    continue
+                if A and B:
+                    self._count_acc += table[l][np.ix_(A, B)].sum(axis=(0, 1))
+                n_a = tc[:, l, A].sum(axis=1) if A else np.zeros(len(tc), dtype=np.int64)
+                n_b = tc[:, l, B].sum(axis=1) if B else np.zeros(len(tc), dtype=np.int64)
+                on = (n_a > 0) & (n_b > 0)           # the leaflet holds both groups (:4965)
+                self._sums_acc += np.array([n_a[on].sum(), n_b[on].sum(), tc[:, l, :].sum()])
+            return
         count, fc = batch.engine.rdf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                      batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
-                                     edges, ba_settings['lateral'], frames=batch.rows)
+                                     self._edges, ba_settings['lateral'], frames=batch.rows)
         fc = fc.cpu().numpy().astype(np.int64)
+        self._count_acc += count.cpu().numpy()
+        self._sums_acc += np.array([fc[:, :, 0].sum(), fc[:, :, 1].sum(), fc[:, :, 2].sum()])
+
+    def finish(self, batch):
         # frame shards: partial histograms and (N_a, N_b, N) sums are all-reduced
-        self._count = batch.allreduce(count.cpu().numpy()).astype(np.float64)
-        sums = batch.allreduce(np.array([fc[:, :, 0].sum(), fc[:, :, 1].sum(), fc[:, :, 2].sum()]))
+        count = batch.allreduce(self._count_acc).astype(np.float64)
+        self._count = count if self._count is None else self._count + count
+        sums = batch.allreduce(self._sums_acc)
         self._N_a += int(sums[0])
         self._N_b += int(sums[1])
         self._N += int(sums[2])
-        lat = list(ba_settings['lateral'])
+        lat = list(batch.lateral)
         # box[lateral].prod() per frame is a float32 product (:5004) pushed into a Welford mean
         areas = batch.box_host[:, lat[0]] * batch.box_host[:, lat[1]]
         if self._area_run.n == 0 and len(areas) and (areas == areas[0]).all():
@@ -477,20 +521,25 @@ class NNFProtocol(AnalysisProtocol):
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
         s = self.settings
-        do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
-        lipid_types, nlipids = _lipid_types_in(batch.first_leaflets, do_leaflet)
-        if s['resname_1'] == 'first':
-            s['resname_1'] = lipid_types[0]
-        if s['resname_2'] == 'first':
-            s['resname_2'] = lipid_types[0]
-        if s['n_neighbors'] > nlipids:                       # :2197-2198
-            s['n_neighbors'] = nlipids - 1
-        self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
+        if batch.first_window:
+            do_leaflet = ['upper', 'lower'] if s['leaflet'] == 'both' else [s['leaflet']]
+            lipid_types, nlipids = _lipid_types_in(batch.first_leaflets, do_leaflet)
+            if s['resname_1'] == 'first':
+                s['resname_1'] = lipid_types[0]
+            if s['resname_2'] == 'first':
+                s['resname_2'] = lipid_types[0]
+            if s['n_neighbors'] > nlipids:                       # :2197-2198
+                s['n_neighbors'] = nlipids - 1
+            self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
+            self._frac = np.zeros(batch.n_frames)
         n_b, frac = batch.engine.nnf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                      batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
                                      s['n_neighbors'], ba_settings['lateral'], frames=batch.rows)
-        self.neighbor_counts = n_b            # device int32 [owned frames, N]; -1 = not a reference lipid
-        rows, self.running = running_rows(batch.times, batch.to_global(frac.cpu().numpy()))
+        self.neighbor_counts = n_b            # device int32 [frames of the last window, N]; -1 = not a reference lipid
+        self._frac[batch.gframes] = frac.cpu().numpy()
+
+    def finish(self, batch):
+        rows, self.running = running_rows(batch.times, batch.allreduce(self._frac))
         self.analysis_output = [list(r) for r in rows]
 
 
@@ -509,8 +558,12 @@ class BTGridProtocol(AnalysisProtocol):
         self.running = RunningStats()
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
-        grids = batch.lipid_grids()
-        rows, self.running = running_rows(batch.times, batch.to_global(grids.thickness_host[:, 0]))
+        if batch.first_window:
+            self._th = np.zeros(batch.n_frames)
+        self._th[batch.gframes] = batch.lipid_grids().thickness_host[:, 0]
+
+    def finish(self, batch):
+        rows, self.running = running_rows(batch.times, batch.allreduce(self._th))
         self.analysis_output = [r for r in rows]
 
     def reset(self):
@@ -535,7 +588,12 @@ class APLGridProtocol(AnalysisProtocol):
 
     def run_batch(self, ba_settings, batch, ba_mda_data):
         grids = batch.lipid_grids()
-        apl = batch.to_global(grids.apl_host)
+        if batch.first_window:
+            self._apl = np.zeros((batch.n_frames, grids.apl_host.shape[1]))
+        self._apl[batch.gframes] = grids.apl_host
+
+    def finish(self, batch):
+        apl = batch.allreduce(self._apl)
         rows, self.running = running_rows(batch.times, apl[:, 0])
         out = {'composite': rows}
         # resnames in the order LipidGrids.area_per_lipid lists them at the first frame

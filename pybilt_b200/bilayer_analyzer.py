@@ -196,15 +196,33 @@ class ReductionBatch(object):
     """What a batched protocol's ``run_batch`` receives: the engine holding the resident
     representations, host metadata, and the leaflets of the first analysed frame."""
 
-    def __init__(self, analyzer, engine, times, box_host, first_leaflets, shard=None):
+    def __init__(self, analyzer, engine, times, box_host, first_leaflets, shard=None, window=None):
         self._analyzer = analyzer
         self.engine = engine
         self.shard = shard                  # pybilt_b200.distributed.Shard or None
+        self.lateral = list(analyzer.settings['lateral'])
         # n_frames / times / box_host describe ALL analysed frames; the engine rows of a
         # shard are [back halo | owned | forward halo | reference row]
         self.n_frames = len(times)
-        self.rows = shard.owned_local() if shard is not None else slice(0, engine.n_done)
-        self.ref_row = shard.n_local if shard is not None else 0     # frame 0 of the whole run
+        if window is None:
+            # resident run: every analysed frame (of this rank's shard) is in the engine
+            self.windowed = False
+            self.rows = shard.owned_local() if shard is not None else slice(0, engine.n_done)
+            self.ref_row = shard.n_local if shard is not None else 0     # frame 0 of the whole run
+            self.gframes = slice(shard.lo, shard.hi) if shard is not None else slice(0, len(times))
+            self.row0_global = shard.first_local if shard is not None else 0
+            self.first_window = self.last_window = True
+            self.sharded = shard is not None
+        else:
+            # streamed run: the engine holds [context rows | the window's frames]; see
+            # BilayerAnalyzer._run_windowed
+            self.windowed = True
+            self.rows = window['rows']
+            self.ref_row = window['ref_row']
+            self.gframes = window['gframes']
+            self.row0_global = window['row0_global']
+            self.first_window, self.last_window = window['first'], window['last']
+            self.sharded = window['sharded']
         self.times = times
         self.box_host = box_host
         self.types = engine.layout.types
@@ -219,11 +237,16 @@ class ReductionBatch(object):
         self.type_code_dev = torch.from_numpy(codes).to(engine.dev)
         self.first_leaflets = first_leaflets
         self._grids = None
+        self._rdf_multi = {}
+
+    def row_of_global(self, g):
+        """engine row of analysed frame g"""
+        return int(g) - self.row0_global
 
     def allreduce(self, values):
         """Sum of a small host array over the ranks (identity when not sharded)."""
         values = np.asarray(values)
-        if self.shard is None:
+        if not self.sharded:
             return values
         dt = torch.int64 if values.dtype.kind in "iu" else torch.float64
         t = torch.as_tensor(values, dtype=dt, device=self.engine.dev)
@@ -244,6 +267,21 @@ class ReductionBatch(object):
         if name == 'all':
             return -1
         return self.type_names.index(name) if name in self.type_names else -2
+
+    def rdf_shared(self, edges, lateral):
+        """(count [2,T,T,n_bins], type_counts [F,2,T]) host arrays of ONE pair sweep over this
+        batch's frames shared by every com_lateral_rdf analysis with these bins, or None when only
+        one analysis wants them / the library has no shared path for the shape."""
+        key = (np.ascontiguousarray(edges, dtype=np.float64).tobytes(), tuple(lateral))
+        if key not in self._rdf_multi:
+            res = None
+            if self._analyzer._rdf_sharers(key) >= 2 and os.environ.get("PBK_NO_RDF_MULTI") is None:
+                r = self.engine.rdf_multi(self.type_code_dev, len(self.type_names), edges, lateral,
+                                          frames=self.rows)
+                if r is not None:
+                    res = (r[0].cpu().numpy(), r[1].cpu().numpy().astype(np.int64))
+            self._rdf_multi[key] = res
+        return self._rdf_multi[key]
 
     def lipid_grids(self) -> GridBatch:
         if self._grids is None:
@@ -275,6 +313,11 @@ class BilayerAnalyzer(object):
             'vector_frame': {'dump': False, 'dump_path': "./", 'ref_atoms': None}}
         self.device = device
         self.batch_frames = None    # frames per host->device batch (None: about 48 MB of positions)
+        # Streamed runs: None = keep every analysed frame's representations resident when they fit
+        # `resident_budget_bytes`, else stream windows of frames through a bounded engine; an int
+        # forces windows of that many frames (see _run_windowed)
+        self.window_frames = None
+        self.resident_budget_bytes = 48 << 30
         self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
         self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
         self._frame_loop_count = 0
@@ -596,13 +639,219 @@ class BilayerAnalyzer(object):
         self._batch = ReductionBatch(self, eng, times_all, dims_all[:, :3].copy(), first_leaflets, shard)
         return self._batch
 
+    # -- streamed (windowed) runs ----------------------------------------------------------------
+    def _check_rep_settings(self):
+        lset = self.rep_settings['leaflets']
+        if lset['assign_method'] != 'avg_norm':
+            raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
+                               "(only 'avg_norm')" % lset['assign_method'])
+        if self.rep_settings['com_frame']['rewrap'] or self.rep_settings['com_frame']['make_whole']:
+            raise RuntimeError("com_frame:rewrap / make_whole are outside the accelerated path")
+
+    def _default_batch_frames(self, n):
+        md = self._mda_data
+        if self.batch_frames is not None:
+            return int(self.batch_frames)
+        return int(max(64, min(n, (48 << 20) // max(1, md.natoms * 12))))
+
+    def _window_choice(self):
+        """Frames per window of a streamed run, or None for a resident run."""
+        protos = [self._analysis_protocol.command_protocol[a] for a in self._analysis_protocol.analysis_ids]
+        streamable = (all(getattr(p, 'batched', False) for p in protos) and
+                      not any(self.rep_settings[r]['dump'] for r in ('com_frame', 'leaflets', 'lipid_grid')))
+        if self.window_frames is not None:
+            if not streamable:
+                raise RuntimeError("window_frames needs batched analyses only and no representation dumps")
+            return int(self.window_frames)
+        if not streamable:
+            return None
+        md = self._mda_data
+        n_res = len(md.resnames)
+        F = len(self.analysed_frame_indices())
+        per_frame = n_res * 56 + 64                  # com + com_unwrap + label + mem_com + box
+        if self.use_lipid_grid_bytes():
+            g = self.rep_settings['lipid_grid']
+            per_frame += 2 * int(g['n_xbins']) * int(g['n_ybins']) * 12 + n_res * 100
+        if F * per_frame <= self.resident_budget_bytes:
+            return None
+        return int(max(256, (8 << 30) // per_frame))
+
+    def _rdf_sharers(self, key):
+        """number of registered com_lateral_rdf analyses with the bins / lateral axes of `key`"""
+        n = 0
+        for a in self._analysis_protocol.analysis_ids:
+            p_ = self._analysis_protocol.command_protocol[a]
+            if p_.analysis_key != 'com_lateral_rdf':
+                continue
+            st = p_.settings
+            _c, e = np.histogram([-1], bins=st['n_bins'], range=[st['range_inner'], st['range_outer']])
+            if (e.tobytes(), tuple(self.settings['lateral'])) == key:
+                n += 1
+        return n
+
+    def use_lipid_grid_bytes(self):
+        return any(self._analysis_protocol.command_protocol[a].analysis_key in ('apl_grid', 'thickness_grid')
+                   for a in self._analysis_protocol.analysis_ids)
+
+    def _push_frames(self, eng, md, frames, times_out=None, dims_out=None, init_images=None, unwrap_only=False):
+        """Host -> device in engine-batch sized pieces (double-buffered on a copy stream) and through
+        the engine.  Returns the device views (x, box) of the last frame pushed."""
+        dev = eng.dev
+        st = getattr(self, '_copy_state', None)
+        B = eng.B
+        if st is None or st['key'] != (id(eng), B, md.natoms):
+            st = {'key': (id(eng), B, md.natoms), 'stream': torch.cuda.Stream(dev),
+                  'bufs': [torch.empty((B, md.natoms, 3), dtype=torch.float32, device=dev) for _ in range(2)],
+                  'boxes': [torch.empty((B, 3), dtype=torch.float32, device=dev) for _ in range(2)],
+                  'ready': [torch.cuda.Event() for _ in range(2)],
+                  'consumed': [torch.cuda.Event() for _ in range(2)], 'k': 0}
+            self._copy_state = st
+        main = torch.cuda.current_stream(dev)
+        last = None
+        for b0 in range(0, len(frames), B):
+            b1 = min(len(frames), b0 + B)
+            k = st['k']
+            st['k'] += 1
+            slot = k % 2
+            x, d, t = md.frames(frames[b0:b1])
+            if times_out is not None:
+                times_out[b0:b1] = t
+                dims_out[b0:b1] = d
+            xh = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            bh = torch.from_numpy(np.ascontiguousarray(d[:, :3]))
+            with torch.cuda.stream(st['stream']):
+                if k >= 2:
+                    st['stream'].wait_event(st['consumed'][slot])
+                st['bufs'][slot][:b1 - b0].copy_(xh, non_blocking=True)
+                st['boxes'][slot][:b1 - b0].copy_(bh, non_blocking=True)
+                st['ready'][slot].record(st['stream'])
+            main.wait_event(st['ready'][slot])
+            xb, bb = st['bufs'][slot][:b1 - b0], st['boxes'][slot][:b1 - b0]
+            if unwrap_only:
+                eng.unwrap_only(xb, bb)
+            else:
+                eng.push(xb, bb, init_images=init_images if b0 == 0 else None)
+            st['consumed'][slot].record(main)
+            last = (xb[b1 - b0 - 1], bb[b1 - b0 - 1])
+        return last
+
+    def _run_windowed(self, W, allow_fused=True):
+        """Streamed run: the analysed frames go through a bounded engine in windows of ``W`` frames;
+        every batched analysis consumes a window (``run_batch``) before the next one replaces it and
+        combines / finalises at the end (``finish``).  Resident per window: [C context rows | W
+        frames | reference row], C = max(1, largest msd_multi n_tau - 1) -- the context rows are the
+        tail of the previous window (origins of multi-origin MSD blocks, previous leaflet labels).
+
+        Frame shards (torch.distributed): rank r streams frames [lo_r - C, hi_r); the first C are
+        its back halo (context only).  The image counts at the first frame of its stream come from
+        a first pass in which every rank advances the unwrap state alone (no reduction) up to the
+        frame where the next rank's stream starts; the counts there are all-gathered and prefixed
+        (pybilt_b200/distributed.py).  No collective runs inside the window loop: ranks may have
+        different numbers of windows."""
+        self._check_rep_settings()
+        md = self._mda_data
+        cset, lset = self.rep_settings['com_frame'], self.rep_settings['leaflets']
+        layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
+                                   cset['name_dict'], cset['multi_bead'])
+        fr_all = self.analysed_frame_indices()
+        F = len(fr_all)
+        protos = [self._analysis_protocol.command_protocol[a] for a in self._analysis_protocol.analysis_ids]
+        C = 1
+        for p_ in protos:
+            if p_.analysis_key == 'msd_multi':
+                C = max(C, int(p_.settings['n_tau']) - 1)
+        world, rank = 1, 0
+        if self.distributed and pd.is_distributed():
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(), dist.get_rank()
+        lo, hi = pd.shard_bounds(F, world, rank)
+        if hi <= lo:
+            raise RuntimeError("more ranks than analysed frames")
+        starts = [max(0, pd.shard_bounds(F, world, q)[0] - C) for q in range(world)]
+        a = starts[rank]
+        W = int(max(W, C + 1))
+        if hasattr(md, '_dimensions') and hasattr(md, '_times'):
+            dims_all = np.asarray(md._dimensions[fr_all], dtype=np.float32)
+            times_all = np.asarray(md._times[fr_all], dtype=np.float64)
+        elif world > 1:
+            raise RuntimeError("sharded runs need in-memory box/time arrays for all frames")
+        else:
+            dims_all = np.zeros((F, 6), dtype=np.float32)
+            times_all = np.zeros(F)
+        eng = LipidReductionEngine(md.masses, layout, C + W + 1, device=self.device, norm=self.settings['norm'],
+                                   leaflet_update_interval=int(lset['update_interval']),
+                                   batch_frames=self._default_batch_frames(W), allow_fused=allow_fused)
+        ref_row = C + W
+        self._copy_state = None
+        init = None
+        if world > 1:
+            # pass A: image counts where the next rank's stream starts
+            net = torch.zeros((md.natoms, 3), dtype=torch.int32, device=eng.dev)
+            if rank < world - 1 and starts[rank + 1] > a:
+                last = self._push_frames(eng, md, fr_all[a:starts[rank + 1] + 1], unwrap_only=True)
+                net = eng.image_counts_last(last[0], last[1])
+            init = pd.image_offsets(net)
+            eng.reset()
+        rejected = False
+        first_leaflets = None
+        g = a
+        first = True
+        try:
+            while g < hi:
+                g1 = min(hi, g + W)
+                if not first:
+                    eng.rewind(C)
+                ctx = eng.n_done
+                if hasattr(md, '_dimensions'):
+                    self._push_frames(eng, md, fr_all[g:g1], init_images=init if first else None)
+                else:
+                    self._push_frames(eng, md, fr_all[g:g1], times_all[g:g1], dims_all[g:g1],
+                                      init_images=init if first else None)
+                eng.check_status()
+                if first:
+                    lab0 = eng.labels[0].clone()
+                    ref = eng.com_unwrap[0].clone()
+                    if world > 1:                       # frame 0 of the run lives on rank 0
+                        pd.broadcast_from_first(lab0)
+                        pd.broadcast_from_first(ref)
+                    eng.com_unwrap[ref_row].copy_(ref)
+                    first_leaflets = lf.leaflets_from_labels(lab0.cpu().numpy(), layout.types, layout.resids)
+                own0 = max(g, lo)
+                if g1 > own0:
+                    win = {'rows': slice(ctx + own0 - g, ctx + g1 - g), 'ref_row': ref_row,
+                           'gframes': slice(own0, g1), 'row0_global': g - ctx, 'first': own0 == lo,
+                           'last': g1 == hi, 'sharded': world > 1}
+                    batch = ReductionBatch(self, eng, times_all, dims_all[:, :3].copy(), first_leaflets,
+                                           None, win)
+                    for p_ in protos:
+                        p_.run_batch(self.settings, batch, md)
+                g = g1
+                first = False
+        except FusedPathRejected:
+            if world == 1:
+                raise
+            rejected = True
+        if world > 1:
+            flag = torch.tensor([1 if rejected else 0], dtype=torch.int64, device=eng.dev)
+            if int(pd.combine_slots(flag)[0]) > 0:
+                raise FusedPathRejected("a rank's fused reduction was rejected")
+        for p_ in protos:
+            p_.finish(batch)
+        self._frames_all = fr_all
+        self._frames = fr_all[a:hi]
+        self._engine = None
+        self._batch = None
+        self._copy_state = None
+        return batch
+
+
     def _build_lipid_grids(self, batch):
         gs = self.rep_settings['lipid_grid']
         lat = self.settings['lateral']
         # grids are built for the owned frames; index 0 = first owned frame (engine row r0)
         r0 = batch.rows.start
         F = batch.rows.stop - batch.rows.start
-        g0 = batch.shard.lo if batch.shard is not None else 0
+        g0 = batch.gframes.start
         if gs['area_per_bin'] is not None:
             bins = [lg.fixed_resolution_bins(batch.box_host[g0 + f][lat[0]], batch.box_host[g0 + f][lat[1]],
                                              gs['area_per_bin']) for f in range(F)]
@@ -637,6 +886,7 @@ class BilayerAnalyzer(object):
             proto = self._analysis_protocol.command_protocol[a_id]
             if getattr(proto, 'batched', False):
                 proto.run_batch(self.settings, batch, self._mda_data)
+                proto.finish(batch)
         self._legacy = [self._analysis_protocol.command_protocol[a] for a in
                         self._analysis_protocol.analysis_ids
                         if not getattr(self._analysis_protocol.command_protocol[a], 'batched', False)]
@@ -712,6 +962,19 @@ class BilayerAnalyzer(object):
         self._iterating_for_user = False
         try:
             if not getattr(self, '_started', False):
+                W = self._window_choice()
+                if W is not None:
+                    try:
+                        self._run_windowed(W, allow_fused=True)
+                    except FusedPathRejected:
+                        self._analysis_protocol.reset()
+                        self._run_windowed(W, allow_fused=False)
+                    n_own = len(self._frames)
+                    self._frame_loop_count += n_own
+                    self.settings['frame_index'] = int(self._frames_all[-1])
+                    self._current_frame = int(self._frames_all[-1]) + self.settings['frame_range'][2]
+                    self._started = False
+                    return
                 self._started = False
                 self._start()
                 self._cursor = self._batch.rows.start

@@ -32,6 +32,7 @@
 
 #define CL_THREADS 256
 #define CL_QCAP 128
+#define CL_MAX_TYPES 8
 
 struct ClGeom {
     int ncx, ncy, ncell, mx, my;
@@ -88,6 +89,9 @@ struct ClParams {
     int *scell;                     // [F][N] leaf*ncell + cell
     unsigned char *sflag;           // [F][N] bit0 type A, bit1 type B
     int32_t *frame_counts;          // RDF output [F][2][3] (may be NULL)
+    int multi, n_types;             // multi != 0: every type pair at once; sflag holds the type code
+    int32_t *type_counts;           // multi: [F][2][n_types] lipids per leaflet and type
+    int32_t *dummy_fc;              // [F][6] scratch for the dense kernel's per-frame counts
 };
 
 struct ClFrame {
@@ -111,9 +115,13 @@ __device__ __forceinline__ ClFrame cl_frame(const ClParams &P, int64_t f)
 __device__ __forceinline__ bool cl_classify(const ClParams &P, const uint8_t *lab, int64_t i, int *leaf,
                                             unsigned *flag)
 {
+    *leaf = lab[i] ? 0 : 1;
+    if (P.multi) {
+        *flag = (unsigned)P.type_code[i];
+        return true;
+    }
     const int t = (P.ta == -1 && P.tb == -1) ? 0 : P.type_code[i];
     const bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
-    *leaf = lab[i] ? 0 : 1;
     *flag = (a ? 1u : 0u) | (b ? 2u : 0u);
     return P.members_all || a || b;
 }
@@ -136,12 +144,20 @@ k_cl_count(ClParams P)
     int *fill = P.cell_fill + f * P.cstride;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int c[7] = {0, 0, 0, 0, 0, 0, 0};
+    __shared__ int s_tc[2 * CL_MAX_TYPES];
+    if (threadIdx.x < 2 * CL_MAX_TYPES) s_tc[threadIdx.x] = 0;
+    __syncthreads();
     if (i < P.N) {
         int leaf;
         unsigned flag;
         const bool listed = cl_classify(P, lab, i, &leaf, &flag);
-        c[leaf * 3 + 0] = flag & 1u;
-        c[leaf * 3 + 1] = (flag >> 1) & 1u;
+        if (P.multi) {
+            c[leaf * 3 + 0] = c[leaf * 3 + 1] = 1;
+            if ((int)flag < P.n_types) atomicAdd(&s_tc[leaf * P.n_types + (int)flag], 1);
+        } else {
+            c[leaf * 3 + 0] = flag & 1u;
+            c[leaf * 3 + 1] = (flag >> 1) & 1u;
+        }
         c[leaf * 3 + 2] = 1;
         if (listed) {
             const double x = cf[i * 3 + P.lat0], y = cf[i * 3 + P.lat1];
@@ -160,6 +176,8 @@ k_cl_count(ClParams P)
     }
     __syncthreads();
     if (threadIdx.x < 7 && s_c[threadIdx.x]) atomicAdd(&P.fcounts[f * 8 + threadIdx.x], s_c[threadIdx.x]);
+    if (P.multi && threadIdx.x < 2 * P.n_types && s_tc[threadIdx.x])
+        atomicAdd(&P.type_counts[f * 2 * P.n_types + threadIdx.x], s_tc[threadIdx.x]);
 }
 
 // one CTA per frame: exclusive scan of the 2*ncell populations (tiles of 4096 entries, 128-bit
@@ -279,14 +297,23 @@ __device__ __forceinline__ int cl_bin(double d2, const double *s_thr, int nb)
 }
 
 // the reference's float64 arithmetic for the unordered pair of sorted slots (p, q)
-template <bool SAME>
+// MODE 0: type_a == type_b (every listed lipid is both); 1: flags per lipid; 2: multi -- every
+// ordered type pair has its own histogram, hist[((leaf*T + t_from)*T + t_to)*nb + bin]
+template <int MODE>
 __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double *gy,
                                          const unsigned char *gflag, const double *s_thr, unsigned *myhist,
-                                         int nb, double Lx, double Ly, double hx, double hy)
+                                         int nb, double Lx, double Ly, double hx, double hy,
+                                         const int *gcell, int ncell, int T)
 {
     const int p = (int)e.x, q = (int)e.y;
     int w1 = 1, w2 = 1;
-    if (!SAME) {
+    unsigned *h1 = myhist, *h2 = myhist;
+    if (MODE == 2) {
+        const int tp = gflag[p], tq = gflag[q], leaf = gcell[p] >= ncell;
+        h1 = myhist + (size_t)((leaf * T + tp) * T + tq) * nb;
+        h2 = myhist + (size_t)((leaf * T + tq) * T + tp) * nb;
+    }
+    if (MODE == 1) {
         const unsigned fp = gflag[p], fq = gflag[q];
         w1 = (fp & 1u) && (fq & 2u);            // ordered p -> q
         w2 = (fq & 1u) && (fp & 2u);            // ordered q -> p
@@ -297,7 +324,10 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
     const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
     if (!(wrx | wry)) {
         const int k = cl_bin(fma(dy, dy, __dmul_rn(dx, dx)), s_thr, nb);
-        if (k >= 0) atomicAdd(&myhist[k], (unsigned)(w1 + w2));
+        if (k >= 0) {
+            if (MODE == 2 && h1 != h2) { atomicAdd(&h1[k], 1u); atomicAdd(&h2[k], 1u); }
+            else atomicAdd(&h1[k], (unsigned)(w1 + w2));
+        }
         return;
     }
     double dx2 = dx, dy2 = dy;                  // the q -> p evaluation
@@ -314,11 +344,11 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
     const int ka = cl_bin(d2a, s_thr, nb);
     int kb = ka;
     if (d2b != d2a) kb = cl_bin(d2b, s_thr, nb);
-    if (ka == kb) {
-        if (ka >= 0) atomicAdd(&myhist[ka], (unsigned)(w1 + w2));
+    if (ka == kb && h1 == h2) {
+        if (ka >= 0) atomicAdd(&h1[ka], (unsigned)(w1 + w2));
     } else {
-        if (w1 && ka >= 0) atomicAdd(&myhist[ka], 1u);
-        if (w2 && kb >= 0) atomicAdd(&myhist[kb], 1u);
+        if (w1 && ka >= 0) atomicAdd(&h1[ka], 1u);
+        if (w2 && kb >= 0) atomicAdd(&h2[kb], 1u);
     }
 }
 
@@ -326,23 +356,26 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
 // table entry also says how many table cells separate the d^2 cell from the nearest bin
 // threshold, and a pair closer to a threshold than the float32 rounding bound (`tolc` cells,
 // see DESIGN.md "Why the RDF fast path is exact") goes to the exact float64 queue instead.
-template <bool SAME>
+template <int MODE>
 __global__ void __launch_bounds__(CL_THREADS, 4)
 k_rdf_cl(ClParams P, ClRdf R)
 {
+    constexpr bool SAME = (MODE == 0);
     extern __shared__ unsigned char smem_raw[];
     const int nb = R.nb;
+    const int T = P.n_types;
+    const int hsize = (MODE == 2) ? 2 * T * T * nb : nb;     // entries per histogram copy
     double *s_thr = reinterpret_cast<double *>(smem_raw);                              // nb+1
     uint2 *s_queue = reinterpret_cast<uint2 *>(s_thr + (nb + 1));                      // warps*QCAP
     unsigned *s_hist = reinterpret_cast<unsigned *>(s_queue + (CL_THREADS / 32) * CL_QCAP);   // copies*nb
-    unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_hist + (size_t)R.hist_copies * nb);
+    unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_hist + (size_t)R.hist_copies * hsize);
     __shared__ int s_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int q = tid; q <= nb; q += blockDim.x) s_thr[q] = R.thr[q];
-    for (int q = tid; q < R.hist_copies * nb; q += blockDim.x) s_hist[q] = 0u;
+    for (int q = tid; q < R.hist_copies * hsize; q += blockDim.x) s_hist[q] = 0u;
     for (int c = tid; c < R.lut_n; c += blockDim.x) s_lut[c] = R.lut[c];
-    unsigned *myhist = s_hist + (size_t)(warp % R.hist_copies) * nb;
+    unsigned *myhist = s_hist + (size_t)(warp % R.hist_copies) * hsize;
     uint2 *myq = s_queue + warp * CL_QCAP;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t per_frame = (P.N + R.chunk - 1) / R.chunk;
@@ -392,7 +425,7 @@ k_rdf_cl(ClParams P, ClRdf R)
             const int p = p0 + tid;
             bool pact = p < p_hi;
             float fpx = 0.f, fpy = 0.f;
-            unsigned pflag = 3u;
+            unsigned pflag = 3u, ptype = 0u, pleaf = 0u;
             int cbase = 0, pcx = 0, pcy = 0;
             if (pact) {
                 int pc = gcell[p];
@@ -401,6 +434,7 @@ k_rdf_cl(ClParams P, ClRdf R)
                 const float2 fp = gf[p];
                 fpx = fp.x; fpy = fp.y;
                 if (!SAME) pflag = gflag[p];
+                if (MODE == 2) { ptype = pflag; pleaf = (unsigned)leaf; pflag = (pleaf * T + ptype) * (unsigned)T; }   // row of the pair table
                 cbase = leaf * g.ncell;
                 pc -= cbase;
                 pcy = pc / ncx;
@@ -440,12 +474,21 @@ k_rdf_cl(ClParams P, ClRdf R)
                             const unsigned bin = e & 0xFFu;
                             if (e >= sure_min) {
                                 if (bin != 0xFFu) {
-                                    unsigned w = 2u;
-                                    if (!SAME) {
-                                        const unsigned fqf = gflag[b + t];
-                                        w = ((pflag & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((pflag >> 1) & 1u));
+                                    if (MODE == 2) {
+                                        // ordered pairs p -> q and q -> p land in their own tables
+                                        const unsigned tq = gflag[b + t];
+                                        const unsigned i1 = (pflag + tq) * (unsigned)nb + bin;
+                                        const unsigned i2 = ((pleaf * T + tq) * T + ptype) * (unsigned)nb + bin;
+                                        if (i1 == i2) atomicAdd(&myhist[i1], 2u);
+                                        else { atomicAdd(&myhist[i1], 1u); atomicAdd(&myhist[i2], 1u); }
+                                    } else {
+                                        unsigned w = 2u;
+                                        if (MODE == 1) {
+                                            const unsigned fqf = gflag[b + t];
+                                            w = ((pflag & 1u) & ((fqf >> 1) & 1u)) + ((fqf & 1u) & ((pflag >> 1) & 1u));
+                                        }
+                                        if (w) atomicAdd(&myhist[bin], w);
                                     }
-                                    if (w) atomicAdd(&myhist[bin], w);
                                 }
                             } else {
                                 hit = !all_exact || d2 < cut2_f;
@@ -457,8 +500,8 @@ k_rdf_cl(ClParams P, ClRdf R)
                             qtail += __popc(m);
                             if (qtail - qhead >= 32) {
                                 __syncwarp();
-                                cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
-                                               fr.Lx, fr.Ly, fr.hx, fr.hy);
+                                cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
+                                               fr.Lx, fr.Ly, fr.hx, fr.hy, gcell, g.ncell, T);
                                 qhead += 32;
                                 __syncwarp();
                             }
@@ -469,14 +512,14 @@ k_rdf_cl(ClParams P, ClRdf R)
         }
         __syncwarp();
         if (lane < qtail - qhead)
-            cl_exact<SAME>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb, fr.Lx, fr.Ly,
-                           fr.hx, fr.hy);
+            cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb, fr.Lx, fr.Ly,
+                           fr.hx, fr.hy, gcell, g.ncell, T);
         __syncwarp();
     }
     __syncthreads();
-    for (int q = tid; q < nb; q += blockDim.x) {
+    for (int q = tid; q < hsize; q += blockDim.x) {
         unsigned long long t = 0;
-        for (int c = 0; c < R.hist_copies; c++) t += s_hist[(size_t)c * nb + q];
+        for (int c = 0; c < R.hist_copies; c++) t += s_hist[(size_t)c * hsize + q];
         if (t) atomicAdd(&R.count[q], t);
     }
 }
@@ -627,7 +670,8 @@ static bool cl_carve(pbk_ctx *ctx, const ClPlan &pl, int64_t N, ClParams &P)
     auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
     const int64_t b_cells = up(Fc * pl.cstride * 4), b_fc = up(Fc * 8 * 4), b_d = up(Fc * N * 8),
                   b_i = up(Fc * N * 4), b_c = up(Fc * N);
-    const int64_t total = 2 * b_cells + b_fc + 3 * b_d + 2 * b_i + b_c;
+    const int64_t b_dummy = up(Fc * 6 * 4);
+    const int64_t total = 2 * b_cells + b_fc + 3 * b_d + 2 * b_i + b_c + b_dummy;
     unsigned char *a = (unsigned char *)pbk_arena(ctx, (size_t)total);
     if (!a) return false;
     P.cell_fill = (int *)a; a += b_cells;
@@ -638,7 +682,8 @@ static bool cl_carve(pbk_ctx *ctx, const ClPlan &pl, int64_t N, ClParams &P)
     P.sf = (float2 *)a; a += b_d;
     P.sidx = (int *)a; a += b_i;
     P.scell = (int *)a; a += b_i;
-    P.sflag = a;
+    P.sflag = a; a += b_c;
+    P.dummy_fc = (int32_t *)a;
     return true;
 }
 
@@ -677,11 +722,17 @@ int pbk_grid_knn_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *l
                                int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, const int *frame_flag,
                                int flag_stride, cudaStream_t stream);
 
-int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
-                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
-                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *edges,
-                  const double *thr, unsigned long long *count, int32_t *frame_counts, cudaStream_t st)
+// n_types > 0: multi mode (count[2][T][T][n_bins], type_counts[F][2][T]; type_a/type_b/leaflet_mask unused)
+static int cl_rdf_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                      const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                      int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                      const double *thr, unsigned long long *count, int32_t *frame_counts, int n_types,
+                      int32_t *type_counts, cudaStream_t st)
 {
+    const bool multi = n_types > 0;
+    const int T = multi ? n_types : 1;
+    if (multi) { type_a = type_b = -1; leaflet_mask = 3; }
+    const size_t hsize = multi ? (size_t)2 * T * T * n_bins : (size_t)n_bins;
     if (!thr || !ctx->work || n_bins > 255 || range_lo < 0 || N > 0x7fffff00LL) return PBK_EUNSUPPORTED;
     int m = 0, lut_n = 0;
     if (!ctx->lut || n_bins > 254 || !pbk_rdf_lut16_shape(n_bins, range_lo, range_hi, &m, &lut_n)) return PBK_EUNSUPPORTED;
@@ -696,13 +747,14 @@ int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
     R.count = count; R.chunk = 2048;
     R.hist_copies = CL_THREADS / 32;
     auto smem_for = [&](int c) {
-        return (size_t)(n_bins + 1) * 8 + (size_t)(CL_THREADS / 32) * CL_QCAP * 8 + (size_t)c * n_bins * 4 +
+        return (size_t)(n_bins + 1) * 8 + (size_t)(CL_THREADS / 32) * CL_QCAP * 8 + (size_t)c * hsize * 4 +
                (size_t)lut_n * 2 + 16;
     };
     while (R.hist_copies > 1 && smem_for(R.hist_copies) > 48 * 1024) R.hist_copies >>= 1;
     const size_t smem = smem_for(R.hist_copies);
+    if (smem > 100 * 1024) return PBK_EUNSUPPORTED;
     const bool same = (type_a == type_b);
-    auto kern = same ? k_rdf_cl<true> : k_rdf_cl<false>;
+    auto kern = multi ? k_rdf_cl<2> : (same ? k_rdf_cl<0> : k_rdf_cl<1>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_rdf_cl smem attribute", e);
     int per_sm = 0;
@@ -714,12 +766,15 @@ int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
     P.N = N; P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
     P.members_all = 0; P.wmin = 0.51 * range_hi + 1e-6; P.range_hi = range_hi; P.occ = 0.0;
     P.ncap = pl.ncap; P.cstride = pl.cstride; P.type_code = type_code;
+    P.multi = multi ? 1 : 0; P.n_types = T; P.type_counts = nullptr;
+    if (multi) P.members_all = 1;
     if (!cl_carve(ctx, pl, N, P)) return pbk_fail(ctx, PBK_ECUDA, "pbk_rdf: scratch arena");
     for (int64_t f0 = 0; f0 < F; f0 += pl.Fc) {
         const int64_t Fc = (F - f0 < pl.Fc) ? F - f0 : pl.Fc;
         P.F = Fc;
         P.com = com + f0 * N * 3; P.labels = labels + f0 * N; P.box = box + f0 * 3;
-        P.frame_counts = frame_counts + f0 * 6;
+        P.frame_counts = multi ? nullptr : frame_counts + f0 * 6;
+        P.type_counts = multi ? type_counts + f0 * 2 * T : nullptr;
         int rc = cl_build(ctx, pl, P, st);
         if (rc) return rc;
         R.work = ctx->work + (ctx->work_next++ % PBK_WORK_SLOTS);
@@ -730,12 +785,53 @@ int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
         if (grid > items) grid = items;
         kern<<<(unsigned)grid, CL_THREADS, smem, st>>>(P, R);
         PBK_CHECK_LAUNCH(ctx, "k_rdf_cl");
-        rc = pbk_rdf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, type_a, type_b,
-                                   leaflet_mask, n_bins, range_lo, range_hi, edges, count, P.frame_counts,
-                                   P.fcounts + 6, 8, st);
-        if (rc) return rc;
+        if (!multi) {
+            rc = pbk_rdf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, type_a, type_b,
+                                       leaflet_mask, n_bins, range_lo, range_hi, edges, count, P.frame_counts,
+                                       P.fcounts + 6, 8, st);
+            if (rc) return rc;
+        } else {
+            // out-of-box frames: the dense kernel per (leaflet, type pair); its per-frame counts go
+            // to the scratch rows behind the cell data (unused here)
+            for (int l = 0; l < 2; l++)
+                for (int ta_ = 0; ta_ < T; ta_++)
+                    for (int tb_ = 0; tb_ < T; tb_++) {
+                        rc = pbk_rdf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, ta_, tb_,
+                                                   1 << l, n_bins, range_lo, range_hi, edges,
+                                                   count + (size_t)((l * T + ta_) * T + tb_) * n_bins, P.dummy_fc,
+                                                   P.fcounts + 6, 8, st);
+                        if (rc) return rc;
+                    }
+        }
     }
     return PBK_OK;
+}
+
+int pbk_rdf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                  int leaflet_mask, int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                  const double *thr, unsigned long long *count, int32_t *frame_counts, cudaStream_t st)
+{
+    return cl_rdf_run(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b, leaflet_mask, n_bins,
+                      range_lo, range_hi, edges, thr, count, frame_counts, 0, nullptr, st);
+}
+
+extern "C" int pbk_rdf_multi(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                             const float *box, int64_t F, int64_t N, int lat0, int lat1, int n_types,
+                             int32_t n_bins, double range_lo, double range_hi, const double *edges,
+                             const double *thr, unsigned long long *count, int32_t *type_counts, void *stream)
+{
+    if (!ctx || !com || !labels || !type_code || !box || !edges || !thr || !count || !type_counts || F < 0 ||
+        N <= 0 || n_bins <= 0 || !(range_hi > range_lo) || n_types < 1 || lat0 < 0 || lat0 > 2 || lat1 < 0 ||
+        lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_rdf_multi: bad argument");
+    if (n_types > CL_MAX_TYPES) return PBK_EUNSUPPORTED;
+    if (F == 0) return PBK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(type_counts, 0, (size_t)F * 2 * n_types * sizeof(int32_t), st);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "pbk_rdf_multi memset", e);
+    return cl_rdf_run(ctx, com, labels, type_code, box, F, N, lat0, lat1, -1, -1, 3, n_bins, range_lo, range_hi,
+                      edges, thr, count, nullptr, n_types, type_counts, st);
 }
 
 template <bool GRID>
@@ -749,6 +845,7 @@ static int cl_knn_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, co
     P.N = N; P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
     P.members_all = 1; P.wmin = 0.0; P.range_hi = 0.0; P.occ = 4.0;
     P.ncap = pl.ncap; P.cstride = pl.cstride; P.type_code = type_code; P.frame_counts = nullptr;
+    P.multi = 0; P.n_types = 1; P.type_counts = nullptr;
     if (!cl_carve(ctx, pl, N, P)) return pbk_fail(ctx, PBK_ECUDA, "pbk knn: scratch arena");
     ClKnn K;
     K.k = k;

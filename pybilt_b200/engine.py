@@ -161,6 +161,8 @@ class LipidReductionEngine:
         self.labels = torch.empty((self.F, self.N), dtype=torch.uint8, device=d)
         self.box = torch.empty((self.F, 3), dtype=torch.float32, device=d)
         self.n_done = 0
+        self.row_offset = 0
+        self.stream_started = False
         self.launches = 0
         # COMTraj arithmetic (pybilt/com_trajectory/COMTraj.py:1067-1085): scalar float32 unwrap
         # rule and membrane COM accumulated atom by atom; only the generic kernels implement it
@@ -183,7 +185,34 @@ class LipidReductionEngine:
     # ---------------------------------------------------------------------------------
     def reset(self):
         self.n_done = 0
+        self.row_offset = 0             # analysed-frame index of engine row 0 (windowed runs)
+        self.stream_started = False     # the next push holds the first frame of the stream
         self.d_status.zero_()
+
+    def rewind(self, keep: int):
+        """Start the next window of a streamed run: the last ``keep`` reduced rows move to the
+        front of the resident buffers (context for multi-origin MSD blocks and for leaflet
+        update intervals), the rest of the buffers is free again.  The unwrap state carries on."""
+        n = self.n_done
+        keep = int(min(keep, n))
+        if keep and n > keep:
+            for t in (self.com, self.com_unwrap, self.mem_com, self.labels, self.box):
+                t[:keep].copy_(t[n - keep:n].clone())
+        self.row_offset += n - keep
+        self.n_done = keep
+
+    def unwrap_only(self, x: torch.Tensor, box: torch.Tensor):
+        """Advance the unwrap state over ``x`` without reducing the frames (first pass of a
+        streamed frame shard: only the image counts at its end are wanted)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        st = self.stream_ptr()
+        for b0 in range(0, int(x.shape[0]), self.B):
+            xb, bb = x[b0:b0 + self.B], box[b0:b0 + self.B]
+            self.ctx.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
+                          0 if self.stream_started else 1, None, 1 if self.comtraj_rules else 0,
+                          int(xb.shape[0]), self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
+            self.stream_started = True
+            self.launches += 1
 
     def stream_ptr(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -202,8 +231,10 @@ class LipidReductionEngine:
         f_total = int(x.shape[0])
         if self.n_done + f_total > self.F:
             raise RuntimeError("more frames pushed than the engine was sized for")
-        if (phase != 3 or init_images is not None) and (f_total > self.B or self.n_done != 0):
-            raise RuntimeError("sharded pushes must be the first push and fit one engine batch")
+        if phase != 3 and (f_total > self.B or self.n_done != 0):
+            raise RuntimeError("two-phase (sharded) pushes must be the first push and fit one engine batch")
+        if init_images is not None and self.stream_started:
+            raise RuntimeError("init_images belongs to the first frame of the stream")
         st = self.stream_ptr()
         c = self.ctx
         for b0 in range(0, f_total, self.B):
@@ -211,6 +242,7 @@ class LipidReductionEngine:
             nb = b1 - b0
             xb, bb = x[b0:b1], box[b0:b1]
             g0 = self.n_done
+            init_b = init_images if b0 == 0 else None      # image counts of the stream's first frame
             if phase & 2:
                 self.box[g0:g0 + nb].copy_(bb)
             p = self.plan
@@ -223,8 +255,8 @@ class LipidReductionEngine:
                                 self.d_leaf_start.data_ptr(), self.d_leaf_len.data_ptr(), p.n_leaves,
                                 self.d_node_left.data_ptr(), self.d_node_right.data_ptr(), p.n_nodes,
                                 self.d_level_off.data_ptr(), p.n_levels, self.total_mass,
-                                self.d_u_state.data_ptr(), 1 if g0 == 0 else 0, nb, self.M, self.N,
-                                self.norm, do_labels, int(phase), _ptr(init_images), _ptr(net_out),
+                                self.d_u_state.data_ptr(), 0 if self.stream_started else 1, nb, self.M, self.N,
+                                self.norm, do_labels, int(phase), _ptr(init_b), _ptr(net_out),
                                 scratch.data_ptr(), int(scratch.numel()),
                                 self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
                                 self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(),
@@ -235,11 +267,12 @@ class LipidReductionEngine:
                     if not (phase & 2):
                         continue
                     if not do_labels:
-                        c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
-                               self.update_interval, prev, self.labels[g0:].data_ptr(),
+                        c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm,
+                               g0 + self.row_offset, self.update_interval, prev, self.labels[g0:].data_ptr(),
                                self.d_status.data_ptr(), st)
                         self.launches += 1
                     self.n_done += nb
+                    self.stream_started = True
                     continue
                 self.allow_fused = False          # frame does not fit in shared memory
                 self.fused_supported = False
@@ -253,7 +286,7 @@ class LipidReductionEngine:
                     net_out.copy_(self.d_img[nb - 1].to(torch.int32))
                 continue
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
-                   1 if g0 == 0 else 0, _ptr(init_images), 1 if self.comtraj_rules else 0, nb, self.M,
+                   0 if self.stream_started else 1, _ptr(init_b), 1 if self.comtraj_rules else 0, nb, self.M,
                    self.d_img.data_ptr(), self.d_status.data_ptr(), st)
             if self.comtraj_rules:
                 c.call("pbk_membrane_com_seq", xb.data_ptr(), bb.data_ptr(), self.d_img.data_ptr(),
@@ -268,10 +301,11 @@ class LipidReductionEngine:
                    self.d_mass.data_ptr(), self.mem_com[g0:].data_ptr(), self.d_seg.data_ptr(),
                    _ptr(self.d_gather), self.d_bead_mass.data_ptr(), nb, self.M, self.N,
                    self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(), st)
-            c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0,
+            c.call("pbk_leaflets", self.com_unwrap[g0:].data_ptr(), nb, self.N, self.norm, g0 + self.row_offset,
                    self.update_interval, prev, self.labels[g0:].data_ptr(), self.d_status.data_ptr(), st)
             self.launches += 5
             self.n_done += nb
+            self.stream_started = True
 
     def image_counts_last(self, x_last: torch.Tensor, box_last: torch.Tensor) -> torch.Tensor:
         """int32 [M, 3] image counts of the last pushed frame, recovered from the carried
@@ -342,6 +376,33 @@ class LipidReductionEngine:
                       count.data_ptr(), fc.data_ptr(), self.stream_ptr())
         self.launches += 2 if (self.N <= 512 and not dense) else 1      # (k_rdf5_lut + k_rdf5 for small systems)
         return count, fc
+
+    def rdf_multi(self, type_code: torch.Tensor, n_types: int, edges, lateral=(0, 1),
+                  frames: Optional[slice] = None):
+        """One pair sweep for every ordered type pair and leaflet: (count int64 [2, T, T, n_bins],
+        type_counts int32 [F, 2, T]), or None when libpbk has no table-per-pair path for this shape
+        (the caller then asks per analysis)."""
+        d = self.dev
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        nb = len(edges) - 1
+        key = np.ascontiguousarray(edges, dtype=np.float64).tobytes()
+        cached = self._rdf_tables.get(key)
+        if cached is None:
+            cached = (torch.as_tensor(np.ascontiguousarray(edges, dtype=np.float64), device=d),
+                      torch.as_tensor(rdf_thresholds(edges), device=d))
+            self._rdf_tables[key] = cached
+        count = torch.zeros((2, n_types, n_types, nb), dtype=torch.int64, device=d)
+        tc = torch.empty((F, 2, n_types), dtype=torch.int32, device=d)
+        ok = self.ctx.try_call("pbk_rdf_multi", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
+                               type_code.data_ptr(), self.box[sl.start:].data_ptr(), F, self.N, int(lateral[0]),
+                               int(lateral[1]), int(n_types), nb, float(edges[0]), float(edges[-1]),
+                               cached[0].data_ptr(), cached[1].data_ptr(), count.data_ptr(), tc.data_ptr(),
+                               self.stream_ptr())
+        if not ok:
+            return None
+        self.launches += 5
+        return count, tc
 
     def nnf(self, type_code: torch.Tensor, type_a: int, type_b: int, leaflet_mask: int, k: int,
             lateral=(0, 1), frames: Optional[slice] = None):

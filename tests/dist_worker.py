@@ -3,6 +3,9 @@
 
 mode cpu : the shard algebra (one-frame back halo, net image counts, exclusive prefix over
            ranks) with the oracle port standing in for the device, gloo backend, no GPU.
+mode cpuwin : the same for streamed shards (context frames before the first owned frame, image
+           counts taken where the next rank's stream starts).
+mode gpuwin : like gpu, but as a streamed run (window_frames = $PBK_TEST_WINDOW).
 mode gpu : pybilt_b200.BilayerAnalyzer sharded over the ranks (NCCL when every rank has its
            own GPU, otherwise gloo with the ranks sharing GPU 0) against the golden fixture.
 """
@@ -47,6 +50,34 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         dist.destroy_process_group()
         sys.exit(0 if int(flag) == 1 else 3)
+    if mode == "cpuwin":
+        # streamed shards (BilayerAnalyzer._run_windowed): rank r's stream starts C frames before its
+        # first owned frame; the image counts there = prefix over ranks of the counts each rank finds,
+        # unwrapping alone, at the frame where the NEXT rank's stream starts
+        from oracle import port
+        dist.init_process_group("gloo")
+        X, box = traj.positions, traj.dimensions[:, :3]
+        F = X.shape[0]
+        C = 2
+        serial = port.unwrap(X, box)
+        starts = [max(0, pd.shard_bounds(F, world, q)[0] - C) for q in range(world)]
+        lo, hi = pd.shard_bounds(F, world, rank)
+        a = starts[rank]
+        net = np.zeros(X.shape[1:], dtype=np.int32)
+        if rank < world - 1 and starts[rank + 1] > a:
+            seg = slice(a, starts[rank + 1] + 1)
+            U = port.unwrap(X[seg], box[seg])
+            net = np.rint((U[-1].astype(np.float64) - X[seg][-1]) / box[seg][-1][None, :]).astype(np.int32)
+        off = pd.image_offsets(torch.from_numpy(net.copy())).numpy()
+        loc = slice(a, hi)
+        U_loc = port.unwrap(X[loc], box[loc])
+        s_loc = np.rint((U_loc.astype(np.float64) - X[loc]) / box[loc][:, None, :]).astype(np.int32)
+        u_true = (X[loc].astype(np.float64) + (s_loc + off[None]) * box[loc][:, None, :].astype(np.float64)).astype(np.float32)
+        ok = np.array_equal(u_true, serial[loc])
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag) == 1 else 3)
     # ---- gpu ----
     ngpu = torch.cuda.device_count()
     own_gpu = ngpu >= world
@@ -63,6 +94,8 @@ def main():
         ba.rep_settings[rep].update(d)
     if c.get("frame_range"):
         ba.set_frame_range(*c["frame_range"])
+    if mode == "gpuwin":
+        ba.window_frames = int(os.environ.get("PBK_TEST_WINDOW", "4"))
     ba.run_analysis()
     flat = cases.flatten_outputs({k: ba.get_analysis_data(k) for k in ba.get_analysis_ids()})
     ok = True
@@ -72,6 +105,13 @@ def main():
         if a.shape != b.shape or not good.all():
             print("rank", rank, "MISMATCH", k, flush=True)
             ok = False
+    if mode == "gpuwin":
+        flag = torch.tensor([1 if ok else 0])
+        if own_gpu:
+            flag = flag.cuda()
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag) == 1 else 3)
     sh = ba._shard
     e = ba._engine
     rows = sh.owned_local()

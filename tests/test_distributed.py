@@ -76,3 +76,19 @@ def test_shard_unwrap_algebra_gloo_cpu(world, case):
 def test_sharded_analyzer_matches_reference(world, case):
     codes, outs = launch(world, "gpu", case)
     assert codes == [0] * world, outs
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["big_steps", "tiny_all"])
+def test_streamed_shard_unwrap_algebra_gloo_cpu(world, case):
+    codes, outs = launch(world, "cpuwin", case)
+    assert codes == [0] * world, outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,case,window", [(2, "tiny_all", 4), (2, "c2_prefix", 7), (3, "c3_small", 2),
+                                               (2, "name_dict", 3), (2, "grid_dense", 1000)])
+def test_streamed_sharded_analyzer_matches_reference(world, case, window, monkeypatch):
+    monkeypatch.setenv("PBK_TEST_WINDOW", str(window))
+    codes, outs = launch(world, "gpuwin", case)
+    assert codes == [0] * world, outs

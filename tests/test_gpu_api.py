@@ -159,3 +159,35 @@ def test_comtraj_matches_reference(name):
     fr = ct.frame[3]
     assert np.array_equal(np.array([l.com_unwrap for l in fr.lipidcom]), gold["com_unwrap"][3])
     assert fr.lipidcom[0].type == top.resnames[0] and len(ct.frame) == ct.nframes
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+@pytest.mark.parametrize("window", [3, 5, 1000])
+def test_windowed_run_matches_resident_run(name, window):
+    """Streamed run (bounded engine, windows of `window` frames with context rows) against the
+    resident run and the literal reference: same outputs, whatever the window size."""
+    gold = load(name)
+    ba, c = make_analyzer(name)
+    ba.run_analysis()
+    want = cases.flatten_outputs({a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()})
+    bw, c = make_analyzer(name)
+    bw.window_frames = window
+    bw.run_analysis()
+    got = cases.flatten_outputs({a_id: bw.get_analysis_data(a_id) for a_id in bw.get_analysis_ids()})
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k]), equal_nan=True), k
+        if k in gold:
+            close(got[k], gold[k], 1e-9, atol=1e-300)
+
+
+def test_window_is_chosen_automatically_when_resident_state_exceeds_budget():
+    ba, c = make_analyzer("c2_prefix")
+    assert ba._window_choice() is None
+    ba.resident_budget_bytes = 1 << 10
+    assert ba._window_choice() >= 256
+    ba.run_analysis()
+    gold = load("c2_prefix")
+    flat = cases.flatten_outputs({a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()})
+    for k in [k for k in gold if k.startswith("out/")]:
+        close(flat[k], gold[k], 1e-9, atol=1e-300)

@@ -105,3 +105,32 @@ def test_cells_out_of_box_frames_nnf_and_grid(monkeypatch):
     want = run_all()
     for i, (g, w) in enumerate(zip(got, want)):
         assert np.array_equal(g, w), i
+
+
+@pytest.mark.parametrize("n_lipids,oob", [(512, False), (2048, False), (6000, True)])
+def test_rdf_multi_tables_equal_per_pair_calls(n_lipids, oob):
+    """pbk_rdf_multi: one sweep, one table per (leaflet, type_i, type_j); every table must equal the
+    per-analysis kernel's histogram, and type_counts its (N_a, N_b, N_leaflet) rows."""
+    e, names, codes = _mid_engine(n_lipids, 3, 41)
+    if oob:
+        L = float(e.box[0, 0])
+        com = e.com.clone()
+        com[1, ::7, 0] += L
+        e.com.copy_(com)
+    T = len(names)
+    for nb, lo, hi in [(25, 0.0, 25.0), (80, 0.0, 40.0), (30, 2.0, 32.0)]:
+        edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
+        table, tc = e.rdf_multi(codes, T, edges)
+        table, tc = table.cpu().numpy(), tc.cpu().numpy()
+        for leaf in range(2):
+            for a in range(T):
+                for b in range(T):
+                    cnt, fc = e.rdf(codes, a, b, 1 << leaf, edges)
+                    assert np.array_equal(table[leaf, a, b], cnt.cpu().numpy()), (nb, leaf, a, b)
+                    fc = fc.cpu().numpy()
+                    on = (tc[:, leaf, a] > 0) & (tc[:, leaf, b] > 0)
+                    assert np.array_equal(fc[:, leaf, 0], np.where(on, tc[:, leaf, a], 0))
+                    assert np.array_equal(fc[:, leaf, 1], np.where(on, tc[:, leaf, b], 0))
+                    assert np.array_equal(fc[:, leaf, 2], tc[:, leaf].sum(axis=1))
+        cnt_all, _ = e.rdf(codes, -1, -1, 3, edges)
+        assert np.array_equal(table.sum(axis=(0, 1, 2)), cnt_all.cpu().numpy())
