@@ -194,6 +194,21 @@ int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_
             const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
             int leaflet_mask, int k, int32_t *n_b, double *frac, void *stream);
 
+/* ---- D3, many analyses at once ------------------------------------------------------------
+ * The prefab drivers request one nnf analysis per ordered resname pair
+ * (pybilt/bilayer_analyzer/prefab_analysis_protocols.py:880-890).  pbk_nnf_multi searches the k
+ * nearest leaflet members of EVERY lipid once and tallies their types:
+ * type_hits[F][N][n_types] int32, type_counts[F][2][n_types] int32 (lipids per leaflet and type).
+ * pbk_nnf_select then forms the n_b[F][N] / frac[F] outputs of pbk_nnf for one
+ * (type_a, type_b, leaflet_mask) from those tallies.  PBK_EUNSUPPORTED for more than 8 types. */
+int pbk_nnf_multi(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                  const float *box, int64_t F, int64_t N, int lat0, int lat1, int n_types, int k,
+                  int32_t *type_hits, int32_t *type_counts, void *stream);
+int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_counts,
+                   const uint8_t *labels, const int32_t *type_code, int64_t F, int64_t N, int n_types,
+                   int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b, double *frac,
+                   void *stream);
+
 /* ---- G1 / G2  lipid grids ---------------------------------------------------------------
  * lipid_grid_opt.LipidGrid2d.__init__ + _knn  pybilt/lipid_grid/lipid_grid_opt.py:155-334,435-468
  * lipid_grid.LipidGrid2d.__init__ (exact)     pybilt/lipid_grid/lipid_grid.py:150-248

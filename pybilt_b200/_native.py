@@ -55,6 +55,10 @@ _SIGNATURES = {
                               c_void_p, c_void_p]),
     "pbk_nnf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pbk_nnf_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pbk_nnf_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_lipid_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

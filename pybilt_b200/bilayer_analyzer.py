@@ -238,6 +238,7 @@ class ReductionBatch(object):
         self.first_leaflets = first_leaflets
         self._grids = None
         self._rdf_multi = {}
+        self._nnf_multi = {}
 
     def row_of_global(self, g):
         """engine row of analysed frame g"""
@@ -282,6 +283,21 @@ class ReductionBatch(object):
                     res = (r[0].cpu().numpy(), r[1].cpu().numpy().astype(np.int64))
             self._rdf_multi[key] = res
         return self._rdf_multi[key]
+
+    def nnf_shared(self, k, lateral):
+        """Device tallies (type_hits [F,N,T], type_counts [F,2,T]) of ONE neighbour search over this
+        batch's frames shared by every nnf analysis with this n_neighbors, or None."""
+        key = (int(k), tuple(lateral))
+        if key not in self._nnf_multi:
+            res = None
+            n = sum(1 for a in self._analyzer._analysis_protocol.analysis_ids
+                    if self._analyzer._analysis_protocol.command_protocol[a].analysis_key == 'nnf' and
+                    int(self._analyzer._analysis_protocol.command_protocol[a].settings['n_neighbors']) == int(k))
+            if n >= 2 and os.environ.get("PBK_NO_NNF_MULTI") is None:
+                res = self.engine.nnf_multi(self.type_code_dev, len(self.type_names), k, lateral,
+                                            frames=self.rows)
+            self._nnf_multi[key] = res
+        return self._nnf_multi[key]
 
     def lipid_grids(self) -> GridBatch:
         if self._grids is None:

@@ -529,16 +529,20 @@ k_rdf_cl(ClParams P, ClRdf R)
 // ---------------------------------------------------------------------------------------
 struct ClKnn {
     int k;
-    int32_t *n_b;                   // NNF: [F][N] count of type-B lipids among the k nearest (-1: not a reference lipid)
+    int32_t *n_b;                   // NNF: [F][N] count of type-B lipids among the k nearest (-1: not a reference lipid);
+                                    // multi: [F][N][n_types] hits per type
     int32_t *knn;                   // grid: [F][N][24] neighbour indices, -1 padded
 };
 
 // GRID: the reference's _knn evaluates each unordered pair once as dist(lower index, higher
 // index) (lipid_grid_opt.py:452-459); NNF: dist(reference lipid, other) (:2204).
-template <int KMAX, bool GRID>
+// MODE 0: NNF counts of type-B neighbours; 1 (GRID): the neighbour table; 2: NNF for every type at
+// once -- hits[f][i][t] = lipids of type t among the k nearest (every lipid is a reference lipid)
+template <int KMAX, int MODE>
 __global__ void __launch_bounds__(128)
 k_knn_cl(ClParams P, ClKnn K)
 {
+    constexpr bool GRID = (MODE == 1);
     const int64_t f = blockIdx.y;
     const int *fc = P.fcounts + f * 8;
     if (fc[6]) return;                                           // out-of-box frame
@@ -555,7 +559,7 @@ k_knn_cl(ClParams P, ClKnn K)
     const int leaf = pc >= g.ncell;
     const int cbase = leaf * g.ncell;
     pc -= cbase;
-    if (!GRID) {
+    if (MODE == 0) {
         const bool on = ((P.leaflet_mask >> leaf) & 1) && fc[leaf * 3] > 0 && fc[leaf * 3 + 1] > 0;
         if (!on || !(P.sflag[f * P.N + p] & 1u)) {
             K.n_b[f * P.N + i] = -1;
@@ -630,6 +634,19 @@ k_knn_cl(ClParams P, ClKnn K)
     if (GRID) {
         int32_t *o = K.knn + (f * P.N + i) * 24;
         for (int t = 0; t < 24; t++) o[t] = t < nbest ? bj[t] : -1;
+    } else if (MODE == 2) {
+        int h[CL_MAX_TYPES];
+#pragma unroll
+        for (int t = 0; t < CL_MAX_TYPES; t++) h[t] = 0;
+        for (int t = 0; t < nbest; t++) {
+            const int tj = P.type_code[bj[t]];
+#pragma unroll
+            for (int u = 0; u < CL_MAX_TYPES; u++) h[u] += (tj == u) ? 1 : 0;
+        }
+        int32_t *o = K.n_b + (f * P.N + i) * P.n_types;
+#pragma unroll
+        for (int u = 0; u < CL_MAX_TYPES; u++)
+            if (u < P.n_types) o[u] = h[u];
     } else {
         int c = 0;
         for (int t = 0; t < nbest; t++) {
@@ -721,6 +738,10 @@ int pbk_nnf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels
 int pbk_grid_knn_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const float *box,
                                int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, const int *frame_flag,
                                int flag_stride, cudaStream_t stream);
+int pbk_nnf_dense_strided(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int k, int32_t *n_b, int out_stride, const int *frame_flag,
+                          int flag_stride, cudaStream_t stream);
 
 // n_types > 0: multi mode (count[2][T][T][n_bins], type_counts[F][2][T]; type_a/type_b/leaflet_mask unused)
 static int cl_rdf_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
@@ -834,18 +855,20 @@ extern "C" int pbk_rdf_multi(pbk_ctx *ctx, const double *com, const uint8_t *lab
                       edges, thr, count, nullptr, n_types, type_counts, st);
 }
 
-template <bool GRID>
+template <int MODE>
 static int cl_knn_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
                       const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
-                      int leaflet_mask, int k, int32_t *n_b, int32_t *knn, cudaStream_t st)
+                      int leaflet_mask, int k, int32_t *n_b, int32_t *knn, int n_types, int32_t *type_counts,
+                      cudaStream_t st)
 {
+    constexpr bool GRID = (MODE == 1);
     if (N > 0x7fffff00LL) return PBK_EUNSUPPORTED;
     ClPlan pl = cl_plan(F, N);
     ClParams P;
     P.N = N; P.lat0 = lat0; P.lat1 = lat1; P.ta = type_a; P.tb = type_b; P.leaflet_mask = leaflet_mask;
     P.members_all = 1; P.wmin = 0.0; P.range_hi = 0.0; P.occ = 4.0;
     P.ncap = pl.ncap; P.cstride = pl.cstride; P.type_code = type_code; P.frame_counts = nullptr;
-    P.multi = 0; P.n_types = 1; P.type_counts = nullptr;
+    P.multi = (MODE == 2) ? 1 : 0; P.n_types = (MODE == 2) ? n_types : 1; P.type_counts = nullptr;
     if (!cl_carve(ctx, pl, N, P)) return pbk_fail(ctx, PBK_ECUDA, "pbk knn: scratch arena");
     ClKnn K;
     K.k = k;
@@ -853,20 +876,26 @@ static int cl_knn_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, co
         const int64_t Fc = (F - f0 < pl.Fc) ? F - f0 : pl.Fc;
         P.F = Fc;
         P.com = com + f0 * N * 3; P.labels = labels + f0 * N; P.box = box + f0 * 3;
-        K.n_b = n_b ? n_b + f0 * N : nullptr;
+        K.n_b = n_b ? n_b + f0 * N * (MODE == 2 ? n_types : 1) : nullptr;
+        P.type_counts = (MODE == 2) ? type_counts + f0 * 2 * n_types : nullptr;
         K.knn = knn ? knn + f0 * N * 24 : nullptr;
         int rc = cl_build(ctx, pl, P, st);
         if (rc) return rc;
         dim3 g((unsigned)((N + 127) / 128), (unsigned)Fc);
-        if (GRID) k_knn_cl<24, true><<<g, 128, 0, st>>>(P, K);
-        else if (k <= 8) k_knn_cl<8, false><<<g, 128, 0, st>>>(P, K);
-        else if (k <= 24) k_knn_cl<24, false><<<g, 128, 0, st>>>(P, K);
-        else k_knn_cl<64, false><<<g, 128, 0, st>>>(P, K);
+        if (GRID) k_knn_cl<24, 1><<<g, 128, 0, st>>>(P, K);
+        else if (k <= 8) k_knn_cl<8, MODE><<<g, 128, 0, st>>>(P, K);
+        else if (k <= 24) k_knn_cl<24, MODE><<<g, 128, 0, st>>>(P, K);
+        else k_knn_cl<64, MODE><<<g, 128, 0, st>>>(P, K);
         PBK_CHECK_LAUNCH(ctx, "k_knn_cl");
         if (GRID)
             rc = pbk_grid_knn_dense_flagged(ctx, P.com, P.labels, P.box, Fc, N, lat0, lat1, K.knn,
                                             P.fcounts + 6, 8, st);
-        else
+        else if (MODE == 2) {
+            // out-of-box frames: the dense kernel once per type (every lipid a reference lipid)
+            for (int t = 0; t < n_types && !rc; t++)
+                rc = pbk_nnf_dense_strided(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, -1, t, 3, k,
+                                           K.n_b + t, n_types, P.fcounts + 6, 8, st);
+        } else
             rc = pbk_nnf_dense_flagged(ctx, P.com, P.labels, type_code, P.box, Fc, N, lat0, lat1, type_a,
                                        type_b, leaflet_mask, k, K.n_b, P.fcounts + 6, 8, st);
         if (rc) return rc;
@@ -878,15 +907,15 @@ int pbk_nnf_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
                   const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
                   int leaflet_mask, int k, int32_t *n_b, cudaStream_t st)
 {
-    return cl_knn_run<false>(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b, leaflet_mask,
-                             k, n_b, nullptr, st);
+    return cl_knn_run<0>(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b, leaflet_mask,
+                         k, n_b, nullptr, 0, nullptr, st);
 }
 
 int pbk_grid_knn_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code_or_null,
                        const float *box, int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, cudaStream_t st)
 {
     (void)type_code_or_null;
-    return cl_knn_run<true>(ctx, com, labels, nullptr, box, F, N, lat0, lat1, -1, -1, 3, 24, nullptr, knn, st);
+    return cl_knn_run<1>(ctx, com, labels, nullptr, box, F, N, lat0, lat1, -1, -1, 3, 24, nullptr, knn, 0, nullptr, st);
 }
 
 // which systems take the cell-list kernels: N above the entry point's threshold, or every
@@ -896,4 +925,21 @@ bool pbk_use_cells(int64_t N, int64_t threshold)
     if (getenv("PBK_NO_CELLS")) return false;
     if (getenv("PBK_FORCE_CELLS")) return true;
     return N > threshold;
+}
+
+// ---- D3, many analyses at once: the k nearest neighbours found once, their types tallied ----
+extern "C" int pbk_nnf_multi(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                             const float *box, int64_t F, int64_t N, int lat0, int lat1, int n_types, int k,
+                             int32_t *type_hits, int32_t *type_counts, void *stream)
+{
+    if (!ctx || !com || !labels || !type_code || !box || !type_hits || !type_counts || F < 0 || N <= 0 ||
+        n_types < 1 || k < 1 || k > 64 || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_nnf_multi: bad argument (1 <= k <= 64)");
+    if (n_types > CL_MAX_TYPES) return PBK_EUNSUPPORTED;
+    if (F == 0) return PBK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(type_counts, 0, (size_t)F * 2 * n_types * sizeof(int32_t), st);
+    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "pbk_nnf_multi memset", e);
+    return cl_knn_run<2>(ctx, com, labels, type_code, box, F, N, lat0, lat1, -1, -1, 3, k, type_hits, nullptr,
+                         n_types, type_counts, st);
 }

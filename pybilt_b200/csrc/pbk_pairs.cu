@@ -170,7 +170,7 @@ int pbk_rdf_dense(pbk_ctx *ctx, const double *com, const uint8_t *labels, const 
 __global__ void __launch_bounds__(PAIR_THREADS)
 k_nnf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
       const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N, int lat0,
-      int lat1, int ta, int tb, int leaflet_mask, int k, int32_t *__restrict__ n_b,
+      int lat1, int ta, int tb, int leaflet_mask, int k, int32_t *__restrict__ n_b, int out_stride,
       const int *__restrict__ frame_flag, int flag_stride)
 {
     if (frame_flag && !frame_flag[(int64_t)blockIdx.x * flag_stride]) return;   // only flagged frames
@@ -232,7 +232,7 @@ k_nnf(const double *__restrict__ com, const uint8_t *__restrict__ labels,
             }
         }
     }
-    if (i < N) n_b[f * N + i] = iact ? __popcll(bmask) : -1;
+    if (i < N) n_b[(f * N + i) * out_stride] = iact ? __popcll(bmask) : -1;
 }
 
 // Welford mean of n_b/k over the reference lipids of a frame, upper members first
@@ -268,15 +268,72 @@ k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ la
     if (lane == 0) frac[f] = m;
 }
 
+int pbk_nnf_dense_strided(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
+                          const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
+                          int leaflet_mask, int k, int32_t *n_b, int out_stride, const int *frame_flag,
+                          int flag_stride, cudaStream_t stream)
+{
+    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
+    k_nnf<<<grid, PAIR_THREADS, 0, stream>>>(com, labels, type_code, box, N, lat0, lat1, type_a, type_b,
+                                             leaflet_mask, k, n_b, out_stride, frame_flag, flag_stride);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf");
+    return PBK_OK;
+}
+
 int pbk_nnf_dense_flagged(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
                           const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
                           int leaflet_mask, int k, int32_t *n_b, const int *frame_flag, int flag_stride,
                           cudaStream_t stream)
 {
-    dim3 grid((unsigned)F, (unsigned)((N + PAIR_THREADS - 1) / PAIR_THREADS));
-    k_nnf<<<grid, PAIR_THREADS, 0, stream>>>(com, labels, type_code, box, N, lat0, lat1, type_a, type_b,
-                                             leaflet_mask, k, n_b, frame_flag, flag_stride);
-    PBK_CHECK_LAUNCH(ctx, "k_nnf");
+    return pbk_nnf_dense_strided(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
+                                 leaflet_mask, k, n_b, 1, frame_flag, flag_stride, stream);
+}
+
+// n_b of one (type_a, type_b, leaflets) analysis from the per-type neighbour tallies of
+// pbk_nnf_multi: a lipid of type_a in a selected leaflet that holds both types gets the number of
+// type_b lipids among its k nearest, everyone else -1.
+__global__ void __launch_bounds__(256)
+k_nnf_select(const int32_t *__restrict__ hits, const int32_t *__restrict__ type_counts,
+             const uint8_t *__restrict__ labels, const int32_t *__restrict__ type_code, int64_t N, int T,
+             int ta, int tb, int leaflet_mask, int32_t *__restrict__ n_b)
+{
+    const int64_t f = blockIdx.x;
+    const int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int leaf = labels[f * N + i] ? 0 : 1;
+    const int32_t *tc = type_counts + (f * 2 + leaf) * T;
+    int ca = 0, cb = 0;
+    for (int t = 0; t < T; t++) {
+        ca += (ta == -1 || t == ta) ? tc[t] : 0;
+        cb += (tb == -1 || t == tb) ? tc[t] : 0;
+    }
+    const int ti = type_code[i];
+    const bool ref = ((leaflet_mask >> leaf) & 1) && ca > 0 && cb > 0 && (ta == -1 || ti == ta);
+    int c = -1;
+    if (ref) {
+        c = 0;
+        const int32_t *h = hits + (f * N + i) * T;
+        for (int t = 0; t < T; t++)
+            if (tb == -1 || t == tb) c += max(0, h[t]);
+    }
+    n_b[f * N + i] = c;
+}
+
+extern "C" int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_counts,
+                              const uint8_t *labels, const int32_t *type_code, int64_t F, int64_t N,
+                              int n_types, int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b,
+                              double *frac, void *stream)
+{
+    if (!ctx || !type_hits || !type_counts || !labels || !type_code || !n_b || !frac || F < 0 || N <= 0 ||
+        n_types < 1 || k < 1 || (leaflet_mask & ~3))
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_nnf_select: bad argument");
+    if (F == 0) return PBK_OK;
+    dim3 g((unsigned)F, (unsigned)((N + 255) / 256));
+    k_nnf_select<<<g, 256, 0, (cudaStream_t)stream>>>(type_hits, type_counts, labels, type_code, N, n_types,
+                                                      type_a, type_b, leaflet_mask, n_b);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf_select");
+    k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;
 }
 

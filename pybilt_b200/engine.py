@@ -419,6 +419,38 @@ class LipidReductionEngine:
         self.launches += 2
         return n_b, frac
 
+    def nnf_multi(self, type_code: torch.Tensor, n_types: int, k: int, lateral=(0, 1),
+                  frames: Optional[slice] = None):
+        """k nearest leaflet members of every lipid, found once: (type_hits int32 [F, N, T],
+        type_counts int32 [F, 2, T]) device tensors for nnf_select, or None (no shared path)."""
+        d = self.dev
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        s0 = sl.start
+        hits = torch.empty((F, self.N, n_types), dtype=torch.int32, device=d)
+        tc = torch.empty((F, 2, n_types), dtype=torch.int32, device=d)
+        ok = self.ctx.try_call("pbk_nnf_multi", self.com[s0:].data_ptr(), self.labels[s0:].data_ptr(),
+                               type_code.data_ptr(), self.box[s0:].data_ptr(), F, self.N, int(lateral[0]),
+                               int(lateral[1]), int(n_types), int(k), hits.data_ptr(), tc.data_ptr(),
+                               self.stream_ptr())
+        if not ok:
+            return None
+        self.launches += 4
+        return hits, tc
+
+    def nnf_select(self, hits: torch.Tensor, tc: torch.Tensor, type_code: torch.Tensor, type_a: int,
+                   type_b: int, leaflet_mask: int, k: int, frames: Optional[slice] = None):
+        """(n_b, frac) of one nnf analysis from the shared tallies of nnf_multi."""
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        n_b = torch.empty((F, self.N), dtype=torch.int32, device=self.dev)
+        frac = torch.empty(F, dtype=torch.float64, device=self.dev)
+        self.ctx.call("pbk_nnf_select", hits.data_ptr(), tc.data_ptr(), self.labels[sl.start:].data_ptr(),
+                      type_code.data_ptr(), F, self.N, int(hits.shape[2]), int(type_a), int(type_b),
+                      int(leaflet_mask), int(k), n_b.data_ptr(), frac.data_ptr(), self.stream_ptr())
+        self.launches += 2
+        return n_b, frac
+
     def lipid_grid(self, nx: int, ny: int, mode: str = "opt", lateral=(0, 1),
                    frames: Optional[slice] = None):
         d = self.dev

@@ -134,3 +134,22 @@ def test_rdf_multi_tables_equal_per_pair_calls(n_lipids, oob):
                     assert np.array_equal(fc[:, leaf, 2], tc[:, leaf].sum(axis=1))
         cnt_all, _ = e.rdf(codes, -1, -1, 3, edges)
         assert np.array_equal(table.sum(axis=(0, 1, 2)), cnt_all.cpu().numpy())
+
+
+@pytest.mark.parametrize("n_lipids,oob", [(256, False), (2048, False), (3000, True)])
+def test_nnf_multi_tallies_equal_per_analysis_calls(n_lipids, oob):
+    """pbk_nnf_multi + pbk_nnf_select (one neighbour search, types tallied) against pbk_nnf."""
+    e, names, codes = _mid_engine(n_lipids, 3, 43)
+    if oob:
+        L = float(e.box[0, 0])
+        com = e.com.clone()
+        com[1, ::7, 0] += L
+        e.com.copy_(com)
+    T = len(names)
+    for k in (5, 6, 30):
+        hits, tc = e.nnf_multi(codes, T, k)
+        for (ta, tb, mask) in [(0, 1, 3), (1, 0, 1), (2, 2, 2), (-1, 1, 3), (0, -1, 3), (1, 5, 3)]:
+            n_b, frac = e.nnf_select(hits, tc, codes, ta if ta < T else -2, tb if tb < T else -2, mask, k)
+            n_b2, frac2 = e.nnf(codes, ta if ta < T else -2, tb if tb < T else -2, mask, k)
+            assert np.array_equal(n_b.cpu().numpy(), n_b2.cpu().numpy()), (k, ta, tb, mask)
+            assert np.array_equal(frac.cpu().numpy(), frac2.cpu().numpy())
