@@ -286,11 +286,11 @@ class MSDProtocol(AnalysisProtocol):
             self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
                                                  self.settings['resname'])
             self._vals = np.zeros(batch.n_frames)
+            self._idx_dev = batch.engine._i32(np.asarray(self._indices, dtype=np.int32))
         rows = batch.rows                    # engine rows of the frames this rank owns
         ends = np.arange(rows.start, rows.stop, dtype=np.int32)
         origins = np.full(len(ends), batch.ref_row, dtype=np.int32)   # frame 0 of the whole run
-        vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32), origins, ends,
-                                      ba_settings['lateral']).cpu().numpy()
+        vals = batch.engine.msd_pairs(self._idx_dev, origins, ends, ba_settings['lateral']).cpu().numpy()
         self._vals[batch.gframes] = vals
 
     def finish(self, batch):
@@ -350,6 +350,7 @@ class MSDMultiProtocol(AnalysisProtocol):
                                                  self.settings['resname'])
             self._finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
             self._out = np.zeros(n_blocks)
+            self._idx_dev = batch.engine._i32(np.asarray(self._indices, dtype=np.int32))
         finished = self._finished
         shard = batch.shard
         if batch.windowed:
@@ -363,7 +364,7 @@ class MSDMultiProtocol(AnalysisProtocol):
             blocks = [b for b in sorted(finished) if shard is None or shard.lo <= finished[b][0] < shard.hi]
         row = batch.row_of_global
         if blocks:
-            vals = batch.engine.msd_pairs(np.asarray(self._indices, dtype=np.int32),
+            vals = batch.engine.msd_pairs(self._idx_dev,
                                           [row(finished[b][0]) for b in blocks],
                                           [row(finished[b][1]) for b in blocks],
                                           ba_settings['lateral']).cpu().numpy()

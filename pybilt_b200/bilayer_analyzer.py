@@ -227,14 +227,18 @@ class ReductionBatch(object):
         self.box_host = box_host
         self.types = engine.layout.types
         self.resids = engine.layout.resids
-        names = []
-        for t in self.types:
-            if t not in names:
-                names.append(t)
-        self.type_names = names
-        codes = np.array([names.index(t) for t in self.types], dtype=np.int32)
-        self.type_code_host = codes
-        self.type_code_dev = torch.from_numpy(codes).to(engine.dev)
+        cache = getattr(engine, '_type_code_cache', None)
+        if cache is None:
+            tarr = np.asarray(self.types, dtype=object).astype(str)
+            uniq, first, inv = np.unique(tarr, return_index=True, return_inverse=True)
+            order = np.argsort(first, kind="stable")             # first-seen order of the resnames
+            rank = np.empty(len(uniq), dtype=np.int32)
+            rank[order] = np.arange(len(uniq), dtype=np.int32)
+            names = [self.types[int(first[k])] for k in order]
+            codes = rank[inv].astype(np.int32)
+            cache = (names, codes, torch.from_numpy(codes).to(engine.dev))
+            engine._type_code_cache = cache
+        self.type_names, self.type_code_host, self.type_code_dev = cache
         self.first_leaflets = first_leaflets
         self._grids = None
         self._rdf_multi = {}
@@ -767,8 +771,13 @@ class BilayerAnalyzer(object):
         self._check_rep_settings()
         md = self._mda_data
         cset, lset = self.rep_settings['com_frame'], self.rep_settings['leaflets']
-        layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
-                                   cset['name_dict'], cset['multi_bead'])
+        lkey = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']))
+        wc = getattr(self, '_win_cache', None) or {}
+        if wc.get('lkey') != lkey:
+            wc = {'lkey': lkey, 'layout': build_bead_layout(md.masses, md.names, md.resindex, md.resnames,
+                                                            md.resids, cset['name_dict'], cset['multi_bead'])}
+        self._win_cache = wc
+        layout = wc['layout']
         fr_all = self.analysed_frame_indices()
         F = len(fr_all)
         protos = [self._analysis_protocol.command_protocol[a] for a in self._analysis_protocol.analysis_ids]
@@ -794,11 +803,19 @@ class BilayerAnalyzer(object):
         else:
             dims_all = np.zeros((F, 6), dtype=np.float32)
             times_all = np.zeros(F)
-        eng = LipidReductionEngine(md.masses, layout, C + W + 1, device=self.device, norm=self.settings['norm'],
-                                   leaflet_update_interval=int(lset['update_interval']),
-                                   batch_frames=self._default_batch_frames(W), allow_fused=allow_fused)
+        ekey = (C + W + 1, self.device, self.settings['norm'], int(lset['update_interval']),
+                self._default_batch_frames(W))
+        if wc.get('ekey') == ekey:                     # buffers, plan and context are reused across reset()
+            eng = wc['engine']
+            eng.reset()
+            eng.allow_fused = allow_fused and eng.fused_supported
+        else:
+            eng = LipidReductionEngine(md.masses, layout, C + W + 1, device=self.device, norm=self.settings['norm'],
+                                       leaflet_update_interval=int(lset['update_interval']),
+                                       batch_frames=self._default_batch_frames(W), allow_fused=allow_fused)
+            wc['ekey'], wc['engine'] = ekey, eng
+            self._copy_state = None
         ref_row = C + W
-        self._copy_state = None
         init = None
         if world > 1:
             # pass A: image counts where the next rank's stream starts
@@ -857,7 +874,6 @@ class BilayerAnalyzer(object):
         self._frames = fr_all[a:hi]
         self._engine = None
         self._batch = None
-        self._copy_state = None
         return batch
 
 

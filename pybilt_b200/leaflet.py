@@ -23,16 +23,44 @@ class LipidGroup(object):
 class Leaflet(object):
     def __init__(self, name):
         self.name = name
-        self.members = []           # [com_index, resname, resid]
+        self._members = []          # [com_index, resname, resid]
+        self._lazy = None           # (indices, resnames, resids) arrays not yet turned into `members`
         self.groups = []
         self.group_dict = {}
+
+    @property
+    def members(self):
+        """[com_index, resname, resid] per member (leaflet.py:58-70); built on first use when the
+        leaflet came from label arrays (a Python list of 10^5 small lists is slow to make)."""
+        if self._lazy is not None:
+            idx, t, r = self._lazy
+            self._lazy = None
+            self._members = [list(m) for m in zip(idx.tolist(), t.tolist(), [int(v) for v in r.tolist()])]
+        return self._members
+
+    @members.setter
+    def members(self, value):
+        self._lazy = None
+        self._members = value
 
     @classmethod
     def from_arrays(cls, name, indices, types, resids):
         """Members in ascending lipid index; groups in first-seen order (leaflet.py:58-91)."""
         leaf = cls(name)
-        for i in indices:
-            leaf.add_member(int(i), types[int(i)], int(resids[int(i)]))
+        idx = np.asarray(indices, dtype=np.int64)
+        if len(idx) == 0:
+            return leaf
+        t = np.asarray(types, dtype=object)[idx]
+        r = np.asarray(resids)[idx]
+        leaf._lazy = (idx, t, r)
+        # groups in first-seen order, members in ascending lipid index (what add_member builds)
+        names, first = np.unique(t.astype(str), return_index=True)
+        for k in np.argsort(first, kind="stable"):
+            nm = t[first[k]]
+            g = LipidGroup(nm)
+            g.lg_members = idx[t == nm].tolist()
+            leaf.group_dict[nm] = len(leaf.groups)
+            leaf.groups.append(g)
         return leaf
 
     def __str__(self):
@@ -42,7 +70,7 @@ class Leaflet(object):
     __repr__ = __str__
 
     def __len__(self):
-        return len(self.members)
+        return len(self._lazy[0]) if self._lazy is not None else len(self._members)
 
     def add_member(self, com_index, resname, resid):
         self.members.append([com_index, resname, resid])
@@ -52,12 +80,18 @@ class Leaflet(object):
         self.groups[self.group_dict[resname]].add_member(com_index)
 
     def get_member_indices(self):
+        if self._lazy is not None:
+            return self._lazy[0].tolist()
         return [m[0] for m in self.members]
 
     def get_member_resids(self):
+        if self._lazy is not None:
+            return [int(v) for v in self._lazy[2].tolist()]
         return [m[2] for m in self.members]
 
     def get_member_resnames(self):
+        if self._lazy is not None:
+            return self._lazy[1].tolist()
         return [m[1] for m in self.members]
 
     def get_group_indices(self, group_name):
