@@ -236,19 +236,29 @@ def main():
     net = torch.zeros((M, 3), dtype=torch.int32, device=dev)
     n_a = (sh.back + sh.n_owned) if sh else F
 
+    # collectives that nothing on the frame data path waits for (the broadcast of frame 0's COMs is
+    # only read by the MSD kernels, the histogram all-reduce by nobody inside the step) run on a side
+    # stream next to the RDF sweep
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    ev_reduced, ev_ref = torch.cuda.Event(), torch.cuda.Event()
+
     def reduce_all():
         e.reset()
         if sh is None:
             e.push(x_dev, box_dev)
             return
-        e.push(x_dev[:n_a], box_dev[:n_a], phase=1, net_out=net)      # count periodic images
+        # [back halo | owned | forward halo] in one push; image counts exchanged after the owned frames
+        e.push(x_dev, box_dev, phase=1, net_out=net, net_frames=n_a)  # count periodic images
         off = pd.image_offsets(net)                                   # NCCL all-gather + prefix
-        e.push(x_dev[:n_a], box_dev[:n_a], phase=2, init_images=off)  # finish from the true counts
-        if sh.fwd:
-            e.push(x_dev[n_a:], box_dev[n_a:])
-        ref = e.com_unwrap[0].clone()
-        pd.broadcast_from_first(ref)                                  # frame 0 of the whole run
-        e.com_unwrap[n_local].copy_(ref)
+        e.push(x_dev, box_dev, phase=2, init_images=off, net_frames=n_a)   # finish from the true counts
+        main = torch.cuda.current_stream(dev)
+        ev_reduced.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_reduced)
+            ref = e.com_unwrap[0].clone()
+            pd.broadcast_from_first(ref)                              # frame 0 of the whole run
+            e.com_unwrap[n_local].copy_(ref)
+            ev_ref.record(comm)
 
     # index list of 'msd ... leaflet both resname all': upper members then lower (frame 0 of the run)
     reduce_all()
@@ -259,22 +269,39 @@ def main():
     idx = torch.from_numpy(np.concatenate([np.nonzero(lab0 == 1)[0], np.nonzero(lab0 == 0)[0]])
                            .astype(np.int32)).to(dev)
 
-    stage_names = ["reduce(unwrap+memCOM+lipidCOM+leaflets)", "msd", "msd_multi", "rdf"]
+    stage_names = (["reduce(unwrap+memCOM+lipidCOM+leaflets)", "msd", "msd_multi", "rdf"] if world == 1 else
+                   ["reduce(unwrap+memCOM+lipidCOM+leaflets)", "rdf", "msd", "msd_multi"])
 
     def step(events=None):
         def mark(i):
             if events is not None:
                 events[i].record()
+        main = torch.cuda.current_stream(dev)
         mark(0)
         reduce_all()
         mark(1)
+        if world > 1:
+            # the RDF sweep does not read the broadcast reference frame: it goes first and overlaps
+            # the broadcast; its partial histograms are all-reduced on the side stream
+            cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev, thr_dev=thr_dev, frames=owned)
+            ev_rdf = torch.cuda.Event()
+            ev_rdf.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_rdf)
+                dist.all_reduce(cnt)        # partial histograms of the frame shards (NCCL, NVLink)
+                cnt.record_stream(comm)
+            mark(2)
+            main.wait_event(ev_ref)
+            m1 = e.msd_pairs(idx, origins, ends)
+            mark(3)
+            m2 = e.msd_pairs(idx, mm_o, mm_e) if len(mm_o) else None
+            mark(4)
+            return m1, m2, cnt
         m1 = e.msd_pairs(idx, origins, ends)
         mark(2)
         m2 = e.msd_pairs(idx, mm_o, mm_e) if len(mm_o) else None
         mark(3)
         cnt, fc = e.rdf(codes, 0, 0, 3, edges, edges_dev=edges_dev, thr_dev=thr_dev, frames=owned)
-        if world > 1:                       # partial histograms of the frame shards (NCCL, NVLink)
-            dist.all_reduce(cnt)
         mark(4)
         return m1, m2, cnt
 
@@ -348,7 +375,9 @@ def main():
     if rank == 0:
         peak, which = peaks()
         dom = int(np.argmax(stage_ms))
-        dom_bytes = [B_COM, B_MSD, B_MSD * max(len(mm_o), 1) / F, B_RDF][dom] * N_LIPIDS * F
+        per_lf = {"reduce(unwrap+memCOM+lipidCOM+leaflets)": B_COM, "msd": B_MSD,
+                  "msd_multi": B_MSD * max(len(mm_o), 1) / F, "rdf": B_RDF}
+        dom_bytes = per_lf[stage_names[dom]] * N_LIPIDS * F
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "lipid-frames/s", "n_gpus": world,

@@ -112,9 +112,12 @@ int pbk_lipid_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t 
  * the outputs must be recomputed with the generic entry points.
  * scratch: pbk_reduce_fused_scratch_bytes(F, M, sm_count) bytes of device memory.
  * phase: 3 = everything; 1 = image-count pre-pass only (writes net_images[M][3], the net
- * image-count change over the batch, when not NULL); 2 = finish from the pre-pass left in
- * scratch, with init_images[M][3] (image counts of frame 0, may be NULL) added -- the two
- * halves of a frame shard, around the exchange of net counts between ranks. */
+ * image-count change over the first net_frames frames of the batch -- 0 = all of it -- when not
+ * NULL); 2 = finish from the pre-pass left in scratch, with init_images[M][3] (image counts of
+ * frame 0, may be NULL) added -- the two halves of a frame shard, around the exchange of net
+ * counts between ranks.  A shard pushes [back halo | owned | forward halo] in one batch with
+ * net_frames = back + owned: the next rank's stream starts at its last owned frame.  Phases 1 and
+ * 2 of one batch must pass the same net_frames. */
 int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
                                    int32_t *n_chunks, int32_t *chunk);
 int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
@@ -123,7 +126,7 @@ int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const doubl
                      const int32_t *node_left, const int32_t *node_right, int32_t K,
                      const int32_t *level_off, int32_t H, double total_mass, float *u_state,
                      int first_frame, int64_t F, int64_t M, int64_t N, int norm, int do_labels,
-                     int phase, const int32_t *init_images, int32_t *net_images,
+                     int phase, const int32_t *init_images, int32_t *net_images, int64_t net_frames,
                      void *scratch, int64_t scratch_bytes, double *com, double *com_unwrap,
                      double *mem_com, uint8_t *labels, int32_t *status, void *stream);
 int pbk_sm_count(const pbk_ctx *ctx);

@@ -41,7 +41,7 @@ _SIGNATURES = {
     "pbk_reduce_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                  c_int32, c_double, c_void_p, c_int, c_int64, c_int64, c_int64, c_int,
-                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbk_leaflets": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),

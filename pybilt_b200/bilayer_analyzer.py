@@ -636,15 +636,18 @@ class BilayerAnalyzer(object):
         xd = xh.to(dev, non_blocking=True)
         bd = torch.from_numpy(np.ascontiguousarray(d[:, :3])).to(dev)
         net = torch.zeros((md.natoms, 3), dtype=torch.int32, device=dev)
-        eng.push(xd[:n_a], bd[:n_a], phase=1, net_out=net)
+        # one push of [back halo | owned | forward halo]; the net image counts are taken after the
+        # owned frames (net_frames), where the next rank's back halo sits
+        eng.push(xd, bd, phase=1, net_out=net, net_frames=n_a)
         off = pd.image_offsets(net)
-        eng.push(xd[:n_a], bd[:n_a], phase=2, init_images=off)
-        seen = eng.image_counts_last(xd[n_a - 1], bd[n_a - 1])
-        if not bool(torch.equal(seen, off + net)):
-            raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
-                               "makes the shard decomposition ambiguous; run on one rank")
-        if shard.fwd:
-            eng.push(xd[n_a:], bd[n_a:])
+        eng.push(xd, bd, phase=2, init_images=off, net_frames=n_a)
+        if not eng.used_fused:
+            # generic kernels: the image counts of the last owned frame must be the rank-local ones
+            # plus the offsets (the fused path checks its own decisions: PBK_ST_UNWRAP_AMBIGUOUS)
+            seen = eng.d_img[n_a - 1].to(torch.int32)
+            if not bool(torch.equal(seen, off + net)):
+                raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
+                                   "makes the shard decomposition ambiguous; run on one rank")
         eng.check_status()
         # frame 0 of the run: leaflets (index lists) and unwrapped COMs (MSD reference)
         lab0 = eng.labels[0].clone()

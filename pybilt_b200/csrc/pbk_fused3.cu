@@ -116,15 +116,32 @@ static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], co
     for (int e = 0; e < 4; e++) pv[e] = xv[e];
 }
 
+// Frames of chunk kc.  Chunks of `chunk` frames tile [0, split) and then, starting again at
+// `split`, [split, F): a frame shard asks for the image counts after its owned frames (`split`),
+// which must be a chunk boundary; split == F is the plain uniform tiling.
+static __device__ __forceinline__ void f3_chunk_range(int kc, int chunk, int64_t split, int64_t F, int64_t *f0,
+                                                      int64_t *f1)
+{
+    const int n1 = (int)((split + chunk - 1) / chunk);
+    if (kc < n1) {
+        *f0 = (int64_t)kc * chunk;
+        *f1 = min(split, *f0 + (int64_t)chunk);
+    } else {
+        *f0 = split + (int64_t)(kc - n1) * chunk;
+        *f1 = min(F, *f0 + (int64_t)chunk);
+    }
+}
+
 __global__ void __launch_bounds__(IMG_THREADS)
 k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float4 *__restrict__ u4,
-       int first_frame, int64_t F, int C3q, int chunk, ImgCol *__restrict__ cols,
+       int first_frame, int64_t F, int64_t split, int C3q, int chunk, ImgCol *__restrict__ cols,
        float *__restrict__ chunk_box, int32_t *status)
 {
     __shared__ float s_L[IMG_MAXF * 3];
     __shared__ int s_red[3];                     // Lmax bits, dL bits, "box differs" flag
     const int kc = blockIdx.y;                   // column blocks vary fastest: neighbouring CTAs read one frame
-    const int64_t f0 = (int64_t)kc * chunk, f1 = min(F, f0 + (int64_t)chunk);
+    int64_t f0, f1;
+    f3_chunk_range(kc, chunk, split, F, &f0, &f1);
     const int nf = (int)(f1 - f0);
     const bool staged = nf <= IMG_MAXF;
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
@@ -348,7 +365,7 @@ struct F3Params {
     int perfect;                // log2(L) when the summation tree is a perfect binary tree, else -1
     double total_mass;
     const float *u_state; float *u_out; int first_frame;
-    int64_t F; int M, N, norm, chunk, n_chunks, do_labels;
+    int64_t F, split; int M, N, norm, chunk, n_chunks, do_labels;
     const int8_t *sstart;       // [n_chunks][3M] image counts at the chunk starts
     const int32_t *init_images;
     double *com, *com_unwrap, *mem_com; uint8_t *labels; int32_t *status;
@@ -501,7 +518,8 @@ k_frames3(F3Params P)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kc = blockIdx.x;
-    const int64_t f0 = (int64_t)kc * P.chunk, f1 = min(P.F, f0 + (int64_t)P.chunk);
+    int64_t f0, f1;
+    f3_chunk_range(kc, P.chunk, P.split, P.F, &f0, &f1);
     if (f0 >= f1) return;
     const uint32_t frame_bytes = (uint32_t)C3 * 4u;
     int bad = 0;
@@ -934,7 +952,8 @@ extern "C" int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count
     int64_t chunk = (F + sm_count - 1) / sm_count;
     if (chunk < 4) chunk = 4;
     int64_t n_chunks = (F + chunk - 1) / chunk;
-    *bytes = 4 * (n_chunks * 3 * M * 16 + n_chunks * 8) + 3 * M * 4 + 256;   // sized for the v1 layout (the larger)
+    // sized for the v1 layout (the larger) and for one extra chunk (a split tiling, see f3_chunk_range)
+    *bytes = 4 * ((n_chunks + 1) * 3 * M * 16 + (n_chunks + 1) * 8) + 3 * M * 4 + 256;
     if (n_chunks_out) *n_chunks_out = (int32_t)n_chunks;
     if (chunk_out) *chunk_out = (int32_t)chunk;
     return PBK_OK;
@@ -947,9 +966,9 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
                                 const int32_t *level_off, int32_t H, double total_mass, float *u_state,
                                 int first_frame, int64_t F, int64_t M, int64_t N, int norm,
                                 int do_labels, int phase, const int32_t *init_images,
-                                int32_t *net_images, void *scratch, int64_t scratch_bytes, double *com,
-                                double *com_unwrap, double *mem_com, uint8_t *labels, int32_t *status,
-                                void *stream)
+                                int32_t *net_images, int64_t net_frames, void *scratch, int64_t scratch_bytes,
+                                double *com, double *com_unwrap, double *mem_com, uint8_t *labels,
+                                int32_t *status, void *stream)
 {
     if ((phase & ~3) || phase == 0 || (init_images && !first_frame))
         return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: bad phase / init_images needs first_frame");
@@ -964,15 +983,20 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     const bool v3 = !getenv("PBK_FUSED_V1") && (M % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
                     (reinterpret_cast<uintptr_t>(u_state) % 16) == 0 && L <= F3_LPW * F3_WARPS &&
                     2 * (int64_t)L + 2 * (int64_t)K + H + 1 <= F3_TAB && smem <= limit && M <= (1 << 20);
-    if (!v3)
+    const int64_t split = (net_frames > 0 && net_frames < F) ? net_frames : F;
+    if (!v3) {
+        if (split != F) return PBK_EUNSUPPORTED;      // the first-generation path has no split tiling
         return pbk_reduce_fused_v1(ctx, x, box, mass, seg, gather, lipid_mass, leaf_start, leaf_len, L,
                                    node_left, node_right, K, level_off, H, total_mass, u_state, first_frame,
                                    F, M, N, norm, do_labels, phase, init_images, net_images, scratch,
                                    scratch_bytes, com, com_unwrap, mem_com, labels, status, stream);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int64_t need; int32_t n_chunks, chunk;
     pbk_reduce_fused_scratch_bytes(F, M, ctx->sm_count, &need, &n_chunks, &chunk);
     if (scratch_bytes < need) return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small");
+    const int32_t n_net = (int32_t)((split + chunk - 1) / chunk);       // chunks tiling [0, split)
+    n_chunks = n_net + (int32_t)((F - split + chunk - 1) / chunk);
     const int C3q = C3 / 4;
     // scratch layout
     unsigned char *sp = reinterpret_cast<unsigned char *>(scratch);
@@ -986,10 +1010,10 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     if (phase & 1) {
         k_img3<<<dim3((C3q + IMG_THREADS - 1) / IMG_THREADS, n_chunks), IMG_THREADS, 0, st>>>(
             reinterpret_cast<const float4 *>(x), box, reinterpret_cast<const float4 *>(u_state), first_frame, F,
-            C3q, chunk, cols, chunk_box, status);
+            split, C3q, chunk, cols, chunk_box, status);
         PBK_CHECK_LAUNCH(ctx, "k_img3");
         if (net_images) {
-            k_net3<<<(C3 + 255) / 256, 256, 0, st>>>(cols, C3, n_chunks, net_images);
+            k_net3<<<(C3 + 255) / 256, 256, 0, st>>>(cols, C3, n_net, net_images);
             PBK_CHECK_LAUNCH(ctx, "k_net3");
         }
     }
@@ -1003,7 +1027,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     P.perfect = f3_perfect(M);
     if (P.perfect >= 0 && ((1 << P.perfect) != L || L > 64)) P.perfect = -1;
     P.u_state = u_state; P.u_out = u_out; P.first_frame = first_frame; P.F = F; P.M = (int)M; P.N = (int)N;
-    P.norm = norm; P.chunk = chunk; P.n_chunks = n_chunks; P.do_labels = do_labels; P.sstart = sstart;
+    P.split = split; P.norm = norm; P.chunk = chunk; P.n_chunks = n_chunks; P.do_labels = do_labels; P.sstart = sstart;
     P.init_images = init_images; P.com = com; P.com_unwrap = com_unwrap; P.mem_com = mem_com;
     P.labels = labels; P.status = status;
     P.prof = (scratch_bytes >= need + 8 * 8 * (int64_t)n_chunks + 64 && getenv("PBK_FUSED_PROF")) ? reinterpret_cast<long long *>(reinterpret_cast<char *>(scratch) + ((need + 63) / 64) * 64) : nullptr;

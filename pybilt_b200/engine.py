@@ -218,14 +218,17 @@ class LipidReductionEngine:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def push(self, x: torch.Tensor, box: torch.Tensor, phase: int = 3,
-             init_images: Optional[torch.Tensor] = None, net_out: Optional[torch.Tensor] = None):
+             init_images: Optional[torch.Tensor] = None, net_out: Optional[torch.Tensor] = None,
+             net_frames: int = 0):
         """Process the next ``x.shape[0]`` analysed frames.  ``x`` float32 [f, M, 3] and ``box``
         float32 [f, 3] are device tensors (any f; split into scratch-sized batches here).
 
         Frame shards (pybilt_b200/distributed.py) call this twice for their first push:
         ``phase=1`` only counts periodic images and writes the net change over the frames into
         ``net_out`` (int32 [M, 3]); after the ranks exchanged those, ``phase=2`` finishes the
-        same frames with ``init_images`` (int32 [M, 3]), the image counts of frame 0."""
+        same frames with ``init_images`` (int32 [M, 3]), the image counts of frame 0.
+        ``net_frames`` (both phases): the net change is taken after that many frames of the push
+        (the frames behind it are the shard's forward halo); 0 = after all of them."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         assert box.is_cuda and box.dtype == torch.float32 and box.is_contiguous()
         f_total = int(x.shape[0])
@@ -256,7 +259,7 @@ class LipidReductionEngine:
                                 self.d_node_left.data_ptr(), self.d_node_right.data_ptr(), p.n_nodes,
                                 self.d_level_off.data_ptr(), p.n_levels, self.total_mass,
                                 self.d_u_state.data_ptr(), 0 if self.stream_started else 1, nb, self.M, self.N,
-                                self.norm, do_labels, int(phase), _ptr(init_b), _ptr(net_out),
+                                self.norm, do_labels, int(phase), _ptr(init_b), _ptr(net_out), int(net_frames),
                                 scratch.data_ptr(), int(scratch.numel()),
                                 self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
                                 self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(),
@@ -283,7 +286,8 @@ class LipidReductionEngine:
                        self.d_status.data_ptr(), st)
                 self.launches += 1
                 if net_out is not None:
-                    net_out.copy_(self.d_img[nb - 1].to(torch.int32))
+                    last = (net_frames if 0 < net_frames < nb else nb) - 1
+                    net_out.copy_(self.d_img[last].to(torch.int32))
                 continue
             c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
                    0 if self.stream_started else 1, _ptr(init_b), 1 if self.comtraj_rules else 0, nb, self.M,
