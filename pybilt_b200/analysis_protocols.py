@@ -22,6 +22,7 @@ import functools
 import warnings
 
 import numpy as np
+import torch
 
 from .running_stats import RunningStats, running_rows
 
@@ -286,14 +287,19 @@ class MSDProtocol(AnalysisProtocol):
             self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
                                                  self.settings['resname'])
             self._vals = np.zeros(batch.n_frames)
+            self._pending = []               # (global frame slice, device values): read back in finish()
             self._idx_dev = batch.engine._i32(np.asarray(self._indices, dtype=np.int32))
         rows = batch.rows                    # engine rows of the frames this rank owns
-        ends = np.arange(rows.start, rows.stop, dtype=np.int32)
-        origins = np.full(len(ends), batch.ref_row, dtype=np.int32)   # frame 0 of the whole run
-        vals = batch.engine.msd_pairs(self._idx_dev, origins, ends, ba_settings['lateral']).cpu().numpy()
-        self._vals[batch.gframes] = vals
+        dev = batch.engine.dev               # built on the device: no small host->device copy has to
+        ends = torch.arange(rows.start, rows.stop, dtype=torch.int32, device=dev)   # queue behind a bulk one
+        origins = torch.full((rows.stop - rows.start,), batch.ref_row, dtype=torch.int32, device=dev)
+        vals = batch.engine.msd_pairs(self._idx_dev, origins, ends, ba_settings['lateral'])
+        self._pending.append((batch.gframes, vals))
 
     def finish(self, batch):
+        for g, v in self._pending:
+            self._vals[g] = v.cpu().numpy()
+        self._pending = []
         vals = batch.allreduce(self._vals)       # every frame has exactly one owner: x + 0 = x
         self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
@@ -350,27 +356,39 @@ class MSDMultiProtocol(AnalysisProtocol):
                                                  self.settings['resname'])
             self._finished, n_blocks = msd_multi_schedule(F, n_tau, n_sigma)
             self._out = np.zeros(n_blocks)
+            self._pending = []
             self._idx_dev = batch.engine._i32(np.asarray(self._indices, dtype=np.int32))
-        finished = self._finished
+        if batch.first_window:
+            # all (origin, end) frame pairs go to the device once; blocks finish in frame order, so
+            # the blocks of a window are a contiguous run of them
+            self._blocks = np.array(sorted(self._finished), dtype=np.int64)
+            self._b_origin = np.array([self._finished[b][0] for b in self._blocks], dtype=np.int64)
+            self._b_end = np.array([self._finished[b][1] for b in self._blocks], dtype=np.int64)
+            self._b_origin_dev = batch.engine._i32(self._b_origin.astype(np.int32))
+            self._b_end_dev = batch.engine._i32(self._b_end.astype(np.int32))
         shard = batch.shard
         if batch.windowed:
             # streamed run: a window evaluates the blocks that END in it; the origin frame lies at
             # most n_tau - 1 frames back, i.e. in the window or in the context rows kept before it
             g = batch.gframes
-            blocks = [b for b in sorted(finished) if g.start <= finished[b][1] < g.stop]
-        else:
-            # resident run: a rank evaluates the blocks whose origin frame it owns (the end frame
+            sel = np.nonzero((self._b_end >= g.start) & (self._b_end < g.stop))[0]
+        elif shard is not None:
+            # resident shard: a rank evaluates the blocks whose origin frame it owns (the end frame
             # lies in its forward halo)
-            blocks = [b for b in sorted(finished) if shard is None or shard.lo <= finished[b][0] < shard.hi]
-        row = batch.row_of_global
-        if blocks:
-            vals = batch.engine.msd_pairs(self._idx_dev,
-                                          [row(finished[b][0]) for b in blocks],
-                                          [row(finished[b][1]) for b in blocks],
-                                          ba_settings['lateral']).cpu().numpy()
-            self._out[blocks] = vals
+            sel = np.nonzero((self._b_origin >= shard.lo) & (self._b_origin < shard.hi))[0]
+        else:
+            sel = np.arange(len(self._blocks))
+        if len(sel):
+            i0, i1 = int(sel[0]), int(sel[-1]) + 1
+            assert i1 - i0 == len(sel)
+            vals = batch.engine.msd_pairs(self._idx_dev, self._b_origin_dev[i0:i1] - batch.row0_global,
+                                          self._b_end_dev[i0:i1] - batch.row0_global, ba_settings['lateral'])
+            self._pending.append((self._blocks[i0:i1], vals))
 
     def finish(self, batch):
+        for blocks, v in self._pending:
+            self._out[blocks] = v.cpu().numpy()
+        self._pending = []
         n_tau = self.settings['n_tau']
         self.analysis_output = list(batch.allreduce(self._out))
         self._tau = batch.times[n_tau - 1] - batch.times[0] if batch.n_frames >= n_tau else 0.0
@@ -434,6 +452,7 @@ class COMLateralRDFProtocol(AnalysisProtocol):
             self._n_leaf = float(len(do_leaflet))
             self._count_acc = np.zeros(s['n_bins'], dtype=np.int64)
             self._sums_acc = np.zeros(3, dtype=np.int64)
+            self._pending = []               # device (count, frame counts) per window, read back in finish()
         shared = batch.rdf_shared(self._edges, ba_settings['lateral'])
         if shared is not None:
             # one sweep binned every (leaflet, type_i, type_j) table; this analysis is a sum of tables
@@ -456,11 +475,14 @@ class COMLateralRDFProtocol(AnalysisProtocol):
         count, fc = batch.engine.rdf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                      batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
                                      self._edges, ba_settings['lateral'], frames=batch.rows)
-        fc = fc.cpu().numpy().astype(np.int64)
-        self._count_acc += count.cpu().numpy()
-        self._sums_acc += np.array([fc[:, :, 0].sum(), fc[:, :, 1].sum(), fc[:, :, 2].sum()])
+        self._pending.append((count, fc))
 
     def finish(self, batch):
+        for count, fc in self._pending:
+            fc = fc.cpu().numpy().astype(np.int64)
+            self._count_acc += count.cpu().numpy()
+            self._sums_acc += np.array([fc[:, :, 0].sum(), fc[:, :, 1].sum(), fc[:, :, 2].sum()])
+        self._pending = []
         # frame shards: partial histograms and (N_a, N_b, N) sums are all-reduced
         count = batch.allreduce(self._count_acc).astype(np.float64)
         self._count = count if self._count is None else self._count + count

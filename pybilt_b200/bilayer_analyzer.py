@@ -332,11 +332,13 @@ class BilayerAnalyzer(object):
                            'area_per_bin': None},
             'vector_frame': {'dump': False, 'dump_path': "./", 'ref_atoms': None}}
         self.device = device
-        self.batch_frames = None    # frames per host->device batch (None: about 48 MB of positions)
+        self.batch_frames = None    # frames per host->device batch (None: about 96 MB of positions)
         # Streamed runs: None = keep every analysed frame's representations resident when they fit
         # `resident_budget_bytes`, else stream windows of frames through a bounded engine; an int
         # forces windows of that many frames (see _run_windowed)
         self.window_frames = None
+        self._incremental = True    # batched analyses consume each host->device batch as it arrives
+        self._incremental_done = False
         self.resident_budget_bytes = 48 << 30
         self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
         self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
@@ -520,10 +522,12 @@ class BilayerAnalyzer(object):
         """Push every analysed frame through the engine (unwrap -> COMs -> leaflets)."""
         if self._batch is not None:
             return self._batch
+        self._incremental_done = False
         try:
             return self._reduce_with(allow_fused=True)
         except FusedPathRejected:
             # a jump the chunked fast path cannot decide locally: sequential kernels instead
+            self._incremental_done = False
             return self._reduce_with(allow_fused=False)
 
     def _reduce_with(self, allow_fused):
@@ -563,9 +567,9 @@ class BilayerAnalyzer(object):
         # as long as nothing that shapes it changed
         batch_frames = self.batch_frames if shard is None else len(fr)
         if batch_frames is None:
-            # ~48 MB of positions per host->device batch: the copy of batch k+1 overlaps the
+            # ~96 MB of positions per host->device batch: the copy of batch k+1 overlaps the
             # reduction of batch k, and only the last batch's kernels are exposed
-            batch_frames = int(max(64, min(len(fr), (48 << 20) // max(1, md.natoms * 12))))
+            batch_frames = int(max(64, min(len(fr), (96 << 20) // max(1, md.natoms * 12))))
         key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), n_rows, self.device,
                self.settings['norm'], int(lset['update_interval']), batch_frames)
         cached = getattr(self, '_engine_cache', None)
@@ -596,7 +600,16 @@ class BilayerAnalyzer(object):
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         main = torch.cuda.current_stream(dev)
-        for k, b0 in enumerate(range(0, len(fr), B)):
+        # batched analyses consume every host->device batch as soon as it is reduced (their kernels
+        # and bookkeeping hide under the copy of the next batches); per-frame plugins, iteration and
+        # representation dumps read the resident representations afterwards
+        protos = [self._analysis_protocol.command_protocol[a] for a in self._analysis_protocol.analysis_ids]
+        inc = [p_ for p_ in protos if getattr(p_, 'batched', False)] if self._incremental else []
+        starts = list(range(0, len(fr), B))
+        first_leaflets = None
+
+        def issue_copy(k):
+            b0 = starts[k]
             b1 = min(len(fr), b0 + B)
             slot = k % 2
             x, d, t = md.frames(fr[b0:b1])
@@ -610,16 +623,34 @@ class BilayerAnalyzer(object):
                 bufs[slot][:b1 - b0].copy_(xh, non_blocking=True)
                 boxes[slot][:b1 - b0].copy_(bh, non_blocking=True)
                 ready[slot].record(copy_stream)
+
+        if starts:
+            issue_copy(0)
+        for k, b0 in enumerate(starts):
+            b1 = min(len(fr), b0 + B)
+            slot = k % 2
             main.wait_event(ready[slot])
             eng.push(bufs[slot][:b1 - b0], boxes[slot][:b1 - b0])
             consumed[slot].record(main)
+            if k + 1 < len(starts):
+                issue_copy(k + 1)            # in flight while this batch is reduced and analysed
+            if inc:
+                if first_leaflets is None:
+                    first_leaflets = lf.leaflets_from_labels(eng.labels[0].cpu().numpy(), layout.types,
+                                                             layout.resids)
+                win = {'rows': slice(b0, b1), 'ref_row': 0, 'gframes': slice(b0, b1), 'row0_global': 0,
+                       'first': b0 == 0, 'last': b1 == len(fr), 'sharded': False}
+                wb = ReductionBatch(self, eng, times, dims_all[:, :3], first_leaflets, None, win)
+                for p_ in inc:
+                    p_.run_batch(self.settings, wb, md)
         eng.check_status()
-        labels0 = eng.labels[0].cpu().numpy()
-        first_leaflets = lf.leaflets_from_labels(labels0, layout.types, layout.resids)
+        if first_leaflets is None:
+            first_leaflets = lf.leaflets_from_labels(eng.labels[0].cpu().numpy(), layout.types, layout.resids)
         self._engine = eng
         self._times = times
         self._dims = dims_all
         self._batch = ReductionBatch(self, eng, times, dims_all[:, :3].copy(), first_leaflets)
+        self._incremental_done = bool(inc)
         return self._batch
 
     def _reduce_sharded(self, eng, md, fr, fr_all, shard, layout):
@@ -675,7 +706,7 @@ class BilayerAnalyzer(object):
         md = self._mda_data
         if self.batch_frames is not None:
             return int(self.batch_frames)
-        return int(max(64, min(n, (48 << 20) // max(1, md.natoms * 12))))
+        return int(max(64, min(n, (96 << 20) // max(1, md.natoms * 12))))
 
     def _window_choice(self):
         """Frames per window of a streamed run, or None for a resident run."""
@@ -920,7 +951,8 @@ class BilayerAnalyzer(object):
         for a_id in self._analysis_protocol.analysis_ids:
             proto = self._analysis_protocol.command_protocol[a_id]
             if getattr(proto, 'batched', False):
-                proto.run_batch(self.settings, batch, self._mda_data)
+                if not self._incremental_done:
+                    proto.run_batch(self.settings, batch, self._mda_data)
                 proto.finish(batch)
         self._legacy = [self._analysis_protocol.command_protocol[a] for a in
                         self._analysis_protocol.analysis_ids

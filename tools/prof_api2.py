@@ -18,7 +18,7 @@ def bench(ba, keys, label, n=4):
         r = [ba.get_analysis_data(k) for k in keys]; torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
     print("%-44s %s" % (label, " ".join("%.2f" % t for t in ts)))
 full = ["msd msd_1", "msd_multi mm n_tau 50 n_sigma 50", "com_lateral_rdf rdf"]
-for bf in (None, 1250, 500, 250, 125):
+for bf in (None, 2500, 1250, 650, 325):
     ba = make(full); ba.batch_frames = bf
     bench(ba, ("msd_1", "mm", "rdf"), "full, batch_frames=%s" % bf)
 ba = make(["msd msd_1"]); ba.batch_frames = 500
