@@ -117,8 +117,9 @@ __device__ __forceinline__ bool cl_classify(const ClParams &P, const uint8_t *la
 {
     *leaf = lab[i] ? 0 : 1;
     if (P.multi) {
-        *flag = (unsigned)P.type_code[i];
-        return true;
+        const int t = P.type_code[i];
+        *flag = (unsigned)t;
+        return t >= 0 && t < P.n_types;          // a code outside the table is not listed (never indexes it)
     }
     const int t = (P.ta == -1 && P.tb == -1) ? 0 : P.type_code[i];
     const bool a = (P.ta == -1 || t == P.ta), b = (P.tb == -1 || t == P.tb);
