@@ -51,6 +51,15 @@ int pbk_ctx_create(int device, pbk_ctx **out);
 void pbk_ctx_destroy(pbk_ctx *ctx);
 const char *pbk_last_error(const pbk_ctx *ctx);
 
+/* ---- N2  trajectory ingestion (the wire format before the path) ---------------------------
+ * MDAData / mda.Universe(psf, dcd)             pybilt/bilayer_analyzer/mda_data.py:14-38
+ * frame.positions[index]                       pybilt/bilayer_analyzer/bilayer_analyzer.py:936
+ * A DCD frame stores X[], Y[], Z[] of all atoms; planes float32 [F][3][Mtot] (as read from the
+ * file) become positions float32 [F][M][3] of the selected atoms sel[M] (int32 indices into
+ * 0..Mtot-1, ascending; NULL = all atoms, M == Mtot).  F <= 65535 per call. */
+int pbk_planes_to_aos(pbk_ctx *ctx, const float *planes, const int32_t *sel, int64_t F, int64_t Mtot,
+                      int64_t M, float *out, void *stream);
+
 /* ---- A1  PBC unwrap ---------------------------------------------------------------------
  * wrap_coordinates(abc, coord, refcoord)      pybilt/mda_tools/mda_unwrap_vectorized.py:12-93
  * + the _oldcoords recurrence                 pybilt/bilayer_analyzer/bilayer_analyzer.py:936-954

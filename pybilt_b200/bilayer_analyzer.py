@@ -33,6 +33,7 @@ from . import com_frame as cf
 from . import leaflet as lf
 from . import lipid_grid as lg
 from . import distributed as pd
+from . import formats as fmt
 from .engine import FusedPathRejected, LipidReductionEngine, build_bead_layout
 
 default_analysis_commands = ['msd msd_1']
@@ -80,8 +81,15 @@ class TrajectoryData(object):
         self.trajectory_file = trajectory if isinstance(trajectory, (str, list)) else None
         self.bilayer_sel_string = sel_string
         self.mda_universe = None
+        self.dcd = None                 # pybilt_b200.formats.DCDChain when read natively
         if isinstance(structure, str):
-            self._from_mdanalysis(structure, trajectory, sel_string)
+            traj_list = [trajectory] if isinstance(trajectory, str) else list(trajectory)
+            native = (structure.lower().endswith(".psf") and
+                      all(isinstance(t, str) and t.lower().endswith(".dcd") for t in traj_list))
+            if native and os.environ.get("PBK_USE_MDANALYSIS") is None:
+                self._from_psf_dcd(structure, traj_list, sel_string)
+            else:
+                self._from_mdanalysis(structure, trajectory, sel_string)
         else:
             self._from_arrays(structure, trajectory, sel_string)
         self.natoms = int(self.masses.shape[0])
@@ -117,10 +125,56 @@ class TrajectoryData(object):
         self.nframes = int(self._dimensions.shape[0])
         self._all_atoms = bool(atom_keep.all())
 
+    # -- psf + dcd, read natively (pybilt_b200/formats.py) ------------------------------------
+    def _from_psf_dcd(self, structure, traj_list, sel):
+        top = fmt.PSFTopology(structure)
+        self.dcd = fmt.DCDChain(traj_list)
+        if self.dcd.n_atoms != top.n_atoms:
+            raise RuntimeError("structure (%d atoms) and trajectory (%d atoms) do not match"
+                               % (top.n_atoms, self.dcd.n_atoms))
+        mask = fmt.select_atoms(top, sel or "all")
+        if not mask.any():
+            raise RuntimeError("the selection %r matches no atom" % sel)
+        # like group.residues.atoms == group: a residue is selected as a whole or not at all
+        res_any = np.zeros(int(top.resindex[-1]) + 1, dtype=bool)
+        res_any[top.resindex[mask]] = True
+        if (res_any[top.resindex] != mask).any():
+            raise RuntimeError("the selection must cover whole residues")
+        self.indices = np.nonzero(mask)[0]
+        self.masses = top.masses[self.indices]
+        self.names = top.names[self.indices]
+        ridx = top.resindex[self.indices]
+        first = np.concatenate([[True], ridx[1:] != ridx[:-1]])
+        self.resindex = np.cumsum(first) - 1
+        self.resnames = list(top.resnames[self.indices][first])
+        self.resids = top.resids[self.indices][first]
+        self.n_atoms_total = top.n_atoms
+        self._all_atoms = bool(mask.all())
+        self._dimensions = self.dcd.all_dimensions()
+        self._times = self.dcd.times(np.arange(self.dcd.n_frames))
+        self.nframes = self.dcd.n_frames
+
+    def read_planes(self, frame_idx, out):
+        """X/Y/Z planes of ALL atoms of the frames into ``out`` (float32 [>=f, 3, n_atoms_total],
+        pinned); runs of consecutive frames are copied record by record."""
+        frame_idx = np.asarray(frame_idx)
+        k = 0
+        while k < len(frame_idx):
+            j = k
+            while j + 1 < len(frame_idx) and frame_idx[j + 1] == frame_idx[j] + 1:
+                j += 1
+            self.dcd.planes(int(frame_idx[k]), int(frame_idx[j]) + 1, out[k:j + 1])
+            k = j + 1
+        return out[:len(frame_idx)]
+
     def frames(self, frame_idx):
         """float32 positions [f, M, 3] (selected atoms), dimensions [f, 6], times [f]."""
         if self.mda_universe is not None:
             return self._read_mda(frame_idx)
+        if self.dcd is not None:
+            frame_idx = np.asarray(frame_idx)
+            x = self.dcd.positions(frame_idx, None if self._all_atoms else self.indices)
+            return x, self._dimensions[frame_idx], self._times[frame_idx]
         x = self._positions
         contiguous = len(frame_idx) > 0 and (np.diff(frame_idx) == 1).all()
         if isinstance(x, FrameWindow):
@@ -173,6 +227,75 @@ class TrajectoryData(object):
             d[k] = ts.dimensions
             t[k] = ts.time
         return x, d, t
+
+
+class _FrameFeeder(object):
+    """Host -> device frame batches, double buffered on a copy stream.  In-memory trajectories are
+    copied as they are ([f, M, 3]); natively read DCD files are copied as the file's X/Y/Z planes
+    of all atoms and interleaved / atom-selected on the device (`pbk_planes_to_aos`)."""
+
+    def __init__(self, md, eng):
+        dev = eng.dev
+        self.md, self.eng, self.B = md, eng, eng.B
+        self.stream = torch.cuda.Stream(dev)
+        self.main = torch.cuda.current_stream(dev)
+        self.bufs = [torch.empty((self.B, md.natoms, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.boxes = [torch.empty((self.B, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [None, None]            # event: the pinned staging buffer of a slot may be rewritten
+        self.n = [0, 0]
+        self.k_issue = 0
+        self.k_take = 0
+        self.planar = md.dcd is not None
+        if self.planar:
+            mt = md.n_atoms_total
+            self.stage = [torch.empty((self.B, 3, mt), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.pdev = [torch.empty((self.B, 3, mt), dtype=torch.float32, device=dev) for _ in range(2)]
+            self.sel = None if md._all_atoms else torch.from_numpy(md.indices.astype(np.int32)).to(dev)
+
+    def issue(self, frames):
+        """Start the copy of the next batch (at most B frames); returns (dimensions, times)."""
+        md = self.md
+        slot = self.k_issue % 2
+        nf = len(frames)
+        if self.planar:
+            if self.copied[slot] is not None:
+                self.copied[slot].synchronize()       # the staging buffer is free again
+            md.read_planes(frames, self.stage[slot].numpy())
+            d, t = md._dimensions[frames], md._times[frames]
+            src, dst = self.stage[slot][:nf], self.pdev[slot][:nf]
+        else:
+            x, d, t = md.frames(frames)
+            src = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            dst = self.bufs[slot][:nf]
+        bh = torch.from_numpy(np.ascontiguousarray(d[:, :3]))
+        with torch.cuda.stream(self.stream):
+            if self.k_issue >= 2:
+                self.stream.wait_event(self.consumed[slot])
+            dst.copy_(src, non_blocking=True)
+            self.boxes[slot][:nf].copy_(bh, non_blocking=True)
+            self.ready[slot].record(self.stream)
+            if self.planar:
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.copied[slot] = ev
+        self.n[slot] = nf
+        self.k_issue += 1
+        return d, t
+
+    def take(self):
+        """Device views (x [f, M, 3], box [f, 3]) of the oldest issued batch, valid until release()."""
+        slot = self.k_take % 2
+        nf = self.n[slot]
+        self.main.wait_event(self.ready[slot])
+        if self.planar:
+            self.eng.planes_to_aos(self.pdev[slot][:nf], self.sel, self.bufs[slot][:nf])
+        return self.bufs[slot][:nf], self.boxes[slot][:nf]
+
+    def release(self):
+        self.consumed[self.k_take % 2].record(self.main)
+        self.k_take += 1
 
 
 class GridBatch(object):
@@ -256,17 +379,6 @@ class ReductionBatch(object):
         dt = torch.int64 if values.dtype.kind in "iu" else torch.float64
         t = torch.as_tensor(values, dtype=dt, device=self.engine.dev)
         return pd.combine_slots(t).cpu().numpy()
-
-    def to_global(self, owned_values):
-        """Per-frame values of the owned frames -> values of all analysed frames (all ranks)."""
-        owned_values = np.asarray(owned_values)
-        if self.shard is None:
-            return owned_values
-        full = torch.zeros((self.n_frames,) + owned_values.shape[1:], dtype=torch.float64,
-                           device=self.engine.dev)
-        full[self.shard.lo:self.shard.hi] = torch.as_tensor(owned_values, dtype=torch.float64,
-                                                            device=self.engine.dev)
-        return pd.combine_slots(full).cpu().numpy()
 
     def type_code_of(self, name):
         if name == 'all':
@@ -591,15 +703,10 @@ class BilayerAnalyzer(object):
             return self._reduce_sharded(eng, md, fr, fr_all, shard, layout)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
         dev = eng.dev
-        copy_stream = torch.cuda.Stream(dev)
         times = np.empty(len(fr))
         dims_all = np.empty((len(fr), 6), dtype=np.float32)
         B = eng.B
-        bufs = [torch.empty((B, md.natoms, 3), dtype=torch.float32, device=dev) for _ in range(2)]
-        boxes = [torch.empty((B, 3), dtype=torch.float32, device=dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        main = torch.cuda.current_stream(dev)
+        feeder = self._feeder_for(md, eng)
         # batched analyses consume every host->device batch as soon as it is reduced (their kernels
         # and bookkeeping hide under the copy of the next batches); per-frame plugins, iteration and
         # representation dumps read the resident representations afterwards
@@ -611,27 +718,17 @@ class BilayerAnalyzer(object):
         def issue_copy(k):
             b0 = starts[k]
             b1 = min(len(fr), b0 + B)
-            slot = k % 2
-            x, d, t = md.frames(fr[b0:b1])
+            d, t = feeder.issue(fr[b0:b1])
             times[b0:b1] = t
             dims_all[b0:b1] = d
-            xh = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-            bh = torch.from_numpy(np.ascontiguousarray(d[:, :3]))
-            with torch.cuda.stream(copy_stream):
-                if k >= 2:
-                    copy_stream.wait_event(consumed[slot])
-                bufs[slot][:b1 - b0].copy_(xh, non_blocking=True)
-                boxes[slot][:b1 - b0].copy_(bh, non_blocking=True)
-                ready[slot].record(copy_stream)
 
         if starts:
             issue_copy(0)
         for k, b0 in enumerate(starts):
             b1 = min(len(fr), b0 + B)
-            slot = k % 2
-            main.wait_event(ready[slot])
-            eng.push(bufs[slot][:b1 - b0], boxes[slot][:b1 - b0])
-            consumed[slot].record(main)
+            xb, bb = feeder.take()
+            eng.push(xb, bb)
+            feeder.release()
             if k + 1 < len(starts):
                 issue_copy(k + 1)            # in flight while this batch is reduced and analysed
             if inc:
@@ -723,7 +820,7 @@ class BilayerAnalyzer(object):
         n_res = len(md.resnames)
         F = len(self.analysed_frame_indices())
         per_frame = n_res * 56 + 64                  # com + com_unwrap + label + mem_com + box
-        if self.use_lipid_grid_bytes():
+        if self._uses_lipid_grids():
             g = self.rep_settings['lipid_grid']
             per_frame += 2 * int(g['n_xbins']) * int(g['n_ybins']) * 12 + n_res * 100
         if F * per_frame <= self.resident_budget_bytes:
@@ -743,50 +840,47 @@ class BilayerAnalyzer(object):
                 n += 1
         return n
 
-    def use_lipid_grid_bytes(self):
+    def _uses_lipid_grids(self):
         return any(self._analysis_protocol.command_protocol[a].analysis_key in ('apl_grid', 'thickness_grid')
                    for a in self._analysis_protocol.analysis_ids)
+
+    def _feeder_for(self, md, eng):
+        """The host->device pipeline of (trajectory, engine): device and pinned staging buffers are
+        kept as long as the engine is."""
+        fc = getattr(self, '_feeder_cache', None)
+        if fc is None or fc[0] is not md or fc[1] is not eng or fc[2].B != eng.B:
+            fc = (md, eng, _FrameFeeder(md, eng))
+            self._feeder_cache = fc
+        return fc[2]
 
     def _push_frames(self, eng, md, frames, times_out=None, dims_out=None, init_images=None, unwrap_only=False):
         """Host -> device in engine-batch sized pieces (double-buffered on a copy stream) and through
         the engine.  Returns the device views (x, box) of the last frame pushed."""
-        dev = eng.dev
-        st = getattr(self, '_copy_state', None)
+        feeder = self._feeder_for(md, eng)
         B = eng.B
-        if st is None or st['key'] != (id(eng), B, md.natoms):
-            st = {'key': (id(eng), B, md.natoms), 'stream': torch.cuda.Stream(dev),
-                  'bufs': [torch.empty((B, md.natoms, 3), dtype=torch.float32, device=dev) for _ in range(2)],
-                  'boxes': [torch.empty((B, 3), dtype=torch.float32, device=dev) for _ in range(2)],
-                  'ready': [torch.cuda.Event() for _ in range(2)],
-                  'consumed': [torch.cuda.Event() for _ in range(2)], 'k': 0}
-            self._copy_state = st
-        main = torch.cuda.current_stream(dev)
-        last = None
-        for b0 in range(0, len(frames), B):
+        starts = list(range(0, len(frames), B))
+
+        def issue(k):
+            b0 = starts[k]
             b1 = min(len(frames), b0 + B)
-            k = st['k']
-            st['k'] += 1
-            slot = k % 2
-            x, d, t = md.frames(frames[b0:b1])
+            d, t = feeder.issue(frames[b0:b1])
             if times_out is not None:
                 times_out[b0:b1] = t
                 dims_out[b0:b1] = d
-            xh = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-            bh = torch.from_numpy(np.ascontiguousarray(d[:, :3]))
-            with torch.cuda.stream(st['stream']):
-                if k >= 2:
-                    st['stream'].wait_event(st['consumed'][slot])
-                st['bufs'][slot][:b1 - b0].copy_(xh, non_blocking=True)
-                st['boxes'][slot][:b1 - b0].copy_(bh, non_blocking=True)
-                st['ready'][slot].record(st['stream'])
-            main.wait_event(st['ready'][slot])
-            xb, bb = st['bufs'][slot][:b1 - b0], st['boxes'][slot][:b1 - b0]
+
+        last = None
+        if starts:
+            issue(0)
+        for k, b0 in enumerate(starts):
+            xb, bb = feeder.take()
             if unwrap_only:
                 eng.unwrap_only(xb, bb)
             else:
                 eng.push(xb, bb, init_images=init_images if b0 == 0 else None)
-            st['consumed'][slot].record(main)
-            last = (xb[b1 - b0 - 1], bb[b1 - b0 - 1])
+            last = (xb[-1].clone(), bb[-1].clone())
+            feeder.release()
+            if k + 1 < len(starts):
+                issue(k + 1)
         return last
 
     def _run_windowed(self, W, allow_fused=True):
@@ -848,7 +942,6 @@ class BilayerAnalyzer(object):
                                        leaflet_update_interval=int(lset['update_interval']),
                                        batch_frames=self._default_batch_frames(W), allow_fused=allow_fused)
             wc['ekey'], wc['engine'] = ekey, eng
-            self._copy_state = None
         ref_row = C + W
         init = None
         if world > 1:

@@ -214,6 +214,19 @@ class LipidReductionEngine:
             self.stream_started = True
             self.launches += 1
 
+    def planes_to_aos(self, planes: torch.Tensor, sel: Optional[torch.Tensor], out: torch.Tensor):
+        """Device-side interleave + atom selection of DCD coordinate planes: ``planes`` float32
+        [f, 3, Mtot] -> ``out`` float32 [f, M, 3] (``sel`` int32 [M] or None for all atoms)."""
+        assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        f, _three, mtot = planes.shape
+        st = self.stream_ptr()
+        for f0 in range(0, f, 65535):
+            f1 = min(f, f0 + 65535)
+            self.ctx.call("pbk_planes_to_aos", planes[f0:f1].data_ptr(), _ptr(sel), f1 - f0, int(mtot),
+                          int(out.shape[1]), out[f0:f1].data_ptr(), st)
+            self.launches += 1
+
     def stream_ptr(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 

@@ -191,3 +191,43 @@ def test_window_is_chosen_automatically_when_resident_state_exceeds_budget():
     flat = cases.flatten_outputs({a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()})
     for k in [k for k in gold if k.startswith("out/")]:
         close(flat[k], gold[k], 1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("name,window", [("tiny_all", None), ("c3_small", None), ("name_dict", None), ("tiny_all", 5)])
+def test_run_from_psf_dcd_files_matches_in_memory_run(name, window, tmp_path):
+    """Native psf + dcd ingestion (pybilt_b200/formats.py + the device-side plane interleave and
+    atom selection) against the same system handed over as arrays: identical representations
+    and analysis outputs (the time column only to float32(delta) accuracy, as DCD stores it)."""
+    from pybilt_b200 import BilayerAnalyzer
+    from tests.test_formats_cpu import export_system
+    psf, dcds, top, traj, lipid, pos = export_system(tmp_path, name=name, split=3)
+    c = cases.CASES[name]
+    bas = []
+    for structure, trajectory, sel in ((top, traj, "all"),
+                                       (psf, dcds, "not resname CLA and not resname TIP3 and not resname POT")):
+        ba = BilayerAnalyzer(structure=structure, trajectory=trajectory, selection=sel)
+        ba.remove_analysis("msd_1")
+        for a in c["analyses"]:
+            ba.add_analysis(a)
+        for rep, d in (c.get("rep_settings") or {}).items():
+            for k, v in d.items():
+                ba.rep_settings[rep][k] = v
+        if c.get("frame_range"):
+            ba.set_frame_range(*c["frame_range"])
+        ba.window_frames = window
+        ba.run_analysis()
+        bas.append(ba)
+    mem, fil = bas
+    if window is None:
+        for attr in ("com", "com_unwrap", "mem_com", "labels"):
+            assert np.array_equal(getattr(mem._engine, attr).cpu().numpy(), getattr(fil._engine, attr).cpu().numpy())
+    want = cases.flatten_outputs({k: mem.get_analysis_data(k) for k in mem.get_analysis_ids()})
+    got = cases.flatten_outputs({k: fil.get_analysis_data(k) for k in fil.get_analysis_ids()})
+    assert sorted(want) == sorted(got)
+    for k in want:
+        a, b = np.asarray(got[k], dtype=float), np.asarray(want[k], dtype=float)
+        if a.ndim == 2 and a.shape[1] in (2, 4) and not np.array_equal(a, b):
+            assert np.array_equal(a[:, 1:], b[:, 1:], equal_nan=True), k      # data columns exact
+            close(a[:, 0], b[:, 0], 1e-6)                                       # time column
+        else:
+            close(a, b, 1e-6, atol=1e-300)        # msd_multi's D divides by tau = t[n_tau-1] - t[0]
