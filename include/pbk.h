@@ -54,10 +54,13 @@ const char *pbk_last_error(const pbk_ctx *ctx);
 /* ---- N2  trajectory ingestion (the wire format before the path) ---------------------------
  * MDAData / mda.Universe(psf, dcd)             pybilt/bilayer_analyzer/mda_data.py:14-38
  * frame.positions[index]                       pybilt/bilayer_analyzer/bilayer_analyzer.py:936
- * A DCD frame stores X[], Y[], Z[] of all atoms; planes float32 [F][3][Mtot] (as read from the
- * file) become positions float32 [F][M][3] of the selected atoms sel[M] (int32 indices into
- * 0..Mtot-1, ascending; NULL = all atoms, M == Mtot).  F <= 65535 per call. */
-int pbk_planes_to_aos(pbk_ctx *ctx, const float *planes, const int32_t *sel, int64_t F, int64_t Mtot,
+ * A DCD frame stores the records X[], Y[], Z[] of all atoms.  `frames` are F frames exactly as
+ * they lie in the file (raw bytes viewed as float32, frame_stride floats apart, the X / Y / Z
+ * records starting off_x / off_y / off_z floats into a frame; byteswap != 0 for a file of the
+ * other endianness); out = positions float32 [F][M][3] of the selected atoms sel[M] (int32 atom
+ * indices, ascending; NULL = the first M atoms in file order).  F <= 65535 per call. */
+int pbk_planes_to_aos(pbk_ctx *ctx, const float *frames, const int32_t *sel, int64_t F,
+                      int64_t frame_stride, int64_t off_x, int64_t off_y, int64_t off_z, int byteswap,
                       int64_t M, float *out, void *stream);
 
 /* ---- A1  PBC unwrap ---------------------------------------------------------------------

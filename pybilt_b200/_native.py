@@ -25,7 +25,8 @@ _SIGNATURES = {
     "pbk_ctx_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "pbk_ctx_destroy": (None, [c_void_p]),
     "pbk_last_error": (ctypes.c_char_p, [c_void_p]),
-    "pbk_planes_to_aos": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "pbk_planes_to_aos": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                  c_int, c_int64, c_void_p, c_void_p]),
     "pbk_unwrap_images": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64,
                                   c_int64, c_void_p, c_void_p, c_void_p]),
     "pbk_membrane_com_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

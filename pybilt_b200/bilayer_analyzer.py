@@ -154,16 +154,16 @@ class TrajectoryData(object):
         self._times = self.dcd.times(np.arange(self.dcd.n_frames))
         self.nframes = self.dcd.n_frames
 
-    def read_planes(self, frame_idx, out):
-        """X/Y/Z planes of ALL atoms of the frames into ``out`` (float32 [>=f, 3, n_atoms_total],
-        pinned); runs of consecutive frames are copied record by record."""
+    def read_raw_frames(self, frame_idx, out):
+        """The frames exactly as they lie in the file(s) into ``out`` (uint8 [>= f, frame_bytes],
+        pinned); runs of consecutive frames are read in one go."""
         frame_idx = np.asarray(frame_idx)
         k = 0
         while k < len(frame_idx):
             j = k
             while j + 1 < len(frame_idx) and frame_idx[j + 1] == frame_idx[j] + 1:
                 j += 1
-            self.dcd.planes(int(frame_idx[k]), int(frame_idx[j]) + 1, out[k:j + 1])
+            self.dcd.read_raw(int(frame_idx[k]), int(frame_idx[j]) + 1, out[k:j + 1])
             k = j + 1
         return out[:len(frame_idx)]
 
@@ -231,8 +231,9 @@ class TrajectoryData(object):
 
 class _FrameFeeder(object):
     """Host -> device frame batches, double buffered on a copy stream.  In-memory trajectories are
-    copied as they are ([f, M, 3]); natively read DCD files are copied as the file's X/Y/Z planes
-    of all atoms and interleaved / atom-selected on the device (`pbk_planes_to_aos`)."""
+    copied as they are ([f, M, 3]); natively read DCD files go to the device as the raw bytes of
+    their frames (threaded positional reads into pinned staging) and are interleaved / atom-selected
+    / byte-swapped there (`pbk_planes_to_aos`)."""
 
     def __init__(self, md, eng):
         dev = eng.dev
@@ -247,11 +248,12 @@ class _FrameFeeder(object):
         self.n = [0, 0]
         self.k_issue = 0
         self.k_take = 0
-        self.planar = md.dcd is not None
+        lay = md.dcd.raw_layout if md.dcd is not None else None
+        self.planar = lay is not None           # natively read DCD: raw file frames go to the device
         if self.planar:
-            mt = md.n_atoms_total
-            self.stage = [torch.empty((self.B, 3, mt), dtype=torch.float32).pin_memory() for _ in range(2)]
-            self.pdev = [torch.empty((self.B, 3, mt), dtype=torch.float32, device=dev) for _ in range(2)]
+            fb, self.frame_floats, self.plane_offsets, self.byteswap = lay
+            self.stage = [torch.empty((self.B, fb), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.pdev = [torch.empty((self.B, fb), dtype=torch.uint8, device=dev) for _ in range(2)]
             self.sel = None if md._all_atoms else torch.from_numpy(md.indices.astype(np.int32)).to(dev)
 
     def issue(self, frames):
@@ -262,7 +264,7 @@ class _FrameFeeder(object):
         if self.planar:
             if self.copied[slot] is not None:
                 self.copied[slot].synchronize()       # the staging buffer is free again
-            md.read_planes(frames, self.stage[slot].numpy())
+            md.read_raw_frames(frames, self.stage[slot].numpy())
             d, t = md._dimensions[frames], md._times[frames]
             src, dst = self.stage[slot][:nf], self.pdev[slot][:nf]
         else:
@@ -290,7 +292,8 @@ class _FrameFeeder(object):
         nf = self.n[slot]
         self.main.wait_event(self.ready[slot])
         if self.planar:
-            self.eng.planes_to_aos(self.pdev[slot][:nf], self.sel, self.bufs[slot][:nf])
+            self.eng.planes_to_aos(self.pdev[slot][:nf].view(torch.float32), self.sel, self.bufs[slot][:nf],
+                                   self.plane_offsets, self.byteswap)
         return self.bufs[slot][:nf], self.boxes[slot][:nf]
 
     def release(self):

@@ -453,34 +453,45 @@ extern "C" int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, 
 }
 
 // ---------------------------------------------------------------------------------------
-// K0  trajectory ingestion: DCD frames hold the coordinates as three planes X[], Y[], Z[] of ALL
-// atoms; the reduction wants MDAnalysis' layout [selected atom][xyz].  One thread per (frame,
-// selected atom): three coalesced plane reads (gathered through `sel` when the selection is not
-// everything), one 12-byte write; a warp writes 384 contiguous bytes.
+// K0  trajectory ingestion: a DCD frame holds the coordinates as three records X[], Y[], Z[] of
+// ALL atoms (between Fortran record markers, behind an optional unit-cell record); the reduction
+// wants MDAnalysis' layout [selected atom][xyz].  The frames arrive on the device as the raw
+// bytes of the file; one thread per (frame, selected atom) makes three coalesced record reads
+// (gathered through `sel` when the selection is not everything, byte-swapped for files written
+// on a big-endian machine) and one 12-byte write; a warp writes 384 contiguous bytes.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_planes_to_aos(const float *__restrict__ planes, const int32_t *__restrict__ sel, int64_t F, int64_t Mtot,
-                int64_t M, float *__restrict__ out)
+k_planes_to_aos(const float *__restrict__ frames, const int32_t *__restrict__ sel, int64_t frame_stride,
+                int64_t off_x, int64_t off_y, int64_t off_z, int byteswap, int64_t M, float *__restrict__ out)
 {
     const int64_t f = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int64_t a = sel ? (int64_t)sel[i] : i;
-    const float *p = planes + f * 3 * Mtot;
-    float *o = out + (f * M + i) * 3;
-    o[0] = p[a];
-    o[1] = p[Mtot + a];
-    o[2] = p[2 * Mtot + a];
+    const unsigned *p = reinterpret_cast<const unsigned *>(frames + f * frame_stride);
+    unsigned vx = p[off_x + a], vy = p[off_y + a], vz = p[off_z + a];
+    if (byteswap) {
+        vx = __byte_perm(vx, 0, 0x0123);
+        vy = __byte_perm(vy, 0, 0x0123);
+        vz = __byte_perm(vz, 0, 0x0123);
+    }
+    unsigned *o = reinterpret_cast<unsigned *>(out + (f * M + i) * 3);
+    o[0] = vx;
+    o[1] = vy;
+    o[2] = vz;
 }
 
-extern "C" int pbk_planes_to_aos(pbk_ctx *ctx, const float *planes, const int32_t *sel, int64_t F, int64_t Mtot,
-                                 int64_t M, float *out, void *stream)
+extern "C" int pbk_planes_to_aos(pbk_ctx *ctx, const float *frames, const int32_t *sel, int64_t F,
+                                 int64_t frame_stride, int64_t off_x, int64_t off_y, int64_t off_z,
+                                 int byteswap, int64_t M, float *out, void *stream)
 {
-    if (!ctx || !planes || !out || F < 0 || Mtot <= 0 || M <= 0 || M > Mtot || F > 65535)
+    if (!ctx || !frames || !out || F < 0 || frame_stride <= 0 || off_x < 0 || off_y < 0 || off_z < 0 ||
+        M <= 0 || F > 65535)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_planes_to_aos: bad argument (F <= 65535 per call)");
     if (F == 0) return PBK_OK;
     dim3 g((unsigned)((M + 255) / 256), (unsigned)F);
-    k_planes_to_aos<<<g, 256, 0, (cudaStream_t)stream>>>(planes, sel, F, Mtot, M, out);
+    k_planes_to_aos<<<g, 256, 0, (cudaStream_t)stream>>>(frames, sel, frame_stride, off_x, off_y, off_z,
+                                                         byteswap, M, out);
     PBK_CHECK_LAUNCH(ctx, "k_planes_to_aos");
     return PBK_OK;
 }

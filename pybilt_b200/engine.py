@@ -214,16 +214,19 @@ class LipidReductionEngine:
             self.stream_started = True
             self.launches += 1
 
-    def planes_to_aos(self, planes: torch.Tensor, sel: Optional[torch.Tensor], out: torch.Tensor):
-        """Device-side interleave + atom selection of DCD coordinate planes: ``planes`` float32
-        [f, 3, Mtot] -> ``out`` float32 [f, M, 3] (``sel`` int32 [M] or None for all atoms)."""
-        assert planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()
+    def planes_to_aos(self, raw: torch.Tensor, sel: Optional[torch.Tensor], out: torch.Tensor,
+                      offsets, byteswap: bool = False):
+        """Device-side interleave + atom selection of DCD frames: ``raw`` float32 [f, frame_floats]
+        (the frames as they lie in the file) -> ``out`` float32 [f, M, 3]; ``offsets`` = float index
+        of the X, Y, Z records inside a frame; ``sel`` int32 [M] or None for the first M atoms."""
+        assert raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous()
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
-        f, _three, mtot = planes.shape
+        f, stride = raw.shape
         st = self.stream_ptr()
         for f0 in range(0, f, 65535):
             f1 = min(f, f0 + 65535)
-            self.ctx.call("pbk_planes_to_aos", planes[f0:f1].data_ptr(), _ptr(sel), f1 - f0, int(mtot),
+            self.ctx.call("pbk_planes_to_aos", raw[f0:f1].data_ptr(), _ptr(sel), f1 - f0, int(stride),
+                          int(offsets[0]), int(offsets[1]), int(offsets[2]), 1 if byteswap else 0,
                           int(out.shape[1]), out[f0:f1].data_ptr(), st)
             self.launches += 1
 

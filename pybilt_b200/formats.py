@@ -17,7 +17,7 @@ is not part of this image, so what it would return is restated here from the fil
   in AKMA units (4.888821e-2 ps).  Parity of this piece against MDAnalysis itself is UNPINNED
   (nothing to execute here); positions are the file's float32 values bit for bit either way.
 
-Coordinates leave the file as three planes (X, Y, Z); they are interleaved to MDAnalysis'
+X
 ``[atom, xyz]`` layout ON THE DEVICE (``pbk_planes_to_aos``), together with the atom selection,
 so the host never touches individual atoms.
 """
@@ -26,11 +26,21 @@ from __future__ import annotations
 import fnmatch
 import os
 import struct
+import sys
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
 AKMA_PS = 4.888821e-2          # one AKMA time unit in ps (MDAnalysis.units)
+
+_POOLS = {}
+
+
+def _pool(threads: int) -> ThreadPoolExecutor:
+    if threads not in _POOLS:
+        _POOLS[threads] = ThreadPoolExecutor(max_workers=threads)
+    return _POOLS[threads]
 
 
 # ---------------------------------------------------------------------------------------
@@ -258,6 +268,40 @@ class DCDFile(object):
         self._mm = np.memmap(path, dtype=self.frame_dtype, mode="r", offset=self.header_bytes,
                              shape=(self.n_frames,))
         self.dt = float(self.delta) * self.nsavc * AKMA_PS      # ps between stored frames
+        # raw layout for the device-side interleave: float32 index of the X / Y / Z records in a frame
+        self.frame_floats = self.frame_bytes // 4
+        self.plane_offsets = tuple(self.frame_dtype.fields[ax][1] // 4 for ax in "xyz")
+        self.foreign_endian = (self.endian == ">") != (sys.byteorder == "big")
+        self._fd = None
+
+    def read_raw(self, f0: int, f1: int, out: np.ndarray, threads: Optional[int] = None):
+        """Frames f0..f1-1 exactly as they lie in the file into ``out`` (uint8 [>= f1-f0, frame_bytes],
+        e.g. pinned memory): positional reads straight into the buffer, several threads (os.preadv
+        releases the GIL), no per-atom work on the host."""
+        if self._fd is None:
+            self._fd = os.open(self.path, os.O_RDONLY)
+        if threads is None:
+            threads = int(os.environ.get("PBK_READ_THREADS", min(16, os.cpu_count() or 1)))
+        nbytes = (f1 - f0) * self.frame_bytes
+        flat = out.reshape(-1)[:nbytes]
+        base = self.header_bytes + f0 * self.frame_bytes
+        piece = max(1 << 20, -(-nbytes // max(1, threads)))
+        jobs = [(o, min(piece, nbytes - o)) for o in range(0, nbytes, piece)]
+
+        def rd(job):
+            o, n = job
+            got = 0
+            while got < n:
+                r = os.preadv(self._fd, [memoryview(flat[o + got:o + n])], base + o + got)
+                if r <= 0:
+                    raise RuntimeError("short read from %s" % self.path)
+                got += r
+
+        if len(jobs) == 1:
+            rd(jobs[0])
+        else:
+            list(_pool(threads).map(rd, jobs))
+        return out[:f1 - f0]
 
     # -- what MDAnalysis' DCDReader hands over ---------------------------------------------
     def dimensions(self, frames) -> np.ndarray:
@@ -367,6 +411,26 @@ class DCDChain(object):
             self.files[k].planes(l, l + take, out[g - f0:g - f0 + take])
             g += take
         return out[:nf]
+
+    @property
+    def raw_layout(self):
+        """(frame_bytes, frame_floats, plane_offsets, foreign_endian) when every file shares one
+        frame layout (then batches can be shipped to the device as raw file bytes), else None."""
+        f0 = self.files[0]
+        key = (f0.frame_bytes, f0.frame_floats, f0.plane_offsets, f0.foreign_endian)
+        for f in self.files[1:]:
+            if (f.frame_bytes, f.frame_floats, f.plane_offsets, f.foreign_endian) != key:
+                return None
+        return key
+
+    def read_raw(self, f0: int, f1: int, out: np.ndarray):
+        g = f0
+        while g < f1:
+            k, l = self._locate(g)
+            take = min(f1 - g, self.files[k].n_frames - l)
+            self.files[k].read_raw(l, l + take, out[g - f0:g - f0 + take])
+            g += take
+        return out[:f1 - f0]
 
     def positions(self, frames, atoms=None) -> np.ndarray:
         frames = np.asarray(frames)

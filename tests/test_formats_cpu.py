@@ -102,8 +102,11 @@ def test_trajectory_data_from_files_matches_arrays(tmp_path):
     x, d, t = md.frames(fr)
     xr, dr, tr = ref.frames(fr)
     assert np.array_equal(x, xr) and np.array_equal(d[:, :3], dr[:, :3]) and np.allclose(t, tr, rtol=1e-6)
-    out = np.zeros((8, 3, pos.shape[1]), dtype=np.float32)
-    pl = md.read_planes(fr, out)
-    assert np.array_equal(pl.transpose(0, 2, 1), pos[fr])
+    fb, ff, offs, foreign = md.dcd.raw_layout
+    out = np.zeros((8, fb), dtype=np.uint8)
+    raw = md.read_raw_frames(fr, out).view(np.float32)                 # frames as they lie in the files
+    assert raw.shape == (len(fr), ff) and not foreign
+    got = np.stack([raw[:, o:o + pos.shape[1]] for o in offs], axis=2)
+    assert np.array_equal(got, pos[fr])
     with pytest.raises(RuntimeError):
         TrajectoryData(psf, dcds, "name OH2")          # part of a residue
