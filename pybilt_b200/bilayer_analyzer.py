@@ -34,6 +34,7 @@ from . import leaflet as lf
 from . import lipid_grid as lg
 from . import distributed as pd
 from . import formats as fmt
+from . import plot_protocols as pp
 from .engine import FusedPathRejected, LipidReductionEngine, build_bead_layout
 
 default_analysis_commands = ['msd msd_1']
@@ -477,6 +478,7 @@ class BilayerAnalyzer(object):
         self._analysis_protocol = ap.Analyses(self._commands.get('analysis',
                                                                  default_analysis_commands))
         self._plot_commands = self._commands.get('plot', [])
+        self._plot_protocol = pp.PlotProtocol(self._plot_commands, self._analysis_protocol)
         self._mda_data = TrajectoryData(self._commands['structure'], self._commands['trajectory'],
                                         self._commands['selection'])
         self._current_frame = self.settings['frame_range'][0]
@@ -537,6 +539,31 @@ class BilayerAnalyzer(object):
     # -- analysis protocol ----------------------------------------------------------------
     def print_analysis_protocol(self):
         self._analysis_protocol.print_protocol()
+
+    # -- plots (bilayer_analyzer.py:592-653) ------------------------------------------------------
+    def print_plot_protocol(self):
+        self._plot_protocol.print_protocol()
+
+    def add_plot(self, plot_string):
+        self._plot_protocol.add_plot(plot_string, self._analysis_protocol)
+
+    def remove_plot(self, plot_id):
+        self._plot_protocol.remove_plot(plot_id)
+
+    def print_plot_ids(self):
+        print(self._plot_protocol.plot_ids)
+
+    def get_plot_ids(self):
+        return self._plot_protocol.plot_ids
+
+    def show_plot(self, plot_id):
+        return self._plot_protocol.command_protocol[plot_id].show_plot(self._analysis_protocol)
+
+    def generate_plot(self, plot_id):
+        return self._plot_protocol.command_protocol[plot_id].generate_plot(self._analysis_protocol)
+
+    def save_all_plots(self):
+        self._plot_protocol.save_plots(self._analysis_protocol)
 
     def add_analysis(self, analysis_in):
         self._analysis_protocol.add_analysis(analysis_in)

@@ -231,3 +231,51 @@ def test_run_from_psf_dcd_files_matches_in_memory_run(name, window, tmp_path):
             close(a[:, 0], b[:, 0], 1e-6)                                       # time column
         else:
             close(a, b, 1e-6, atol=1e-300)        # msd_multi's D divides by tau = t[n_tau-1] - t[0]
+
+
+def test_prefab_style_driver_sequence(tmp_path, monkeypatch, capsys):
+    """The calls the reference's prefab drivers make on an analyzer (msd_diffusion,
+    prefab_analysis_protocols.py:80-140; area_per_lipid :363-375): analyses per lipid type and
+    leaflet, plots over them, protocol print-outs, run, dump to a path prefix, save the plots,
+    diffusion estimators on the msd rows."""
+    from pybilt_b200 import BilayerAnalyzer, diffusion as dc
+    monkeypatch.chdir(tmp_path)
+    top, traj = cases.make_inputs("c3_small")
+    ba = BilayerAnalyzer(structure=top, trajectory=traj, selection="all")
+    ba.set_frame_range(0, -1, 1)
+    resnames = ["POPC", "DOPE"]
+    for lt in resnames:
+        ba.add_analysis("msd msd_" + lt + " resname " + lt)
+        ba.add_analysis("msd msd_" + lt + "_upper resname " + lt + " leaflet upper")
+        ba.add_analysis("msd msd_" + lt + "_lower resname " + lt + " leaflet lower")
+    ba.rep_settings['lipid_grid']['n_xbins'] = ba.rep_settings['lipid_grid']['n_ybins'] = 16
+    ba.add_analysis("apl_grid apl_grid")
+    ba.add_analysis("thickness_grid bt")
+    ba.add_plot('msd msd_a msd_1 All')
+    ba.add_plot("msd msd_l " + " ".join("msd_%s %s" % (lt, lt) for lt in resnames))
+    for lt in resnames:
+        ba.add_plot("msd %s_cul msd_%s Composite msd_%s_upper Upper msd_%s_lower Lower" % (lt, lt, lt, lt))
+    ba.add_plot("apl apl_p apl_grid None")
+    ba.add_plot("bilayer_thickness bt_p bt None")
+    ba.print_analysis_protocol()
+    ba.print_plot_protocol()
+    ba.run_analysis()
+    ba.dump_data(path=str(tmp_path) + "/")
+    ba.save_all_plots()
+    assert (tmp_path / "msd_1.pickle").exists() and (tmp_path / "apl_grid.pickle").exists()
+    msd = ba.get_analysis_data('msd_1')
+    ser = ba.generate_plot("msd_l")
+    assert [s[0] for s in ser] == resnames
+    assert np.array_equal(ser[0][2], ba.get_analysis_data("msd_POPC")[:, 1])
+    assert np.allclose(ser[0][1] * 1000.0, msd[:, 0])
+    apl = ba.generate_plot("apl_p")
+    assert [s[0] for s in apl][0] == "composite" and len(apl) == 1 + 3
+    assert np.array_equal(apl[0][2], ba.get_analysis_data("apl_grid")["composite"][:, 2])
+    bt = ba.generate_plot("bt_p")
+    assert np.array_equal(bt[0][2], ba.get_analysis_data("bt")[:, 2])
+    times, vals = msd[:, 0], msd[:, 1]
+    d_e = dc.diffusion_coefficient_Einstein(times, vals)
+    d_l = dc.diffusion_coefficient_linear_fit(times, vals)
+    assert np.isfinite(d_e) and np.isfinite(d_l[0])
+    out = capsys.readouterr().out
+    assert "with plots:" in out and "msd_l" in out

@@ -168,3 +168,31 @@ def test_diffusion_estimators():
     t0 = t.copy()
     dc.diffusion_coefficient_anomalous_fit(t0[1:], msd[1:])
     assert np.array_equal(t0, t)              # unlike the reference, the input is left alone
+
+
+def test_plot_protocol_registry_matches_reference_strings():
+    """add_plot / remove_plot / ids / errors of the plot registry (plot_protocols.py:15-118) on an
+    analyzer that never touches the device."""
+    from pybilt_b200 import BilayerAnalyzer
+    from tests import cases
+    top, traj = cases.make_inputs("tiny_all")
+    ba = BilayerAnalyzer(structure=top, trajectory=traj, selection="all")
+    ba.add_analysis("msd msd_popc resname POPC")
+    ba.add_analysis("apl_grid apl")
+    ba.add_analysis("thickness_grid bt")
+    ba.add_plot("msd msd_a msd_1 All")
+    ba.add_plot("msd msd_l msd_1 All msd_popc POPC")
+    ba.add_plot("apl apl_p apl None")
+    ba.add_plot("bilayer_thickness bt_p bt None")
+    assert ba.get_plot_ids() == ["msd_a", "msd_l", "apl_p", "bt_p"]
+    assert ba._plot_protocol.command_protocol["msd_l"].include == ["msd_1", "msd_popc"]
+    assert ba._plot_protocol.command_protocol["msd_l"].save_file_name == "msd_l.pdf"
+    with pytest.raises(RuntimeError):
+        ba.add_plot("msd msd_a msd_1 All")              # id used twice
+    with pytest.raises(RuntimeError):
+        ba.add_plot("msd other apl Nope")               # not an msd analysis
+    with pytest.raises(RuntimeError):
+        ba.add_plot("rainbow p1 msd_1 All")             # unknown plot key
+    ba.remove_plot("msd_a")
+    assert ba.get_plot_ids() == ["msd_l", "apl_p", "bt_p"]
+    ba.print_plot_protocol()
