@@ -154,6 +154,15 @@ int pbk_leaflets(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N, i
                  int64_t frame0, int update_interval, const uint8_t *prev_labels,
                  uint8_t *labels, int32_t *status, void *stream);
 
+/* ---- N3  thickness from the leaflets' centres of mass --------------------------------------
+ * LeaftoLeafDistProtocol.run_analysis   pybilt/bilayer_analyzer/analysis_protocols.py:1154-1170
+ * COMFrame.coordinates(leaflet=...)      pybilt/bilayer_analyzer/com_frame.py:369-385
+ * out[f] = | mean over upper lipids of com[f][:, norm] - mean over lower lipids |, the means as
+ * ndarray.mean(axis=0) forms them (rows added in lipid order, divided by the count); WRAPPED COMs;
+ * nan when a leaflet is empty. */
+int pbk_leaflet_distance(pbk_ctx *ctx, const double *com, const uint8_t *labels, int64_t F, int64_t N,
+                         int norm, double *out, void *stream);
+
 /* ---- C1 / C2  mean squared displacement -------------------------------------------------
  * MSDProtocol.run_analysis / MSDMultiProtocol.run_analysis
  *                                  pybilt/bilayer_analyzer/analysis_protocols.py:582-667, 781-895

@@ -433,6 +433,26 @@ def nnf(com, labels, types, box, times, leaflet="both", resname_1="first", resna
 
 
 # --------------------------------------------------------------------------------------
+# N3: thickness from the leaflets' centres of mass      analysis_protocols.py:1154-1170
+# --------------------------------------------------------------------------------------
+def leaflet_distance(com, labels, times, norm=2) -> np.ndarray:
+    """rows [time, |mean(com_upper) - mean(com_lower)|[norm], running mean, running deviation].
+    ``coordinates(leaflet=...)`` (com_frame.py:369-385) collects the WRAPPED COMs of the leaflet's
+    lipids in lipid order; ``ndarray.mean(axis=0)`` of that [n, 3] array adds the rows one after
+    the other and divides by n."""
+    F = com.shape[0]
+    run_ = Welford()
+    out = np.zeros((F, 4))
+    for f in range(F):
+        up = com[f][labels[f] == 1]
+        lo = com[f][labels[f] == 0]
+        cur = np.abs(up.mean(axis=0) - lo.mean(axis=0))[norm]
+        run_.push(cur)
+        out[f] = [times[f], cur, run_.mean(), run_.deviation()]
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # G1-G4: lipid grids         pybilt/lipid_grid/lipid_grid_opt.py, lipid_grid.py
 # --------------------------------------------------------------------------------------
 def grid_geometry(boxl: np.float32, nbins: int):
@@ -670,6 +690,12 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
                               int(kv.get("n_neighbors", 5)), lateral, return_counts=True)
             out[a_id] = res
             out[a_id + ":counts"] = counts
+        elif key == "thickness_leaflet_distance":
+            if int(lf.get("update_interval", 1)) != 1 and len(fr) > 1:
+                # frames between leaflet rebuilds carry no leaflet names: the reference's mean of an
+                # empty selection is a nan scalar and indexing it raises (analysis_protocols.py:1158)
+                raise IndexError("invalid index to scalar variable.")
+            out[a_id] = leaflet_distance(com, labels, times, norm)
         elif key in ("apl_grid", "thickness_grid"):
             if grids is None:
                 grids = [lipid_grid_frame(com[f], comu[f], labels[f], box[f],

@@ -574,6 +574,42 @@ class NNFProtocol(AnalysisProtocol):
 
 
 # ---------------------------------------------------------------------------------------
+@_protocol('thickness_leaflet_distance', 'com_frame')
+class LeaftoLeafDistProtocol(AnalysisProtocol):
+    """Bilayer thickness as the distance between the leaflets' centres of mass along the normal,
+    rows [time, thickness, running mean, running deviation] (analysis_protocols.py:1105-1176)."""
+    _short_description = "Distance between the leaflets' centers of mass along the normal."
+    _related = list(['lipid_length', 'thickness_grid', 'thickness_peak_distance',
+                     'thickness_mass_weighted_std'])
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self.running = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        if batch.first_window:
+            self._vals = np.zeros(batch.n_frames)
+            self._pending = []
+        if batch.engine.update_interval != 1 and batch.n_frames > 1:
+            # frames between leaflet rebuilds carry no leaflet names in the reference: its mean over
+            # an empty selection is a nan scalar and `[norm_ind]` on it raises (:1158)
+            raise IndexError("invalid index to scalar variable.")
+        self._pending.append((batch.gframes, batch.engine.leaflet_distance(frames=batch.rows)))
+
+    def finish(self, batch):
+        for g, v in self._pending:
+            self._vals[g] = v.cpu().numpy()
+        self._pending = []
+        rows, self.running = running_rows(batch.times, batch.allreduce(self._vals))
+        self.analysis_output = [r for r in rows]
+
+    def reset(self):
+        self.running.reset()
+        self.analysis_output = []
+
+
+# ---------------------------------------------------------------------------------------
 @_protocol('thickness_grid', 'lipid_grid')
 class BTGridProtocol(AnalysisProtocol):
     """Bilayer thickness from the lipid grids, rows [time, thickness, running mean, running

@@ -495,3 +495,51 @@ extern "C" int pbk_planes_to_aos(pbk_ctx *ctx, const float *frames, const int32_
     PBK_CHECK_LAUNCH(ctx, "k_planes_to_aos");
     return PBK_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// K10  thickness from the leaflets' centres of mass (thickness_leaflet_distance):
+// |mean_upper(com[norm]) - mean_lower(com[norm])| per frame.  NumPy's mean(axis=0) of the [n, 3]
+// coordinate array adds the rows in lipid order, so the sums are sequential: one warp per frame
+// loads labels and coordinates coalesced and replays the order through ballots (two independent
+// chains, one per leaflet).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_leaflet_distance(const double *__restrict__ com, const uint8_t *__restrict__ labels, int64_t F, int64_t N,
+                   int norm, double *__restrict__ out)
+{
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const double *cf = com + f * N * 3;
+    const uint8_t *lab = labels + f * N;
+    double su = 0.0, sl = 0.0;
+    long long nu = 0, nl = 0;
+    for (int64_t base = 0; base < N; base += 32) {
+        const int64_t i = base + lane;
+        double z = 0.0;
+        int l = -1;
+        if (i < N) { z = cf[i * 3 + norm]; l = lab[i] ? 1 : 0; }
+        unsigned mu = __ballot_sync(0xffffffffu, l == 1), ml = __ballot_sync(0xffffffffu, l == 0);
+        nu += __popc(mu);
+        nl += __popc(ml);
+        while (mu) { const int s = __ffs(mu) - 1; mu &= mu - 1; su = __dadd_rn(su, __shfl_sync(0xffffffffu, z, s)); }
+        while (ml) { const int s = __ffs(ml) - 1; ml &= ml - 1; sl = __dadd_rn(sl, __shfl_sync(0xffffffffu, z, s)); }
+    }
+    if (lane == 0) {
+        // an empty leaflet: numpy's mean of nothing is nan
+        const double mu_ = nu ? __ddiv_rn(su, (double)nu) : nan("");
+        const double ml_ = nl ? __ddiv_rn(sl, (double)nl) : nan("");
+        out[f] = fabs(__dsub_rn(mu_, ml_));
+    }
+}
+
+extern "C" int pbk_leaflet_distance(pbk_ctx *ctx, const double *com, const uint8_t *labels, int64_t F, int64_t N,
+                                    int norm, double *out, void *stream)
+{
+    if (!ctx || !com || !labels || !out || F < 0 || N <= 0 || norm < 0 || norm > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_leaflet_distance: bad argument");
+    if (F == 0) return PBK_OK;
+    k_leaflet_distance<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(com, labels, F, N, norm, out);
+    PBK_CHECK_LAUNCH(ctx, "k_leaflet_distance");
+    return PBK_OK;
+}

@@ -347,6 +347,16 @@ class LipidReductionEngine:
     # ---------------------------------------------------------------------------------
     # analyses over the resident representations
     # ---------------------------------------------------------------------------------
+    def leaflet_distance(self, frames: Optional[slice] = None) -> torch.Tensor:
+        """|mean(com_upper) - mean(com_lower)| along the bilayer normal, float64 [frames]."""
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        out = torch.empty(F, dtype=torch.float64, device=self.dev)
+        self.ctx.call("pbk_leaflet_distance", self.com[sl.start:].data_ptr(), self.labels[sl.start:].data_ptr(),
+                      F, self.N, self.norm, out.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return out
+
     def msd_pairs(self, idx: np.ndarray, origins: Sequence[int], ends: Sequence[int],
                   lateral=(0, 1)) -> torch.Tensor:
         d = self.dev

@@ -69,6 +69,10 @@ CASES = {
         spec=syn.BilayerSpec(256, CG3, seed=6, lattice_jitter=0.49), n_frames=2,
         analyses=["apl_grid apl", "thickness_grid bt"],
         rep_settings={"lipid_grid": {"n_xbins": 8, "n_ybins": 8}}),
+    # thickness from the leaflets' centres of mass
+    "leaflet_dist": dict(
+        spec=syn.BilayerSpec(96, MIX3, seed=13, box_z=72.0, npt=1e-3), n_frames=12,
+        analyses=["thickness_leaflet_distance tld", "msd msd_1"]),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,

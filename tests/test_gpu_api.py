@@ -279,3 +279,15 @@ def test_prefab_style_driver_sequence(tmp_path, monkeypatch, capsys):
     assert np.isfinite(d_e) and np.isfinite(d_l[0])
     out = capsys.readouterr().out
     assert "with plots:" in out and "msd_l" in out
+
+
+def test_leaflet_distance_with_update_interval_raises_like_the_reference():
+    """Between leaflet rebuilds the reference's COM frame carries no leaflet names; its mean over an
+    empty selection is a nan scalar and indexing it raises IndexError (analysis_protocols.py:1158)."""
+    from pybilt_b200 import BilayerAnalyzer
+    top, traj = cases.make_inputs("leaflet_dist")
+    ba = BilayerAnalyzer(structure=top, trajectory=traj, selection="all")
+    ba.add_analysis("thickness_leaflet_distance tld")
+    ba.rep_settings["leaflets"]["update_interval"] = 3
+    with pytest.raises(IndexError):
+        ba.run_analysis()

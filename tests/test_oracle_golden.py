@@ -132,3 +132,9 @@ def test_port_comtraj_matches_reference(name):
     close(port.comtraj_msd(ct, "lower", str(gold["first_group"])), gold["msd_lower_first"])
     assert np.array_equal(port.comtraj_group_indices(ct["labels0"], ct["types"], "upper", "all"),
                           gold["upper_all"])
+
+
+def test_port_leaflet_distance_raises_with_update_interval():
+    top, traj = cases.make_inputs("leaflet_dist")
+    with pytest.raises(IndexError):
+        port.run(top, traj, ["thickness_leaflet_distance tld"], {"leaflets": {"update_interval": 3}})
