@@ -433,6 +433,25 @@ def nnf(com, labels, types, box, times, leaflet="both", resname_1="first", resna
 
 
 # --------------------------------------------------------------------------------------
+# N3: lateral box-area fluctuation      analysis_protocols.py:4486-4498
+# --------------------------------------------------------------------------------------
+def area_fluctuation(box, times, lateral=(0, 1)) -> np.ndarray:
+    """rows [time, area, sqrt(<A^2> - <A>^2)] with the float32 box product of the COM frame and
+    Welford running means of A and A*A (float32 on the first push, running_stats.py:34-52)."""
+    run_a, run_sq = Welford(), Welford()
+    out = []
+    for f in range(box.shape[0]):
+        area = box[f][list(lateral)].prod()              # float32 product
+        run_a.push(area)
+        run_sq.push(area * area)
+        if f == 0:
+            out.append([times[f], area, 0.0])
+        else:
+            out.append([times[f], area, np.sqrt(run_sq.mean() - run_a.mean() ** 2)])
+    return np.array(out)
+
+
+# --------------------------------------------------------------------------------------
 # N3: thickness from the leaflets' centres of mass      analysis_protocols.py:1154-1170
 # --------------------------------------------------------------------------------------
 def leaflet_distance(com, labels, times, norm=2) -> np.ndarray:
@@ -690,6 +709,8 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
                               int(kv.get("n_neighbors", 5)), lateral, return_counts=True)
             out[a_id] = res
             out[a_id + ":counts"] = counts
+        elif key == "area_fluctuation":
+            out[a_id] = area_fluctuation(box, times, lateral)
         elif key == "thickness_leaflet_distance":
             if int(lf.get("update_interval", 1)) != 1 and len(fr) > 1:
                 # frames between leaflet rebuilds carry no leaflet names: the reference's mean of an

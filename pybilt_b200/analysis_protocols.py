@@ -610,6 +610,46 @@ class LeaftoLeafDistProtocol(AnalysisProtocol):
 
 
 # ---------------------------------------------------------------------------------------
+@_protocol('area_fluctuation', 'com_frame')
+class AreaFluctuationProtocol(AnalysisProtocol):
+    """Fluctuation of the lateral box area, rows [time, area, sqrt(<A^2> - <A>^2)]
+    (analysis_protocols.py:4452-4510).  Box arithmetic only, O(frames): done on the host in
+    finish(), in the reference's float32 / Welford order."""
+    _short_description = "Bilayer lateral box area fluctuation."
+    _related = list(['acm', 'ac'])
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self._first_frame = True
+        self._area_run = RunningStats()
+        self._area_sq_run = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        pass                                  # nothing to do per window: the boxes are host metadata
+
+    def finish(self, batch):
+        lat = list(batch.lateral)
+        with np.errstate(invalid="ignore"):
+            for f in range(batch.n_frames):
+                area = batch.box_host[f][lat].prod()          # float32 product (com_frame.box)
+                self._area_run.push(area)
+                self._area_sq_run.push(area * area)
+                if self._first_frame:
+                    self.analysis_output.append([batch.times[f], area, 0.0])
+                    self._first_frame = False
+                else:
+                    fluct = np.sqrt(self._area_sq_run.mean() - self._area_run.mean() ** 2)
+                    self.analysis_output.append([batch.times[f], area, fluct])
+
+    def reset(self):
+        self._first_frame = True
+        self.analysis_output = []
+        self._area_run.reset()
+        self._area_sq_run.reset()
+
+
+# ---------------------------------------------------------------------------------------
 @_protocol('thickness_grid', 'lipid_grid')
 class BTGridProtocol(AnalysisProtocol):
     """Bilayer thickness from the lipid grids, rows [time, thickness, running mean, running
