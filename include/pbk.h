@@ -247,6 +247,21 @@ int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com_unwrap,
                    int lat1, int norm, int nx, int ny, int mode, int32_t *knn_scratch,
                    int32_t *grid_idx, double *grid_z, void *stream);
 
+/* ---- N3  Halperin-Nelson hexatic invariant ------------------------------------------------
+ * HalperinNelsonProtocol._6nn / run_analysis   pybilt/bilayer_analyzer/analysis_protocols.py:4362-4425
+ * pbk_knn24: the 24 nearest same-class neighbours of every lipid, knn[F][N][24] int32 (-1 padded),
+ * in (distance, index) order, each pair evaluated as dist(lower index, higher index) -- the table of
+ * lipid_grid_opt._knn, exported on its own; `labels` is any per-frame class byte (leaflet labels, or
+ * a membership mask repeated for every frame).
+ * pbk_halperin_nelson: out[f] = mean over the lipids with member[i] != 0 of
+ * |(1/6) sum_{j in first six neighbours} exp(6 i a_ij)|^2, a_ij = x component of the unit vector
+ * from i to j in the reference's arithmetic (it feeds that cosine to exp as an angle). */
+int pbk_knn24(pbk_ctx *ctx, const double *com, const uint8_t *labels, const float *box, int64_t F, int64_t N,
+              int lat0, int lat1, int32_t *knn, void *stream);
+int pbk_halperin_nelson(pbk_ctx *ctx, const double *com, const uint8_t *member, const float *box,
+                        const int32_t *knn, int64_t F, int64_t N, int lat0, int lat1, int64_t n_members,
+                        double *out, void *stream);
+
 /* ---- G3  grid reductions ----------------------------------------------------------------
  * LipidGrids.average_thickness / area_per_lipid   pybilt/lipid_grid/lipid_grid_opt.py:496-526,553-597
  * thickness[F][2] = (mean, population std) over cells of grid_z[upper]-grid_z[lower];

@@ -433,6 +433,49 @@ def nnf(com, labels, types, box, times, leaflet="both", resname_1="first", resna
 
 
 # --------------------------------------------------------------------------------------
+# N3: Halperin-Nelson hexatic invariant      analysis_protocols.py:4337-4425
+# --------------------------------------------------------------------------------------
+def halperin_nelson(com, box, times, idx, lateral=(0, 1)) -> np.ndarray:
+    """rows [time, mean_l |(1/6) sum_{j in 6nn(l)} exp(6i a_lj)|^2] over the lipids ``idx`` (the
+    first frame's leaflet members).  Every pair (lower, higher position) is evaluated once with
+    distance_euclidean_pbc; a stable sort of all pairs by distance hands each lipid its six nearest
+    in (distance, partner index) order; the "angle" is the x component of the unit separation
+    vector, used as an angle as the reference does."""
+    import cmath
+    lx, ly = lateral
+    n = len(idx)
+    out = []
+    for f in range(com.shape[0]):
+        bl = np.array([box[f, lx], box[f, ly]], dtype=np.float32)
+        c = bl / 2.0
+        pos = com[f][:, [lx, ly]]
+        pairs = []
+        for a in range(n - 1):
+            for b in range(a + 1, n):
+                va, vb = pos[idx[a]] - c, pos[idx[b]] - c
+                dv = va - vb
+                for k in range(2):
+                    if abs(dv[k]) > bl[k] / 2.0:
+                        dv[k] = bl[k] - abs(va[k]) - abs(vb[k])
+                pairs.append((idx[a], idx[b], np.sqrt(np.dot(dv, dv)), dv))
+        pairs.sort(key=lambda p: p[2])
+        knn = {i: [] for i in idx}
+        for i, j, r, dv in pairs:
+            if len(knn[i]) < 6:
+                knn[i].append((r, -dv))
+            if len(knn[j]) < 6:
+                knn[j].append((r, dv))
+        hn = []
+        for i in idx:
+            acc = 0.0
+            for r, vec in knn[i]:
+                acc += cmath.exp(6j * (np.dot(vec, np.array([1.0, 0.0])) / r))
+            hn.append(abs(acc / 6.0) ** 2)
+        out.append([times[f], np.array(hn).mean()])
+    return np.array(out)
+
+
+# --------------------------------------------------------------------------------------
 # N3: lateral box-area fluctuation      analysis_protocols.py:4486-4498
 # --------------------------------------------------------------------------------------
 def area_fluctuation(box, times, lateral=(0, 1)) -> np.ndarray:
@@ -709,6 +752,10 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
                               int(kv.get("n_neighbors", 5)), lateral, return_counts=True)
             out[a_id] = res
             out[a_id + ":counts"] = counts
+        elif key == "halperin_nelson":
+            leaf = kv.get("leaflet", "upper")
+            v = views0[leaf if leaf in ("upper", "lower") else "upper"]
+            out[a_id] = halperin_nelson(com, box, times, list(v.members), lateral)
         elif key == "area_fluctuation":
             out[a_id] = area_fluctuation(box, times, lateral)
         elif key == "thickness_leaflet_distance":

@@ -62,6 +62,10 @@ _SIGNATURES = {
                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_nnf_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pbk_knn24": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+                          c_void_p]),
+    "pbk_halperin_nelson": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                    c_int, c_int64, c_void_p, c_void_p]),
     "pbk_lipid_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

@@ -610,6 +610,45 @@ class LeaftoLeafDistProtocol(AnalysisProtocol):
 
 
 # ---------------------------------------------------------------------------------------
+@_protocol('halperin_nelson', 'com_frame')
+class HalperinNelsonProtocol(AnalysisProtocol):
+    """Halperin and Nelson's hexagonal-packing invariant averaged over a leaflet, rows
+    [time, mean phi] (analysis_protocols.py:4286-4440).  The lipid list is the first frame's
+    leaflet ('upper' unless 'lower' is asked for)."""
+    _short_description = "Halperin and Nelson's rotational invariant."
+    _related = None
+    batched = True
+
+    def __init__(self, args):
+        self._indices = []
+        self._setup({'leaflet': 'upper'}, args)
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        if batch.first_window:
+            leaf = self.settings['leaflet'] if self.settings['leaflet'] in ('upper', 'lower') else 'upper'
+            self._indices = batch.first_leaflets[leaf].get_member_indices()
+            mask = np.zeros(len(batch.types), dtype=np.uint8)
+            mask[np.asarray(self._indices, dtype=np.int64)] = 1
+            self._member_dev = torch.from_numpy(mask).to(batch.engine.dev)
+            self._vals = np.zeros(batch.n_frames)
+            self._pending = []
+        self._pending.append((batch.gframes,
+                              batch.engine.halperin_nelson(self._member_dev, ba_settings['lateral'],
+                                                           frames=batch.rows)))
+
+    def finish(self, batch):
+        for g, v in self._pending:
+            self._vals[g] = v.cpu().numpy()
+        self._pending = []
+        vals = batch.allreduce(self._vals)
+        self.analysis_output = [[t, v] for t, v in zip(np.asarray(batch.times, dtype=np.float64), vals)]
+
+    def reset(self):
+        self.analysis_output = []
+        self._indices = []
+
+
+# ---------------------------------------------------------------------------------------
 @_protocol('area_fluctuation', 'com_frame')
 class AreaFluctuationProtocol(AnalysisProtocol):
     """Fluctuation of the lateral box area, rows [time, area, sqrt(<A^2> - <A>^2)]

@@ -217,6 +217,86 @@ int pbk_grid_knn_cells(pbk_ctx *ctx, const double *com, const uint8_t *labels, c
                        const float *box, int64_t F, int64_t N, int lat0, int lat1, int32_t *knn, cudaStream_t st);
 bool pbk_use_cells(int64_t N, int64_t threshold);
 
+// the 24 nearest same-class neighbours of every lipid (class = its label byte): cell lists for large
+// systems, the dense kernel otherwise and for frames with a lipid outside the box
+extern "C" int pbk_knn24(pbk_ctx *ctx, const double *com, const uint8_t *labels, const float *box, int64_t F,
+                         int64_t N, int lat0, int lat1, int32_t *knn, void *stream)
+{
+    if (!ctx || !com || !labels || !box || !knn || F < 0 || N <= 0 || lat0 < 0 || lat0 > 2 || lat1 < 0 ||
+        lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_knn24: bad argument");
+    if (F == 0) return PBK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PBK_EUNSUPPORTED;
+    if (pbk_use_cells(N, 1024))
+        rc = pbk_grid_knn_cells(ctx, com, labels, nullptr, box, F, N, lat0, lat1, knn, st);
+    if (rc == PBK_EUNSUPPORTED)
+        rc = pbk_grid_knn_dense_flagged(ctx, com, labels, box, F, N, lat0, lat1, knn, nullptr, 0, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// K11  Halperin-Nelson hexatic invariant (halperin_nelson).  Per member lipid l: its six nearest
+// members (first six entries of the 24-neighbour table, already in (distance, index) order),
+// a = x component of the unit separation vector in the reference's rounding (the pair is
+// evaluated as dist(lower index, higher index), the vector handed to l points from l to j),
+// phi_l = |(1/6) sum exp(6 i a)|^2; out[f] = mean over the members.  One CTA per frame.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_halperin_nelson(const double *__restrict__ com, const uint8_t *__restrict__ member,
+                  const float *__restrict__ box, const int32_t *__restrict__ knn, int64_t N, int lat0, int lat1,
+                  int64_t n_members, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    const int64_t f = blockIdx.x;
+    const double *cf = com + f * N * 3;
+    const float bxf = box[f * 3 + lat0], byf = box[f * 3 + lat1];
+    const float cxf = bxf * 0.5f, cyf = byf * 0.5f;
+    const double Lx = (double)bxf, Ly = (double)byf, hx = (double)cxf, hy = (double)cyf;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        if (!member[i]) continue;
+        const double ix = __dsub_rn(cf[i * 3 + lat0], hx), iy = __dsub_rn(cf[i * 3 + lat1], hy);
+        const int32_t *row = knn + (f * N + i) * GRID_NNK;
+        double re = 0.0, im = 0.0;
+        for (int t = 0; t < 6; t++) {
+            const int j = row[t];
+            if (j < 0) break;
+            const double jx = __dsub_rn(cf[(int64_t)j * 3 + lat0], hx), jy = __dsub_rn(cf[(int64_t)j * 3 + lat1], hy);
+            // pair evaluated as (a = lower index, b = higher index): d = a' - b', minimum image per axis
+            const bool i_low = i < j;
+            const double ax = i_low ? ix : jx, ay = i_low ? iy : jy, bx = i_low ? jx : ix, by = i_low ? jy : iy;
+            double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+            if (fabs(dx) > hx) dx = __dsub_rn(__dsub_rn(Lx, fabs(ax)), fabs(bx));
+            if (fabs(dy) > hy) dy = __dsub_rn(__dsub_rn(Ly, fabs(ay)), fabs(by));
+            const double r = sqrt(fma(dy, dy, __dmul_rn(dx, dx)));
+            const double vx = i_low ? -dx : dx;            // vector stored for lipid i
+            const double a6 = __dmul_rn(6.0, __ddiv_rn(vx, r));
+            double sn, cs;
+            sincos(a6, &sn, &cs);
+            re = __dadd_rn(re, cs);
+            im = __dadd_rn(im, sn);
+        }
+        const double h = hypot(__ddiv_rn(re, 6.0), __ddiv_rn(im, 6.0));
+        acc += __dmul_rn(h, h);
+    }
+    acc = pbk_block_sum(acc, red);
+    if (threadIdx.x == 0) out[f] = n_members > 0 ? acc / (double)n_members : nan("");
+}
+
+extern "C" int pbk_halperin_nelson(pbk_ctx *ctx, const double *com, const uint8_t *member, const float *box,
+                                   const int32_t *knn, int64_t F, int64_t N, int lat0, int lat1, int64_t n_members,
+                                   double *out, void *stream)
+{
+    if (!ctx || !com || !member || !box || !knn || !out || F < 0 || N <= 0 || lat0 < 0 || lat0 > 2 ||
+        lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_halperin_nelson: bad argument");
+    if (F == 0) return PBK_OK;
+    k_halperin_nelson<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(com, member, box, knn, N, lat0, lat1, n_members, out);
+    PBK_CHECK_LAUNCH(ctx, "k_halperin_nelson");
+    return PBK_OK;
+}
+
 extern "C" int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com_unwrap,
                               const uint8_t *labels, const float *box, int64_t F, int64_t N,
                               int lat0, int lat1, int norm, int nx, int ny, int mode,
@@ -229,11 +309,7 @@ extern "C" int pbk_lipid_grid(pbk_ctx *ctx, const double *com, const double *com
     if (F == 0) return PBK_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 1) {
-        int rc = PBK_EUNSUPPORTED;
-        if (pbk_use_cells(N, 1024))
-            rc = pbk_grid_knn_cells(ctx, com, labels, nullptr, box, F, N, lat0, lat1, knn_scratch, st);
-        if (rc == PBK_EUNSUPPORTED)
-            rc = pbk_grid_knn_dense_flagged(ctx, com, labels, box, F, N, lat0, lat1, knn_scratch, nullptr, 0, st);
+        const int rc = pbk_knn24(ctx, com, labels, box, F, N, lat0, lat1, knn_scratch, stream);
         if (rc) return rc;
     }
     dim3 g2((unsigned)F, 2);

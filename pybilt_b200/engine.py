@@ -481,6 +481,24 @@ class LipidReductionEngine:
         self.launches += 2
         return n_b, frac
 
+    def halperin_nelson(self, member: torch.Tensor, lateral=(0, 1), frames: Optional[slice] = None):
+        """Mean hexatic invariant of the lipids ``member`` (uint8 [N], 1 = included) per frame,
+        float64 [frames]: six nearest members from the 24-neighbour search, then the invariant."""
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        s0 = sl.start
+        cls = member.to(torch.uint8).unsqueeze(0).expand(F, self.N).contiguous()     # class byte per frame
+        knn = torch.empty((F, self.N, 24), dtype=torch.int32, device=self.dev)
+        out = torch.empty(F, dtype=torch.float64, device=self.dev)
+        st = self.stream_ptr()
+        self.ctx.call("pbk_knn24", self.com[s0:].data_ptr(), cls.data_ptr(), self.box[s0:].data_ptr(), F, self.N,
+                      int(lateral[0]), int(lateral[1]), knn.data_ptr(), st)
+        self.ctx.call("pbk_halperin_nelson", self.com[s0:].data_ptr(), member.data_ptr(), self.box[s0:].data_ptr(),
+                      knn.data_ptr(), F, self.N, int(lateral[0]), int(lateral[1]), int(member.sum().item()),
+                      out.data_ptr(), st)
+        self.launches += 2
+        return out
+
     def lipid_grid(self, nx: int, ny: int, mode: str = "opt", lateral=(0, 1),
                    frames: Optional[slice] = None):
         d = self.dev

@@ -153,3 +153,16 @@ def test_nnf_multi_tallies_equal_per_analysis_calls(n_lipids, oob):
             n_b2, frac2 = e.nnf(codes, ta if ta < T else -2, tb if tb < T else -2, mask, k)
             assert np.array_equal(n_b.cpu().numpy(), n_b2.cpu().numpy()), (k, ta, tb, mask)
             assert np.array_equal(frac.cpu().numpy(), frac2.cpu().numpy())
+
+
+def test_halperin_nelson_cells_equal_dense(monkeypatch):
+    """The hexatic invariant from the cell-list neighbour search equals the one from the dense
+    search (same six neighbours in the same order, hence the same bits)."""
+    e, names, codes = _mid_engine(3000, 3, 47)
+    member = (e.labels[0] == 1).to(torch.uint8)
+    monkeypatch.setenv("PBK_FORCE_CELLS", "1")
+    a = e.halperin_nelson(member).cpu().numpy()
+    monkeypatch.delenv("PBK_FORCE_CELLS")
+    monkeypatch.setenv("PBK_NO_CELLS", "1")
+    b = e.halperin_nelson(member).cpu().numpy()
+    assert np.array_equal(a, b) and (a > 0).all() and (a < 1).all()
