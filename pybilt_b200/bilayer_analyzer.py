@@ -743,6 +743,10 @@ class BilayerAnalyzer(object):
         protos = [self._analysis_protocol.command_protocol[a] for a in self._analysis_protocol.analysis_ids]
         inc = [p_ for p_ in protos if getattr(p_, 'batched', False)] if self._incremental else []
         starts = list(range(0, len(fr), B))
+        if len(inc) * len(starts) > 32:
+            # many analyses x many batches: per-launch latencies and host bookkeeping of the
+            # per-batch calls would cost more than the overlap hides -- analyse once at the end
+            inc = []
         first_leaflets = None
 
         def issue_copy(k):
