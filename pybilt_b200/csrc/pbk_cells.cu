@@ -573,9 +573,32 @@ k_knn_cl(ClParams P, ClKnn K)
     const int pcy = pc / ncx, pcx = pc - pcy * ncx;
     const int lox = (ncx - 1) / 2, hix = ncx / 2, loy = (ncy - 1) / 2, hiy = ncy / 2;
     const int Rmax = max(hix, hiy);
+    // the k best so far live in a binary MAX-heap on the key (distance, lipid index): its root is
+    // the entry a candidate has to beat and stays in registers (r0, j0), so a rejected candidate
+    // costs no local-memory access; an accepted one costs one sift (log2 k steps), not a shift of
+    // a sorted array.  All keys are distinct, so the k smallest are the same set however they are
+    // kept; the sorted order is produced once at the end.
     double best[KMAX];
     int bj[KMAX];
     int nbest = 0;
+    double r0 = 0.0;
+    int j0 = 0;
+    auto key_gt = [](double ra, int ja, double rb, int jb) { return ra > rb || (ra == rb && ja > jb); };
+    // place (r, j) into the heap of `n` entries starting at the vacant root, sifting it down
+    auto sift_down = [&](double r, int j, int n) {
+        int h = 0;
+        for (;;) {
+            int c = 2 * h + 1;
+            if (c >= n) break;
+            if (c + 1 < n && key_gt(best[c + 1], bj[c + 1], best[c], bj[c])) c++;
+            if (!key_gt(best[c], bj[c], r, j)) break;
+            best[h] = best[c];
+            bj[h] = bj[c];
+            h = c;
+        }
+        best[h] = r;
+        bj[h] = j;
+    };
 
     auto visit = [&](int s0, int s1) {
         for (int q = s0; q < s1; q++) {
@@ -586,16 +609,22 @@ k_knn_cl(ClParams P, ClKnn K)
                                                : pbk_pbc_dist2(qx, qy, apx, apy, fr.Lx, fr.Ly, fr.hx, fr.hy);
             const double r = sqrt(d2);
             if (nbest == k) {
-                const double rl = best[k - 1];
-                if (!(r < rl || (r == rl && j < bj[k - 1]))) continue;
+                if (!key_gt(r0, j0, r, j)) continue;          // not better than the current k-th
+                sift_down(r, j, k);                           // replaces the root
+            } else {
+                int h = nbest++;                              // append and sift up
+                while (h > 0) {
+                    const int par = (h - 1) >> 1;
+                    if (!key_gt(r, j, best[par], bj[par])) break;
+                    best[h] = best[par];
+                    bj[h] = bj[par];
+                    h = par;
+                }
+                best[h] = r;
+                bj[h] = j;
             }
-            int pos = nbest < k ? nbest : k - 1;
-            const int last = pos;
-            while (pos > 0 && (best[pos - 1] > r || (best[pos - 1] == r && bj[pos - 1] > j))) pos--;
-            for (int t = last; t > pos; t--) { best[t] = best[t - 1]; bj[t] = bj[t - 1]; }
-            best[pos] = r;
-            bj[pos] = j;
-            if (nbest < k) nbest++;
+            r0 = best[0];
+            j0 = bj[0];
         }
     };
     // cells [c0, c1] (offsets from pcx, c1 - c0 + 1 <= ncx) of row `row`
@@ -629,12 +658,17 @@ k_knn_cl(ClParams P, ClKnn K)
         if (nbest == k) {
             const double bx = (R >= hix) ? 1e300 : R * g.wx, by = (R >= hiy) ? 1e300 : R * g.wy;
             const double bound = fmin(bx, by);
-            if (best[k - 1] < bound * (1.0 - 1e-9) - 1e-9) break;
+            if (r0 < bound * (1.0 - 1e-9) - 1e-9) break;
         }
     }
     if (GRID) {
+        // ascending (distance, index) order: pop the maximum into the last free slot, repeatedly
         int32_t *o = K.knn + (f * P.N + i) * 24;
-        for (int t = 0; t < 24; t++) o[t] = t < nbest ? bj[t] : -1;
+        for (int t = nbest; t < 24; t++) o[t] = -1;
+        for (int n = nbest; n > 0; n--) {
+            o[n - 1] = bj[0];
+            if (n > 1) sift_down(best[n - 1], bj[n - 1], n - 1);
+        }
     } else if (MODE == 2) {
         int h[CL_MAX_TYPES];
 #pragma unroll
