@@ -540,7 +540,7 @@ struct ClKnn {
 // MODE 0: NNF counts of type-B neighbours; 1 (GRID): the neighbour table; 2: NNF for every type at
 // once -- hits[f][i][t] = lipids of type t among the k nearest (every lipid is a reference lipid)
 template <int KMAX, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 12)
 k_knn_cl(ClParams P, ClKnn K)
 {
     constexpr bool GRID = (MODE == 1);
