@@ -379,18 +379,33 @@ k_grid_apl(const int32_t *__restrict__ cells, const uint8_t *__restrict__ labels
     float M32 = 0.0f;
     long long n = 0;
     for (int pass = 1; pass >= 0; pass--) {
-        for (int64_t i = 0; i < N; i++) {
-            if (lab[i] != pass) continue;
-            if (t > 0 && type_code[i] != t - 1) continue;
-            const float a = __fmul_rn(apb, (float)cnt[i]);      // area_per_bin*nlocs, float32
-            n++;
-            if (n == 1) {
-                M32 = a; M = (double)a; S = 0.0;
-            } else {
-                const double diff = (n == 2) ? (double)__fsub_rn(a, M32) : __dsub_rn((double)a, M);
-                const double mn = __dadd_rn(M, __ddiv_rn(diff, (double)n));
-                S = __dadd_rn(S, __dmul_rn(diff, __dsub_rn((double)a, mn)));
-                M = mn;
+        // the recurrence is sequential, its inputs are not: eight lipids' label / type / cell count
+        // are loaded together (independent loads), then pushed one after the other
+        for (int64_t i0 = 0; i0 < N; i0 += 8) {
+            int use[8], cn[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int64_t i = i0 + u;
+                use[u] = 0;
+                cn[u] = 0;
+                if (i < N) {
+                    use[u] = (lab[i] == pass) && (t == 0 || type_code[i] == t - 1);
+                    cn[u] = cnt[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (!use[u]) continue;
+                const float a = __fmul_rn(apb, (float)cn[u]);   // area_per_bin*nlocs, float32
+                n++;
+                if (n == 1) {
+                    M32 = a; M = (double)a; S = 0.0;
+                } else {
+                    const double diff = (n == 2) ? (double)__fsub_rn(a, M32) : __dsub_rn((double)a, M);
+                    const double mn = __dadd_rn(M, __ddiv_rn(diff, (double)n));
+                    S = __dadd_rn(S, __dmul_rn(diff, __dsub_rn((double)a, mn)));
+                    M = mn;
+                }
             }
         }
     }
