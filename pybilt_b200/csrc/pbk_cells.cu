@@ -83,7 +83,7 @@ struct ClParams {
     int *cell_fill;                 // [F][cstride] populations, then running fill pointers
     int *cell_start;                // [F][cstride]
     int *fcounts;                   // [F][8]: (N_a, N_b, N_leaf) upper, lower; out-of-box; listed
-    double *sx, *sy;                // [F][N] b' = x - box/2 in cell order
+    double2 *sxy;                   // [F][N] b' = (x, y) - box/2 in cell order (one 16-byte load per lipid)
     float2 *sf;                     // [F][N] float32 copy
     int *sidx;                      // [F][N] original lipid index
     int *scell;                     // [F][N] leaf*ncell + cell
@@ -266,8 +266,7 @@ k_cl_scatter(ClParams P)
     const int cell = leaf * fr.g.ncell + cl_cell(fr, x, y);
     const int64_t slot = f * P.N + atomicAdd(&fill[cell], 1);
     const double bx = __dsub_rn(x, fr.hx), by = __dsub_rn(y, fr.hy);
-    P.sx[slot] = bx;
-    P.sy[slot] = by;
+    P.sxy[slot] = make_double2(bx, by);
     P.sf[slot] = make_float2((float)bx, (float)by);
     P.sidx[slot] = (int)i;
     P.scell[slot] = cell;
@@ -301,7 +300,7 @@ __device__ __forceinline__ int cl_bin(double d2, const double *s_thr, int nb)
 // MODE 0: type_a == type_b (every listed lipid is both); 1: flags per lipid; 2: multi -- every
 // ordered type pair has its own histogram, hist[((leaf*T + t_from)*T + t_to)*nb + bin]
 template <int MODE>
-__device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double *gy,
+__device__ __forceinline__ void cl_exact(uint2 e, const double2 *gxy,
                                          const unsigned char *gflag, const double *s_thr, unsigned *myhist,
                                          int nb, double Lx, double Ly, double hx, double hy,
                                          const int *gcell, int ncell, int T)
@@ -320,7 +319,8 @@ __device__ __forceinline__ void cl_exact(uint2 e, const double *gx, const double
         w2 = (fq & 1u) && (fp & 2u);            // ordered q -> p
         if (!(w1 | w2)) return;
     }
-    const double apx = gx[p], apy = gy[p], bqx = gx[q], bqy = gy[q];
+    const double2 ap = gxy[p], bq = gxy[q];
+    const double apx = ap.x, apy = ap.y, bqx = bq.x, bqy = bq.y;
     double dx = __dsub_rn(apx, bqx), dy = __dsub_rn(apy, bqy);
     const bool wrx = fabs(dx) > hx, wry = fabs(dy) > hy;
     if (!(wrx | wry)) {
@@ -403,7 +403,7 @@ k_rdf_cl(ClParams P, ClRdf R)
         const int p_hi = min(n_u, p_lo + R.chunk);
         bool on[2];
         for (int l = 0; l < 2; l++) on[l] = ((P.leaflet_mask >> l) & 1) && fc[l * 3] > 0 && fc[l * 3 + 1] > 0;
-        const double *gx = P.sx + f * P.N, *gy = P.sy + f * P.N;
+        const double2 *gxy = P.sxy + f * P.N;
         const float2 *gf = P.sf + f * P.N;
         const int *gcell = P.scell + f * P.N;
         const unsigned char *gflag = P.sflag + f * P.N;
@@ -501,7 +501,7 @@ k_rdf_cl(ClParams P, ClRdf R)
                             qtail += __popc(m);
                             if (qtail - qhead >= 32) {
                                 __syncwarp();
-                                cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb,
+                                cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gxy, gflag, s_thr, myhist, nb,
                                                fr.Lx, fr.Ly, fr.hx, fr.hy, gcell, g.ncell, T);
                                 qhead += 32;
                                 __syncwarp();
@@ -513,7 +513,7 @@ k_rdf_cl(ClParams P, ClRdf R)
         }
         __syncwarp();
         if (lane < qtail - qhead)
-            cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gx, gy, gflag, s_thr, myhist, nb, fr.Lx, fr.Ly,
+            cl_exact<MODE>(myq[(qhead + lane) & (CL_QCAP - 1)], gxy, gflag, s_thr, myhist, nb, fr.Lx, fr.Ly,
                            fr.hx, fr.hy, gcell, g.ncell, T);
         __syncwarp();
     }
@@ -553,7 +553,7 @@ k_knn_cl(ClParams P, ClKnn K)
     const int n_u = cstart[2 * g.ncell];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_u) return;
-    const double *gx = P.sx + f * P.N, *gy = P.sy + f * P.N;
+    const double2 *gxy = P.sxy + f * P.N;
     const int *gidx = P.sidx + f * P.N;
     const int i = gidx[p];
     int pc = P.scell[f * P.N + p];
@@ -568,7 +568,7 @@ k_knn_cl(ClParams P, ClKnn K)
         }
     }
     const int k = K.k;
-    const double apx = gx[p], apy = gy[p];
+    const double apx = gxy[p].x, apy = gxy[p].y;
     const int ncx = g.ncx, ncy = g.ncy;
     const int pcy = pc / ncx, pcx = pc - pcy * ncx;
     const int lox = (ncx - 1) / 2, hix = ncx / 2, loy = (ncy - 1) / 2, hiy = ncy / 2;
@@ -604,7 +604,8 @@ k_knn_cl(ClParams P, ClKnn K)
         for (int q = s0; q < s1; q++) {
             if (q == p) continue;
             const int j = gidx[q];
-            const double qx = gx[q], qy = gy[q];
+            const double2 qv = gxy[q];
+            const double qx = qv.x, qy = qv.y;
             const double d2 = (!GRID || j > i) ? pbk_pbc_dist2(apx, apy, qx, qy, fr.Lx, fr.Ly, fr.hx, fr.hy)
                                                : pbk_pbc_dist2(qx, qy, apx, apy, fr.Lx, fr.Ly, fr.hx, fr.hy);
             const double r = sqrt(d2);
@@ -729,8 +730,7 @@ static bool cl_carve(pbk_ctx *ctx, const ClPlan &pl, int64_t N, ClParams &P)
     P.cell_fill = (int *)a; a += b_cells;
     P.fcounts = (int *)a; a += b_fc;                             // zeroed together with cell_fill
     P.cell_start = (int *)a; a += b_cells;
-    P.sx = (double *)a; a += b_d;
-    P.sy = (double *)a; a += b_d;
+    P.sxy = (double2 *)a; a += 2 * b_d;
     P.sf = (float2 *)a; a += b_d;
     P.sidx = (int *)a; a += b_i;
     P.scell = (int *)a; a += b_i;
