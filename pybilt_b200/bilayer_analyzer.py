@@ -456,6 +456,7 @@ class BilayerAnalyzer(object):
         self._incremental = True    # batched analyses consume each host->device batch as it arrives
         self._incremental_done = False
         self.resident_budget_bytes = 48 << 30
+        self.positions_budget_bytes = 64 << 30   # streamed shards keep their positions on the device up to this
         self.grid_mode = 'opt'      # 'opt' = lipid_grid_opt.py (reference default), 'exact' = lipid_grid.py
         self._input_script_name = os.path.abspath(input_file) if input_file is not None else None
         self._frame_loop_count = 0
@@ -887,9 +888,11 @@ class BilayerAnalyzer(object):
             self._feeder_cache = fc
         return fc[2]
 
-    def _push_frames(self, eng, md, frames, times_out=None, dims_out=None, init_images=None, unwrap_only=False):
+    def _push_frames(self, eng, md, frames, times_out=None, dims_out=None, init_images=None, unwrap_only=False,
+                     keep=None, copy_only=False):
         """Host -> device in engine-batch sized pieces (double-buffered on a copy stream) and through
-        the engine.  Returns the device views (x, box) of the last frame pushed."""
+        the engine.  Returns the device views (x, box) of the last frame pushed.  ``keep`` =
+        (x [n, M, 3], box [n, 3], first row): the batches are also retained there on the device."""
         feeder = self._feeder_for(md, eng)
         B = eng.B
         starts = list(range(0, len(frames), B))
@@ -907,7 +910,13 @@ class BilayerAnalyzer(object):
             issue(0)
         for k, b0 in enumerate(starts):
             xb, bb = feeder.take()
-            if unwrap_only:
+            if keep is not None:
+                r0 = keep[2] + b0
+                keep[0][r0:r0 + xb.shape[0]].copy_(xb)
+                keep[1][r0:r0 + xb.shape[0]].copy_(bb)
+            if copy_only:
+                pass
+            elif unwrap_only:
                 eng.unwrap_only(xb, bb)
             else:
                 eng.push(xb, bb, init_images=init_images if b0 == 0 else None)
@@ -978,12 +987,29 @@ class BilayerAnalyzer(object):
             wc['ekey'], wc['engine'] = ekey, eng
         ref_row = C + W
         init = None
+        retained = None
         if world > 1:
             # pass A: image counts where the next rank's stream starts
             net = torch.zeros((md.natoms, 3), dtype=torch.int32, device=eng.dev)
             if rank < world - 1 and starts[rank + 1] > a:
-                last = self._push_frames(eng, md, fr_all[a:starts[rank + 1] + 1], unwrap_only=True)
+                stop = starts[rank + 1]
+                # when the shard's positions fit on the device they are retained during this pass and
+                # the window loop reads them from there (one host->device transfer instead of two)
+                if (hi - a) * md.natoms * 12 <= self.positions_budget_bytes:
+                    retained = (torch.empty((hi - a, md.natoms, 3), dtype=torch.float32, device=eng.dev),
+                                torch.empty((hi - a, 3), dtype=torch.float32, device=eng.dev))
+                last = self._push_frames(eng, md, fr_all[a:stop + 1], unwrap_only=True,
+                                         keep=None if retained is None else (retained[0], retained[1], 0))
                 net = eng.image_counts_last(last[0], last[1])
+                if retained is not None and stop + 1 < hi:
+                    self._push_frames(eng, md, fr_all[stop + 1:hi], copy_only=True,
+                                      keep=(retained[0], retained[1], stop + 1 - a))
+            elif rank == world - 1 and (hi - a) * md.natoms * 12 <= self.positions_budget_bytes:
+                # the last rank has no counts to report: it uses the wait for the others' first pass to
+                # bring its positions over
+                retained = (torch.empty((hi - a, md.natoms, 3), dtype=torch.float32, device=eng.dev),
+                            torch.empty((hi - a, 3), dtype=torch.float32, device=eng.dev))
+                self._push_frames(eng, md, fr_all[a:hi], copy_only=True, keep=(retained[0], retained[1], 0))
             init = pd.image_offsets(net)
             eng.reset()
         rejected = False
@@ -996,7 +1022,12 @@ class BilayerAnalyzer(object):
                 if not first:
                     eng.rewind(C)
                 ctx = eng.n_done
-                if hasattr(md, '_dimensions'):
+                if retained is not None:
+                    xs, bs = retained[0][g - a:g1 - a], retained[1][g - a:g1 - a]
+                    for b0 in range(0, g1 - g, eng.B):
+                        eng.push(xs[b0:b0 + eng.B], bs[b0:b0 + eng.B],
+                                 init_images=init if (first and b0 == 0) else None)
+                elif hasattr(md, '_dimensions'):
                     self._push_frames(eng, md, fr_all[g:g1], init_images=init if first else None)
                 else:
                     self._push_frames(eng, md, fr_all[g:g1], times_all[g:g1], dims_all[g:g1],

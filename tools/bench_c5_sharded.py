@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=48)
     ap.add_argument("--window", type=int, default=16)
     ap.add_argument("--lipids", type=int, default=262144)
+    ap.add_argument("--tile", type=int, default=1, help="repeat the generated frames along time (generation is the slow part)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -39,12 +40,20 @@ def main():
     spec, _ = syn.config_spec("C5")
     if a.lipids != 262144:
         spec = syn.BilayerSpec(a.lipids, spec.types, seed=spec.seed)
-    F = a.frames_per_gpu * world
+    F = a.frames_per_gpu * a.tile * world
     lo, hi = pd.shard_bounds(F, world, rank)
     first = max(0, lo - 1)                       # the stream starts one context frame early
-    top, traj = syn.generate(spec, hi - first, first_frame=first)
-    x_host = torch.from_numpy(traj.positions).pin_memory()
-    dims = syn.box_at(spec, np.arange(F))
+    if a.tile > 1:
+        # the same generated frames repeated along time (the seams are ordinary small jumps)
+        top, traj = syn.generate(spec, a.frames_per_gpu)
+        reps = -(-(hi - first) // a.frames_per_gpu) + 1
+        off = first % a.frames_per_gpu
+        x_host = torch.from_numpy(traj.positions).repeat(reps, 1, 1)[off:off + hi - first].contiguous().pin_memory()
+        dims = np.tile(traj.dimensions, (F // a.frames_per_gpu + 1, 1))[:F]
+    else:
+        top, traj = syn.generate(spec, hi - first, first_frame=first)
+        x_host = torch.from_numpy(traj.positions).pin_memory()
+        dims = syn.box_at(spec, np.arange(F))
     ba = BilayerAnalyzer(structure=top, trajectory=(FrameWindow(x_host, first, F), dims, np.arange(F) * spec.dt),
                          selection="all", device=local)
     ba.add_analysis("com_lateral_rdf rdf resname_1 all resname_2 all")
@@ -68,7 +77,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"workload": "C5 shape: %d lipids, %d frames per GPU, msd + com_lateral_rdf(all, all), "
-                                      "streamed in windows of %d frames" % (a.lipids, a.frames_per_gpu, a.window),
+                                      "streamed in windows of %d frames" % (a.lipids, a.frames_per_gpu * a.tile, a.window),
                           "n_gpus": world, "seconds": float(t[0]),
                           "lipid_frames_per_s_e2e": a.lipids * F / float(t[0]),
                           "msd_last": float(msd[-1, 1]), "rdf_peak": float(np.nanmax(rdf)),
