@@ -8,6 +8,35 @@ from __future__ import annotations
 import numpy as np
 
 
+_TYPE_TABLES = {}
+
+
+def _type_table(types):
+    """(object array of the resnames, int code per lipid, code -> resname) of a resname list; kept
+    per list object, since the same topology is asked for every run (10^5 strings are slow to
+    re-encode)."""
+    key = id(types)
+    hit = _TYPE_TABLES.get(key)
+    if hit is not None and hit[0] is types:
+        return hit[1]
+    tarr = np.asarray(types, dtype=object)
+    uniq, inv = np.unique(tarr.astype(str), return_inverse=True)
+    names = [str(u) for u in uniq]
+    # keep the caller's own string objects as names where possible
+    first = {}
+    for i, code in enumerate(inv.tolist()):
+        if code not in first:
+            first[code] = tarr[i]
+            if len(first) == len(names):
+                break
+    names = [first[k] for k in range(len(names))]
+    table = (tarr, inv.astype(np.int32), names)
+    if len(_TYPE_TABLES) > 8:
+        _TYPE_TABLES.clear()
+    _TYPE_TABLES[key] = (types, table)
+    return table
+
+
 class LipidGroup(object):
     def __init__(self, name):
         self.lg_members = []
@@ -50,15 +79,16 @@ class Leaflet(object):
         idx = np.asarray(indices, dtype=np.int64)
         if len(idx) == 0:
             return leaf
-        t = np.asarray(types, dtype=object)[idx]
+        tarr, codes, names = _type_table(types)
         r = np.asarray(resids)[idx]
-        leaf._lazy = (idx, t, r)
+        leaf._lazy = (idx, tarr[idx], r)
         # groups in first-seen order, members in ascending lipid index (what add_member builds)
-        names, first = np.unique(t.astype(str), return_index=True)
+        c = codes[idx]
+        present, first = np.unique(c, return_index=True)
         for k in np.argsort(first, kind="stable"):
-            nm = t[first[k]]
+            nm = names[int(present[k])]
             g = LipidGroup(nm)
-            g.lg_members = idx[t == nm].tolist()
+            g.lg_members = idx[c == present[k]].tolist()
             leaf.group_dict[nm] = len(leaf.groups)
             leaf.groups.append(g)
         return leaf
