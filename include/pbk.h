@@ -233,6 +233,12 @@ int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_c
                    int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b, double *frac,
                    void *stream);
 
+/* pbk_nnf_select for n_specs analyses at once: specs[n_specs][3] int32 = (type_a, type_b,
+ * leaflet_mask) on the device; n_b[n_specs][F][N], frac[n_specs][F]. */
+int pbk_nnf_select_many(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_counts,
+                        const uint8_t *labels, const int32_t *type_code, int64_t F, int64_t N, int n_types,
+                        int n_specs, const int32_t *specs, int k, int32_t *n_b, double *frac, void *stream);
+
 /* ---- G1 / G2  lipid grids ---------------------------------------------------------------
  * lipid_grid_opt.LipidGrid2d.__init__ + _knn  pybilt/lipid_grid/lipid_grid_opt.py:155-334,435-468
  * lipid_grid.LipidGrid2d.__init__ (exact)     pybilt/lipid_grid/lipid_grid.py:150-248

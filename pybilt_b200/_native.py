@@ -66,6 +66,8 @@ _SIGNATURES = {
                           c_void_p]),
     "pbk_halperin_nelson": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                     c_int, c_int64, c_void_p, c_void_p]),
+    "pbk_nnf_select_many": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                    c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_lipid_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

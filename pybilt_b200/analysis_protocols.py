@@ -555,12 +555,11 @@ class NNFProtocol(AnalysisProtocol):
                 s['n_neighbors'] = nlipids - 1
             self.lipid_types, self.n_ltypes = lipid_types, len(lipid_types)
             self._frac = np.zeros(batch.n_frames)
-        shared = batch.nnf_shared(s['n_neighbors'], ba_settings['lateral'])
-        if shared is not None:      # one neighbour search for every nnf analysis with this k
-            n_b, frac = batch.engine.nnf_select(shared[0], shared[1], batch.type_code_dev,
-                                                batch.type_code_of(s['resname_1']),
-                                                batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),
-                                                s['n_neighbors'], frames=batch.rows)
+        shared = batch.nnf_shared(s['n_neighbors'], ba_settings['lateral'],
+                                  (batch.type_code_of(s['resname_1']), batch.type_code_of(s['resname_2']),
+                                   _leaflet_mask(s['leaflet'])))
+        if shared is not None:      # one neighbour search (and one selection pass) for every nnf analysis with this k
+            n_b, frac = shared
         else:
             n_b, frac = batch.engine.nnf(batch.type_code_dev, batch.type_code_of(s['resname_1']),
                                          batch.type_code_of(s['resname_2']), _leaflet_mask(s['leaflet']),

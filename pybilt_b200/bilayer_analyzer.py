@@ -404,20 +404,42 @@ class ReductionBatch(object):
             self._rdf_multi[key] = res
         return self._rdf_multi[key]
 
-    def nnf_shared(self, k, lateral):
-        """Device tallies (type_hits [F,N,T], type_counts [F,2,T]) of ONE neighbour search over this
-        batch's frames shared by every nnf analysis with this n_neighbors, or None."""
+    def nnf_shared(self, k, lateral, spec):
+        """(n_b [F, N], frac [F]) device tensors of the nnf analysis ``spec`` = (type_a, type_b,
+        leaflet_mask) from ONE neighbour search over this batch's frames shared by every nnf
+        analysis with this n_neighbors, or None (a single analysis, or no shared path)."""
         key = (int(k), tuple(lateral))
         if key not in self._nnf_multi:
             res = None
-            n = sum(1 for a in self._analyzer._analysis_protocol.analysis_ids
-                    if self._analyzer._analysis_protocol.command_protocol[a].analysis_key == 'nnf' and
-                    int(self._analyzer._analysis_protocol.command_protocol[a].settings['n_neighbors']) == int(k))
-            if n >= 2 and os.environ.get("PBK_NO_NNF_MULTI") is None:
-                res = self.engine.nnf_multi(self.type_code_dev, len(self.type_names), k, lateral,
-                                            frames=self.rows)
+            protos = [self._analyzer._analysis_protocol.command_protocol[a]
+                      for a in self._analyzer._analysis_protocol.analysis_ids]
+            mine = [p_ for p_ in protos if p_.analysis_key == 'nnf' and int(p_.settings['n_neighbors']) == int(k)]
+            if len(mine) >= 2 and os.environ.get("PBK_NO_NNF_MULTI") is None:
+                m = self.engine.nnf_multi(self.type_code_dev, len(self.type_names), k, lateral, frames=self.rows)
+                if m is not None:
+                    specs = []
+                    for p_ in mine:
+                        st = p_.settings
+                        sp = (self.type_code_of(st['resname_1']), self.type_code_of(st['resname_2']),
+                              {"both": 3, "upper": 1, "lower": 2}.get(st['leaflet'], 0))
+                        if sp not in specs:
+                            specs.append(sp)
+                    # 'first' resnames are resolved by each protocol before it asks: specs that still hold
+                    # an unresolved name (-2) simply never match a request
+                    n_b, frac = self.engine.nnf_select_many(m[0], m[1], self.type_code_dev, specs, k,
+                                                            frames=self.rows)
+                    res = {sp: (n_b[i], frac[i]) for i, sp in enumerate(specs)}
+                    res['_tallies'] = m
             self._nnf_multi[key] = res
-        return self._nnf_multi[key]
+        table = self._nnf_multi[key]
+        if table is None:
+            return None
+        if spec not in table:           # e.g. a resname resolved from 'first' after the table was made
+            m = table['_tallies']
+            n_b, frac = self.engine.nnf_select(m[0], m[1], self.type_code_dev, spec[0], spec[1], spec[2], k,
+                                               frames=self.rows)
+            table[spec] = (n_b, frac)
+        return table[spec]
 
     def lipid_grids(self) -> GridBatch:
         if self._grids is None:

@@ -319,6 +319,88 @@ k_nnf_select(const int32_t *__restrict__ hits, const int32_t *__restrict__ type_
     n_b[f * N + i] = c;
 }
 
+// the same for A analyses in one launch each: specs[a] = (type_a, type_b, leaflet_mask); outputs
+// n_b[A][F][N], frac[A][F].  One grid over (analysis, frame) keeps the sequential frame means of all
+// analyses running side by side instead of one launch latency after the other.
+__global__ void __launch_bounds__(256)
+k_nnf_select_many(const int32_t *__restrict__ hits, const int32_t *__restrict__ type_counts,
+                  const uint8_t *__restrict__ labels, const int32_t *__restrict__ type_code, int64_t F, int64_t N,
+                  int T, const int32_t *__restrict__ specs, int32_t *__restrict__ n_b)
+{
+    const int64_t af = blockIdx.x;                    // a * F + f
+    const int64_t a = af / F, f = af - a * F;
+    const int ta = specs[a * 3], tb = specs[a * 3 + 1], leaflet_mask = specs[a * 3 + 2];
+    const int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int leaf = labels[f * N + i] ? 0 : 1;
+    const int32_t *tc = type_counts + (f * 2 + leaf) * T;
+    int ca = 0, cb = 0;
+    for (int t = 0; t < T; t++) {
+        ca += (ta == -1 || t == ta) ? tc[t] : 0;
+        cb += (tb == -1 || t == tb) ? tc[t] : 0;
+    }
+    const int ti = type_code[i];
+    const bool ref = ((leaflet_mask >> leaf) & 1) && ca > 0 && cb > 0 && (ta == -1 || ti == ta);
+    int c = -1;
+    if (ref) {
+        c = 0;
+        const int32_t *h = hits + (f * N + i) * T;
+        for (int t = 0; t < T; t++)
+            if (tb == -1 || t == tb) c += max(0, h[t]);
+    }
+    n_b[af * N + i] = c;
+}
+
+__global__ void __launch_bounds__(128)
+k_nnf_frame_mean_many(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels, int64_t A, int64_t F,
+                      int64_t N, int k, double *__restrict__ frac)
+{
+    const int64_t af = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (af >= A * F) return;
+    const int64_t f = af % F;
+    const int32_t *c = n_b + af * N;
+    const uint8_t *lab = labels + f * N;
+    double m = 0.0;
+    int64_t n = 0;
+    for (int pass = 1; pass >= 0; pass--) {
+        for (int64_t base = 0; base < N; base += 32) {
+            const int64_t i = base + lane;
+            int ci = -1;
+            if (i < N && lab[i] == pass) ci = c[i];
+            unsigned mask = __ballot_sync(0xffffffffu, ci >= 0);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double v = __ddiv_rn((double)__shfl_sync(0xffffffffu, ci, src), (double)k);
+                n++;
+                m = (n == 1) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)n));
+            }
+        }
+    }
+    if (lane == 0) frac[af] = m;
+}
+
+extern "C" int pbk_nnf_select_many(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_counts,
+                                   const uint8_t *labels, const int32_t *type_code, int64_t F, int64_t N,
+                                   int n_types, int n_specs, const int32_t *specs, int k, int32_t *n_b,
+                                   double *frac, void *stream)
+{
+    if (!ctx || !type_hits || !type_counts || !labels || !type_code || !specs || !n_b || !frac || F < 0 ||
+        N <= 0 || n_types < 1 || n_specs < 1 || k < 1 || (int64_t)n_specs * F > 0x7fffffffLL)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_nnf_select_many: bad argument");
+    if (F == 0) return PBK_OK;
+    dim3 g((unsigned)((int64_t)n_specs * F), (unsigned)((N + 255) / 256));
+    k_nnf_select_many<<<g, 256, 0, (cudaStream_t)stream>>>(type_hits, type_counts, labels, type_code, F, N,
+                                                           n_types, specs, n_b);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf_select_many");
+    const int64_t n_af = (int64_t)n_specs * F;
+    k_nnf_frame_mean_many<<<(unsigned)((n_af + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, n_specs, F, N,
+                                                                                         k, frac);
+    PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean_many");
+    return PBK_OK;
+}
+
 extern "C" int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int32_t *type_counts,
                               const uint8_t *labels, const int32_t *type_code, int64_t F, int64_t N,
                               int n_types, int type_a, int type_b, int leaflet_mask, int k, int32_t *n_b,

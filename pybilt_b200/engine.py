@@ -481,6 +481,22 @@ class LipidReductionEngine:
         self.launches += 2
         return n_b, frac
 
+    def nnf_select_many(self, hits: torch.Tensor, tc: torch.Tensor, type_code: torch.Tensor, specs, k: int,
+                        frames: Optional[slice] = None):
+        """(n_b [A, F, N], frac [A, F]) of the analyses ``specs`` = [(type_a, type_b, leaflet_mask)]
+        from the shared tallies of nnf_multi, in two launches for all of them."""
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        A = len(specs)
+        d_specs = torch.as_tensor(np.asarray(specs, dtype=np.int32).reshape(A, 3), device=self.dev)
+        n_b = torch.empty((A, F, self.N), dtype=torch.int32, device=self.dev)
+        frac = torch.empty((A, F), dtype=torch.float64, device=self.dev)
+        self.ctx.call("pbk_nnf_select_many", hits.data_ptr(), tc.data_ptr(), self.labels[sl.start:].data_ptr(),
+                      type_code.data_ptr(), F, self.N, int(hits.shape[2]), A, d_specs.data_ptr(), int(k),
+                      n_b.data_ptr(), frac.data_ptr(), self.stream_ptr())
+        self.launches += 2
+        return n_b, frac
+
     def halperin_nelson(self, member: torch.Tensor, lateral=(0, 1), frames: Optional[slice] = None):
         """Mean hexatic invariant of the lipids ``member`` (uint8 [N], 1 = included) per frame,
         float64 [frames]: six nearest members from the 24-neighbour search, then the invariant."""

@@ -153,6 +153,11 @@ def test_nnf_multi_tallies_equal_per_analysis_calls(n_lipids, oob):
             n_b2, frac2 = e.nnf(codes, ta if ta < T else -2, tb if tb < T else -2, mask, k)
             assert np.array_equal(n_b.cpu().numpy(), n_b2.cpu().numpy()), (k, ta, tb, mask)
             assert np.array_equal(frac.cpu().numpy(), frac2.cpu().numpy())
+        specs = [(0, 1, 3), (1, 0, 1), (2, 2, 2), (-1, 1, 3), (0, -1, 3), (-2, 1, 3)]
+        nb_all, fr_all = e.nnf_select_many(hits, tc, codes, specs, k)          # all analyses in two launches
+        for a, (ta, tb, mask) in enumerate(specs):
+            n_b2, frac2 = e.nnf(codes, ta, tb, mask, k)
+            assert torch.equal(nb_all[a], n_b2) and torch.equal(fr_all[a], frac2), (k, ta, tb, mask)
 
 
 def test_halperin_nelson_cells_equal_dense(monkeypatch):
