@@ -65,6 +65,11 @@ class Welford:
     def mean(self):
         return self._m if self.n >= 1 else 0.0
 
+    def variance(self):
+        if self.n > 1:
+            return self._s / (np.float64(self.n) - np.float64(1.0))
+        return 0.0
+
     def deviation(self):
         if self.n > 1:
             return np.sqrt(self._s / (np.float64(self.n) - np.float64(1.0)))
@@ -476,6 +481,49 @@ def halperin_nelson(com, box, times, idx, lateral=(0, 1)) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# box-only analyses: apl_box (analysis_protocols.py:991-1006), acm (:3181-3207)
+# --------------------------------------------------------------------------------------
+def apl_box(dims, times, n_residues, lateral=(0, 1)) -> np.ndarray:
+    """rows [time, 2 A_xy / N_lipids, running mean, running deviation]; float32 box arithmetic."""
+    run_ = Welford()
+    out = np.zeros((dims.shape[0], 4))
+    for f in range(dims.shape[0]):
+        plane = dims[f][0:3][list(lateral)]
+        apl = plane[0] * plane[1] * 2.0 / n_residues
+        run_.push(apl)
+        out[f] = [times[f], apl, run_.mean(), run_.deviation()]
+    return out
+
+
+def acm(dims, times, norm=2, temperature=298.15) -> np.ndarray:
+    """Area compressibility modulus rows [time, Ka, Ka error, area] from the running mean and
+    variance of the lateral box area (box product / normal edge, float32)."""
+    import scipy.constants as scicon
+    run_ = Welford()
+    out = []
+    first = True
+    with np.errstate(all="ignore"):
+        for f in range(dims.shape[0]):
+            d = dims[f][0:3]
+            area = d.prod() / d[norm]
+            run_.push(area)
+            ka, ka_err = 1.0, 0.0
+            if first:
+                first = False
+                ka = 0.0
+            else:
+                ka = (run_.mean() * scicon.k * temperature) / run_.variance()
+                sd, mean, n = run_.deviation(), run_.mean(), run_.n
+                var_of_var = (np.sqrt(2.0) * sd ** 2) / np.sqrt(n - 1)
+                sd_of_var = np.sqrt(var_of_var)
+                ka_err = np.sqrt((sd / mean) ** 2 + (sd_of_var / sd ** 2) ** 2) * ka
+            ka *= 10.0 ** 23
+            ka_err *= 10.0 ** 23
+            out.append([times[f], ka, ka_err, area])
+    return np.array(out)
+
+
+# --------------------------------------------------------------------------------------
 # N3: lateral box-area fluctuation      analysis_protocols.py:4486-4498
 # --------------------------------------------------------------------------------------
 def area_fluctuation(box, times, lateral=(0, 1)) -> np.ndarray:
@@ -756,6 +804,10 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
             leaf = kv.get("leaflet", "upper")
             v = views0[leaf if leaf in ("upper", "lower") else "upper"]
             out[a_id] = halperin_nelson(com, box, times, list(v.members), lateral)
+        elif key == "apl_box":
+            out[a_id] = apl_box(dims, times, top.n_residues, lateral)
+        elif key == "acm":
+            out[a_id] = acm(dims, times, norm, float(kv.get("temperature", 298.15)))
         elif key == "area_fluctuation":
             out[a_id] = area_fluctuation(box, times, lateral)
         elif key == "thickness_leaflet_distance":

@@ -648,6 +648,85 @@ class HalperinNelsonProtocol(AnalysisProtocol):
 
 
 # ---------------------------------------------------------------------------------------
+@_protocol('apl_box', 'mda_frame')
+class APLBoxProtocol(AnalysisProtocol):
+    """Area per lipid from the lateral box area, rows [time, 2 A_xy / N_lipids, running mean,
+    running deviation] (analysis_protocols.py:945-1012).  Box arithmetic only (float32, like the
+    trajectory's dimensions), done on the host in finish()."""
+    _short_description = "Area per lipid using box dimensions."
+    _related = list(['apl_grid'])
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self.running = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        self._n_residues = ba_mda_data.n_residues
+
+    def finish(self, batch):
+        lat = list(batch.lateral)
+        for f in range(batch.n_frames):
+            plane = batch.box_host[f][lat]
+            apl = plane[0] * plane[1] * 2.0 / self._n_residues
+            self.running.push(apl)
+            self.analysis_output.append(np.array([batch.times[f], apl, self.running.mean(),
+                                                  self.running.deviation()]))
+
+    def reset(self):
+        self.running.reset()
+        self.analysis_output = []
+
+
+@_protocol('acm', 'mda_frame')
+class AreaCompressibilityModulusProtocol(AnalysisProtocol):
+    """Area compressibility modulus from the fluctuation of the lateral box area, rows
+    [time, Ka, Ka error, area] (analysis_protocols.py:3100-3210).  Host-side box arithmetic."""
+    _short_description = "Area compressibility modulus."
+    _related = list(['area_fluctuation', 'ac'])
+    _casts = {'temperature': float}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'temperature': 298.15}, args)
+        self.n_frames = 0
+        self.area_run = RunningStats()
+        self.first_comp = True
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        self._norm = ba_settings['norm']
+
+    def finish(self, batch):
+        import scipy.constants as scicon
+        with np.errstate(all="ignore"):
+            for f in range(batch.n_frames):
+                d = batch.box_host[f]
+                area = d.prod() / d[self._norm]
+                self.area_run.push(area)
+                ka, ka_err = 1.0, 0.0
+                if self.first_comp:
+                    self.first_comp = False
+                    self.n_frames += 1
+                    ka = 0.0
+                else:
+                    ka = (self.area_run.mean() * scicon.k * self.settings['temperature']) / self.area_run.variance()
+                    sd, mean, n = self.area_run.deviation(), self.area_run.mean(), self.area_run.n
+                    var_of_var = (np.sqrt(2.0) * sd ** 2) / np.sqrt(n - 1)
+                    sd_of_var = np.sqrt(var_of_var)
+                    ka_err = np.sqrt((sd / mean) ** 2 + (sd_of_var / sd ** 2) ** 2) * ka
+                ka *= 10.0 ** 23
+                ka_err *= 10.0 ** 23
+                self.analysis_output.append([batch.times[f], ka, ka_err, area])
+                self.n_frames += 1
+
+    def reset(self):
+        self.n_frames = 0
+        self.area_run.reset()
+        self.analysis_output = []
+        self.first_comp = True
+
+
+# ---------------------------------------------------------------------------------------
 @_protocol('area_fluctuation', 'com_frame')
 class AreaFluctuationProtocol(AnalysisProtocol):
     """Fluctuation of the lateral box area, rows [time, area, sqrt(<A^2> - <A>^2)]
