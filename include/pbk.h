@@ -174,6 +174,15 @@ int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
                   const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
                   double *out, void *stream);
 
+/* ---- N3  average lateral displacement ------------------------------------------------------
+ * ALDProtocol.run_analysis             pybilt/bilayer_analyzer/analysis_protocols.py:3262-3339
+ * Same arguments as pbk_msd_pairs; out[p] = mean_{i in idx} |r_{end[p], i} - r_{origin[p], i}|
+ * (the length, not its square). */
+int pbk_ald_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
+                  const int32_t *idx, int32_t n_idx, int lat0, int lat1,
+                  const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
+                  double *out, void *stream);
+
 /* ---- D1 + D2  COM lateral RDF -----------------------------------------------------------
  * COMLateralRDFProtocol.run_analysis   pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006
  * distance_euclidean_pbc               pybilt/common/distance_cutoff_clustering.py:27-71

@@ -481,6 +481,24 @@ def halperin_nelson(com, box, times, idx, lateral=(0, 1)) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# N3: average lateral displacement      analysis_protocols.py:3262-3339
+# --------------------------------------------------------------------------------------
+def ald(com_unwrap, times, idx, lateral=(0, 1)) -> np.ndarray:
+    """rows [time, running mean over frames of L_t], L_t = sum_i |r_i(t) - r_i(0)| / n over the lipids
+    ``idx`` (unwrapped lateral COMs; |.| = sqrt(np.dot(dr, dr)), np.sum of the list)."""
+    run_ = Welford()
+    ref = com_unwrap[0][idx][:, list(lateral)]
+    out = np.zeros((com_unwrap.shape[0], 2))
+    for f in range(com_unwrap.shape[0]):
+        dr = com_unwrap[f][idx][:, list(lateral)] - ref
+        m_dr = [np.sqrt(np.dot(v, v)) for v in dr]
+        L = np.abs(m_dr).sum() / len(m_dr)
+        run_.push(L)
+        out[f] = [times[f], run_.mean()]
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # box-only analyses: apl_box (analysis_protocols.py:991-1006), acm (:3181-3207)
 # --------------------------------------------------------------------------------------
 def apl_box(dims, times, n_residues, lateral=(0, 1)) -> np.ndarray:
@@ -804,6 +822,9 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
             leaf = kv.get("leaflet", "upper")
             v = views0[leaf if leaf in ("upper", "lower") else "upper"]
             out[a_id] = halperin_nelson(com, box, times, list(v.members), lateral)
+        elif key == "ald":
+            idx = _indices_for(views0, kv.get("leaflet", "both"), kv.get("resname", "all"))
+            out[a_id] = ald(comu, times, idx, lateral)
         elif key == "apl_box":
             out[a_id] = apl_box(dims, times, top.n_residues, lateral)
         elif key == "acm":

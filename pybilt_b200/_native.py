@@ -50,6 +50,8 @@ _SIGNATURES = {
     "pbk_leaflet_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "pbk_msd_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int, c_int,
                               c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "pbk_ald_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int, c_int,
+                              c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "pbk_rdf": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                         c_int, c_int, c_int, c_int, c_int32, c_double, c_double, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p]),

@@ -304,6 +304,47 @@ class MSDProtocol(AnalysisProtocol):
         self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
 
+@_protocol('ald', 'com_frame')
+class ALDProtocol(AnalysisProtocol):
+    """Average lateral displacement, rows [time, running mean over frames of the mean displacement
+    length from the first frame] (analysis_protocols.py:3218-3345)."""
+    _short_description = "Average lateral displacement."
+    batched = True
+
+    def __init__(self, args):
+        self._indices = []
+        self._setup({'leaflet': 'both', 'resname': 'all'}, args)
+        self.L_stat = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        if batch.first_window:
+            self._indices = _first_frame_indices(batch.first_leaflets, self.settings['leaflet'],
+                                                 self.settings['resname'])
+            self._vals = np.zeros(batch.n_frames)
+            self._pending = []
+            self._idx_dev = batch.engine._i32(np.asarray(self._indices, dtype=np.int32))
+        rows = batch.rows
+        dev = batch.engine.dev
+        ends = torch.arange(rows.start, rows.stop, dtype=torch.int32, device=dev)
+        origins = torch.full((rows.stop - rows.start,), batch.ref_row, dtype=torch.int32, device=dev)
+        vals = batch.engine.msd_pairs(self._idx_dev, origins, ends, ba_settings['lateral'], lengths=True)
+        self._pending.append((batch.gframes, vals))
+
+    def finish(self, batch):
+        for g, v in self._pending:
+            self._vals[g] = v.cpu().numpy()
+        self._pending = []
+        vals = batch.allreduce(self._vals)
+        for t, L in zip(np.asarray(batch.times, dtype=np.float64), vals):
+            self.L_stat.push(L)
+            self.analysis_output.append(np.array([t, self.L_stat.mean()]))
+
+    def reset(self):
+        self.L_stat.reset()
+        self.analysis_output = []
+        self._indices = []
+
+
 def msd_multi_schedule(n_frames, n_tau, n_sigma):
     """Replay of the block counters of MSDMultiProtocol.run_analysis
     (analysis_protocols.py:833-888): returns ({block: (origin, end frame)}, n_blocks).

@@ -417,10 +417,11 @@ extern "C" int pbk_leaflets(pbk_ctx *ctx, const double *com_unwrap, int64_t F, i
 // ---------------------------------------------------------------------------------------
 // K5  MSD over (origin, end) frame pairs; one CTA per pair, fixed-order tree mean.
 // ---------------------------------------------------------------------------------------
+// mode 0: mean squared displacement; mode 1: mean displacement length (ald: sqrt(np.dot(dr, dr)))
 __global__ void __launch_bounds__(256)
 k_msd_pairs(const double *__restrict__ cu, int64_t N, const int32_t *__restrict__ idx, int32_t n,
             int lat0, int lat1, const int32_t *__restrict__ po, const int32_t *__restrict__ pe,
-            double *__restrict__ out)
+            double *__restrict__ out, int mode)
 {
     __shared__ double red[32];
     int p = blockIdx.x;
@@ -431,7 +432,8 @@ k_msd_pairs(const double *__restrict__ cu, int64_t N, const int32_t *__restrict_
         int64_t i = idx[t];
         double dx = __dsub_rn(a[i * 3 + lat0], b[i * 3 + lat0]);
         double dy = __dsub_rn(a[i * 3 + lat1], b[i * 3 + lat1]);
-        s += __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (mode == 0) s += __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        else s += sqrt(fma(dy, dy, __dmul_rn(dx, dx)));
     }
     s = pbk_block_sum(s, red);
     if (threadIdx.x == 0) out[p] = n > 0 ? s / (double)n : 0.0;
@@ -447,8 +449,23 @@ extern "C" int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, 
         return pbk_fail(ctx, PBK_EINVAL, "pbk_msd_pairs: bad argument");
     if (n_pairs == 0) return PBK_OK;
     k_msd_pairs<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
-        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out);
+        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out, 0);
     PBK_CHECK_LAUNCH(ctx, "k_msd_pairs");
+    return PBK_OK;
+}
+
+extern "C" int pbk_ald_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
+                             const int32_t *idx, int32_t n_idx, int lat0, int lat1,
+                             const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
+                             double *out, void *stream)
+{
+    if (!ctx || !com_unwrap || !idx || !pair_origin || !pair_end || !out || F <= 0 || N <= 0 ||
+        n_idx < 0 || n_pairs < 0 || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_ald_pairs: bad argument");
+    if (n_pairs == 0) return PBK_OK;
+    k_msd_pairs<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
+        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out, 1);
+    PBK_CHECK_LAUNCH(ctx, "k_msd_pairs(ald)");
     return PBK_OK;
 }
 

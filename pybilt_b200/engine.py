@@ -358,11 +358,12 @@ class LipidReductionEngine:
         return out
 
     def msd_pairs(self, idx: np.ndarray, origins: Sequence[int], ends: Sequence[int],
-                  lateral=(0, 1)) -> torch.Tensor:
+                  lateral=(0, 1), lengths: bool = False) -> torch.Tensor:
+        """mean squared displacement per (origin, end) pair; ``lengths``: mean displacement length."""
         d = self.dev
         d_idx, d_o, d_e = (self._i32(v) for v in (idx, origins, ends))
         out = torch.empty(len(d_o), dtype=torch.float64, device=d)
-        self.ctx.call("pbk_msd_pairs", self.com_unwrap.data_ptr(), self.n_done, self.N,
+        self.ctx.call("pbk_ald_pairs" if lengths else "pbk_msd_pairs", self.com_unwrap.data_ptr(), self.n_done, self.N,
                       d_idx.data_ptr(), int(d_idx.numel()), int(lateral[0]), int(lateral[1]),
                       d_o.data_ptr(), d_e.data_ptr(), int(d_o.numel()), out.data_ptr(), self.stream_ptr())
         self.launches += 1

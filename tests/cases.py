@@ -74,7 +74,8 @@ CASES = {
         spec=syn.BilayerSpec(96, MIX3, seed=13, box_z=72.0, npt=1e-3), n_frames=12,
         analyses=["thickness_leaflet_distance tld", "msd msd_1", "area_fluctuation af",
                   "halperin_nelson hn", "halperin_nelson hn_lo leaflet lower", "apl_box apl_b",
-                  "acm acm_1", "acm acm_t temperature 310.0"]),
+                  "acm acm_1", "acm acm_t temperature 310.0", "ald ald_1",
+                  "ald ald_up leaflet upper resname POPC"]),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,
