@@ -541,6 +541,35 @@ def acm(dims, times, norm=2, temperature=298.15) -> np.ndarray:
     return np.array(out)
 
 
+def area_compressibility(dims, times, norm=2, temperature=298.15) -> np.ndarray:
+    """ac (analysis_protocols.py:3431-3445): rows [time, var(A) / (<A> k T) * 1e-23]."""
+    import scipy.constants as scicon
+    run_ = Welford()
+    out = []
+    with np.errstate(all="ignore"):
+        for f in range(dims.shape[0]):
+            d = dims[f][0:3]
+            area = d.prod() / d[norm]
+            run_.push(area)
+            x_t = run_.variance() / (run_.mean() * scicon.k * temperature)
+            x_t *= 10.0 ** (-23)
+            out.append([times[f], x_t])
+    return np.array(out)
+
+
+def volume_compressibility_modulus(dims, times, temperature=298.15) -> np.ndarray:
+    """vcm (analysis_protocols.py:3071-3091): rows [time, <V> k T / dev(V)^2], 0 on the first frame."""
+    import scipy.constants as scicon
+    run_ = Welford()
+    out = []
+    with np.errstate(all="ignore"):
+        for f in range(dims.shape[0]):
+            run_.push(dims[f][0:3].prod())
+            kv = 0.0 if f == 0 else (run_.mean() * scicon.k * temperature) / run_.deviation() ** 2
+            out.append([times[f], kv])
+    return np.array(out)
+
+
 # --------------------------------------------------------------------------------------
 # N3: lateral box-area fluctuation      analysis_protocols.py:4486-4498
 # --------------------------------------------------------------------------------------
@@ -825,6 +854,10 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
         elif key == "ald":
             idx = _indices_for(views0, kv.get("leaflet", "both"), kv.get("resname", "all"))
             out[a_id] = ald(comu, times, idx, lateral)
+        elif key == "ac":
+            out[a_id] = area_compressibility(dims, times, norm, float(kv.get("temperature", 298.15)))
+        elif key == "vcm":
+            out[a_id] = volume_compressibility_modulus(dims, times, float(kv.get("temperature", 298.15)))
         elif key == "apl_box":
             out[a_id] = apl_box(dims, times, top.n_residues, lateral)
         elif key == "acm":

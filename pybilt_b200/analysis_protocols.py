@@ -767,6 +767,85 @@ class AreaCompressibilityModulusProtocol(AnalysisProtocol):
         self.first_comp = True
 
 
+@_protocol('ac', 'mda_frame')
+class AreaCompressibilityProtocol(AnalysisProtocol):
+    """Isothermal area compressibility, rows [time, var(A) / (<A> k T) * 1e-23]
+    (analysis_protocols.py:3349-3450).  Host-side box arithmetic."""
+    _short_description = "Isothermal area compressibility."
+    _related = list(['acm', 'vcm'])
+    _casts = {'temperature': float}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'temperature': 298.15}, args)
+        self.n_frames = 0
+        self.area_run = RunningStats()
+        self.area_fluctuation = RunningStats()
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        self._norm = ba_settings['norm']
+
+    def finish(self, batch):
+        import scipy.constants as scicon
+        with np.errstate(all="ignore"):
+            for f in range(batch.n_frames):
+                d = batch.box_host[f]
+                area = d.prod() / d[self._norm]
+                self.area_run.push(area)
+                area_mean = self.area_run.mean()
+                self.area_fluctuation.push((area - area_mean) ** 2)
+                x_t = self.area_run.variance() / (area_mean * scicon.k * self.settings['temperature'])
+                x_t *= 10.0 ** (-23)
+                self.analysis_output.append([batch.times[f], x_t])
+                self.n_frames += 1
+
+    def reset(self):
+        self.n_frames = 0
+        self.area_run.reset()
+        self.area_fluctuation.reset()
+        self.analysis_output = []
+
+
+@_protocol('vcm', 'mda_frame')
+class VolumeCompressibilityModulusProtocol(AnalysisProtocol):
+    """Volume compressibility modulus, rows [time, <V> k T / dev(V)^2] (0 on the first frame)
+    (analysis_protocols.py:2997-3092).  Host-side box arithmetic."""
+    _short_description = "Volume compressibility modulus."
+    _related = list(['acm', 'ac'])
+    _casts = {'temperature': float}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'temperature': 298.15}, args)
+        self.n_frames = 0
+        self.volume_run = RunningStats()
+        self.first_comp = True
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        pass
+
+    def finish(self, batch):
+        import scipy.constants as scicon
+        with np.errstate(all="ignore"):
+            for f in range(batch.n_frames):
+                self.volume_run.push(batch.box_host[f].prod())
+                if self.first_comp:
+                    self.first_comp = False
+                    self.n_frames += 1
+                    kv = 0.0
+                else:
+                    kv = (self.volume_run.mean() * scicon.k * self.settings['temperature']) / \
+                        self.volume_run.deviation() ** 2
+                self.analysis_output.append([batch.times[f], kv])
+                self.n_frames += 1
+
+    def reset(self):
+        self.n_frames = 0
+        self.volume_run.reset()
+        self.analysis_output = []
+        self.first_comp = True
+
+
 # ---------------------------------------------------------------------------------------
 @_protocol('area_fluctuation', 'com_frame')
 class AreaFluctuationProtocol(AnalysisProtocol):

@@ -75,7 +75,7 @@ CASES = {
         analyses=["thickness_leaflet_distance tld", "msd msd_1", "area_fluctuation af",
                   "halperin_nelson hn", "halperin_nelson hn_lo leaflet lower", "apl_box apl_b",
                   "acm acm_1", "acm acm_t temperature 310.0", "ald ald_1",
-                  "ald ald_up leaflet upper resname POPC"]),
+                  "ald ald_up leaflet upper resname POPC", "ac ac_1", "vcm vcm_1 temperature 303.0"]),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,
