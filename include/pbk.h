@@ -163,6 +163,14 @@ int pbk_leaflets(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N, i
 int pbk_leaflet_distance(pbk_ctx *ctx, const double *com, const uint8_t *labels, int64_t F, int64_t N,
                          int norm, double *out, void *stream);
 
+/* ---- N3  flip-flop detection ----------------------------------------------------------------
+ * FlipFlopProtocol.run_analysis          pybilt/bilayer_analyzer/analysis_protocols.py:3784-3833
+ * changed[f] = number of lipids whose leaflet label differs between frame f and frame f-1 (frame 0
+ * of the call against prev_row[N]; prev_row NULL: 0).  The reference's reference leaflets are always
+ * the previous frame's, so changed[f] != 0 marks the frames that produce events. */
+int pbk_label_changes(pbk_ctx *ctx, const uint8_t *labels, const uint8_t *prev_row, int64_t F, int64_t N,
+                      int32_t *changed, void *stream);
+
 /* ---- C1 / C2  mean squared displacement -------------------------------------------------
  * MSDProtocol.run_analysis / MSDMultiProtocol.run_analysis
  *                                  pybilt/bilayer_analyzer/analysis_protocols.py:582-667, 781-895

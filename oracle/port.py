@@ -481,6 +481,36 @@ def halperin_nelson(com, box, times, idx, lateral=(0, 1)) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# N3: flip-flop events      analysis_protocols.py:3784-3833
+# --------------------------------------------------------------------------------------
+def flip_flop(labels, types, resids, times, frame_numbers) -> dict:
+    """{resname: {'count', 'events': [[frame, time, resid, from, to], ...]}}.  Only the first leaflet
+    ('upper') is examined; the reference leaflets are replaced whenever anything changed, i.e. they
+    are always the previous frame's.  Events of a frame come in the iteration order of the Python
+    sets ``curr.difference(ref)`` then ``ref.difference(curr)`` -- reproduced by making the same sets."""
+    views0 = leaflet_views(labels[0], types)
+    names = []
+    for ln in ("upper", "lower"):
+        for g in views0[ln].group_names:
+            if g not in names:
+                names.append(g)
+    out = {r: {'count': 0, 'events': []} for r in names}
+    ref = set(np.nonzero(labels[0] == 1)[0].tolist())
+    for f in range(1, labels.shape[0]):
+        curr = set(np.nonzero(labels[f] == 1)[0].tolist())
+        fwd, bwd = curr.difference(ref), ref.difference(curr)
+        for index in fwd:
+            out[types[index]]['count'] += 1
+            out[types[index]]['events'].append([frame_numbers[f], times[f], resids[index], 'lower', 'upper'])
+        for index in bwd:
+            out[types[index]]['count'] += 1
+            out[types[index]]['events'].append([frame_numbers[f], times[f], resids[index], 'upper', 'lower'])
+        if fwd or bwd:
+            ref = curr
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # N3: average lateral displacement      analysis_protocols.py:3262-3339
 # --------------------------------------------------------------------------------------
 def ald(com_unwrap, times, idx, lateral=(0, 1)) -> np.ndarray:
@@ -851,6 +881,8 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
             leaf = kv.get("leaflet", "upper")
             v = views0[leaf if leaf in ("upper", "lower") else "upper"]
             out[a_id] = halperin_nelson(com, box, times, list(v.members), lateral)
+        elif key == "flip_flop":
+            out[a_id] = flip_flop(labels, types, resids, times, fr)
         elif key == "ald":
             idx = _indices_for(views0, kv.get("leaflet", "both"), kv.get("resname", "all"))
             out[a_id] = ald(comu, times, idx, lateral)

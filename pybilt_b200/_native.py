@@ -48,6 +48,7 @@ _SIGNATURES = {
     "pbk_leaflets": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
     "pbk_leaflet_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "pbk_label_changes": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "pbk_msd_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int, c_int,
                               c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "pbk_ald_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int, c_int,

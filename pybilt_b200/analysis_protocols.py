@@ -304,6 +304,65 @@ class MSDProtocol(AnalysisProtocol):
         self.analysis_output = np.stack([np.asarray(batch.times, dtype=np.float64), vals], axis=1)
 
 
+@_protocol('flip_flop', 'com_frame')
+class FlipFlopProtocol(AnalysisProtocol):
+    """Lipid flip-flop events: {resname: {'count': n, 'events': [[frame, time, resid, from, to]]}}
+    (analysis_protocols.py:3731-3868).  The device flags the frames in which any label changed
+    (`pbk_label_changes`); for those the events are listed on the host with the same Python set
+    operations the reference uses, so that their order within a frame is the reference's."""
+    _short_description = "Count lipid flip flops."
+    _related = None
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'none': None}, args)
+        self.analysis_output = {}
+        self._resnames = []
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        if batch.first_window:
+            self._resnames = []
+            for leaflet in batch.first_leaflets.keys():
+                for resname in batch.first_leaflets[leaflet].get_group_names():
+                    if resname not in self._resnames:
+                        self._resnames.append(resname)
+            self._events = []                     # (resname, event) in frame order, this rank's frames
+        rows, g0 = batch.rows, batch.gframes.start
+        changed = batch.engine.label_changes(frames=rows).cpu().numpy()
+        labels = batch.engine.labels
+        for k in np.nonzero(changed)[0]:
+            r, g = rows.start + int(k), g0 + int(k)
+            if g == 0:
+                continue                          # the first analysed frame only sets the reference
+            pair = labels[r - 1:r + 1].cpu().numpy()
+            ref = set(np.nonzero(pair[0] == 1)[0].tolist())
+            curr = set(np.nonzero(pair[1] == 1)[0].tolist())
+            frame, time = int(batch.frame_numbers[g]), batch.times[g]
+            for index in curr.difference(ref):                       # lower -> upper
+                self._events.append((batch.types[index], [frame, time, batch.resids[index], 'lower', 'upper']))
+            for index in ref.difference(curr):                       # upper -> lower
+                self._events.append((batch.types[index], [frame, time, batch.resids[index], 'upper', 'lower']))
+
+    def finish(self, batch):
+        events = self._events
+        if batch.sharded:
+            import torch.distributed as dist
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, events)                    # rank order = frame order
+            events = [e for part in parts for e in part]
+        self.analysis_output = {r: {'count': 0, 'events': []} for r in self._resnames}
+        for resname, ev in events:
+            self.analysis_output[resname]['count'] += 1
+            self.analysis_output[resname]['events'].append(ev)
+
+    def get_data(self):
+        return self.analysis_output
+
+    def reset(self):
+        self.analysis_output = {}
+        self._resnames = []
+
+
 @_protocol('ald', 'com_frame')
 class ALDProtocol(AnalysisProtocol):
     """Average lateral displacement, rows [time, running mean over frames of the mean displacement

@@ -328,6 +328,7 @@ class ReductionBatch(object):
         self.engine = engine
         self.shard = shard                  # pybilt_b200.distributed.Shard or None
         self.lateral = list(analyzer.settings['lateral'])
+        self.frame_numbers = analyzer.analysed_frame_indices()      # MD frame index of every analysed frame
         # n_frames / times / box_host describe ALL analysed frames; the engine rows of a
         # shard are [back halo | owned | forward halo | reference row]
         self.n_frames = len(times)

@@ -560,3 +560,36 @@ extern "C" int pbk_leaflet_distance(pbk_ctx *ctx, const double *com, const uint8
     PBK_CHECK_LAUNCH(ctx, "k_leaflet_distance");
     return PBK_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// K12  flip-flop detection (flip_flop): how many lipids changed leaflet between consecutive frames.
+// One warp per frame; frame 0 of the call is compared with prev_row (NULL: nothing to compare, 0).
+// The events themselves (which lipid, in the reference's set-iteration order) are listed on the host
+// for the flagged frames only.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_label_changes(const uint8_t *__restrict__ labels, const uint8_t *__restrict__ prev_row, int64_t F, int64_t N,
+                int32_t *__restrict__ changed)
+{
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const uint8_t *cur = labels + f * N;
+    const uint8_t *prv = f > 0 ? labels + (f - 1) * N : prev_row;
+    int c = 0;
+    if (prv)
+        for (int64_t i = lane; i < N; i += 32) c += (cur[i] != prv[i]) ? 1 : 0;
+    c = pbk_warp_sum(c);
+    if (lane == 0) changed[f] = c;
+}
+
+extern "C" int pbk_label_changes(pbk_ctx *ctx, const uint8_t *labels, const uint8_t *prev_row, int64_t F, int64_t N,
+                                 int32_t *changed, void *stream)
+{
+    if (!ctx || !labels || !changed || F < 0 || N <= 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_label_changes: bad argument");
+    if (F == 0) return PBK_OK;
+    k_label_changes<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(labels, prev_row, F, N, changed);
+    PBK_CHECK_LAUNCH(ctx, "k_label_changes");
+    return PBK_OK;
+}

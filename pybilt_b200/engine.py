@@ -347,6 +347,18 @@ class LipidReductionEngine:
     # ---------------------------------------------------------------------------------
     # analyses over the resident representations
     # ---------------------------------------------------------------------------------
+    def label_changes(self, frames: Optional[slice] = None) -> torch.Tensor:
+        """int32 [frames]: lipids whose leaflet label differs from the previous resident row (0 for
+        row 0, which has no predecessor)."""
+        sl = frames or slice(0, self.n_done)
+        F = sl.stop - sl.start
+        out = torch.empty(F, dtype=torch.int32, device=self.dev)
+        prev = self.labels[sl.start - 1].data_ptr() if sl.start > 0 else None
+        self.ctx.call("pbk_label_changes", self.labels[sl.start:].data_ptr(), prev, F, self.N, out.data_ptr(),
+                      self.stream_ptr())
+        self.launches += 1
+        return out
+
     def leaflet_distance(self, frames: Optional[slice] = None) -> torch.Tensor:
         """|mean(com_upper) - mean(com_lower)| along the bilayer normal, float64 [frames]."""
         sl = frames or slice(0, self.n_done)

@@ -76,6 +76,10 @@ CASES = {
                   "halperin_nelson hn", "halperin_nelson hn_lo leaflet lower", "apl_box apl_b",
                   "acm acm_1", "acm acm_t temperature 310.0", "ald ald_1",
                   "ald ald_up leaflet upper resname POPC", "ac ac_1", "vcm vcm_1 temperature 303.0"]),
+    # lipids hopping across the mid-plane: flip_flop events (order within a frame included)
+    "flip_flop": dict(
+        spec=syn.BilayerSpec(48, CG3, seed=17, leaflet_z=1.2, z_step=0.8), n_frames=10,
+        analyses=["flip_flop ff", "msd msd_1"]),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,
@@ -106,6 +110,13 @@ def flatten_outputs(out: dict) -> dict:
     for a_id, v in out.items():
         if isinstance(v, dict):
             for k, arr in v.items():
+                if isinstance(arr, dict) and "events" in arr:
+                    # flip_flop: {'count': n, 'events': [[frame, time, resid, from, to], ...]}
+                    flat[f"out/{a_id}/{k}/count"] = np.asarray(arr["count"])
+                    ev = [[e[0], e[1], e[2], 1.0 if e[3] == "upper" else 0.0, 1.0 if e[4] == "upper" else 0.0]
+                          for e in arr["events"]]
+                    flat[f"out/{a_id}/{k}/events"] = np.asarray(ev, dtype=np.float64).reshape(-1, 5)
+                    continue
                 flat[f"out/{a_id}/{k}"] = np.asarray(arr)
         elif isinstance(v, tuple):
             flat[f"out/{a_id}/rdf"] = np.asarray(v[0])

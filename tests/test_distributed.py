@@ -72,7 +72,8 @@ def test_shard_unwrap_algebra_gloo_cpu(world, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,case", [(2, "tiny_all"), (2, "c2_prefix"), (3, "c3_small"),
-                                        (2, "name_dict"), (2, "grid_dense")])
+                                        (2, "name_dict"), (2, "grid_dense"), (3, "flip_flop"),
+                                        (2, "leaflet_dist")])
 def test_sharded_analyzer_matches_reference(world, case):
     codes, outs = launch(world, "gpu", case)
     assert codes == [0] * world, outs
@@ -87,7 +88,8 @@ def test_streamed_shard_unwrap_algebra_gloo_cpu(world, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,case,window", [(2, "tiny_all", 4), (2, "c2_prefix", 7), (3, "c3_small", 2),
-                                               (2, "name_dict", 3), (2, "grid_dense", 1000)])
+                                               (2, "name_dict", 3), (2, "grid_dense", 1000),
+                                               (2, "flip_flop", 3), (2, "leaflet_dist", 5)])
 def test_streamed_sharded_analyzer_matches_reference(world, case, window, monkeypatch):
     monkeypatch.setenv("PBK_TEST_WINDOW", str(window))
     codes, outs = launch(world, "gpuwin", case)
