@@ -756,7 +756,6 @@ class BilayerAnalyzer(object):
         if shard is not None:
             return self._reduce_sharded(eng, md, fr, fr_all, shard, layout)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
-        dev = eng.dev
         times = np.empty(len(fr))
         dims_all = np.empty((len(fr), 6), dtype=np.float32)
         B = eng.B
@@ -1150,7 +1149,7 @@ class BilayerAnalyzer(object):
     def frame_views(self, f, need_grid=None):
         """Host views of analysed frame ``f``: the objects the reference rebuilds per frame."""
         h = self._host_arrays()
-        e, lay = self._engine, self._engine.layout
+        lay = self._engine.layout
         g = int(f)
         upd = int(self.rep_settings['leaflets']['update_interval'])
         src = g - (g % upd)
