@@ -17,7 +17,7 @@ def build(force: bool = False) -> str:
     if (not force and os.path.exists(OUT)
             and os.path.getmtime(OUT) >= os.path.getmtime(SRC)):
         return OUT
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", OUT, SRC, "-lm"]
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", OUT, SRC, "-lm"]
     subprocess.run(cmd, check=True)
     return OUT
 

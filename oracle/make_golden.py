@@ -97,8 +97,36 @@ def make_comtraj(name: str) -> str:
     return path
 
 
+def make_estimators() -> str:
+    """The reference's diffusion estimators (pybilt/diffusion/diffusion_coefficients.py:17-167)
+    on the msd rows of fixture c2_prefix and on a noisy straight line, with and without time_range."""
+    with rh.quiet():
+        import pybilt.diffusion.diffusion_coefficients as dc
+    g = np.load(os.path.join(GOLDEN, "c2_prefix.npz"))
+    rows = g["out/msd_1"]
+    rng = np.random.default_rng(0)
+    t_lin = np.linspace(0.0, 100.0, 400)
+    sets = {"c2": (rows[:, 0].copy(), rows[:, 1].copy()),
+            "line": (t_lin, 4.0 * 2.0 * t_lin + rng.normal(0, 0.05, t_lin.size))}
+    flat = {}
+    for key, (t, y) in sets.items():
+        flat[key + "/t"], flat[key + "/msd"] = t.copy(), y.copy()
+        for tag, tr in (("full", None), ("range", [float(t[len(t) // 4]), float(t[3 * len(t) // 4])])):
+            flat[f"{key}/{tag}/time_range"] = np.array(tr if tr else [np.nan, np.nan])
+            for dim in (2, 3):
+                flat[f"{key}/{tag}/einstein/{dim}"] = np.array(dc.diffusion_coefficient_Einstein(t.copy(), y, dim=dim, time_range=tr))
+                flat[f"{key}/{tag}/linear/{dim}"] = np.array(dc.diffusion_coefficient_linear_fit(t.copy(), y, dim=dim, time_range=tr))
+                flat[f"{key}/{tag}/anomalous/{dim}"] = np.array(dc.diffusion_coefficient_anomalous_fit(t[1:].copy(), y[1:], dim=dim, time_range=tr))
+    path = os.path.join(GOLDEN, "estimators.npz")
+    np.savez_compressed(path, **flat)
+    return path
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES])
+    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES] + ["estimators"])
     for n in names:
-        p = make_comtraj(n.split(":", 1)[1]) if n.startswith("comtraj:") else make(n)
+        if n == "estimators":
+            p = make_estimators()
+        else:
+            p = make_comtraj(n.split(":", 1)[1]) if n.startswith("comtraj:") else make(n)
         print(n, "->", p, os.path.getsize(p), "bytes")

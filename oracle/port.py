@@ -29,6 +29,7 @@ def lib():
         _lib = ctypes.CDLL(_build.build())
         _lib.pc_pairwise_sum.restype = ctypes.c_double
         _lib.pc_leaflet_labels.restype = ctypes.c_int64
+        _lib.pc_rdf_accumulate_cells.restype = ctypes.c_int64
     return _lib
 
 
@@ -326,7 +327,9 @@ def msd_multi(com_unwrap, times, idx, n_tau=50, n_sigma=50, lateral=(0, 1)) -> n
 # D2: COM lateral RDF        analysis_protocols.py:4900-5062
 # --------------------------------------------------------------------------------------
 def rdf(com, labels, types, box, leaflet="both", resname_1="first", resname_2="first",
-        n_bins=25, range_inner=0.0, range_outer=25.0, lateral=(0, 1)):
+        n_bins=25, range_inner=0.0, range_outer=25.0, lateral=(0, 1), cells=False):
+    """``cells``: use the cell-list form of the pair loop (portc.c: pc_rdf_accumulate_cells, same
+    arithmetic, for the 10^5-lipid leaflets of configs C4/C5); raises if a COM lies outside the box."""
     F = com.shape[0]
     lx, ly = lateral
     do_leaflet = ["upper", "lower"] if leaflet == "both" else [leaflet]
@@ -356,11 +359,14 @@ def rdf(com, labels, types, box, leaflet="both", resname_1="first", resname_2="f
                 ib = _i64(v.get_group_indices(resname_2))
                 N_a += len(ia)
                 N_b += len(ib)
-                lib().pc_rdf_accumulate(_p(pos), _p(ia), ctypes.c_int64(len(ia)), _p(ib),
-                                        ctypes.c_int64(len(ib)), ctypes.c_float(bx),
-                                        ctypes.c_float(by), ctypes.c_int(n_bins),
-                                        ctypes.c_double(range_inner), ctypes.c_double(range_outer),
-                                        _p(edges), _p(count))
+                fn = lib().pc_rdf_accumulate_cells if cells else lib().pc_rdf_accumulate
+                rc = fn(_p(pos), _p(ia), ctypes.c_int64(len(ia)), _p(ib),
+                        ctypes.c_int64(len(ib)), ctypes.c_float(bx),
+                        ctypes.c_float(by), ctypes.c_int(n_bins),
+                        ctypes.c_double(range_inner), ctypes.c_double(range_outer),
+                        _p(edges), _p(count))
+                if cells and rc != 0:
+                    raise ValueError("cell-list RDF oracle: a COM outside the box or a box below 3 cells")
         area.push(box[f][[lx, ly]].prod())                        # float32 product (:5004)
     return rdf_finalize(count, edges, N_a, N_b, N_tot, float(len(do_leaflet)), F, area.mean(),
                         resname_1, resname_2), count
@@ -666,8 +672,9 @@ def grid_bins(box_xy, nxbins, nybins, area_per_bin=None):
 
 
 def lipid_grid_frame(com_f, comu_f, label_f, box_f, nxbins=10, nybins=10, mode="opt",
-                     plane=(0, 1), area_per_bin=None):
-    """LipidGrids for one frame: per leaflet (grid_idx[nx,ny] i64, grid_z[nx,ny] f64),
+                     plane=(0, 1), area_per_bin=None, lean_knn=False):
+    """``lean_knn``: the 24-neighbour table without the n x n matrix (portc.c: pc_knn_lean).
+    LipidGrids for one frame: per leaflet (grid_idx[nx,ny] i64, grid_z[nx,ny] f64),
     plus (x_incr, y_incr).  mode 'opt' = lipid_grid_opt.py:237-334 (what BilayerAnalyzer
     builds), 'exact' = lipid_grid.py:217-248."""
     ix, iy = plane
@@ -695,8 +702,9 @@ def lipid_grid_frame(com_f, comu_f, label_f, box_f, nxbins=10, nybins=10, mode="
         else:
             nn_k = 24
             knn = np.full((n, nn_k), -1, dtype=np.int64)
-            lib().pc_knn(_p(pos), _p(idx), ctypes.c_int64(n), ctypes.c_int(nn_k),
-                         ctypes.c_float(boxx), ctypes.c_float(boxy), _p(knn))
+            (lib().pc_knn_lean if lean_knn else lib().pc_knn)(
+                _p(pos), _p(idx), ctypes.c_int64(n), ctypes.c_int(nn_k),
+                ctypes.c_float(boxx), ctypes.c_float(boxy), _p(knn))
             pos_of = np.full(com_f.shape[0], -1, dtype=np.int64)
             pos_of[idx] = np.arange(n)
             lib().pc_grid_opt(_p(pos), _p(z), _p(idx), ctypes.c_int64(n), _p(knn), ctypes.c_int(nn_k),

@@ -4,7 +4,7 @@
  * path, used by oracle/port.py (the CPU checker and the reported CPU baseline).
  * Each function cites the reference file:line (relative to /root/reference) whose
  * arithmetic it follows.  Built by oracle/build.py with
- *     gcc -O2 -ffp-contract=off -fPIC -shared
+ *     gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared
  * (-ffp-contract=off: the only fused multiply-add is the explicit fma() below).
  */
 #include <math.h>
@@ -308,4 +308,109 @@ void pc_unwrap_axis(const float *x, const float *uprev, int64_t n, int64_t strid
         }
         u[i * stride] = (float)((double)xv + s * (double)L);
     }
+}
+
+/* ======================================================================================
+ * Large-shape variants (BASELINE configs C3-C5).  Same arithmetic as the functions above --
+ * the identical pbc_dist / hist_bin calls in the identical argument order -- reorganised so
+ * that 32,768- and 131,072-lipid leaflets finish in seconds: rows spread over OpenMP threads,
+ * no n x n matrix, and for the RDF a cell list that only skips pairs which cannot land in a
+ * bin.  tests/test_oracle_golden.py pins each of them to its dense counterpart above.
+ * ====================================================================================== */
+
+/* ---- LipidGrid2d._knn (lipid_grid_opt.py:435-468) without the n x n matrix: row p keeps its
+ * nn_k best (distance, position) in ascending order; a candidate enters behind every entry of
+ * equal distance (candidates arrive in ascending position order, so this is the stable sort
+ * of pc_knn).  Each pair is evaluated as dist(lower position, higher position) like there. */
+void pc_knn_lean(const double *pos, const int64_t *idx, int64_t n, int nn_k, float boxx, float boxy,
+                 int64_t *out_nn)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < n; p++) {
+        double bd[64];
+        int64_t bj[64];
+        int m = 0;
+        for (int64_t q = 0; q < n; q++) {
+            if (q == p) continue;
+            int64_t lo = p < q ? p : q, hi = p < q ? q : p;
+            double r = pbc_dist(pos[2 * idx[lo]], pos[2 * idx[lo] + 1], pos[2 * idx[hi]], pos[2 * idx[hi] + 1],
+                                boxx, boxy);
+            if (m == nn_k && !(r < bd[m - 1])) continue;
+            int k = m < nn_k ? m : nn_k - 1;
+            while (k > 0 && bd[k - 1] > r) { bd[k] = bd[k - 1]; bj[k] = bj[k - 1]; k--; }
+            bd[k] = r;
+            bj[k] = idx[q];
+            if (m < nn_k) m++;
+        }
+        for (int t = 0; t < nn_k; t++) out_nn[p * nn_k + t] = (t < m) ? bj[t] : -1;
+    }
+}
+
+/* ---- COMLateralRDFProtocol.run_analysis inner loops (analysis_protocols.py:4973-4998) over a
+ * cell list.  Only valid when every position lies inside [0, box) on both lateral axes (then
+ * the reference's formula is the minimum image and |d| <= r_out implies neighbouring cells);
+ * returns -1 without counting otherwise.  Cells have edge >= hi (the outer range), at least 3
+ * per axis, so the 3 x 3 block around a cell holds every partner within range exactly once.
+ * The pairs are visited as ordered pairs (a in A, b in B, a != b) with pbc_dist(a, b) -- the
+ * argument order matters for the rounding of the wrapped branch. */
+int64_t pc_rdf_accumulate_cells(const double *pos, const int64_t *ia, int64_t na, const int64_t *ib,
+                                int64_t nb_idx, float boxx, float boxy, int nbins, double lo, double hi,
+                                const double *edges, int64_t *count)
+{
+    if (!(hi > 0.0)) return -1;
+    int ncx = (int)floor((double)boxx / hi), ncy = (int)floor((double)boxy / hi);
+    if (ncx < 3 || ncy < 3) return -1;
+    if (ncx > 1024) ncx = 1024;
+    if (ncy > 1024) ncy = 1024;
+    const double wx = (double)boxx / ncx, wy = (double)boxy / ncy;
+    for (int64_t j = 0; j < nb_idx; j++) {
+        double x = pos[2 * ib[j]], y = pos[2 * ib[j] + 1];
+        if (!(x >= 0.0 && x < (double)boxx && y >= 0.0 && y < (double)boxy)) return -1;
+    }
+    for (int64_t i = 0; i < na; i++) {
+        double x = pos[2 * ia[i]], y = pos[2 * ia[i] + 1];
+        if (!(x >= 0.0 && x < (double)boxx && y >= 0.0 && y < (double)boxy)) return -1;
+    }
+    int64_t ncell = (int64_t)ncx * ncy;
+    int64_t *start = (int64_t *)calloc((size_t)ncell + 1, sizeof(int64_t));
+    int64_t *cell_of = (int64_t *)malloc((size_t)nb_idx * sizeof(int64_t));
+    int64_t *order = (int64_t *)malloc((size_t)nb_idx * sizeof(int64_t));
+    for (int64_t j = 0; j < nb_idx; j++) {
+        int cx = (int)(pos[2 * ib[j]] / wx), cy = (int)(pos[2 * ib[j] + 1] / wy);
+        if (cx >= ncx) cx = ncx - 1;
+        if (cy >= ncy) cy = ncy - 1;
+        cell_of[j] = (int64_t)cx * ncy + cy;
+        start[cell_of[j] + 1]++;
+    }
+    for (int64_t c = 0; c < ncell; c++) start[c + 1] += start[c];
+    int64_t *fill = (int64_t *)malloc((size_t)ncell * sizeof(int64_t));
+    memcpy(fill, start, (size_t)ncell * sizeof(int64_t));
+    for (int64_t j = 0; j < nb_idx; j++) order[fill[cell_of[j]]++] = ib[j];
+#pragma omp parallel
+    {
+        int64_t *mine = (int64_t *)calloc((size_t)nbins, sizeof(int64_t));
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < na; i++) {
+            int64_t a = ia[i];
+            int cx = (int)(pos[2 * a] / wx), cy = (int)(pos[2 * a + 1] / wy);
+            if (cx >= ncx) cx = ncx - 1;
+            if (cy >= ncy) cy = ncy - 1;
+            for (int ox = -1; ox <= 1; ox++)
+                for (int oy = -1; oy <= 1; oy++) {
+                    int64_t c = (int64_t)((cx + ox + ncx) % ncx) * ncy + (cy + oy + ncy) % ncy;
+                    for (int64_t s = start[c]; s < start[c + 1]; s++) {
+                        int64_t b = order[s];
+                        if (a == b) continue;
+                        double r = pbc_dist(pos[2 * a], pos[2 * a + 1], pos[2 * b], pos[2 * b + 1], boxx, boxy);
+                        int k = hist_bin(r, lo, hi, nbins, edges);
+                        if (k >= 0) mine[k] += 1;
+                    }
+                }
+        }
+#pragma omp critical
+        for (int k = 0; k < nbins; k++) count[k] += mine[k];
+        free(mine);
+    }
+    free(start); free(cell_of); free(order); free(fill);
+    return 0;
 }

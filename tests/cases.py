@@ -50,6 +50,17 @@ CASES = {
                                                   "TLCL2": ["P1", "P3"]}},
                       "leaflets": {"update_interval": 3}},
         frame_range=(2, -2, 2)),
+    # one bead per listed atom name (com_frame.py:188-231): beads of one residue interleave in the
+    # atom order, bead masses differ, leaflets are built from the beads
+    "multi_bead": dict(
+        spec=syn.BilayerSpec(80, MIX3, seed=19, box_z=72.0, npt=1e-3), n_frames=8,
+        analyses=["msd msd_1", "msd msd_dope resname DOPE leaflet lower",
+                  "nnf nnf_a resname_1 POPC resname_2 DOPE n_neighbors 4",
+                  "com_lateral_rdf rdf resname_1 all resname_2 TLCL2 n_bins 30 range_outer 32.0",
+                  "thickness_leaflet_distance tld"],
+        rep_settings={"com_frame": {"name_dict": {"POPC": ["P", "N"], "DOPE": ["N", "P"],
+                                                  "TLCL2": ["P1", "P3"]},
+                                    "multi_bead": True}}),
     # first frames of BASELINE configs[1]: 512-lipid POPC CG bilayer, MSD + multi-origin MSD
     "c2_prefix": dict(
         spec=syn.config_spec("C2")[0], n_frames=60,

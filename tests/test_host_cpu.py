@@ -197,3 +197,45 @@ def test_plot_protocol_registry_matches_reference_strings():
     ba.remove_plot("msd_a")
     assert ba.get_plot_ids() == ["msd_l", "apl_p", "bt_p"]
     ba.print_plot_protocol()
+
+
+def test_diffusion_estimators_match_reference_fixture():
+    """pybilt/diffusion/diffusion_coefficients.py:17-167 executed by oracle/make_golden.py
+    (tests/golden/estimators.npz): Einstein, linear fit (slope and its error) and the anomalous fit,
+    2-D and 3-D, with and without time_range, on the c2_prefix msd rows and on a noisy line."""
+    import os
+    import warnings
+    from pybilt_b200 import diffusion as dc
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "estimators.npz"))
+    for key in ("c2", "line"):
+        t, y = g[key + "/t"], g[key + "/msd"]
+        for tag in ("full", "range"):
+            tr = g[f"{key}/{tag}/time_range"]
+            tr = None if np.isnan(tr).any() else [float(tr[0]), float(tr[1])]
+            for dim in (2, 3):
+                assert np.isclose(dc.diffusion_coefficient_Einstein(t, y, dim=dim, time_range=tr),
+                                  g[f"{key}/{tag}/einstein/{dim}"], rtol=1e-14, atol=0)
+                assert np.allclose(dc.diffusion_coefficient_linear_fit(t, y, dim=dim, time_range=tr),
+                                   g[f"{key}/{tag}/linear/{dim}"], rtol=1e-12, atol=0)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    p = dc.diffusion_coefficient_anomalous_fit(t[1:], y[1:], dim=dim, time_range=tr)
+                assert np.allclose(p, g[f"{key}/{tag}/anomalous/{dim}"], rtol=1e-9, atol=0)
+
+
+def test_host_blas_ddot_fuses_like_the_fixtures_assume():
+    """The reference's np.dot(d, d) of two float64 goes through the host BLAS' ddot; the golden
+    fixtures (and the kernels' d2 = fma(dy, dy, dx*dx)) encode the FMA accumulation of OpenBLAS' x86
+    kernels (DESIGN.md "Arithmetic").  A host whose BLAS does not fuse would make the oracle differ
+    from the fixtures by 1 ulp at bin-edge ties: detect that here instead of in a parity test."""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    v = rng.normal(0, 30, (4000, 2))
+    fused = plain = 0
+    for a, b in v:
+        got = float(np.dot(np.array([a, b]), np.array([a, b])))
+        want_fma = float(Fraction(b) * Fraction(b) + Fraction(a * a))     # one rounding: fma(b, b, a*a)
+        fused += got == want_fma
+        plain += got == a * a + b * b
+    assert fused == len(v), "np.dot(float64[2]) is not fma(b, b, a*a) on this host (%d/%d; a*a+b*b: %d)" % (
+        fused, len(v), plain)

@@ -138,3 +138,32 @@ def test_port_leaflet_distance_raises_with_update_interval():
     top, traj = cases.make_inputs("leaflet_dist")
     with pytest.raises(IndexError):
         port.run(top, traj, ["thickness_leaflet_distance tld"], {"leaflets": {"update_interval": 3}})
+
+
+def test_large_shape_oracle_variants_equal_the_dense_ones():
+    """portc.c's cell-list RDF loop and matrix-free 24-neighbour table (used for the named shapes
+    C3-C5 in tests/test_gpu_named_shapes.py) are the dense loops reorganised: identical outputs."""
+    from pybilt_b200 import synthetic as syn
+    spec = syn.BilayerSpec(2048, cases.CG3, seed=17)
+    top, traj = syn.generate(spec, 2)
+    _o, reps = port.run(top, traj, [], {}, return_reps=True)
+    types = list(top.resnames)
+    box = np.ascontiguousarray(traj.dimensions[:, :3])
+    for kw in (dict(resname_1="all", resname_2="all", n_bins=25, range_outer=25.0),
+               dict(resname_1="POPC", resname_2="DOPE", leaflet="lower", n_bins=80, range_outer=40.0),
+               dict(resname_1="CHOL", resname_2="all", n_bins=30, range_inner=2.0, range_outer=31.0)):
+        (_g, _b), dense = port.rdf(reps["com"], reps["labels"], types, box, **kw)
+        (_g, _b), cl = port.rdf(reps["com"], reps["labels"], types, box, cells=True, **kw)
+        assert dense.sum() > 0 and np.array_equal(dense, cl)
+    a = port.lipid_grid_frame(reps["com"][1], reps["com_unwrap"][1], reps["labels"][1], box[1], 32, 32)
+    b = port.lipid_grid_frame(reps["com"][1], reps["com_unwrap"][1], reps["labels"][1], box[1], 32, 32,
+                              lean_knn=True)
+    for k in ("knn_upper", "knn_lower"):
+        assert np.array_equal(a[k], b[k])
+    for k in ("upper", "lower"):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1])
+    # a COM outside the box: the cell-list form refuses instead of miscounting
+    com = reps["com"].copy()
+    com[0, 0, 0] = -1.0
+    with pytest.raises(ValueError):
+        port.rdf(com, reps["labels"], types, box, resname_1="all", resname_2="all", cells=True)
