@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 6
+#define PBK_ABI_VERSION 7
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -142,6 +142,32 @@ int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, const doubl
                      void *scratch, int64_t scratch_bytes, double *com, double *com_unwrap,
                      double *mem_com, uint8_t *labels, int32_t *status, void *stream);
 int pbk_sm_count(const pbk_ctx *ctx);
+
+/* ---- A1-A4 + B1 streamed  (large systems: a frame does not fit in shared memory) -----------
+ * Same results as pbk_unwrap_images + pbk_membrane_com + pbk_lipid_com + pbk_leaflets with TWO
+ * reads of the positions and no per-frame image-count array.  Sweep A (one CTA per summation
+ * leaf, frames in time order, the leaf's slice of every frame arriving by TMA bulk copy in a
+ * shared-memory ring) decides the image counts, forms the NumPy-pairwise leaf sums of m*f64(u)
+ * -> mem_com, and leaves the image counts of every 32nd frame behind; sweep B (a thread per
+ * lipid, axis and 32-frame chunk) repeats the recurrence from there and forms both COMs; the
+ * labels come from the compact bilayer-normal components.
+ * max_bead_atoms: the largest seg[i+1]-seg[i] (<= 800, else PBK_EUNSUPPORTED).  No atom may
+ * belong to two beads.  phase / init_images / net_images / net_frames as for pbk_reduce_fused
+ * (phase 1 = image counts only, which is also how a shard advances u_state without reducing;
+ * net_images may also be asked for in phase 2 / 3: the image counts of frame net_frames-1);
+ * frame0 / update_interval / prev_labels as for pbk_leaflets.
+ * scratch: pbk_reduce_stream_scratch_bytes(F, M, N, L, K). */
+int pbk_reduce_stream_scratch_bytes(int64_t F, int64_t M, int64_t N, int32_t L, int32_t K, int64_t *bytes);
+int pbk_reduce_stream(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
+                      const int32_t *seg, const int32_t *gather, const double *lipid_mass,
+                      int32_t max_bead_atoms, const int32_t *leaf_start, const int32_t *leaf_len,
+                      int32_t L, const int32_t *node_left, const int32_t *node_right, int32_t K,
+                      const int32_t *level_off, int32_t H, double total_mass, float *u_state,
+                      int first_frame, int64_t F, int64_t M, int64_t N, int norm, int phase,
+                      const int32_t *init_images, int32_t *net_images, int64_t net_frames,
+                      int64_t frame0, int update_interval, const uint8_t *prev_labels, void *scratch,
+                      int64_t scratch_bytes, double *com, double *com_unwrap, double *mem_com,
+                      uint8_t *labels, int32_t *status, void *stream);
 
 /* ---- B1  leaflet assignment -------------------------------------------------------------
  * BilayerAnalyzer._build_leaflets             pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847

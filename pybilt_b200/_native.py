@@ -45,6 +45,13 @@ _SIGNATURES = {
                                  c_int32, c_double, c_void_p, c_int, c_int64, c_int64, c_int64, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pbk_reduce_stream_scratch_bytes": (c_int, [c_int64, c_int64, c_int64, c_int32, c_int32,
+                                                ctypes.POINTER(c_int64)]),
+    "pbk_reduce_stream": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                  c_int32, c_double, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int,
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbk_leaflets": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
     "pbk_leaflet_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
@@ -97,7 +104,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.pbk_abi_version() != 6:
+        if lib.pbk_abi_version() != 7:
             raise RuntimeError("pybilt_b200: libpbk ABI version mismatch")
         _lib = lib
     return _lib

@@ -825,11 +825,14 @@ class BilayerAnalyzer(object):
         # owned frames (net_frames), where the next rank's back halo sits
         eng.push(xd, bd, phase=1, net_out=net, net_frames=n_a)
         off = pd.image_offsets(net)
-        eng.push(xd, bd, phase=2, init_images=off, net_frames=n_a)
+        seen = torch.zeros_like(net)
+        eng.push(xd, bd, phase=2, init_images=off, net_frames=n_a, net_out=seen)
         if not eng.used_fused:
-            # generic kernels: the image counts of the last owned frame must be the rank-local ones
-            # plus the offsets (the fused path checks its own decisions: PBK_ST_UNWRAP_AMBIGUOUS)
-            seen = eng.d_img[n_a - 1].to(torch.int32)
+            # streamed / generic kernels: the image counts of the last owned frame must be the
+            # rank-local ones plus the offsets (the fused path checks its own decisions:
+            # PBK_ST_UNWRAP_AMBIGUOUS)
+            if not eng.used_stream:
+                seen = eng.d_img[n_a - 1].to(torch.int32)
             if not bool(torch.equal(seen, off + net)):
                 raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
                                    "makes the shard decomposition ambiguous; run on one rank")

@@ -208,6 +208,15 @@ k_mem_tree(const int32_t *__restrict__ node_left, const int32_t *__restrict__ no
     }
 }
 
+int pbk_launch_mem_tree(pbk_ctx *ctx, const int32_t *node_left, const int32_t *node_right, const int32_t *level_off,
+                        int32_t H, int32_t L, int32_t K, double total_mass, int64_t F, double *node_vals,
+                        double *mem_com, cudaStream_t st)
+{
+    k_mem_tree<<<(unsigned)F, 256, 0, st>>>(node_left, node_right, level_off, H, L, K, total_mass, node_vals, mem_com);
+    PBK_CHECK_LAUNCH(ctx, "k_mem_tree");
+    return PBK_OK;
+}
+
 extern "C" int pbk_membrane_com(pbk_ctx *ctx, const float *x, const float *box, const int16_t *img,
                                 const double *mass, int64_t F, int64_t M,
                                 const int32_t *leaf_start, const int32_t *leaf_len, int32_t L,

@@ -76,6 +76,19 @@ def build_bead_layout(masses, names, resindex, resnames, resids, name_dict=None,
     return BeadLayout(seg, gather, types, np.asarray(rid, dtype=np.int64), bead_mass)
 
 
+def stream_bead_limit(layout: BeadLayout):
+    """Largest number of atoms in a bead when the streamed reduction (pbk_reduce_stream,
+    include/pbk.h) can take the layout, else None (an atom in two beads, an empty bead, or a
+    bead of more than 800 atoms)."""
+    seg = layout.seg.astype(np.int64)
+    sizes = np.diff(seg)
+    if len(sizes) == 0 or sizes.min() < 1 or sizes.max() > 800:
+        return None
+    if layout.gather is not None and len(np.unique(layout.gather)) != len(layout.gather):
+        return None
+    return int(sizes.max())
+
+
 def rdf_thresholds(edges: np.ndarray) -> np.ndarray:
     """Histogram edges expressed on d^2 so that binning needs no square root.
 
@@ -120,7 +133,8 @@ class LipidReductionEngine:
 
     def __init__(self, masses, layout: BeadLayout, n_frames: int, device: int = 0, norm: int = 2,
                  leaflet_update_interval: int = 1, batch_frames: Optional[int] = None,
-                 scratch_bytes: int = 4 << 30, allow_fused: bool = True, comtraj_rules: bool = False):
+                 scratch_bytes: int = 4 << 30, allow_fused: bool = True, comtraj_rules: bool = False,
+                 allow_stream: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pybilt_b200: a CUDA device is required (no CPU fallback)")
         self.ctx = _native.Context(device)
@@ -145,13 +159,22 @@ class LipidReductionEngine:
         self.d_node_left = torch.from_numpy(plan.node_left).to(d) if plan.n_nodes else torch.zeros(1, dtype=torch.int32, device=d)
         self.d_node_right = torch.from_numpy(plan.node_right).to(d) if plan.n_nodes else torch.zeros(1, dtype=torch.int32, device=d)
         self.d_level_off = torch.from_numpy(plan.level_off).to(d)
-        # per-frame scratch: image counts (6 B/atom) + tree nodes
-        per_frame = self.M * 6 + (plan.n_leaves + plan.n_nodes) * 24
+        # streamed reduction (frames that do not fit in shared memory): tiles of lipids
+        self.comtraj_rules = bool(comtraj_rules)
+        self.stream_plan = None if (self.comtraj_rules or not allow_stream) else stream_bead_limit(layout)
+        # per-frame scratch: image counts (6 B/atom) + tree nodes (generic kernels), or tree nodes +
+        # compact normal components + tile partials (streamed reduction)
+        nodes = plan.n_leaves + plan.n_nodes
+        if self.stream_plan is not None:
+            per_frame = nodes * 24 + self.N * 8 + self.M // 4 + 64
+        else:
+            per_frame = self.M * 6 + nodes * 24
         if batch_frames is None:
             batch_frames = max(1, min(self.F, scratch_bytes // max(per_frame, 1)))
         self.B = int(batch_frames)
-        self.d_img = torch.empty((self.B, self.M, 3), dtype=torch.int16, device=d)
-        self.d_nodes = torch.empty((self.B, plan.n_leaves + plan.n_nodes, 3), dtype=torch.float64, device=d)
+        self._d_img = None
+        self._d_nodes = None
+        self._stream_scratch = None
         self.d_u_state = torch.empty((self.M, 3), dtype=torch.float32, device=d)
         self.d_status = torch.zeros(1, dtype=torch.int32, device=d)
         # resident representations of every analysed frame
@@ -166,12 +189,53 @@ class LipidReductionEngine:
         self.launches = 0
         # COMTraj arithmetic (pybilt/com_trajectory/COMTraj.py:1067-1085): scalar float32 unwrap
         # rule and membrane COM accumulated atom by atom; only the generic kernels implement it
-        self.comtraj_rules = bool(comtraj_rules)
         self.allow_fused = bool(allow_fused) and not self.comtraj_rules
         self.fused_supported = True       # cleared when libpbk answers PBK_EUNSUPPORTED
         self.used_fused = False
+        self.used_stream = False
         self._fused_scratch = None
         self._rdf_tables = {}
+
+    # scratch of the generic kernels, allocated when they are first used
+    @property
+    def d_img(self) -> torch.Tensor:
+        if self._d_img is None:
+            self._d_img = torch.empty((self.B, self.M, 3), dtype=torch.int16, device=self.dev)
+        return self._d_img
+
+    @property
+    def d_nodes(self) -> torch.Tensor:
+        if self._d_nodes is None:
+            p = self.plan
+            self._d_nodes = torch.empty((self.B, p.n_leaves + p.n_nodes, 3), dtype=torch.float64, device=self.dev)
+        return self._d_nodes
+
+    def _stream_scratch_for(self, nb: int) -> torch.Tensor:
+        import ctypes
+        need = ctypes.c_int64(0)
+        p = self.plan
+        self.ctx.lib.pbk_reduce_stream_scratch_bytes(nb, self.M, self.N, p.n_leaves, p.n_nodes, ctypes.byref(need))
+        if self._stream_scratch is None or self._stream_scratch.numel() < need.value:
+            self._stream_scratch = torch.empty(int(need.value), dtype=torch.uint8, device=self.dev)
+        return self._stream_scratch
+
+    def _stream_call(self, xb, bb, nb, phase, init_b, net_out, net_frames, g0, prev):
+        """pbk_reduce_stream over one batch; False when libpbk has no streamed path for the shape."""
+        p = self.plan
+        scratch = self._stream_scratch_for(nb)
+        ok = self.ctx.try_call(
+            "pbk_reduce_stream", xb.data_ptr(), bb.data_ptr(), self.d_mass.data_ptr(), self.d_seg.data_ptr(),
+            _ptr(self.d_gather), self.d_bead_mass.data_ptr(), int(self.stream_plan), self.d_leaf_start.data_ptr(),
+            self.d_leaf_len.data_ptr(), p.n_leaves, self.d_node_left.data_ptr(), self.d_node_right.data_ptr(),
+            p.n_nodes, self.d_level_off.data_ptr(), p.n_levels, self.total_mass, self.d_u_state.data_ptr(),
+            0 if self.stream_started else 1, nb, self.M, self.N, self.norm, int(phase), _ptr(init_b), _ptr(net_out),
+            int(net_frames), g0 + self.row_offset, self.update_interval, prev, scratch.data_ptr(),
+            int(scratch.numel()), self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
+            self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(), self.d_status.data_ptr(), self.stream_ptr())
+        if ok:
+            self.launches += 5 if (phase & 2) else 2
+            self.used_stream = True
+        return ok
 
     def _fused_scratch_for(self, nb: int) -> torch.Tensor:
         import ctypes
@@ -208,6 +272,9 @@ class LipidReductionEngine:
         st = self.stream_ptr()
         for b0 in range(0, int(x.shape[0]), self.B):
             xb, bb = x[b0:b0 + self.B], box[b0:b0 + self.B]
+            if self.stream_plan is not None and self._stream_call(xb, bb, int(xb.shape[0]), 1, None, None, 0, 0, None):
+                self.stream_started = True
+                continue
             self.ctx.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(),
                           0 if self.stream_started else 1, None, 1 if self.comtraj_rules else 0,
                           int(xb.shape[0]), self.M, self.d_img.data_ptr(), self.d_status.data_ptr(), st)
@@ -295,6 +362,13 @@ class LipidReductionEngine:
                     continue
                 self.allow_fused = False          # frame does not fit in shared memory
                 self.fused_supported = False
+            if self.stream_plan is not None:
+                if self._stream_call(xb, bb, nb, phase, init_b, net_out if b0 == 0 else None, net_frames, g0, prev):
+                    if phase & 2:
+                        self.n_done += nb
+                        self.stream_started = True
+                    continue
+                self.stream_plan = None           # shape outside the streamed path: generic kernels from here on
             if phase == 1:
                 # generic path: a plain unwrap of the shard; its last row is the net change
                 c.call("pbk_unwrap_images", xb.data_ptr(), bb.data_ptr(), self.d_u_state.data_ptr(), 1, None,

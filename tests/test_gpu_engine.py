@@ -27,7 +27,7 @@ def rel_close(a, b, rtol, atol=0.0):
     assert (err <= lim).all(), f"max rel err {np.max(err / np.maximum(np.abs(b), 1e-300))}"
 
 
-def run_engine(name, batch_frames=None, fused=True):
+def run_engine(name, batch_frames=None, fused=True, stream=True):
     from pybilt_b200 import engine as eng
     c = cases.CASES[name]
     top, traj = cases.make_inputs(name)
@@ -38,7 +38,7 @@ def run_engine(name, batch_frames=None, fused=True):
                                    cf.get("name_dict"), cf.get("multi_bead", False))
     e = eng.LipidReductionEngine(top.masses, layout, len(fr), norm=2,
                                  leaflet_update_interval=lf.get("update_interval", 1),
-                                 batch_frames=batch_frames, allow_fused=fused)
+                                 batch_frames=batch_frames, allow_fused=fused, allow_stream=stream)
     x = torch.from_numpy(np.ascontiguousarray(traj.positions[fr])).cuda()
     box = torch.from_numpy(np.ascontiguousarray(traj.dimensions[fr][:, :3])).cuda()
     e.push(x, box)
@@ -48,18 +48,23 @@ def run_engine(name, batch_frames=None, fused=True):
 
 @pytest.mark.parametrize("name", list(cases.CASES))
 @pytest.mark.parametrize("batch", [None, 5])
-@pytest.mark.parametrize("fused", [True, False])
-def test_representations_match_reference(name, batch, fused):
+@pytest.mark.parametrize("path", ["fused", "stream", "generic"])
+def test_representations_match_reference(name, batch, path):
     from pybilt_b200.engine import FusedPathRejected
     gold = load(name)
+    fused = path == "fused"
     try:
-        e, top, traj, fr, layout = run_engine(name, batch, fused)
+        e, top, traj, fr, layout = run_engine(name, batch, fused, stream=path != "generic")
     except FusedPathRejected:
         # only the adversarial case (jumps of many box lengths) may be refused by the fast path
         assert fused and name == "big_steps"
         return
     if fused and name not in ("big_steps",):
         assert e.used_fused
+    if path == "stream":
+        assert e.used_stream and not e.used_fused
+    if path == "generic":
+        assert not e.used_stream and not e.used_fused
     com = e.com.cpu().numpy()
     comu = e.com_unwrap.cpu().numpy()
     rel_close(com, gold["rep/com"], COM_RTOL)
