@@ -33,6 +33,8 @@
 // jump that stays clear of +-L/2 by the rounding bound keeps the count; everything else runs
 // the reference's float64 loops.  Counts beyond +-127 switch the owning thread to the exact
 // rule for every frame (the bound is derived for |s| <= 127).
+#include <stdlib.h>
+
 #include "pbk_common.cuh"
 
 // pbk_com.cu: combines leaf sums [F][L+K][3] along the recursion tree -> mem_com[F][3]
@@ -44,30 +46,31 @@ int pbk_launch_mem_tree(pbk_ctx *ctx, const int32_t *node_left, const int32_t *n
 // helpers
 // ------------------------------------------------------------------------------------------
 static __device__ __forceinline__ uint32_t sw_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-static __device__ __forceinline__ void sw_mbar_init(uint64_t *bar, uint32_t count)
+// (all helpers take 32-bit shared-window addresses formed ONCE per kernel: converting a generic
+//  pointer inside a loop costs an S2R SR_CgaCtaId round trip every time)
+static __device__ __forceinline__ void sw_mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-static __device__ __forceinline__ void sw_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+static __device__ __forceinline__ void sw_mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-static __device__ __forceinline__ void sw_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+static __device__ __forceinline__ void sw_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sw_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sw_smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-static __device__ __forceinline__ void sw_cp4(void *dst, const void *src)
+static __device__ __forceinline__ void sw_cp4(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sw_smem_u32(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-static __device__ __forceinline__ void sw_cp_arrive(uint64_t *bar)
+static __device__ __forceinline__ void sw_cp_arrive(uint32_t bar)
 {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sw_smem_u32(bar)) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-static __device__ __forceinline__ bool sw_mbar_wait(uint64_t *bar, uint32_t parity)
+static __device__ __forceinline__ bool sw_mbar_wait(uint32_t a, uint32_t parity)
 {
-    const uint32_t a = sw_smem_u32(bar);
     for (int it = 0; it < (1 << 20); it++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -129,209 +132,361 @@ __global__ void k_box_table(const float *__restrict__ box, int64_t F, float *__r
 }
 
 // ------------------------------------------------------------------------------------------
-// k_sweep_a
+// k_sweep_a: persistent CTAs over tasks (leaf, block of SW_CHUNK frames) in task order
+// task = block * L + leaf.  Task (leaf, b) starts from the image counts task (leaf, b-1) left in
+// `snap` (a flag per leaf says how many blocks are done); since every CTA takes its tasks in
+// increasing order and all CTAs are resident, the lowest unfinished task can always run.
 // ------------------------------------------------------------------------------------------
-#define SW_CHUNK 32                  // frames per time chunk of the second sweep
-#define SA_THREADS 128
-#define SA_DEPTH 6
+#define SW_CHUNK 32                  // frames per block of sweep A = frames per time chunk of sweep B
+#define SA_THREADS 160                  // warps 0-2 columns, warp 3 reducer, warp 4 producer (TMA issue, box rows)
+#define SA_SUB 4                     // frames per barrier interval = frames per group of the shared ring
+#define SA_GROUPS 3                  // groups in the ring: SA_GROUPS - 1 sub-blocks of positions in flight per CTA
 #define SA_LEAF_FLOATS 384           // 128 atoms x 3
 
 struct SweepAParams {
     const float *x; const float *boxtab; const double *mass;
     const int32_t *leaf_start, *leaf_len;
-    int L, nodes_per_frame;
+    int L, nodes_per_frame, nblk;
     const float *prev0;             // u_state (later batches) or x (first frame: frame 0 is its own reference)
     const int32_t *init_images;
-    int64_t F; int64_t M; int64_t net_frame;
+    int F; int64_t M; int net_frame;
     int32_t *net_images; float *u_out; double *node_vals; int32_t *status;
-    int16_t *snap;                  // [n_chunks][3M] image counts at frame c*SW_CHUNK - 1 (row 0 unused)
+    int16_t *snap;                  // [nblk][3M] image counts at frame b*SW_CHUNK - 1 (row 0 unused)
+    int *flags;                     // [L] blocks finished per leaf
     int store_sums;
 };
 
+// exact reference rule for one component (rare): new image count as a float
+static __device__ __noinline__ float sa_exact(float xv, float pv, float sf, float Lc, float Lp, int *bad)
+{
+    const int s = (int)sf;
+    return (float)sw_shift(__fsub_rn(xv, pbk_unwrapped(pv, s, Lp)), Lc, bad);
+}
+
+// phase cycle counters (tools/prof_sweep.py), compiled in with -DPBK_SWEEP_PROFILE only
+#ifdef PBK_SWEEP_PROFILE
+__device__ unsigned long long g_sa_prof[16];
+// (a barrier only blocks at the next use of protected state: the clock read is made to depend on a
+//  shared-memory load issued after it)
+#define SA_MARK(i) do { long long n_; const int dep_ = *(volatile int *)&s_full[0]; \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "r"(dep_)); pc[i] += n_ - tk; tk = n_; } while (0)
+extern "C" int pbk_debug_sweep_prof(unsigned long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_sa_prof, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_sa_prof, z, sizeof(z));
+    return 0;
+}
+#else
+#define SA_MARK(i) do { } while (0)
+#endif
+
+// one frame of the reducing phase (generic: any number of pending frames)
+static __device__ __forceinline__ void sa_reduce_one(const double *pp, int lane, int nq, int n, int s1, int s2, int s4,
+                                                     double *out)
+{
+    double r = 0.0;
+    if (lane < 24 && nq > 0) {
+        r = pp[lane];
+        for (int q = 1; q < nq; q++) r = __dadd_rn(r, pp[q * 24 + lane]);
+    }
+    const bool act = lane < 24;
+    double o = __shfl_sync(0xffffffffu, r, act ? s1 : lane);
+    r = __dadd_rn(r, o);
+    o = __shfl_sync(0xffffffffu, r, act ? s2 : lane);
+    r = __dadd_rn(r, o);
+    o = __shfl_sync(0xffffffffu, r, act ? s4 : lane);
+    r = __dadd_rn(r, o);
+    if (lane < 3) {
+        int i0 = 8 * nq;
+        if (nq == 0) { r = 0.0; i0 = 0; }
+        for (int i = i0; i < n; i++) r = __dadd_rn(r, pp[3 * i + lane]);
+        out[lane] = r;
+    }
+}
+
 template <bool BULK>
-__global__ void __launch_bounds__(SA_THREADS)
+__global__ void __launch_bounds__(SA_THREADS, 4)
 k_sweep_a(SweepAParams P)
 {
-    __shared__ __align__(128) float s_x[SA_DEPTH][SA_LEAF_FLOATS];
-    __shared__ __align__(16) double s_p[2][SA_LEAF_FLOATS];
-    __shared__ uint64_t s_full[SA_DEPTH];
+#ifdef PBK_SWEEP_PROFILE
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tk = clock64();
+#endif
+    __shared__ __align__(128) float s_x[SA_GROUPS][SA_SUB][SA_LEAF_FLOATS];
+    __shared__ __align__(16) double s_p[2][SA_SUB][SA_LEAF_FLOATS];
+    __shared__ uint64_t s_full[SA_GROUPS];       // one mbarrier per group
+    __shared__ float s_boxes[2][SW_CHUNK][8];    // box rows of the task's frames (no global load inside the frame loop);
+                                                 // the producer warp stages the next task's rows during the current one
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int leaf = blockIdx.x;
-    const int ls = P.leaf_start[leaf], n = P.leaf_len[leaf];
-    const int nfl = 3 * n;                       // floats of the leaf per frame
-    const int ncol = (nfl + 3) >> 2;
+    const int G = gridDim.x;
+    const int n_tasks = P.L * P.nblk;
     const int64_t C3 = 3 * P.M;
-    const float *xl = P.x + 3 * (int64_t)ls;     // the leaf inside frame 0
     int bad = 0;
 
+    const uint32_t a_full = sw_smem_u32(&s_full[0]), a_x = sw_smem_u32(&s_x[0][0][0]);
     if (tid == 0)
-        for (int d = 0; d < SA_DEPTH; d++) sw_mbar_init(&s_full[d], BULK ? 1u : 32u);
+        for (int g = 0; g < SA_GROUPS; g++) sw_mbar_init(a_full + 8u * g, BULK ? 1u : 32u);
+    int prev_leaf = -1, prev_blk = -1;           // the task before (column state stays in registers when the leaf continues)
     sw_fence_async();
     __syncthreads();
 
-    auto issue = [&](int64_t t) {                // warp 3 only
-        const int slot = (int)(t % SA_DEPTH);
-        const float *src = xl + t * C3;
+    // ---- prefetch cursor (warp 4): one group (= one sub-block of frames) per call, two groups ahead
+    // of the arithmetic, across tasks.  (Leaf geometry is reloaded only when the cursor moves to
+    // another task: no global load per sub-block.)
+    int pf_task = blockIdx.x, pf_left = 0, pf_grp = 0, pf_nfl = 0;
+    const float *pf_src = nullptr;
+    auto prefetch = [&]() {
+        if (pf_left == 0) {
+            if (pf_task >= n_tasks) return;
+            const int leaf = pf_task % P.L, blk = pf_task / P.L;
+            const int f0 = blk * SW_CHUNK;
+            pf_left = min(P.F, f0 + SW_CHUNK) - f0;
+            pf_nfl = 3 * P.leaf_len[leaf];
+            pf_src = P.x + (int64_t)f0 * C3 + 3 * (int64_t)P.leaf_start[leaf];
+            pf_task += G;
+        }
+        const int nf = min(SA_SUB, pf_left);
+        const uint32_t bar = a_full + 8u * (pf_grp % SA_GROUPS), dst = a_x + (uint32_t)(pf_grp % SA_GROUPS) * (SA_SUB * SA_LEAF_FLOATS * 4u);
         if (BULK) {
             if (lane == 0) {
-                sw_mbar_expect_tx(&s_full[slot], (uint32_t)nfl * 4u);
-                sw_bulk_g2s(&s_x[slot][0], src, (uint32_t)nfl * 4u, &s_full[slot]);
+                sw_mbar_expect_tx(bar, (uint32_t)(nf * pf_nfl) * 4u);
+                for (int u = 0; u < nf; u++)
+                    sw_bulk_g2s(dst + (uint32_t)u * (SA_LEAF_FLOATS * 4u), pf_src + (int64_t)u * C3, (uint32_t)pf_nfl * 4u, bar);
             }
         } else {
-            for (int c = lane; c < nfl; c += 32) sw_cp4(&s_x[slot][c], src + c);
-            sw_cp_arrive(&s_full[slot]);
+            for (int u = 0; u < nf; u++)
+                for (int c = lane; c < pf_nfl; c += 32) sw_cp4(dst + (uint32_t)u * (SA_LEAF_FLOATS * 4u) + 4u * c, pf_src + (int64_t)u * C3 + c);
+            sw_cp_arrive(bar);
         }
+        pf_grp++;
+        pf_left -= nf;
+        pf_src += (int64_t)nf * C3;
     };
-    if (warp == 3)
-        for (int64_t t = 0; t < P.F && t < SA_DEPTH; t++) issue(t);
+    if (warp == 4)
+        for (int g = 0; g < SA_GROUPS; g++) prefetch();
 
-    // ---- column role (warps 0-2) -------------------------------------------------------------
-    const int col = tid;
-    const bool col_on = warp < 3 && col < ncol;
-    const int nvalid = col_on ? min(4, nfl - 4 * col) : 0;
-    const int k0 = col % 3;                       // axis of comp e is (k0 + e) % 3
-    float pv[4] = {0.f, 0.f, 0.f, 0.f};
-    int sc[4] = {0, 0, 0, 0};
-    float sf[4] = {0.f, 0.f, 0.f, 0.f};
-    double ma = 0.0, mb = 0.0;
+    // roles.  Warps 0-2 (columns): warp = axis k, lane = atoms lane + 32 j.  Warp 3 (reducer), lanes 0-23:
+    // (accumulator rj, axis rk) of the frames of the sub-block before, their chains interleaved.
+    const int k = warp < 3 ? warp : 0;             // a column warp = one axis; its lane owns atoms lane, lane+32, lane+64, lane+96
+    const int rj = lane / 3, rk = lane % 3;        // (stride-3 shared accesses: conflict-free for both floats and doubles)
+    const int s1 = ((rj ^ 1) * 3 + rk) & 31, s2 = ((rj ^ 2) * 3 + rk) & 31, s4 = ((rj ^ 4) * 3 + rk) & 31;
+    int sub = 0;                                  // sub-blocks processed by this CTA (group = sub % SA_GROUPS)
+    float pv[4] = {0.f, 0.f, 0.f, 0.f}, sf[4] = {0.f, 0.f, 0.f, 0.f}, Lp = 0.f;     // column state
+    double mj[4] = {0.0, 0.0, 0.0, 0.0};
+    int cj[4] = {0, 0, 0, 0};
     int wide = 0;
-    if (col_on) {
-        const int a0 = ls + (4 * col) / 3;
-        ma = P.mass[a0];
-        mb = (a0 + 1 < ls + n) ? P.mass[a0 + 1] : 0.0;
-        const float *p0 = P.prev0 + 3 * (int64_t)ls + 4 * col;
+
+    int tpar = 0;
+    for (int task = blockIdx.x; task < n_tasks; task += G, tpar ^= 1) {
+        const int leaf = task % P.L, blk = task / P.L;
+        const int f0 = blk * SW_CHUNK, f1 = min(P.F, f0 + SW_CHUNK);
+        const int ls = P.leaf_start[leaf], n = P.leaf_len[leaf];
+        const int nq = n >= 8 ? n / 8 : 0;
+        float (*s_box)[8] = s_boxes[tpar];
+        if (task == (int)blockIdx.x)
+            for (int r = tid; r < (f1 - f0) * 8; r += SA_THREADS) s_box[r >> 3][r & 7] = P.boxtab[f0 * 8 + r];
+        if (blk > 0 && tid == 0 && !(leaf == prev_leaf && blk == prev_blk + 1)) {
+            int it = 0;
+            while (*(volatile int *)(P.flags + leaf) < blk && ++it < (1 << 26)) __nanosleep(32);
+            if (it >= (1 << 26)) bad |= 2;
+            __threadfence();
+        }
+        __syncthreads();
+        if (warp == 4 && task + G < n_tasks) {       // box rows of the next task
+            const int nb = (task + G) / P.L;
+            const int g0 = nb * SW_CHUNK, g1 = min(P.F, g0 + SW_CHUNK);
+            for (int r = lane; r < (g1 - g0) * 8; r += 32) s_boxes[tpar ^ 1][r >> 3][r & 7] = P.boxtab[g0 * 8 + r];
+        }
+        SA_MARK(0);      // task start: box rows, flag wait
+        // ---- column state ---------------------------------------------------------------------
+        const int nval = warp < 3 ? max(0, min(4, (n - lane + 31) >> 5)) : 0;
+        const bool cont = leaf == prev_leaf && blk == prev_blk + 1;
+        prev_leaf = leaf; prev_blk = blk;
+        if (!cont) { wide = 0; Lp = P.boxtab[(blk == 0 ? 0 : f0 - 1) * 8 + k]; }
+        if (nval > 0 && !cont) {
+            const float *prow = blk == 0 ? P.prev0 : P.x + (int64_t)(f0 - 1) * C3;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (e < nvalid) {
-                pv[e] = p0[e];
-                int s0 = P.init_images ? P.init_images[3 * (int64_t)ls + 4 * col + e] : 0;
+            for (int j = 0; j < 4; j++) {
+                const int a = min(lane + 32 * j, n - 1);        // atoms past the leaf's end repeat its last one with mass 0
+                cj[j] = 3 * a + k;
+                const int64_t gc = 3 * (int64_t)ls + cj[j];
+                mj[j] = (j < nval) ? P.mass[ls + a] : 0.0;
+                pv[j] = prow[gc];
+                int s0 = blk == 0 ? (P.init_images ? P.init_images[gc] : 0) : (int)P.snap[(int64_t)blk * C3 + gc];
                 if (s0 > 32767 || s0 < -32767) { bad |= 1; s0 = 0; }
-                sc[e] = s0;
-                sf[e] = (float)s0;
                 if (s0 > 127 || s0 < -127) wide = 1;
+                sf[j] = (float)s0;
             }
         }
-    }
-    const int n_first = 3 - k0;                   // comps e < n_first belong to the column's first atom
+        const bool has_net = P.net_images && P.net_frame >= f0 && P.net_frame < f1;
+        bool task_slow = false;                   // a box edge >= 2^13 in the task: the float64 unwrap for every frame
+        for (int r = 0; r < f1 - f0; r++) task_slow = task_slow || s_box[r][6] != 0.0f;
 
-    // ---- reducing role (warp 3, lanes 0-23) ---------------------------------------------------
-    const int rj = lane / 3, rk = lane % 3;
-    const bool red_on = warp == 3 && lane < 24;
-    const int nq = n >= 8 ? n / 8 : 0;
-
-    float Lp[3] = {0.f, 0.f, 0.f};
-    float4 nb0 = __ldg(reinterpret_cast<const float4 *>(P.boxtab)), nb1 = __ldg(reinterpret_cast<const float4 *>(P.boxtab) + 1);
-    Lp[0] = nb0.x; Lp[1] = nb0.y; Lp[2] = nb0.z;
-    for (int64_t t = 0; t <= P.F; t++) {
-        if (warp < 3) {
-            if (t < P.F) {
-                const int slot = (int)(t % SA_DEPTH);
-                const float4 b0 = nb0, b1 = nb1;
-                if (t + 1 < P.F) {             // box row of the next frame: its latency hides behind this frame
-                    nb0 = __ldg(reinterpret_cast<const float4 *>(P.boxtab + (t + 1) * 8));
-                    nb1 = __ldg(reinterpret_cast<const float4 *>(P.boxtab + (t + 1) * 8) + 1);
-                }
-                if (!sw_mbar_wait(&s_full[slot], (uint32_t)(t / SA_DEPTH) & 1u)) bad |= 2;
-                if (col_on) {
-                    const float Lc[3] = {b0.x, b0.y, b0.z}, hc[3] = {b0.w, b1.x, b1.y};
-                    const bool Lbig = b1.z != 0.0f;
-                    const float4 v = reinterpret_cast<const float4 *>(&s_x[slot][0])[col];
-                    const float xv[4] = {v.x, v.y, v.z, v.w};
-                    float Le[4], he[4];
+        int pend = 0, pend_t0 = 0;
+        SA_MARK(1);      // state init
+        for (int t0 = f0; t0 < f1 || pend > 0; t0 += SA_SUB) {
+            const int nfu = max(0, min(SA_SUB, f1 - t0));
+            if (warp == 3) {
+                // ---- reducer: NumPy's pairwise leaf sums of the frames of the sub-block before
+                //   r[j] = a[j]; r[j] += a[8q + j];  res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); tail sequentially
+                //   (numpy/_core/src/umath/loops_utils.h.src); the chains of the frames are interleaved
+                if (pend > 0 && P.store_sums) {
+                    const int pb = (sub + 1) & 1;
+                    double *out = P.node_vals + ((int64_t)pend_t0 * P.nodes_per_frame + leaf) * 3;
+                    const int64_t ostr = (int64_t)P.nodes_per_frame * 3;
+                    if (pend == SA_SUB && nq > 0 && (n & 7) == 0) {
+                        double r[SA_SUB];
+                        const int l24 = lane < 24 ? lane : 0;
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int k = (k0 + e) % 3;
-                        Le[e] = k == 0 ? Lc[0] : (k == 1 ? Lc[1] : Lc[2]);
-                        he[e] = k == 0 ? hc[0] : (k == 1 ? hc[1] : hc[2]);
+                        for (int u = 0; u < SA_SUB; u++) r[u] = s_p[pb][u][l24];
+#pragma unroll 4
+                        for (int q = 1; q < nq; q++) {
+#pragma unroll
+                            for (int u = 0; u < SA_SUB; u++) r[u] = __dadd_rn(r[u], s_p[pb][u][q * 24 + l24]);
+                        }
+                        const bool act = lane < 24;
+#pragma unroll
+                        for (int u = 0; u < SA_SUB; u++) r[u] = __dadd_rn(r[u], __shfl_sync(0xffffffffu, r[u], act ? s1 : lane));
+#pragma unroll
+                        for (int u = 0; u < SA_SUB; u++) r[u] = __dadd_rn(r[u], __shfl_sync(0xffffffffu, r[u], act ? s2 : lane));
+#pragma unroll
+                        for (int u = 0; u < SA_SUB; u++) r[u] = __dadd_rn(r[u], __shfl_sync(0xffffffffu, r[u], act ? s4 : lane));
+                        if (lane < 3) {
+#pragma unroll
+                            for (int u = 0; u < SA_SUB; u++) out[u * ostr + lane] = r[u];
+                        }
+                    } else {
+                        for (int u = 0; u < pend; u++) sa_reduce_one(&s_p[pb][u][0], lane, nq, n, s1, s2, s4, out + u * ostr);
                     }
-                    float sl[4];
+                }
+                SA_MARK(2);
+            } else if (warp < 3 && nfu > 0) {
+                // ---- columns: image counts and products m*f64(u) of frames t0 .. t0+nfu-1 -------------
+                const int grp2 = sub % SA_GROUPS, pb2 = sub & 1;
+                if (!sw_mbar_wait(a_full + 8u * grp2, (uint32_t)(sub / SA_GROUPS) & 1u)) bad |= 2;
+                SA_MARK(3);  // waiting for the frames
+                if (nval > 0) {
+                    // Fast path (almost every sub-block): the same-image tests only compare consecutive RAW
+                    // frames, so all SA_SUB frames are tested at once; when every test passes the image
+                    // counts do not change and the 4 x SA_SUB products are independent of each other.
+                    bool fast = nfu == SA_SUB && !wide && !task_slow && !(has_net && P.net_frame >= t0 && P.net_frame < t0 + SA_SUB);
+                    float xa[SA_SUB][4], Lcs[SA_SUB];
+                    if (fast) {
+                        float mn = 3.0e38f, tiny = 3.0e38f;
 #pragma unroll
-                    for (int e = 0; e < 4; e++) sl[e] = (e < nvalid) ? he[e] - fabsf(__fsub_rn(xv[e], pv[e])) : 1.0f;
-                    const float mn = fminf(fminf(sl[0], sl[1]), fminf(sl[2], sl[3]));
-                    if (!(mn > 0.0f) || !(sl[0] > 0.0f) || !(sl[1] > 0.0f) || !(sl[2] > 0.0f) || !(sl[3] > 0.0f) || wide) {
+                        for (int u = 0; u < SA_SUB; u++) {
+                            Lcs[u] = s_box[t0 - f0 + u][k];
+                            const float hc = s_box[t0 - f0 + u][3 + k];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (e < nvalid && (wide || !(sl[e] > 0.0f))) {
-                                const int k = (k0 + e) % 3;
-                                const float Lpk = k == 0 ? Lp[0] : (k == 1 ? Lp[1] : Lp[2]);
-                                const int sn = sw_shift(__fsub_rn(xv[e], pbk_unwrapped(pv[e], sc[e], Lpk)), Le[e], &bad);
-                                sc[e] = sn;
-                                sf[e] = (float)sn;
-                                if (sn > 127 || sn < -127) wide = 1;
+                            for (int j = 0; j < 4; j++) {
+                                xa[u][j] = s_x[grp2][u][cj[j]];
+                                mn = fminf(mn, hc - fabsf(__fsub_rn(xa[u][j], u == 0 ? pv[j] : xa[u - 1][j])));
+                                tiny = fminf(tiny, fabsf(xa[u][j]));
+                            }
+                        }
+                        fast = mn > 0.0f && tiny >= 0.00390625f;
+                    }
+                    if (fast) {
+#pragma unroll
+                        for (int u = 0; u < SA_SUB; u++) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const double pr = __dmul_rn(mj[j], (double)__fmaf_rn(sf[j], Lcs[u], xa[u][j]));
+                                if (nval == 4 || j < nval) s_p[pb2][u][cj[j]] = pr;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) pv[j] = xa[SA_SUB - 1][j];
+                        Lp = Lcs[SA_SUB - 1];
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < SA_SUB; u++) {
+                            if (u < nfu) {
+                                const int t = t0 + u;
+                                const float Lc = s_box[t - f0][k], hc = wide ? -1.0f : s_box[t - f0][3 + k];
+                                const bool slow = s_box[t - f0][6] != 0.0f || wide;
+                                float xv[4], d[4];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) xv[j] = s_x[grp2][u][cj[j]];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) d[j] = hc - fabsf(__fsub_rn(xv[j], pv[j]));
+                                if (!(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) > 0.0f)) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) {
+                                        if (!(d[j] > 0.0f)) {
+                                            sf[j] = sa_exact(xv[j], pv[j], sf[j], Lc, Lp, &bad);
+                                            if (fabsf(sf[j]) > 127.0f) wide = 1;
+                                        }
+                                    }
+                                }
+                                float uu[4];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) uu[j] = __fmaf_rn(sf[j], Lc, xv[j]);
+                                if (!(fminf(fminf(fabsf(xv[0]), fabsf(xv[1])), fminf(fabsf(xv[2]), fabsf(xv[3]))) >= 0.00390625f) || slow) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) uu[j] = sw_unwrap_slow(xv[j], (int)sf[j], Lc);
+                                }
+                                if (nval == 4) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) s_p[pb2][u][cj[j]] = __dmul_rn(mj[j], (double)uu[j]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) if (j < nval) s_p[pb2][u][cj[j]] = __dmul_rn(mj[j], (double)uu[j]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; j++) pv[j] = xv[j];
+                                if (has_net && t == P.net_frame) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++)
+                                        if (j < nval) P.net_images[3 * (int64_t)ls + cj[j]] = (int)sf[j];
+                                }
+                                Lp = Lc;
                             }
                         }
                     }
-                    float uv[4];
+                    if (t0 + nfu == f1) {           // state after the task's last frame
+                        if (f1 < P.F) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) uv[e] = __fmaf_rn(sf[e], Le[e], xv[e]);
-                    {
-                        const float tiny = fminf(fminf(fabsf(xv[0]), fabsf(xv[1])), fminf(fabsf(xv[2]), fabsf(xv[3])));
-                        if (!(tiny >= 0.00390625f) || Lbig || wide) {
+                            for (int j = 0; j < 4; j++)
+                                if (j < nval) P.snap[(int64_t)(blk + 1) * C3 + 3 * (int64_t)ls + cj[j]] = (int16_t)(int)sf[j];
+                        } else if (P.u_out) {
 #pragma unroll
-                            for (int e = 0; e < 4; e++) uv[e] = (e < nvalid) ? sw_unwrap_slow(xv[e], sc[e], Le[e]) : 0.0f;
+                            for (int j = 0; j < 4; j++)
+                                if (j < nval) P.u_out[3 * (int64_t)ls + cj[j]] = pbk_unwrapped(pv[j], (int)sf[j], Lp);
                         }
                     }
-                    double pr[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) pr[e] = __dmul_rn(e < n_first ? ma : mb, (double)uv[e]);
-                    double2 *dst = reinterpret_cast<double2 *>(&s_p[t & 1][4 * col]);
-                    dst[0] = make_double2(pr[0], pr[1]);
-                    dst[1] = make_double2(pr[2], pr[3]);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) pv[e] = xv[e];
-                    if (t == P.F - 1 && P.u_out) {
-                        float *uo = P.u_out + 3 * (int64_t)ls + 4 * col;
-#pragma unroll
-                        for (int e = 0; e < 4; e++) if (e < nvalid) uo[e] = pbk_unwrapped(xv[e], sc[e], Le[e]);
-                    }
-                    if (P.snap && ((t + 1) % SW_CHUNK) == 0 && t + 1 < P.F) {
-                        int16_t *so = P.snap + ((t + 1) / SW_CHUNK) * C3 + 3 * (int64_t)ls + 4 * col;
-#pragma unroll
-                        for (int e = 0; e < 4; e++) if (e < nvalid) so[e] = (int16_t)sc[e];
-                    }
-                    if (t == P.net_frame && P.net_images) {
-                        int32_t *no = P.net_images + 3 * (int64_t)ls + 4 * col;
-#pragma unroll
-                        for (int e = 0; e < 4; e++) if (e < nvalid) no[e] = sc[e];
-                    }
                 }
-                Lp[0] = b0.x; Lp[1] = b0.y; Lp[2] = b0.z;
-                sw_fence_async();               // generic reads of the slot before its refill by the async proxy
+                SA_MARK(4);  // column arithmetic
+                // (no proxy fence: the group is only READ here, and its refill by the async proxy is ordered
+                //  behind those reads by the barrier below -- the consumer-release pattern of TMA pipelines)
             }
-        } else if (t > 0 && P.store_sums) {
-            // NumPy's pairwise leaf sum of frame t-1 (numpy/_core/src/umath/loops_utils.h.src):
-            //   r[j] = a[j]; r[j] += a[8q + j];  res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); tail sequentially
-            const double *pp = &s_p[(t - 1) & 1][0];
-            double r = 0.0;
-            if (red_on && nq > 0) {
-                r = pp[lane];
-#pragma unroll 4
-                for (int q = 1; q < nq; q++) r = __dadd_rn(r, pp[q * 24 + lane]);
+            __syncthreads();
+            SA_MARK(6);  // barrier
+            if (nfu > 0) {
+                // the group of this sub-block is free again: the prefetch cursor moves one group on
+                if (warp == 4) prefetch();
+                sub++;
             }
-            {
-                const bool act = lane < 24;
-                const int s1 = ((rj ^ 1) * 3 + rk) & 31, s2 = ((rj ^ 2) * 3 + rk) & 31, s4 = ((rj ^ 4) * 3 + rk) & 31;
-                double o = __shfl_sync(0xffffffffu, r, act ? s1 : lane);
-                r = __dadd_rn(r, o);
-                o = __shfl_sync(0xffffffffu, r, act ? s2 : lane);
-                r = __dadd_rn(r, o);
-                o = __shfl_sync(0xffffffffu, r, act ? s4 : lane);
-                r = __dadd_rn(r, o);
-            }
-            if (lane < 3) {
-                int i0 = 8 * nq;
-                if (nq == 0) { r = 0.0; i0 = 0; }
-                for (int i = i0; i < n; i++) r = __dadd_rn(r, pp[3 * i + lane]);
-                P.node_vals[((t - 1) * (int64_t)P.nodes_per_frame + leaf) * 3 + lane] = r;
-            }
+            SA_MARK(7);
+            pend = nfu;
+            pend_t0 = t0;
         }
-        __syncthreads();
-        // the slot of frame t is free again: refill it with frame t + DEPTH
-        if (warp == 3 && t + SA_DEPTH < P.F) issue(t + SA_DEPTH);
+        // this leaf's block is done: its image counts (snap) are visible before the flag
+        if (f1 < P.F && tid == 0) {
+            __threadfence();
+            *(volatile int *)(P.flags + leaf) = blk + 1;
+        }
     }
+#ifdef PBK_SWEEP_PROFILE
+    if (tid == 0 || tid == 96)
+        for (int i = 0; i < 8; i++) atomicAdd(&g_sa_prof[(tid == 0 ? 0 : 8) + i], (unsigned long long)pc[i]);
+#endif
     if (bad) atomicOr(P.status, (bad & 1 ? PBK_ST_IMAGE_OVERFLOW : 0) | (bad & 2 ? PBK_ST_INTERNAL : 0));
 }
 
+// ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // k_sweep_b<NA>: NA > 0 -- every bead has at most NA atoms, state in registers;
 //                NA == 0 -- any bead size, image counts in shared memory [atom][thread], previous
@@ -553,7 +708,7 @@ k_leaflets_c(const double *__restrict__ zc, int64_t N, int64_t frame0, int inter
 static inline size_t sw_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct SweepScratch {
-    float *boxtab; double *node_vals; float *u_out; double *zc; int16_t *snap;
+    float *boxtab; double *node_vals; float *u_out; double *zc; int16_t *snap; int *flags;
     size_t total;
 };
 
@@ -568,6 +723,7 @@ static SweepScratch sw_layout(void *base, int64_t F, int64_t M, int64_t N, int32
     s.u_out = reinterpret_cast<float *>(b + o); o += sw_align((size_t)M * 12);
     s.zc = reinterpret_cast<double *>(b + o); o += sw_align((size_t)F * N * 8);
     s.snap = reinterpret_cast<int16_t *>(b + o); o += sw_align((size_t)nch * M * 6);
+    s.flags = reinterpret_cast<int *>(b + o); o += sw_align((size_t)L * 4);
     s.total = o;
     return s;
 }
@@ -621,15 +777,28 @@ extern "C" int pbk_reduce_stream(pbk_ctx *ctx, const float *x, const float *box,
     k_box_table<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(box, F, S.boxtab);
     PBK_CHECK_LAUNCH(ctx, "k_box_table");
     {
+        if (F >= ((int64_t)1 << 26)) return PBK_EUNSUPPORTED;
         SweepAParams A;
         A.x = x; A.boxtab = S.boxtab; A.mass = mass; A.leaf_start = leaf_start; A.leaf_len = leaf_len;
-        A.L = L; A.nodes_per_frame = L + K; A.prev0 = first_frame ? x : u_state; A.init_images = init_images;
-        A.F = F; A.M = M; A.net_frame = ((net_frames > 0 && net_frames < F) ? net_frames : F) - 1;
+        A.L = L; A.nodes_per_frame = L + K; A.nblk = (int)nch; A.prev0 = first_frame ? x : u_state;
+        A.init_images = init_images; A.F = (int)F; A.M = M;
+        A.net_frame = (int)(((net_frames > 0 && net_frames < F) ? net_frames : F) - 1);
         A.net_images = net_images; A.u_out = S.u_out; A.node_vals = S.node_vals; A.status = status;
-        A.snap = (phase & 2) ? S.snap : nullptr;
+        A.snap = S.snap; A.flags = S.flags;
         A.store_sums = (phase & 2) ? 1 : 0;
-        if (bulk) k_sweep_a<true><<<(unsigned)L, SA_THREADS, 0, st>>>(A);
-        else k_sweep_a<false><<<(unsigned)L, SA_THREADS, 0, st>>>(A);
+        cudaError_t e = cudaMemsetAsync(S.flags, 0, (size_t)L * 4, st);
+        if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "flags memset", e);
+        // persistent grid: every CTA resident (tasks wait for each other through flags)
+        void (*ka)(SweepAParams) = bulk ? k_sweep_a<true> : k_sweep_a<false>;
+        cudaFuncSetAttribute(ka, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ka, SA_THREADS, 0);
+        if (e != cudaSuccess || per_sm < 1) return pbk_fail(ctx, PBK_ECUDA, "k_sweep_a occupancy", e);
+        // grid = L when every leaf can have its own CTA (the CTA then continues its leaf block after
+        // block, no waiting on another CTA); otherwise every resident slot, tasks round-robin
+        int64_t grid = (int64_t)per_sm * ctx->sm_count;
+        if (grid > L) grid = L;
+        ka<<<(unsigned)grid, SA_THREADS, 0, st>>>(A);
         PBK_CHECK_LAUNCH(ctx, "k_sweep_a");
     }
     if (phase & 2) {
