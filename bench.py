@@ -41,6 +41,11 @@ B_MSD = 16
 B_RDF = 16 + 2
 B_PIPE = B_COM + B_MSD + B_RDF       # = 12*A + 83
 METRIC = "lipid-frames/s (COM+MSD+lateral RDF)"
+WORKLOAD = ("C2: 512-lipid POPC CG bilayer (12 beads/lipid), %d frames per GPU; COM+unwrap+leaflets, msd, "
+            "msd_multi(50,50), com_lateral_rdf(25 bins, 0-25 A, both leaflets)")
+# the other named shapes of BASELINE.json, measured at a bounded number of frames (frames resident in
+# HBM; generated frames x tile along time) and reported in the same line under "configs"
+OTHER_CONFIGS = (("C3", 64, 4), ("C4", 32, 8), ("C5", 48, 4))
 
 
 def peaks():
@@ -146,8 +151,12 @@ def reference_arm(a):
     import multiprocessing as mp
     from oracle import build as obuild
     obuild.build()
-    per = max(50, FRAMES // procs)
-    jobs = [(i, i * per, per) for i in range(procs)]
+    # exactly FRAMES frames (the GPU arm's workload), split as evenly as the core count allows
+    procs = max(1, min(procs, FRAMES // 50))
+    cuts = [FRAMES * i // procs for i in range(procs + 1)]
+    jobs = [(i, cuts[i], cuts[i + 1] - cuts[i]) for i in range(procs)]
+    n_frames = cuts[-1]
+    per = max(j[2] for j in jobs)
     times = []
     with mp.get_context("spawn").Pool(procs) as pool:
         for _ in range(a.warmup):
@@ -155,18 +164,17 @@ def reference_arm(a):
         for _ in range(a.steps):
             times.append(max(pool.map(cpu_port_run, jobs)))
     ms = 1e3 * sum(times) / len(times)
-    value = N_LIPIDS * per * procs / (ms * 1e-3)
+    value = N_LIPIDS * n_frames / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "lipid-frames/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "C2: 512-lipid POPC CG bilayer (12 beads), %d frames per step; "
-                                   "COM + msd + msd_multi(50,50) + com_lateral_rdf(25 bins, 25 A)"
-                                   % (per * procs)},
+            "config": {"workload": WORKLOAD % n_frames, "frames_per_gpu": n_frames, "lipids": N_LIPIDS,
+                       "atoms": N_LIPIDS * BEADS, "sharding": "frames"},
             "cpu_baseline": {"value": value, "unit": "lipid-frames/s", "cores": procs,
                              "kind": "port",
-                             "sample": "%d frames in %d frame-range shards of %d (oracle/port.py, "
-                                       "one process per host core)" % (per * procs, procs, per)},
+                             "sample": "all %d frames in %d frame-range shards of at most %d (oracle/port.py, "
+                                       "one process per host core)" % (n_frames, procs, per)},
             "e2e": {"value": value, "unit": "lipid-frames/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -181,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: config C2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 stage timings and the C5 sharded leg")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)
@@ -374,6 +383,15 @@ def main():
     value = total_lf / (ms_step * 1e-3)
     e2e_val = total_lf / (e2e_ms / a.steps * 1e-3)
 
+    # ---- the C5 shape as a streamed, frame-sharded run through the public API (every rank) ----------
+    c5_leg = None
+    if not a.no_configs:
+        del ba, e, x_dev
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_c5_sharded
+        c5_leg = bench_c5_sharded.measure(frames_per_gpu=48, window=96, tile=4, reps=2)
+
     if rank == 0:
         peak, which = peaks()
         dom = int(np.argmax(stage_ms))
@@ -385,9 +403,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "lipid-frames/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 512-lipid POPC CG bilayer (12 beads/lipid), %d frames per GPU; "
-                                   "COM+unwrap+leaflets, msd, msd_multi(50,50), com_lateral_rdf(25 bins, "
-                                   "0-25 A, both leaflets)" % F,
+            "config": {"workload": WORKLOAD % F,
                        "frames_per_gpu": F, "lipids": N_LIPIDS, "atoms": M,
                        "l2": "inputs larger than L2 (%.0f MB of positions per step)" % (h2d / 1e6),
                        "sharding": "frames"},
@@ -404,6 +420,19 @@ def main():
                          "pipeline_frac": B_PIPE * N_LIPIDS * F / (ms_step * 1e-3) / 1e9 / peak},
             "stages_ms": {n: float(v) for n, v in zip(stage_names, stage_ms)},
         }
+        if c5_leg is not None:
+            line["c5_sharded"] = c5_leg
+        if not a.no_configs and world == 1:
+            # stage times and roofline fractions of the other named shapes (one GPU)
+            import bench_configs
+            line["configs"] = {}
+            for cfg, frames, tile in OTHER_CONFIGS:
+                r = bench_configs.measure(cfg, frames, 3, False, tile, peak_gbs=peak)
+                line["configs"][cfg] = {"lipids": r["lipids"], "atoms": r["atoms"], "frames": r["frames"],
+                                        "stages": {k: {"ms": v["ms"], "GBps_algorithmic": v["GBps_algorithmic"],
+                                                       "frac": v.get("frac"), "bytes_per_lipid_frame": v["bytes_per_lipid_frame"]}
+                                                   for k, v in r["stages"].items()},
+                                        "lipid_frames_per_s": r["lipid_frames_per_s"]}
         if not a.no_cpu_baseline and world == 1:
             v, nfr, wall = cpu_baseline(FRAMES, 1)
             line["cpu_baseline"] = {"value": v, "unit": "lipid-frames/s", "cores": 1, "kind": "port",

@@ -719,7 +719,9 @@ class BilayerAnalyzer(object):
                 proto = self._analysis_protocol.command_protocol[a_id]
                 if proto.analysis_key == 'msd_multi':
                     fwd = max(fwd, int(proto.settings['n_tau']) - 1)
-            shard = pd.make_shard(len(fr_all), dist.get_world_size(), dist.get_rank(), fwd)
+            shard = pd.make_shard(len(fr_all), dist.get_world_size(), dist.get_rank(), fwd,
+                                  align=int(lset['update_interval']))
+            self._shard_fwd = fwd
             if shard.n_owned == 0:
                 raise RuntimeError("more ranks than analysed frames")
             fr = fr_all[shard.first_local:shard.first_local + shard.n_local]
@@ -813,7 +815,9 @@ class BilayerAnalyzer(object):
         # metadata of ALL analysed frames (tiny) is known to every rank
         dims_all = np.asarray(md._dimensions[fr_all], dtype=np.float32) if hasattr(md, '_dimensions') else None
         times_all = np.asarray(md._times[fr_all], dtype=np.float64) if hasattr(md, '_times') else None
-        n_a = shard.back + shard.n_owned
+        # frames after which the image counts are handed on: up to local row 0 of the next rank
+        n_a = pd.net_frames_of(shard, getattr(self, '_shard_fwd', 0), int(self.rep_settings['leaflets']['update_interval']))
+        eng.row_offset = shard.first_local      # leaflet rebuild frames are counted in analysed frames of the RUN
         x, d, t = md.frames(fr)
         if dims_all is None:                 # MDAnalysis input: only the shard was read
             raise RuntimeError("sharded runs need in-memory box/time arrays for all frames")
@@ -827,16 +831,19 @@ class BilayerAnalyzer(object):
         off = pd.image_offsets(net)
         seen = torch.zeros_like(net)
         eng.push(xd, bd, phase=2, init_images=off, net_frames=n_a, net_out=seen)
+        mismatch = 0
         if not eng.used_fused:
             # streamed / generic kernels: the image counts of the last owned frame must be the
             # rank-local ones plus the offsets (the fused path checks its own decisions:
             # PBK_ST_UNWRAP_AMBIGUOUS)
             if not eng.used_stream:
                 seen = eng.d_img[n_a - 1].to(torch.int32)
-            if not bool(torch.equal(seen, off + net)):
-                raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
-                                   "makes the shard decomposition ambiguous; run on one rank")
-        eng.check_status()
+            mismatch = 0 if bool(torch.equal(seen, off + net)) else 32
+        # the status words are OR-ed over the ranks before anything else is exchanged: a rejection (or
+        # an error) on one rank is raised on every rank, never leaving the others in a collective
+        if eng.check_status(agree=True, extra_bits=mismatch) & 32:
+            raise RuntimeError("frame-sharded unwrap: a jump within rounding distance of half a box "
+                               "makes the shard decomposition ambiguous; run on one rank")
         # frame 0 of the run: leaflets (index lists) and unwrapped COMs (MSD reference)
         lab0 = eng.labels[0].clone()
         pd.broadcast_from_first(lab0)
@@ -988,7 +995,10 @@ class BilayerAnalyzer(object):
         lo, hi = pd.shard_bounds(F, world, rank)
         if hi <= lo:
             raise RuntimeError("more ranks than analysed frames")
+        # a stream starts C frames before the first owned one, moved back to a leaflet rebuild frame
+        ival = max(1, int(lset['update_interval']))
         starts = [max(0, pd.shard_bounds(F, world, q)[0] - C) for q in range(world)]
+        starts = [s_ - s_ % ival for s_ in starts]
         a = starts[rank]
         W = int(max(W, C + 1))
         if hasattr(md, '_dimensions') and hasattr(md, '_times'):
@@ -1037,7 +1047,9 @@ class BilayerAnalyzer(object):
                 self._push_frames(eng, md, fr_all[a:hi], copy_only=True, keep=(retained[0], retained[1], 0))
             init = pd.image_offsets(net)
             eng.reset()
+        eng.row_offset = a                      # analysed-frame index (of the run) of engine row 0
         rejected = False
+        failure = None
         first_leaflets = None
         g = a
         first = True
@@ -1057,7 +1069,9 @@ class BilayerAnalyzer(object):
                 else:
                     self._push_frames(eng, md, fr_all[g:g1], times_all[g:g1], dims_all[g:g1],
                                       init_images=init if first else None)
-                eng.check_status()
+                # first window: every rank is here, the status is agreed on before the broadcasts below;
+                # later windows differ in number between ranks, a failure there is exchanged after the loop
+                eng.check_status(agree=first and world > 1)
                 if first:
                     lab0 = eng.labels[0].clone()
                     ref = eng.com_unwrap[0].clone()
@@ -1078,12 +1092,23 @@ class BilayerAnalyzer(object):
                 g = g1
                 first = False
         except FusedPathRejected:
-            if world == 1:
+            if world == 1 or first:              # (first window: raised on every rank together)
                 raise
             rejected = True
+        except (KeyError, RuntimeError) as exc:
+            if world == 1 or first:
+                raise
+            failure = exc
         if world > 1:
-            flag = torch.tensor([1 if rejected else 0], dtype=torch.int64, device=eng.dev)
-            if int(pd.combine_slots(flag)[0]) > 0:
+            bits = pd.agree_bits((1 if rejected else 0) | (2 if isinstance(failure, KeyError) else 0) |
+                                 (4 if isinstance(failure, RuntimeError) else 0), eng.dev)
+            if failure is not None:
+                raise failure
+            if bits & 2:
+                raise KeyError("")
+            if bits & 4:
+                raise RuntimeError("a rank's reduction failed")
+            if bits & 1:
                 raise FusedPathRejected("a rank's fused reduction was rejected")
         for p_ in protos:
             p_.finish(batch)

@@ -647,14 +647,104 @@ k_sweep_b(SweepBParams P)
 // Frame g = frame0 + f takes the labels of src = g - g % interval (bilayer_analyzer.py:969-981);
 // src before the batch: the row before the batch (or a copy of it).
 // ------------------------------------------------------------------------------------------
+#define LB_THREADS 256
+#define LB_VPT 8
+#define LB_SLICE (LB_THREADS * LB_VPT)
+
+// per (slice of 2,048 lipids, frame): (sum, max |z|) of the compact normal components
+__global__ void __launch_bounds__(LB_THREADS)
+k_zpart(const double *__restrict__ zc, int64_t N, double *__restrict__ zpart)
+{
+    __shared__ double red[32];
+    const int64_t f = blockIdx.y;
+    const double *z = zc + f * N;
+    const int64_t i0 = (int64_t)blockIdx.x * LB_SLICE + threadIdx.x;
+    double s = 0.0, mx = 0.0;
+#pragma unroll
+    for (int e = 0; e < LB_VPT; e++) {
+        const int64_t i = i0 + (int64_t)e * LB_THREADS;
+        const double v = i < N ? z[i] : 0.0;
+        s += v;
+        mx = fmax(mx, fabs(v));
+    }
+    s = pbk_block_sum(s, red);
+    mx = pbk_block_max(mx, red);
+    if (threadIdx.x == 0) {
+        zpart[(f * gridDim.x + blockIdx.x) * 2] = s;
+        zpart[(f * gridDim.x + blockIdx.x) * 2 + 1] = mx;
+    }
+}
+
+// zstat[f] = (tree mean of the normal components, rounding bound) from the slice partials
+__global__ void __launch_bounds__(256)
+k_zmean(const double *__restrict__ zpart, int n_part, int64_t N, double *__restrict__ zstat, int *__restrict__ flags)
+{
+    __shared__ double red[32];
+    const int64_t f = blockIdx.x;
+    double s = 0.0, mx = 0.0;
+    for (int q = threadIdx.x; q < n_part; q += blockDim.x) {
+        s += zpart[(f * n_part + q) * 2];
+        mx = fmax(mx, zpart[(f * n_part + q) * 2 + 1]);
+    }
+    s = pbk_block_sum(s, red);
+    mx = pbk_block_max(mx, red);
+    if (threadIdx.x == 0) {
+        zstat[f * 2] = s / (double)N;
+        zstat[f * 2 + 1] = 64.0 * (double)N * 2.220446049250313e-16 * mx;
+        flags[f] = 0;
+    }
+}
+
+// grid (slices, frames): labels of 2,048 lipids against the tree mean of frame src; a lipid within
+// the rounding bound of the mean flags the frame for k_leaflets_c (sequential Welford mean)
+__global__ void __launch_bounds__(LB_THREADS)
+k_labels(const double *__restrict__ zc, const double *__restrict__ zstat, int64_t N, int64_t frame0, int interval,
+         const uint8_t *__restrict__ prev, uint8_t *__restrict__ labels, int *flags, int32_t *status)
+{
+    const int64_t f = blockIdx.y;
+    const int64_t g = frame0 + f;
+    const int64_t src = g - (g % interval);
+    uint8_t *out = labels + f * N;
+    const int64_t i0 = (int64_t)blockIdx.x * LB_SLICE + threadIdx.x;
+    if (src < frame0) {
+        for (int e = 0; e < LB_VPT; e++) {
+            const int64_t i = i0 + (int64_t)e * LB_THREADS;
+            if (i < N) out[i] = prev ? prev[i] : 0;
+        }
+        return;
+    }
+    const int64_t fs = src - frame0;
+    const double *z = zc + fs * N;
+    const double mean = zstat[fs * 2], tol = zstat[fs * 2 + 1];
+    double v[LB_VPT];
+#pragma unroll
+    for (int e = 0; e < LB_VPT; e++) {
+        const int64_t i = i0 + (int64_t)e * LB_THREADS;
+        v[e] = i < N ? z[i] : mean + 2.0 * tol + 1.0;
+    }
+    int close = 0, tie = 0;
+#pragma unroll
+    for (int e = 0; e < LB_VPT; e++) {
+        const int64_t i = i0 + (int64_t)e * LB_THREADS;
+        if (i < N) {
+            if (fabs(v[e] - mean) <= tol) close = 1;
+            if (v[e] > mean) out[i] = 1;
+            else { out[i] = 0; if (!(v[e] < mean)) tie = 1; }
+        }
+    }
+    if (close) atomicOr(flags + f, 1);
+    else if (tie) atomicOr(status, PBK_ST_LEAFLET_TIE);
+}
+
 __global__ void __launch_bounds__(512)
 k_leaflets_c(const double *__restrict__ zc, int64_t N, int64_t frame0, int interval, const uint8_t *__restrict__ prev,
-             uint8_t *__restrict__ labels, int32_t *status)
+             uint8_t *__restrict__ labels, const int *__restrict__ only_flagged, int32_t *status)
 {
     __shared__ double red[32];
     __shared__ double zexact;
     __shared__ int need_exact;
     const int64_t f = blockIdx.x;
+    if (only_flagged && !only_flagged[f]) return;
     const int64_t g = frame0 + f;
     const int64_t src = g - (g % interval);
     uint8_t *out = labels + f * N;
@@ -709,6 +799,7 @@ static inline size_t sw_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct SweepScratch {
     float *boxtab; double *node_vals; float *u_out; double *zc; int16_t *snap; int *flags;
+    double *zpart, *zstat; int *lflags;   // labels: sweep-B partials [F][n_part][2], (mean, bound) [F][2], flags [F]
     size_t total;
 };
 
@@ -724,6 +815,9 @@ static SweepScratch sw_layout(void *base, int64_t F, int64_t M, int64_t N, int32
     s.zc = reinterpret_cast<double *>(b + o); o += sw_align((size_t)F * N * 8);
     s.snap = reinterpret_cast<int16_t *>(b + o); o += sw_align((size_t)nch * M * 6);
     s.flags = reinterpret_cast<int *>(b + o); o += sw_align((size_t)L * 4);
+    s.zpart = reinterpret_cast<double *>(b + o); o += sw_align((size_t)F * ((N + LB_SLICE - 1) / LB_SLICE) * 16);
+    s.zstat = reinterpret_cast<double *>(b + o); o += sw_align((size_t)F * 16);
+    s.lflags = reinterpret_cast<int *>(b + o); o += sw_align((size_t)F * 4);
     s.total = o;
     return s;
 }
@@ -818,7 +912,18 @@ extern "C" int pbk_reduce_stream(pbk_ctx *ctx, const float *x, const float *box,
         else if (max_bead_atoms <= 16) e = sw_launch_b<16>(B, nch, st);
         else e = sw_launch_b<0>(B, nch, st);
         if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_sweep_b", e);
-        k_leaflets_c<<<(unsigned)F, 512, 0, st>>>(S.zc, N, frame0, update_interval, prev_labels, labels, status);
+        const int64_t n_slices = (N + LB_SLICE - 1) / LB_SLICE;
+        if (F <= 65535) {                                 // (frames are the y dimension of the grid)
+            k_zpart<<<dim3((unsigned)n_slices, (unsigned)F), LB_THREADS, 0, st>>>(S.zc, N, S.zpart);
+            PBK_CHECK_LAUNCH(ctx, "k_zpart");
+            k_zmean<<<(unsigned)F, 256, 0, st>>>(S.zpart, (int)n_slices, N, S.zstat, S.lflags);
+            PBK_CHECK_LAUNCH(ctx, "k_zmean");
+            k_labels<<<dim3((unsigned)n_slices, (unsigned)F), LB_THREADS, 0, st>>>(
+                S.zc, S.zstat, N, frame0, update_interval, prev_labels, labels, S.lflags, status);
+            PBK_CHECK_LAUNCH(ctx, "k_labels");
+        }
+        k_leaflets_c<<<(unsigned)F, 512, 0, st>>>(S.zc, N, frame0, update_interval, prev_labels, labels,
+                                                  F <= 65535 ? S.lflags : nullptr, status);
         PBK_CHECK_LAUNCH(ctx, "k_leaflets_c");
     }
     cudaError_t e = cudaMemcpyAsync(u_state, S.u_out, (size_t)M * 12, cudaMemcpyDeviceToDevice, st);

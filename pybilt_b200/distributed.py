@@ -78,11 +78,36 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def make_shard(n_total: int, world: int, rank: int, forward_halo: int = 0) -> Shard:
+def make_shard(n_total: int, world: int, rank: int, forward_halo: int = 0, align: int = 1) -> Shard:
+    """``align`` > 1 (leaflet update interval): the back halo reaches to the last frame whose index is
+    a multiple of ``align`` before the first owned one, so that local row 0 is a frame on which the
+    reference rebuilds the leaflets (bilayer_analyzer.py:969-981) and every later frame of the shard
+    finds the labels it copies inside the shard."""
     lo, hi = shard_bounds(n_total, world, rank)
-    back = 1 if (rank > 0 and hi > lo) else 0
+    back = (((lo - 1) % max(1, int(align))) + 1) if (rank > 0 and hi > lo) else 0
     fwd = max(0, min(forward_halo, n_total - hi)) if hi > lo else 0
     return Shard(rank, world, n_total, lo, hi, back, fwd)
+
+
+def net_frames_of(shard: Shard, forward_halo: int = 0, align: int = 1) -> int:
+    """Local frames after which a rank reports its image counts: up to and including local row 0 of
+    the next rank (its last owned frame when the back halo is one frame)."""
+    if shard.rank >= shard.world - 1:
+        return shard.back + shard.n_owned
+    nxt = make_shard(shard.n_total, shard.world, shard.rank + 1, forward_halo, align)
+    if nxt.hi <= nxt.lo:
+        return shard.back + shard.n_owned
+    return nxt.first_local - shard.first_local + 1
+
+
+def agree_bits(local_bits: int, device, group=None, width: int = 8) -> int:
+    """Bitwise OR over the ranks of a small non-negative integer (a MAX over its bits: NCCL has no
+    bitwise reductions).  Every rank gets the same answer, so status-dependent control flow -- raising,
+    re-running on another path -- stays in step across the ranks."""
+    v = torch.tensor([(int(local_bits) >> b) & 1 for b in range(width)], dtype=torch.int32, device=device)
+    w = _wire(v, group)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX, group=group)
+    return sum(int(x) << b for b, x in enumerate(w.tolist()))
 
 
 def _wire(t: torch.Tensor, group=None) -> torch.Tensor:

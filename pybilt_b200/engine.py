@@ -166,7 +166,7 @@ class LipidReductionEngine:
         # compact normal components + tile partials (streamed reduction)
         nodes = plan.n_leaves + plan.n_nodes
         if self.stream_plan is not None:
-            per_frame = nodes * 24 + self.N * 8 + self.M // 4 + 64
+            per_frame = nodes * 24 + self.N * 8 + self.M // 4 + (3 * self.N // 128 + 1) * 16 + 96
         else:
             per_frame = self.M * 6 + nodes * 24
         if batch_frames is None:
@@ -406,9 +406,16 @@ class LipidReductionEngine:
         unwrapped state: u = f32(x + s*L)  =>  s = rint((u - x) / L)."""
         return torch.round((self.d_u_state.double() - x_last.double()) / box_last.double()[None, :]).to(torch.int32)
 
-    def check_status(self):
-        """Synchronises; raises like the reference does for data-dependent failures."""
-        s = int(self.d_status.item())
+    def check_status(self, agree: bool = False, extra_bits: int = 0) -> int:
+        """Synchronises; raises like the reference does for data-dependent failures.  ``agree``
+        (frame shards): the status word is OR-ed over the ranks first, so that every rank raises --
+        or carries on -- together and no rank is left alone in a collective; ``extra_bits`` are
+        caller-defined bits (>= 32) that take part in the agreement and are returned."""
+        s = int(self.d_status.item()) | int(extra_bits)
+        if agree:
+            from . import distributed as pd
+            if pd.is_distributed():
+                s = pd.agree_bits(s, self.dev)
         if s & _native.ST_INTERNAL:
             raise RuntimeError("libpbk: a bulk copy did not complete (internal error)")
         if s & (_native.ST_UNWRAP_AMBIGUOUS | _native.ST_FUSED_RANGE):
@@ -417,6 +424,7 @@ class LipidReductionEngine:
             raise KeyError("")      # bilayer_analyzer.py:838-845: pos stays '' -> leaflets['']
         if s & _native.ST_IMAGE_OVERFLOW:
             raise RuntimeError("unwrap: image count outside int16 or non-positive box length")
+        return s
 
     # ---------------------------------------------------------------------------------
     # analyses over the resident representations

@@ -91,6 +91,14 @@ CASES = {
     "flip_flop": dict(
         spec=syn.BilayerSpec(48, CG3, seed=17, leaflet_z=1.2, z_step=0.8), n_frames=10,
         analyses=["flip_flop ff", "msd msd_1"]),
+    # the same hopping lipids with leaflets rebuilt every 3rd frame only: the labels of a frame are those
+    # of the last rebuild frame (bilayer_analyzer.py:969-981), which a frame shard has to get right
+    "flip_interval": dict(
+        spec=syn.BilayerSpec(48, CG3, seed=23, leaflet_z=1.2, z_step=0.8), n_frames=14,
+        analyses=["msd msd_1", "msd msd_up leaflet upper",
+                  "nnf nnf_pd resname_1 POPC resname_2 DOPE n_neighbors 4",
+                  "com_lateral_rdf rdf resname_1 all resname_2 all n_bins 20 range_outer 20.0"],
+        rep_settings={"leaflets": {"update_interval": 3}}),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,

@@ -43,6 +43,14 @@ def test_shard_bounds_cover_all_frames():
             assert cover == list(range(n))
     sh = pd.make_shard(100, 4, 2, forward_halo=9)
     assert (sh.lo, sh.hi, sh.back, sh.fwd, sh.first_local, sh.n_local) == (50, 75, 1, 9, 49, 35)
+    assert pd.net_frames_of(sh, 9) == sh.back + sh.n_owned
+    # leaflet update interval 4: local row 0 is a rebuild frame, and the image counts are handed on at
+    # local row 0 of the next rank
+    for r in range(1, 4):
+        al = pd.make_shard(100, 4, r, forward_halo=9, align=4)
+        assert al.first_local % 4 == 0 and 1 <= al.back <= 4
+        prv = pd.make_shard(100, 4, r - 1, forward_halo=9, align=4)
+        assert prv.first_local + pd.net_frames_of(prv, 9, 4) - 1 == al.first_local
     assert sh.local_of(50) == 1 and sh.owned_local() == slice(1, 26)
     last = pd.make_shard(100, 4, 3, forward_halo=9)
     assert last.fwd == 0 and last.hi == 100
@@ -73,7 +81,13 @@ def test_shard_unwrap_algebra_gloo_cpu(world, case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,case", [(2, "tiny_all"), (2, "c2_prefix"), (3, "c3_small"),
                                         (2, "name_dict"), (2, "grid_dense"), (3, "flip_flop"),
-                                        (2, "leaflet_dist")])
+                                        (2, "leaflet_dist"),
+                                        # leaflets rebuilt every 3rd frame while lipids hop: shards must copy
+                                        # the labels of the right rebuild frame
+                                        (2, "flip_interval"), (3, "flip_interval"),
+                                        # jumps of many box lengths: the fast path is refused on SOME ranks
+                                        # only; all ranks have to fall back together
+                                        (2, "big_steps"), (3, "big_steps")])
 def test_sharded_analyzer_matches_reference(world, case):
     codes, outs = launch(world, "gpu", case)
     assert codes == [0] * world, outs
@@ -89,7 +103,9 @@ def test_streamed_shard_unwrap_algebra_gloo_cpu(world, case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,case,window", [(2, "tiny_all", 4), (2, "c2_prefix", 7), (3, "c3_small", 2),
                                                (2, "name_dict", 3), (2, "grid_dense", 1000),
-                                               (2, "flip_flop", 3), (2, "leaflet_dist", 5)])
+                                               (2, "flip_flop", 3), (2, "leaflet_dist", 5),
+                                               (2, "flip_interval", 4), (3, "flip_interval", 2),
+                                               (2, "big_steps", 5), (3, "big_steps", 3)])
 def test_streamed_sharded_analyzer_matches_reference(world, case, window, monkeypatch):
     monkeypatch.setenv("PBK_TEST_WINDOW", str(window))
     codes, outs = launch(world, "gpuwin", case)

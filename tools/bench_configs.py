@@ -41,6 +41,11 @@ def type_codes(types):
 
 
 def run(cfg: str, F: int, reps: int, dense_check: bool, tile: int = 1):
+    print(json.dumps(measure(cfg, F, reps, dense_check, tile)), flush=True)
+
+
+def measure(cfg: str, F: int, reps: int, dense_check: bool = False, tile: int = 1, peak_gbs: float = None):
+    """Stage timings of one named shape (frames resident in HBM, CUDA events); see the module docstring."""
     import torch
     from pybilt_b200 import engine as eng, synthetic as syn
     spec, f_full = syn.config_spec(cfg)
@@ -65,7 +70,10 @@ def run(cfg: str, F: int, reps: int, dense_check: bool, tile: int = 1):
         lf = N * F
         d = {"ms": round(ms, 4), "lipid_frames_per_s": lf / (ms * 1e-3),
              "GBps_algorithmic": bytes_per_lf * lf / (ms * 1e-3) / 1e9,
+             "bytes_per_lipid_frame": bytes_per_lf,
              "full_config_s": ms * 1e-3 * f_full / F}
+        if peak_gbs:
+            d["frac"] = d["GBps_algorithmic"] / peak_gbs
         if extra:
             d.update(extra)
         out["stages"][name] = d
@@ -75,7 +83,7 @@ def run(cfg: str, F: int, reps: int, dense_check: bool, tile: int = 1):
         e.push(x, box)
     ms, _ = timed(reduce, reps)
     e.check_status()
-    rec("reduce", ms, 12 * A + 49, {"fused": bool(e.used_fused)})
+    rec("reduce", ms, 12 * A + 49, {"fused": bool(e.used_fused), "streamed": bool(e.used_stream)})
 
     lab0 = e.labels[0].cpu().numpy()
     idx = np.concatenate([np.nonzero(lab0 == 1)[0], np.nonzero(lab0 == 0)[0]]).astype(np.int32)
@@ -109,7 +117,9 @@ def run(cfg: str, F: int, reps: int, dense_check: bool, tile: int = 1):
     tot = sum(s["ms"] for s in out["stages"].values())
     out["total_ms"] = tot
     out["lipid_frames_per_s"] = N * F / (tot * 1e-3)
-    print(json.dumps(out), flush=True)
+    del e
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
