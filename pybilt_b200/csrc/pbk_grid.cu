@@ -5,6 +5,8 @@
 //   exact grid     pybilt/lipid_grid/lipid_grid.py:150-248
 //   heuristic grid pybilt/lipid_grid/lipid_grid_opt.py:155-334 (+ _knn :435-468)
 //   reductions     pybilt/lipid_grid/lipid_grid_opt.py:496-526, 553-597
+#include <stdlib.h>
+
 #include "pbk_common.cuh"
 
 #define GRID_NNK 24
@@ -418,6 +420,101 @@ k_grid_apl(const int32_t *__restrict__ cells, const uint8_t *__restrict__ labels
     }
 }
 
+// Parallel form of the same statistics (default; PBK_SEQ_WELFORD=1 selects the sequential replay
+// above, which the tests keep as the bit-exact restatement).  One CTA per (frame, state).
+// The reference's first two pushes are replayed literally (the second one subtracts in float32,
+// running_stats.py:34-52 with NumPy float32 inputs); the other n - 2 samples are reduced in
+// parallel -- their sum in float64 is exact (float32 values of similar magnitude), the squared
+// deviations are summed about their own mean -- and merged with Chan's pairwise update, which is
+// what the sequential recurrence computes in exact arithmetic.  Differs from the sequential
+// replay by its accumulated rounding only (~1e-14 relative at 65,536 lipids).
+__global__ void __launch_bounds__(256)
+k_grid_apl_par(const int32_t *__restrict__ cells, const uint8_t *__restrict__ labels,
+               const int32_t *__restrict__ type_code, const float *__restrict__ box, int64_t N,
+               int lat0, int lat1, int nx, int ny, int n_types, double *__restrict__ apl)
+{
+    __shared__ double red[32];
+    __shared__ long long s_k[2];
+    __shared__ double s_v[4];
+    const int64_t f = blockIdx.x;
+    const int t = blockIdx.y;
+    const int32_t *cnt = cells + f * N;
+    const uint8_t *lab = labels + f * N;
+    const float stepx = __fdiv_rn(box[f * 3 + lat0], (float)nx), stepy = __fdiv_rn(box[f * 3 + lat1], (float)ny);
+    const float apb = __fmul_rn(stepx, stepy);                  // x_incr*y_incr, float32
+    const long long INF = 4 * (long long)N;
+    // push order: upper members by index, then lower members by index -> key
+    long long k1 = INF, k2 = INF, n_loc = 0;
+    double sum = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        if (t != 0 && type_code[i] != t - 1) continue;
+        const long long key = (lab[i] == 1 ? 0 : (long long)N) + i;
+        const double a = (double)__fmul_rn(apb, (float)cnt[i]);
+        n_loc++;
+        sum += a;
+        if (key < k1) { k2 = k1; k1 = key; }
+        else if (key < k2) k2 = key;
+    }
+    sum = pbk_block_sum(sum, red);
+    const long long n = (long long)(pbk_block_sum((double)n_loc, red) + 0.5);
+    // the two smallest keys of the block
+    if (threadIdx.x == 0) { s_k[0] = INF; s_k[1] = INF; }
+    __syncthreads();
+    atomicMin((unsigned long long *)&s_k[0], (unsigned long long)k1);
+    __syncthreads();
+    const long long m1 = s_k[0];
+    atomicMin((unsigned long long *)&s_k[1], (unsigned long long)(k1 == m1 ? k2 : k1));
+    __syncthreads();
+    const long long m2 = s_k[1];
+    double *o = apl + f * (1 + 2 * n_types);
+    if (n == 0) {
+        if (threadIdx.x == 0) {
+            if (t == 0) o[0] = 0.0;
+            else { o[2 * t - 1] = nan(""); o[2 * t] = nan(""); }
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const float a1 = __fmul_rn(apb, (float)cnt[m1 % N]);
+        double M = (double)a1, S = 0.0, a2d = 0.0;
+        if (n >= 2) {
+            const float a2 = __fmul_rn(apb, (float)cnt[m2 % N]);
+            a2d = (double)a2;
+            const double diff = (double)__fsub_rn(a2, a1);
+            const double mn = __dadd_rn(M, __ddiv_rn(diff, 2.0));
+            S = __dmul_rn(diff, __dsub_rn(a2d, mn));
+            M = mn;
+        }
+        s_v[0] = M; s_v[1] = S; s_v[2] = (double)a1; s_v[3] = a2d;
+    }
+    __syncthreads();
+    double M = s_v[0], S = s_v[1];
+    if (n > 2) {
+        const double nr = (double)(n - 2);
+        const double sum_r = sum - s_v[2] - s_v[3];
+        const double m_r = sum_r / nr;
+        double q = 0.0;
+        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+            if (t != 0 && type_code[i] != t - 1) continue;
+            const long long key = (lab[i] == 1 ? 0 : (long long)N) + i;
+            if (key == m1 || key == m2) continue;
+            const double d = (double)__fmul_rn(apb, (float)cnt[i]) - m_r;
+            q += d * d;
+        }
+        q = pbk_block_sum(q, red);
+        const double dm = m_r - M;
+        S = S + q + dm * dm * (2.0 * nr / (double)n);
+        M = (2.0 * M + sum_r) / (double)n;
+    }
+    if (threadIdx.x == 0) {
+        if (t == 0) o[0] = M;
+        else {
+            o[2 * t - 1] = M;
+            o[2 * t] = n > 1 ? sqrt(S / (double)(n - 1)) : 0.0;
+        }
+    }
+}
+
 extern "C" int pbk_grid_reduce(pbk_ctx *ctx, const int32_t *grid_idx, const double *grid_z,
                                const uint8_t *labels, const int32_t *type_code, const float *box,
                                int64_t F, int64_t N, int lat0, int lat1, int nx, int ny, int n_types,
@@ -431,6 +528,12 @@ extern "C" int pbk_grid_reduce(pbk_ctx *ctx, const int32_t *grid_idx, const doub
     k_grid_reduce<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(grid_idx, grid_z, N, nx, ny,
                                                                 cells_per_lipid, thickness);
     PBK_CHECK_LAUNCH(ctx, "k_grid_reduce");
+    if (!getenv("PBK_SEQ_WELFORD") && F <= 0x7fffffff) {
+        k_grid_apl_par<<<dim3((unsigned)F, (unsigned)(n_types + 1)), 256, 0, (cudaStream_t)stream>>>(
+            cells_per_lipid, labels, type_code, box, N, lat0, lat1, nx, ny, n_types, apl);
+        PBK_CHECK_LAUNCH(ctx, "k_grid_apl_par");
+        return PBK_OK;
+    }
     const int64_t n_thr = F * (n_types + 1);
     k_grid_apl<<<(unsigned)((n_thr + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
         cells_per_lipid, labels, type_code, box, F, N, lat0, lat1, nx, ny, n_types, apl);

@@ -5,6 +5,8 @@
 //   distance       pybilt/common/distance_cutoff_clustering.py:27-71
 //   com_lateral_rdf pybilt/bilayer_analyzer/analysis_protocols.py:4900-5006
 //   nnf            pybilt/bilayer_analyzer/analysis_protocols.py:2174-2257
+#include <stdlib.h>
+
 #include "pbk_common.cuh"
 
 #define PAIR_TJ 1024         // lipids staged in shared memory per tile
@@ -268,6 +270,31 @@ k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ la
     if (lane == 0) frac[f] = m;
 }
 
+// Parallel form of the frame mean (default; PBK_SEQ_WELFORD=1 selects the sequential replays): the
+// running mean of RunningStats.push equals sum / n in exact arithmetic, and the values are the
+// k + 1 quotients c / k, so a lane-strided float64 sum with a fixed combination tree differs from
+// the sequential recurrence by rounding noise only (~1e-15 relative).  One warp per (analysis, frame).
+__global__ void __launch_bounds__(128)
+k_nnf_frame_mean_par(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels, int64_t AF, int64_t F,
+                     int64_t N, int k, double *__restrict__ frac)
+{
+    const int64_t af = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (af >= AF) return;
+    const int32_t *c = n_b + af * N;
+    double s = 0.0, n = 0.0;
+    const double kd = (double)k;
+    for (int64_t i = lane; i < N; i += 32) {
+        const int ci = c[i];
+        if (ci >= 0) { s += __ddiv_rn((double)ci, kd); n += 1.0; }
+    }
+    s = pbk_warp_sum(s);
+    n = pbk_warp_sum(n);
+    if (lane == 0) frac[af] = n > 0.0 ? s / n : 0.0;
+}
+
+static bool pbk_seq_welford() { return getenv("PBK_SEQ_WELFORD") != nullptr; }
+
 int pbk_nnf_dense_strided(pbk_ctx *ctx, const double *com, const uint8_t *labels, const int32_t *type_code,
                           const float *box, int64_t F, int64_t N, int lat0, int lat1, int type_a, int type_b,
                           int leaflet_mask, int k, int32_t *n_b, int out_stride, const int *frame_flag,
@@ -395,6 +422,11 @@ extern "C" int pbk_nnf_select_many(pbk_ctx *ctx, const int32_t *type_hits, const
                                                            n_types, specs, n_b);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_select_many");
     const int64_t n_af = (int64_t)n_specs * F;
+    if (!pbk_seq_welford()) {
+        k_nnf_frame_mean_par<<<(unsigned)((n_af + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, n_af, F, N, k, frac);
+        PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean_par");
+        return PBK_OK;
+    }
     k_nnf_frame_mean_many<<<(unsigned)((n_af + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, n_specs, F, N,
                                                                                          k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean_many");
@@ -414,7 +446,8 @@ extern "C" int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int3
     k_nnf_select<<<g, 256, 0, (cudaStream_t)stream>>>(type_hits, type_counts, labels, type_code, N, n_types,
                                                       type_a, type_b, leaflet_mask, n_b);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_select");
-    k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
+    if (pbk_seq_welford()) k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
+    else k_nnf_frame_mean_par<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;
 }
@@ -442,8 +475,8 @@ extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
         rc = pbk_nnf_dense_flagged(ctx, com, labels, type_code, box, F, N, lat0, lat1, type_a, type_b,
                                    leaflet_mask, k, n_b, nullptr, 0, (cudaStream_t)stream);
     if (rc) return rc;
-    k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N,
-                                                                                  k, frac);
+    if (pbk_seq_welford()) k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
+    else k_nnf_frame_mean_par<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;
 }

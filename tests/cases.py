@@ -145,3 +145,16 @@ def flatten_outputs(out: dict) -> dict:
         else:
             flat[f"out/{a_id}"] = np.asarray(v)
     return flat
+
+
+def output_atol(key: str, gold_value) -> float:
+    """Absolute tolerance that goes with the 1e-9 relative one when an analysis output is compared with
+    the executed reference.  The grid area per lipid is a mean over all lipids that the device forms with
+    a parallel (Chan) Welford update: each per-frame value agrees with the reference's sequential
+    recurrence to ~1e-14 relative, but its running DEVIATION over frames can be pure rounding noise (the
+    composite area is box area / lipids, constant in an NVT run), so that column is held to 1e-9 of the
+    area scale instead of 1e-9 of itself."""
+    g = np.asarray(gold_value, dtype=np.float64)
+    if "/apl" in key and g.ndim == 2 and g.shape[1] >= 2:
+        return 1e-9 * float(np.nanmax(np.abs(g[:, 1])))
+    return 1e-300

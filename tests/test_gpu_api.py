@@ -52,7 +52,7 @@ def test_api_outputs_match_reference(name):
     for k in keys:
         # msd / msd_multi / nnf / thickness / apl rows: 1e-9 relative (north_star);
         # RDF: counts are exact, so the normalised g(r) agrees to rounding
-        close(flat[k], gold[k], 1e-9, atol=1e-300)
+        close(flat[k], gold[k], 1e-9, atol=cases.output_atol(k, gold[k]))
 
 
 def test_iterator_views_match_reference():
@@ -178,7 +178,7 @@ def test_windowed_run_matches_resident_run(name, window):
     for k in want:
         assert np.array_equal(np.asarray(got[k]), np.asarray(want[k]), equal_nan=True), k
         if k in gold:
-            close(got[k], gold[k], 1e-9, atol=1e-300)
+            close(got[k], gold[k], 1e-9, atol=cases.output_atol(k, gold[k]))
 
 
 def test_window_is_chosen_automatically_when_resident_state_exceeds_budget():
@@ -190,7 +190,7 @@ def test_window_is_chosen_automatically_when_resident_state_exceeds_budget():
     gold = load("c2_prefix")
     flat = cases.flatten_outputs({a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()})
     for k in [k for k in gold if k.startswith("out/")]:
-        close(flat[k], gold[k], 1e-9, atol=1e-300)
+        close(flat[k], gold[k], 1e-9, atol=cases.output_atol(k, gold[k]))
 
 
 @pytest.mark.parametrize("name,window", [("tiny_all", None), ("c3_small", None), ("name_dict", None), ("tiny_all", 5)])

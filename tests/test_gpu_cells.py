@@ -23,13 +23,13 @@ def test_cells_rdf_matches_port(name, force_cells):
 
 
 @pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
-def test_cells_nnf_matches_port(name, force_cells):
-    tge.test_nnf_counts_match_port(name)
+def test_cells_nnf_matches_port(name, force_cells, monkeypatch):
+    tge.test_nnf_counts_match_port(name, False, monkeypatch)
 
 
 @pytest.mark.parametrize("name,nx", [("tiny_all", 8), ("grid_dense", 16), ("grid_sparse", 8), ("c3_small", 32)])
-def test_cells_grid_knn_matches_port(name, nx, force_cells):
-    tge.test_lipid_grid_matches_port(name, nx, "opt")
+def test_cells_grid_knn_matches_port(name, nx, force_cells, monkeypatch):
+    tge.test_lipid_grid_matches_port(name, nx, "opt", monkeypatch)
 
 
 def test_cells_rdf_out_of_box_frames_go_dense(force_cells):

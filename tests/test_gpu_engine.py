@@ -167,8 +167,12 @@ def test_rdf_pair_list_reuse_matches_dense(name, chunk, skin, monkeypatch):
         assert np.array_equal(fc.cpu().numpy(), fc_d.cpu().numpy())
 
 
+@pytest.mark.parametrize("seq", [False, True])
 @pytest.mark.parametrize("name", ["tiny_all", "c1_sample", "c3_small", "name_dict"])
-def test_nnf_counts_match_port(name):
+def test_nnf_counts_match_port(name, seq, monkeypatch):
+    # seq: the sequential Welford replays (bit-exact restatement); default: the parallel means
+    if seq:
+        monkeypatch.setenv("PBK_SEQ_WELFORD", "1")
     e, top, traj, fr, layout = run_engine(name)
     reps = port_reps(name)
     names, codes = type_codes(layout.types)
@@ -185,13 +189,18 @@ def test_nnf_counts_match_port(name):
             got = np.concatenate([n_b[f][(lab[f] == 1) & (n_b[f] >= 0)],
                                   n_b[f][(lab[f] == 0) & (n_b[f] >= 0)]])
             assert np.array_equal(got, counts[f]), (name, f)              # bit-exact neighbour counts
-        rel_close(frac.cpu().numpy(), res[:, 1], 1e-15)
+        # parallel frame mean: the sequential Welford recurrence up to its rounding (PBK_SEQ_WELFORD=1: 1e-15)
+        rel_close(frac.cpu().numpy(), res[:, 1], 1e-15 if seq else 1e-12)
 
 
 @pytest.mark.parametrize("name,nx", [("tiny_all", 8), ("grid_dense", 16), ("grid_sparse", 8),
                                      ("c3_small", 32)])
-@pytest.mark.parametrize("mode", ["opt", "exact"])
-def test_lipid_grid_matches_port(name, nx, mode):
+@pytest.mark.parametrize("mode", ["opt", "exact", "opt-seq"])
+def test_lipid_grid_matches_port(name, nx, mode, monkeypatch):
+    seq = mode.endswith("-seq")
+    if seq:
+        monkeypatch.setenv("PBK_SEQ_WELFORD", "1")
+        mode = "opt"
     e, top, traj, fr, layout = run_engine(name)
     reps = port_reps(name)
     names, codes = type_codes(layout.types)
@@ -213,9 +222,9 @@ def test_lipid_grid_matches_port(name, nx, mode):
         t = port.grid_thickness(g)
         rel_close(thick[f], np.array(t), 1e-12)
         avg, by_res, area_of = port.grid_apl(g, reps["labels"][f], reps["types"])
-        rel_close(apl[f, 0], avg, 1e-15)
+        rel_close(apl[f, 0], avg, 1e-15 if seq else 1e-12)      # parallel Welford / sequential replay
         for ti, nm in enumerate(names):
-            rel_close(apl[f, 1 + 2 * ti], by_res[nm][0], 1e-15)
+            rel_close(apl[f, 1 + 2 * ti], by_res[nm][0], 1e-15 if seq else 1e-12)
             rel_close(apl[f, 2 + 2 * ti], by_res[nm][1], 1e-12)
         cnt_want = np.zeros(len(layout.types), dtype=np.int64)
         for li, leaf in enumerate(("upper", "lower")):
