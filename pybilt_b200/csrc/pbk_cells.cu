@@ -540,7 +540,7 @@ struct ClKnn {
 // MODE 0: NNF counts of type-B neighbours; 1 (GRID): the neighbour table; 2: NNF for every type at
 // once -- hits[f][i][t] = lipids of type t among the k nearest (every lipid is a reference lipid)
 template <int KMAX, int MODE>
-__global__ void __launch_bounds__(128, 12)
+__global__ void __launch_bounds__(128)
 k_knn_cl(ClParams P, ClKnn K)
 {
     constexpr bool GRID = (MODE == 1);
@@ -578,8 +578,14 @@ k_knn_cl(ClParams P, ClKnn K)
     // costs no local-memory access; an accepted one costs one sift (log2 k steps), not a shift of
     // a sorted array.  All keys are distinct, so the k smallest are the same set however they are
     // kept; the sorted order is produced once at the end.
-    double best[KMAX];
-    int bj[KMAX];
+    // The heap lives in SHARED memory as [slot][thread]: a thread's column sits in one bank whatever the
+    // slot, so the data-dependent indexing of the sifts is conflict free (as a per-thread local array the
+    // same accesses scatter over 32 cache lines per warp instruction and dominated the kernel).
+    extern __shared__ __align__(16) unsigned char knn_raw[];
+    double *const sbest = reinterpret_cast<double *>(knn_raw) + threadIdx.x;
+    int *const sbj = reinterpret_cast<int *>(knn_raw + (size_t)KMAX * 128 * 8) + threadIdx.x;
+#define best(h) sbest[(h) * 128]
+#define bj(h) sbj[(h) * 128]
     int nbest = 0;
     double r0 = 0.0;
     int j0 = 0;
@@ -590,19 +596,37 @@ k_knn_cl(ClParams P, ClKnn K)
         for (;;) {
             int c = 2 * h + 1;
             if (c >= n) break;
-            if (c + 1 < n && key_gt(best[c + 1], bj[c + 1], best[c], bj[c])) c++;
-            if (!key_gt(best[c], bj[c], r, j)) break;
-            best[h] = best[c];
-            bj[h] = bj[c];
+            if (c + 1 < n && key_gt(best(c + 1), bj(c + 1), best(c), bj(c))) c++;
+            if (!key_gt(best(c), bj(c), r, j)) break;
+            best(h) = best(c);
+            bj(h) = bj(c);
             h = c;
         }
-        best[h] = r;
-        bj[h] = j;
+        best(h) = r;
+        bj(h) = j;
     };
 
+    // float32 screen: once k candidates are held, a candidate whose float32 minimum-image d^2 exceeds the
+    // k-th best by more than the float32 rounding bound (the bound of k_rdf_cl: 2^-23 (r+1)(8L+4(r+1)))
+    // cannot enter the heap and costs one 8-byte load and a few float operations, no float64 at all
+    const float2 *gf = P.sf + f * P.N;
+    const float fpx = (float)apx, fpy = (float)apy;
+    const float Lmaxf = fmaxf(fr.bxf, fr.byf);
+    float screen = 3.0e38f;
+    auto set_screen = [&]() {
+        const float rf = (float)r0 * 1.0000002f;
+        screen = rf * rf * 1.0000003f + 2.4e-7f * (rf + 1.0f) * (8.0f * Lmaxf + 4.0f * (rf + 1.0f));
+    };
     auto visit = [&](int s0, int s1) {
         for (int q = s0; q < s1; q++) {
             if (q == p) continue;
+            {
+                const float2 fq = gf[q];
+                float dx = fabsf(fpx - fq.x), dy = fabsf(fpy - fq.y);
+                dx = fminf(dx, fr.bxf - dx);
+                dy = fminf(dy, fr.byf - dy);
+                if (fmaf(dy, dy, dx * dx) > screen) continue;
+            }
             const int j = gidx[q];
             const double2 qv = gxy[q];
             const double qx = qv.x, qy = qv.y;
@@ -616,16 +640,17 @@ k_knn_cl(ClParams P, ClKnn K)
                 int h = nbest++;                              // append and sift up
                 while (h > 0) {
                     const int par = (h - 1) >> 1;
-                    if (!key_gt(r, j, best[par], bj[par])) break;
-                    best[h] = best[par];
-                    bj[h] = bj[par];
+                    if (!key_gt(r, j, best(par), bj(par))) break;
+                    best(h) = best(par);
+                    bj(h) = bj(par);
                     h = par;
                 }
-                best[h] = r;
-                bj[h] = j;
+                best(h) = r;
+                bj(h) = j;
             }
-            r0 = best[0];
-            j0 = bj[0];
+            r0 = best(0);
+            j0 = bj(0);
+            if (nbest == k) set_screen();
         }
     };
     // cells [c0, c1] (offsets from pcx, c1 - c0 + 1 <= ncx) of row `row`
@@ -667,15 +692,15 @@ k_knn_cl(ClParams P, ClKnn K)
         int32_t *o = K.knn + (f * P.N + i) * 24;
         for (int t = nbest; t < 24; t++) o[t] = -1;
         for (int n = nbest; n > 0; n--) {
-            o[n - 1] = bj[0];
-            if (n > 1) sift_down(best[n - 1], bj[n - 1], n - 1);
+            o[n - 1] = bj(0);
+            if (n > 1) sift_down(best(n - 1), bj(n - 1), n - 1);
         }
     } else if (MODE == 2) {
         int h[CL_MAX_TYPES];
 #pragma unroll
         for (int t = 0; t < CL_MAX_TYPES; t++) h[t] = 0;
         for (int t = 0; t < nbest; t++) {
-            const int tj = P.type_code[bj[t]];
+            const int tj = P.type_code[bj(t)];
 #pragma unroll
             for (int u = 0; u < CL_MAX_TYPES; u++) h[u] += (tj == u) ? 1 : 0;
         }
@@ -686,12 +711,14 @@ k_knn_cl(ClParams P, ClKnn K)
     } else {
         int c = 0;
         for (int t = 0; t < nbest; t++) {
-            const int tj = P.type_code[bj[t]];
+            const int tj = P.type_code[bj(t)];
             c += (P.tb == -1 || tj == P.tb) ? 1 : 0;
         }
         K.n_b[f * P.N + i] = c;
     }
 }
+#undef best
+#undef bj
 
 // ---------------------------------------------------------------------------------------
 // host side
@@ -917,10 +944,13 @@ static int cl_knn_run(pbk_ctx *ctx, const double *com, const uint8_t *labels, co
         int rc = cl_build(ctx, pl, P, st);
         if (rc) return rc;
         dim3 g((unsigned)((N + 127) / 128), (unsigned)Fc);
-        if (GRID) k_knn_cl<24, 1><<<g, 128, 0, st>>>(P, K);
-        else if (k <= 8) k_knn_cl<8, MODE><<<g, 128, 0, st>>>(P, K);
-        else if (k <= 24) k_knn_cl<24, MODE><<<g, 128, 0, st>>>(P, K);
-        else k_knn_cl<64, MODE><<<g, 128, 0, st>>>(P, K);
+        if (GRID) k_knn_cl<24, 1><<<g, 128, 24 * 128 * 12, st>>>(P, K);
+        else if (k <= 8) k_knn_cl<8, MODE><<<g, 128, 8 * 128 * 12, st>>>(P, K);
+        else if (k <= 24) k_knn_cl<24, MODE><<<g, 128, 24 * 128 * 12, st>>>(P, K);
+        else {
+            cudaFuncSetAttribute(k_knn_cl<64, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 12);
+            k_knn_cl<64, MODE><<<g, 128, 64 * 128 * 12, st>>>(P, K);
+        }
         PBK_CHECK_LAUNCH(ctx, "k_knn_cl");
         if (GRID)
             rc = pbk_grid_knn_dense_flagged(ctx, P.com, P.labels, P.box, Fc, N, lat0, lat1, K.knn,

@@ -6,6 +6,8 @@
 //   lipid COM     pybilt/bilayer_analyzer/com_frame.py:43-96,163-185 (MDAnalysis center_of_mass)
 //   leaflets      pybilt/bilayer_analyzer/bilayer_analyzer.py:826-847
 //   msd           pybilt/bilayer_analyzer/analysis_protocols.py:582-667, 781-895
+#include <stdlib.h>
+
 #include "pbk_common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -448,6 +450,82 @@ k_msd_pairs(const double *__restrict__ cu, int64_t N, const int32_t *__restrict_
     if (threadIdx.x == 0) out[p] = n > 0 ? s / (double)n : 0.0;
 }
 
+// Large systems: the index list of an MSD analysis ("upper members, then lower members") walks the COM rows
+// with a stride, so one CTA per pair reads every row's sector without using half of it and has little in
+// flight.  Instead the list becomes a per-lipid weight (how often the lipid is listed), and a grid of
+// (slice of lipids, pair) CTAs streams the rows of both frames in order -- the sum does not depend on the
+// order of the list -- with four rows in flight per thread; a second small kernel adds the slice partials in
+// slice order and divides.
+#define MSD_SLICE 4096
+__global__ void k_msd_weights(const int32_t *__restrict__ idx, int32_t n, int32_t *__restrict__ w)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) atomicAdd(&w[idx[t]], 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_msd_slices(const double *__restrict__ cu, int64_t N, const int32_t *__restrict__ w, int lat0, int lat1,
+             const int32_t *__restrict__ po, const int32_t *__restrict__ pe, double *__restrict__ part, int mode)
+{
+    __shared__ double red[32];
+    const int p = blockIdx.y;
+    const double *a = cu + (int64_t)pe[p] * N * 3;
+    const double *b = cu + (int64_t)po[p] * N * 3;
+    const int64_t i0 = (int64_t)blockIdx.x * MSD_SLICE;
+    double s = 0.0;
+#pragma unroll 4
+    for (int r = threadIdx.x; r < MSD_SLICE; r += 256) {
+        const int64_t i = i0 + r;
+        if (i < N) {
+            const int wi = __ldg(w + i);
+            const double dx = __dsub_rn(a[i * 3 + lat0], b[i * 3 + lat0]);
+            const double dy = __dsub_rn(a[i * 3 + lat1], b[i * 3 + lat1]);
+            const double v = mode == 0 ? __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) : sqrt(fma(dy, dy, __dmul_rn(dx, dx)));
+            s += (double)wi * v;
+        }
+    }
+    s = pbk_block_sum(s, red);
+    if (threadIdx.x == 0) part[(int64_t)p * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void k_msd_final(const double *__restrict__ part, int n_slices, int32_t n, int32_t n_pairs, double *__restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    double s = 0.0;
+    for (int q = 0; q < n_slices; q++) s += part[(int64_t)p * n_slices + q];
+    out[p] = n > 0 ? s / (double)n : 0.0;
+}
+
+static int pbk_msd_run(pbk_ctx *ctx, const double *com_unwrap, int64_t N, const int32_t *idx, int32_t n_idx, int lat0,
+                       int lat1, const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs, double *out,
+                       int mode, cudaStream_t st)
+{
+    const int64_t n_slices = (N + MSD_SLICE - 1) / MSD_SLICE;
+    if (N >= 16384 && !getenv("PBK_MSD_SIMPLE")) {
+        const size_t need = (size_t)N * 4 + (size_t)n_pairs * n_slices * 8 + 256;
+        unsigned char *ar = reinterpret_cast<unsigned char *>(pbk_arena(ctx, need));
+        if (ar) {
+            int32_t *w = reinterpret_cast<int32_t *>(ar);
+            double *part = reinterpret_cast<double *>(ar + (((size_t)N * 4 + 255) & ~(size_t)255));
+            cudaError_t e = cudaMemsetAsync(w, 0, (size_t)N * 4, st);
+            if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "msd weights memset", e);
+            if (n_idx > 0) k_msd_weights<<<(n_idx + 255) / 256, 256, 0, st>>>(idx, n_idx, w);
+            for (int32_t p0 = 0; p0 < n_pairs; p0 += 65535) {      // (pairs are the y dimension of the grid)
+                const int32_t np = n_pairs - p0 < 65535 ? n_pairs - p0 : 65535;
+                k_msd_slices<<<dim3((unsigned)n_slices, (unsigned)np), 256, 0, st>>>(
+                    com_unwrap, N, w, lat0, lat1, pair_origin + p0, pair_end + p0, part + (size_t)p0 * n_slices, mode);
+            }
+            k_msd_final<<<(n_pairs + 127) / 128, 128, 0, st>>>(part, (int)n_slices, n_idx, n_pairs, out);
+            PBK_CHECK_LAUNCH(ctx, "k_msd_slices");
+            return PBK_OK;
+        }
+    }
+    k_msd_pairs<<<(unsigned)n_pairs, 256, 0, st>>>(com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out, mode);
+    PBK_CHECK_LAUNCH(ctx, "k_msd_pairs");
+    return PBK_OK;
+}
+
 extern "C" int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
                              const int32_t *idx, int32_t n_idx, int lat0, int lat1,
                              const int32_t *pair_origin, const int32_t *pair_end, int32_t n_pairs,
@@ -457,10 +535,8 @@ extern "C" int pbk_msd_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, 
         n_idx < 0 || n_pairs < 0 || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_msd_pairs: bad argument");
     if (n_pairs == 0) return PBK_OK;
-    k_msd_pairs<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
-        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out, 0);
-    PBK_CHECK_LAUNCH(ctx, "k_msd_pairs");
-    return PBK_OK;
+    return pbk_msd_run(ctx, com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, n_pairs, out, 0,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int pbk_ald_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, int64_t N,
@@ -472,10 +548,8 @@ extern "C" int pbk_ald_pairs(pbk_ctx *ctx, const double *com_unwrap, int64_t F, 
         n_idx < 0 || n_pairs < 0 || lat0 < 0 || lat0 > 2 || lat1 < 0 || lat1 > 2)
         return pbk_fail(ctx, PBK_EINVAL, "pbk_ald_pairs: bad argument");
     if (n_pairs == 0) return PBK_OK;
-    k_msd_pairs<<<(unsigned)n_pairs, 256, 0, (cudaStream_t)stream>>>(
-        com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, out, 1);
-    PBK_CHECK_LAUNCH(ctx, "k_msd_pairs(ald)");
-    return PBK_OK;
+    return pbk_msd_run(ctx, com_unwrap, N, idx, n_idx, lat0, lat1, pair_origin, pair_end, n_pairs, out, 1,
+                       (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------
