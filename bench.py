@@ -249,6 +249,9 @@ def main():
     # only read by the MSD kernels, the histogram all-reduce by nobody inside the step) run on a side
     # stream next to the RDF sweep
     comm = torch.cuda.Stream(dev) if world > 1 else None
+    pc_side = pd.peer_comm(dev, 1 << 16, lane="side") if world > 1 else None
+    if world > 1:
+        pd.peer_comm(dev, M * 12)          # the image-count prefix (pd.image_offsets) uses the main lane
     ev_reduced, ev_ref = torch.cuda.Event(), torch.cuda.Event()
 
     def reduce_all():
@@ -297,7 +300,12 @@ def main():
             ev_rdf.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev_rdf)
-                dist.all_reduce(cnt)        # partial histograms of the frame shards (NCCL, NVLink)
+                # partial histograms of the frame shards: one libpbk kernel over NVLink peer memory
+                # (pbk_allreduce_u64), NCCL where the ranks have no peer access
+                if pc_side is not None:
+                    pc_side.allreduce_(cnt)
+                else:
+                    dist.all_reduce(cnt)
                 cnt.record_stream(comm)
             mark(2)
             main.wait_event(ev_ref)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PBK_ABI_VERSION 7
+#define PBK_ABI_VERSION 8
 
 #define PBK_OK 0
 #define PBK_EINVAL (-1) /* bad argument */
@@ -320,6 +320,33 @@ int pbk_grid_reduce(pbk_ctx *ctx, const int32_t *grid_idx, const double *grid_z,
                     const uint8_t *labels, const int32_t *type_code, const float *box, int64_t F,
                     int64_t N, int lat0, int lat1, int nx, int ny, int n_types,
                     int32_t *cells_per_lipid, double *thickness, double *apl, void *stream);
+
+/* ---- (e)  exchanges of a frame-sharded run over NVLink peer memory -------------------------
+ * The reference has no distributed path (its only parallelism is multiprocessing.Pool over frame
+ * ranges, pybilt/com_trajectory/COMTraj.py:2139-2232); these are the exchange steps of SURVEY.md 8e
+ * as pybilt_b200/distributed.py defines them, one process per GPU on one node.
+ * pbk_comm_create allocates this rank's exchange window (world slots of slot_bytes + flags);
+ * pbk_comm_handle returns its 64-byte CUDA IPC handle, which the host exchanges by any means
+ * (torch.distributed.all_gather in pybilt_b200/distributed.py); pbk_comm_connect maps the peers'
+ * windows from handles[world][64] (the own entry is ignored).
+ * Each collective is ONE kernel: it pushes the contribution into the peers' windows with plain
+ * stores over NVLink, releases a per-call epoch flag, acquires the other ranks' flags and combines
+ * their slots out of the own window -- no NCCL launch and no host round trip on the critical path.
+ *   pbk_comm_prefix_i32  out = sum over ranks q < rank of src_q   (net periodic-image counts
+ *                        [M][3] between the two phases of a shard's reduction)
+ *   pbk_allreduce_u64 / pbk_allreduce_f64  out = sum over all ranks, in rank order on every rank
+ *                        (partial RDF histograms; per-frame slot vectors)
+ * n * sizeof(element) <= slot_bytes.  A rank that never sees a peer's flag raises PBK_ST_INTERNAL in
+ * `status` instead of spinning forever.  All ranks must issue the same sequence of collectives. */
+typedef struct pbk_comm pbk_comm;
+int pbk_comm_create(pbk_ctx *ctx, int rank, int world, int64_t slot_bytes, pbk_comm **out);
+int pbk_comm_handle(pbk_comm *comm, unsigned char *handle64);
+int pbk_comm_connect(pbk_comm *comm, const unsigned char *handles);
+void pbk_comm_destroy(pbk_comm *comm);
+int pbk_comm_prefix_i32(pbk_comm *comm, const int32_t *src, int32_t *out, int64_t n, int32_t *status, void *stream);
+int pbk_allreduce_u64(pbk_comm *comm, const unsigned long long *src, unsigned long long *out, int64_t n,
+                      int32_t *status, void *stream);
+int pbk_allreduce_f64(pbk_comm *comm, const double *src, double *out, int64_t n, int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,13 @@ _SIGNATURES = {
     "pbk_grid_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "pbk_comm_create": (c_int, [c_void_p, c_int, c_int, c_int64, ctypes.POINTER(c_void_p)]),
+    "pbk_comm_handle": (c_int, [c_void_p, c_void_p]),
+    "pbk_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "pbk_comm_destroy": (None, [c_void_p]),
+    "pbk_comm_prefix_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "pbk_allreduce_u64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "pbk_allreduce_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -104,7 +111,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.pbk_abi_version() != 7:
+        if lib.pbk_abi_version() != 8:
             raise RuntimeError("pybilt_b200: libpbk ABI version mismatch")
         _lib = lib
     return _lib

@@ -121,12 +121,107 @@ def _wire(t: torch.Tensor, group=None) -> torch.Tensor:
 _gather_cache = {}
 
 
+class PeerComm:
+    """NVLink peer-memory exchanges of libpbk (include/pbk.h: pbk_comm_*): every rank maps the
+    others' exchange windows through CUDA IPC once; a collective is then ONE kernel that pushes the
+    contribution into the peers' windows, releases an epoch flag and combines the slots -- no NCCL
+    launch on the critical path.  One node, one GPU per rank (NCCL backend)."""
+
+    def __init__(self, device: torch.device, slot_bytes: int, group=None):
+        import ctypes
+        from . import _native
+        self.dev = device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.slot_bytes = int(slot_bytes)
+        self.ctx = _native.Context(device.index)
+        self.lib = self.ctx.lib
+        h = ctypes.c_void_p()
+        rc = self.lib.pbk_comm_create(self.ctx._h, self.rank, self.world, self.slot_bytes, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("pbk_comm_create failed (%d): %s" % (rc, (self.lib.pbk_last_error(self.ctx._h) or b"").decode()))
+        self._h = h
+        mine = (ctypes.c_ubyte * 64)()
+        if self.lib.pbk_comm_handle(self._h, mine) != 0:
+            raise RuntimeError("pbk_comm_handle failed: %s" % (self.lib.pbk_last_error(self.ctx._h) or b"").decode())
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        buf = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+        ok = self.lib.pbk_comm_connect(self._h, buf) == 0
+        # all ranks or none: a rank without peer access must not leave the others in a peer collective
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            self.close()
+            raise RuntimeError("pbk_comm_connect: no CUDA IPC peer access between the ranks")
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def _run(self, name, src: torch.Tensor, out: torch.Tensor):
+        assert src.is_cuda and src.is_contiguous() and out.is_contiguous()
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = getattr(self.lib, name)(self._h, src.data_ptr(), out.data_ptr(), int(src.numel()), self.status.data_ptr(), st)
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (name, rc, (self.lib.pbk_last_error(self.ctx._h) or b"").decode()))
+        return out
+
+    def prefix_i32(self, net: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sum of ``net`` (int32) over the ranks before this one."""
+        return self._run("pbk_comm_prefix_i32", net, out if out is not None else torch.empty_like(net))
+
+    def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """Sum over all ranks, in rank order on every rank; int64 / uint64 / float64, in place."""
+        name = "pbk_allreduce_f64" if t.dtype == torch.float64 else "pbk_allreduce_u64"
+        assert t.dtype in (torch.float64, torch.int64)
+        return self._run(name, t.clone(), t)
+
+    def check(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("libpbk peer exchange: a rank never published its contribution")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pbk_comm_destroy(self._h)
+            self._h = None
+
+
+_peer = {}
+
+
+def peer_comm(device: torch.device, nbytes: int, group=None, lane: str = "main") -> Optional["PeerComm"]:
+    """The process-wide PeerComm for `device` when the group runs over NCCL with one GPU per rank
+    (None otherwise, or with PBK_NO_PEER=1: the callers then use NCCL / gloo collectives).
+    Collective: every rank must call it with the same arguments the first time.  Collectives of one
+    PeerComm must be issued on ONE stream; a second stream takes its own instance (``lane``)."""
+    import os
+    if os.environ.get("PBK_NO_PEER") or not is_distributed() or dist.get_backend(group) != "nccl":
+        return None
+    if dist.get_world_size(group) > 16:
+        return None
+    key = (device.index, dist.get_world_size(group), lane)
+    pc = _peer.get(key)
+    if pc is not None and pc.slot_bytes < nbytes:
+        pc = None
+    if pc is None:
+        try:
+            pc = PeerComm(device, max(int(nbytes), 1 << 20), group)
+        except RuntimeError:
+            pc = False                          # no peer access on this box: NCCL from here on
+        _peer[key] = pc
+    return pc or None
+
+
 def image_offsets(net: torch.Tensor, group=None) -> torch.Tensor:
     """Exclusive prefix over ranks of the net image counts (int32 tensor of any shape).
-    One all-gather into a reused [world, ...] buffer and one reduction over the ranks before
-    this one (nothing is allocated per call after the first)."""
+    Over NVLink peer memory in one libpbk kernel when every rank has its own GPU (PeerComm);
+    otherwise one all-gather into a reused [world, ...] buffer and one reduction over the ranks
+    before this one (nothing is allocated per call after the first)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if net.is_cuda and net.dtype == torch.int32:
+        pc = peer_comm(net.device, net.numel() * 4, group)
+        if pc is not None:
+            return pc.prefix_i32(net.contiguous())
     w = _wire(net, group)
     key = (w.device, w.dtype, tuple(w.shape), world)
     buf = _gather_cache.get(key)

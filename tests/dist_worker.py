@@ -78,6 +78,41 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         dist.destroy_process_group()
         sys.exit(0 if int(flag) == 1 else 3)
+    if mode == "peer":
+        # libpbk's NVLink peer-memory collectives (pbk_comm_*) against NCCL, one GPU per rank
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", device_id=dev)
+        pc = pd.peer_comm(dev, 1 << 21)
+        ok = pc is not None
+        if ok:
+            g = torch.Generator(device="cpu").manual_seed(100 + rank)
+            for it in range(40):
+                n = int(torch.randint(1, 200000, (1,), generator=g)) if it else 18432
+                n = int(pd.combine_slots(torch.tensor([n if rank == 0 else 0], device=dev))[0])
+                net = torch.randint(-5, 6, (n,), generator=g, dtype=torch.int32).to(dev)
+                got = pc.prefix_i32(net)
+                alln = [torch.empty_like(net) for _ in range(world)]
+                dist.all_gather(alln, net)
+                want = sum(alln[:rank]) if rank else torch.zeros_like(net)
+                ok = ok and bool(torch.equal(got, want))
+                h = torch.randint(0, 1 << 40, (n,), generator=g, dtype=torch.int64).to(dev)
+                d = torch.rand((n,), generator=g, dtype=torch.float64).to(dev)
+                h2, d2 = h.clone(), d.clone()
+                pc.allreduce_(h2)
+                pc.allreduce_(d2)
+                dist.all_reduce(h)
+                alld = [torch.empty_like(d) for _ in range(world)]
+                dist.all_gather(alld, d)
+                dsum = alld[0].clone()
+                for q in range(1, world):
+                    dsum += alld[q]
+                ok = ok and bool(torch.equal(h2, h)) and bool(torch.equal(d2, dsum))
+            pc.check()
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag) == 1 else 3)
     # ---- gpu ----
     ngpu = torch.cuda.device_count()
     own_gpu = ngpu >= world

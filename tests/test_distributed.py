@@ -110,3 +110,15 @@ def test_streamed_sharded_analyzer_matches_reference(world, case, window, monkey
     monkeypatch.setenv("PBK_TEST_WINDOW", str(window))
     codes, outs = launch(world, "gpuwin", case)
     assert codes == [0] * world, outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_memory_collectives_match_nccl(world):
+    """pbk_comm_prefix_i32 / pbk_allreduce_u64 / pbk_allreduce_f64 over CUDA IPC peer windows against
+    NCCL on random payloads, 40 rounds back to back (needs one GPU per rank)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    codes, outs = launch(world, "peer", "tiny_all")
+    assert codes == [0] * world, outs

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_native.EXPORTS) == syms    # the ctypes stub binds exactly the header
-    assert lib.pbk_abi_version() == 7
+    assert lib.pbk_abi_version() == 8
 
 
 def test_no_cpu_fallback():
