@@ -96,6 +96,19 @@ __device__ __forceinline__ int pbk_hist_bin(double r, double lo, double hi, int 
     return k;
 }
 
+// a / b for a divisor b that is reused (a bead's mass): rb = RN(1 / b) formed once.  q1 is a faithful
+// quotient (one Newton correction of a * rb with an exact residual), and a second correction step
+// from a faithful quotient with the correctly rounded reciprocal returns RN(a / b) (Markstein's
+// theorem; Muller et al., Handbook of Floating-Point Arithmetic, "division with an FMA") -- the value
+// __ddiv_rn gives, in five multiply-adds instead of the division subroutine.  Normal range only
+// (masses and coordinate sums are far from overflow / underflow).
+__device__ __forceinline__ double pbk_div_r(double a, double b, double rb)
+{
+    const double q0 = __dmul_rn(a, rb);
+    const double q1 = __fma_rn(__fma_rn(-q0, b, a), rb, q0);
+    return __fma_rn(__fma_rn(-q1, b, a), rb, q1);
+}
+
 template <typename T>
 __device__ __forceinline__ T pbk_warp_sum(T v)
 {

@@ -48,11 +48,21 @@ def run_engine(name, batch_frames=None, fused=True, stream=True):
 
 @pytest.mark.parametrize("name", list(cases.CASES))
 @pytest.mark.parametrize("batch", [None, 5])
-@pytest.mark.parametrize("path", ["fused", "stream", "generic"])
-def test_representations_match_reference(name, batch, path):
+@pytest.mark.parametrize("path", ["fused", "stream", "stream_seq", "stream_seqb", "stream_v1", "generic"])
+def test_representations_match_reference(name, batch, path, monkeypatch):
     from pybilt_b200.engine import FusedPathRejected
     gold = load(name)
     fused = path == "fused"
+    # the streamed reduction's variants (pbk_sweep.cu): time-parallel front end (default), the
+    # warp-per-leaf sweep it falls back to, sequential chunks in sweep B, the first generation
+    if path == "stream_seq":
+        monkeypatch.setenv("PBK_SWEEP_SEQ_A", "1")
+    if path == "stream_seqb":
+        monkeypatch.setenv("PBK_SWEEP_SEQ_B", "1")
+    if path == "stream_v1":
+        monkeypatch.setenv("PBK_SWEEP_V1", "1")
+    if path.startswith("stream"):
+        path = "stream"
     try:
         e, top, traj, fr, layout = run_engine(name, batch, fused, stream=path != "generic")
     except FusedPathRejected:
