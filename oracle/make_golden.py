@@ -92,6 +92,14 @@ def make_comtraj(name: str) -> str:
             "msd_lower_first": ref["msd_lower_first"], "first_group": np.array(ref["first_group"]),
             "upper_all": np.array(ref["upper_all"]),
             "meta/input_sha256": np.array(cases.input_digest(traj))}
+    for key in ("thick_avgs", "thick_maps", "apl_circle_both", "apl_circle_upper_first", "apl_box_both",
+                "apl_box_lower", "cluster_upper_9", "cluster_both_first_12", "step_vec_2",
+                "step_vec_2_wrapped_upper", "step_vec_frames_2", "voronoi_upper_points0", "voronoi_upper_nregions",
+                "com_unwrap_no_leaflet_motion", "msd_both_no_leaflet_motion"):
+        flat[key] = np.asarray(ref[key])
+    # cluster lists: frame, cluster number and member, one row per clustered lipid
+    flat["cluster_upper_9_lists"] = np.array([(f, c, m) for f, fr in enumerate(ref["cluster_upper_9_lists"])
+                                              for c, cl in enumerate(fr) for m in cl], dtype=np.int64).reshape(-1, 3)
     path = os.path.join(GOLDEN, "comtraj_" + name + ".npz")
     np.savez_compressed(path, **flat)
     return path

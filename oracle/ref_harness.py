@@ -188,4 +188,27 @@ def run_comtraj_reference(top, traj, plane="xy", fstart=0, fend=-1, fskip=1):
         first = obj.leaflets["upper"].get_group_names()[0]
         out["msd_lower_first"] = obj.calc_msd(leaflet="lower", group=first)
         out["first_group"] = first
+        # analyses beyond the MSD
+        zavgs, zmaps = obj.calc_membrane_thickness()
+        out["thick_avgs"], out["thick_maps"] = zavgs, zmaps
+        out["apl_circle_both"] = obj.calc_area_per_lipid_closest_neighbor_circle()
+        out["apl_circle_upper_first"] = obj.calc_area_per_lipid_closest_neighbor_circle(leaflet="upper", group=first)
+        out["apl_box_both"] = obj.calc_area_per_lipid_box()
+        out["apl_box_lower"] = obj.calc_area_per_lipid_box(leaflet="lower")
+        cl = obj.check_clustering(leaflet="upper", dist=9.0)
+        out["cluster_upper_9"] = cl
+        out["cluster_upper_9_lists"] = [[list(map(int, c)) for c in fr] for fr in obj.clusters]
+        out["cluster_both_first_12"] = obj.check_clustering(group=first, dist=12.0)
+        sv = obj.step_vector(fstep=2)
+        out["step_vec_2"] = np.array(sv)
+        out["step_vec_2_wrapped_upper"] = np.array(obj.step_vector(leaflet="upper", fstep=3, wrapped=True))
+        np_int = getattr(np, "int", None)
+        out["step_vec_frames_2"] = np.array(obj.step_vector_frames(fstep=2))
+        vor = obj.voronoi_tesselate(leaflet="upper")
+        out["voronoi_upper_points0"] = np.array(vor[0].points)
+        out["voronoi_upper_nregions"] = np.array([len(v.regions) for v in vor])
+        # last: this one rewrites the stored frames
+        obj.remove_leaflet_com_motion()
+        out["com_unwrap_no_leaflet_motion"] = np.array([[l.com_unwrap for l in obj.frame[f].lipidcom] for f in range(n)])
+        out["msd_both_no_leaflet_motion"] = obj.calc_msd()
     return out

@@ -1,0 +1,129 @@
+// pbk_comtraj.cu -- pair searches of the stand-alone COM trajectory.
+//
+// Reference arithmetic restated (pybilt/com_trajectory/COMTraj.py):
+//   calc_membrane_thickness                      :1244-1408  nearest cross-leaflet partner of every lipid
+//   calc_area_per_lipid_closest_neighbor_circle  :1655-1766  nearest member of the same leaflet
+//   check_clustering                             :1411-1576  pairs within a cut-off (clusters are grown on the host)
+// All three use COMTraj's own minimum image on the WRAPPED COMs (not distance_euclidean_pbc):
+//   d = a - b;  if |d| > h:  d = L - |a - h| - |b - h|      with h = f32(L / 2), L the float32 box edge,
+//   rxy = sqrt(dx*dx + dy*dy)  (two rounded products and a rounded sum -- no FMA),
+// scan the candidates in list order and keep the first strict minimum below the start value 10000.0.
+#include "pbk_common.cuh"
+
+static __device__ __forceinline__ double ct_rxy(double ax, double ay, double bx, double by, double Lx, double Ly,
+                                                double hx, double hy)
+{
+    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+    if (fabs(dx) > hx) dx = __dsub_rn(__dsub_rn(Lx, fabs(__dsub_rn(ax, hx))), fabs(__dsub_rn(bx, hx)));
+    if (fabs(dy) > hy) dy = __dsub_rn(__dsub_rn(Ly, fabs(__dsub_rn(ay, hy))), fabs(__dsub_rn(by, hy)));
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+#define CT_THREADS 128
+#define CT_TILE 256
+
+// grid (ceil(na / CT_THREADS), F): thread = one lipid of list A, candidates of list B staged in
+// shared memory tile by tile, in list order
+__global__ void __launch_bounds__(CT_THREADS)
+k_ct_nearest(const double *__restrict__ com, const float *__restrict__ box, const int32_t *__restrict__ idx_a,
+             int na, const int32_t *__restrict__ idx_b, int nb, int xi, int yi, int exclude_self, int64_t N,
+             int32_t *__restrict__ out_pos, double *__restrict__ out_dist)
+{
+    __shared__ double s_x[CT_TILE], s_y[CT_TILE];
+    __shared__ int s_i[CT_TILE];
+    const int64_t f = blockIdx.y;
+    const double *c = com + f * N * 3;
+    const float Lxf = box[f * 3 + xi], Lyf = box[f * 3 + yi];
+    const double Lx = (double)Lxf, Ly = (double)Lyf, hx = (double)(Lxf * 0.5f), hy = (double)(Lyf * 0.5f);
+    const int a = blockIdx.x * CT_THREADS + threadIdx.x;
+    const int ia = a < na ? idx_a[a] : -1;
+    const double ax = ia >= 0 ? c[3 * (int64_t)ia + xi] : 0.0, ay = ia >= 0 ? c[3 * (int64_t)ia + yi] : 0.0;
+    double best = 10000.0;
+    int pos = -1;
+    for (int b0 = 0; b0 < nb; b0 += CT_TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < CT_TILE && b0 + j < nb; j += CT_THREADS) {
+            const int ib = idx_b[b0 + j];
+            s_i[j] = ib; s_x[j] = c[3 * (int64_t)ib + xi]; s_y[j] = c[3 * (int64_t)ib + yi];
+        }
+        __syncthreads();
+        if (ia >= 0) {
+            const int m = min(CT_TILE, nb - b0);
+            for (int j = 0; j < m; j++) {
+                if (exclude_self && s_i[j] == ia) continue;
+                const double r = ct_rxy(ax, ay, s_x[j], s_y[j], Lx, Ly, hx, hy);
+                if (r < best) { best = r; pos = b0 + j; }
+            }
+        }
+    }
+    if (ia >= 0) {
+        out_pos[f * na + a] = pos;
+        out_dist[f * na + a] = best;
+    }
+}
+
+// grid (ceil(n / CT_THREADS), F): row a of the frame's adjacency matrix, bit b of word b / 32 set when
+// rxy(idx[b], idx[a]) <= dist (evaluated as the reference does: candidate first, cluster seed second)
+__global__ void __launch_bounds__(CT_THREADS)
+k_ct_adjacency(const double *__restrict__ com, const float *__restrict__ box, const int32_t *__restrict__ idx, int n,
+               int xi, int yi, double dist, int64_t N, uint32_t *__restrict__ bits)
+{
+    __shared__ double s_x[CT_TILE], s_y[CT_TILE];
+    const int64_t f = blockIdx.y;
+    const double *c = com + f * N * 3;
+    const float Lxf = box[f * 3 + xi], Lyf = box[f * 3 + yi];
+    const double Lx = (double)Lxf, Ly = (double)Lyf, hx = (double)(Lxf * 0.5f), hy = (double)(Lyf * 0.5f);
+    const int a = blockIdx.x * CT_THREADS + threadIdx.x;
+    const int ia = a < n ? idx[a] : -1;
+    const double ax = ia >= 0 ? c[3 * (int64_t)ia + xi] : 0.0, ay = ia >= 0 ? c[3 * (int64_t)ia + yi] : 0.0;
+    const int nw = (n + 31) / 32;
+    uint32_t *row = bits + (f * n + a) * nw;
+    for (int b0 = 0; b0 < n; b0 += CT_TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < CT_TILE && b0 + j < n; j += CT_THREADS) {
+            const int ib = idx[b0 + j];
+            s_x[j] = c[3 * (int64_t)ib + xi]; s_y[j] = c[3 * (int64_t)ib + yi];
+        }
+        __syncthreads();
+        if (ia >= 0) {
+            const int m = min(CT_TILE, n - b0);
+            for (int w = 0; w < m; w += 32) {
+                uint32_t word = 0u;
+                for (int j = w; j < min(m, w + 32); j++) {
+                    // comc = candidate (b), coms = seed (a):  dx = comc - coms
+                    const double r = ct_rxy(s_x[j], s_y[j], ax, ay, Lx, Ly, hx, hy);
+                    if (r <= dist) word |= 1u << (j - w);
+                }
+                row[(b0 + w) / 32] = word;
+            }
+        }
+    }
+}
+
+extern "C" int pbk_ct_nearest(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx_a, int32_t na,
+                              const int32_t *idx_b, int32_t nb, int xi, int yi, int exclude_self, int64_t F, int64_t N,
+                              int32_t *out_pos, double *out_dist, void *stream)
+{
+    if (!ctx || !com || !box || !out_pos || !out_dist || na < 0 || nb < 0 || F < 0 || N <= 0 || xi < 0 || xi > 2 ||
+        yi < 0 || yi > 2 || (na > 0 && !idx_a) || (nb > 0 && !idx_b))
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_ct_nearest: bad argument");
+    if (F == 0 || na == 0) return PBK_OK;
+    if (F > 65535) return PBK_EUNSUPPORTED;
+    k_ct_nearest<<<dim3((unsigned)((na + CT_THREADS - 1) / CT_THREADS), (unsigned)F), CT_THREADS, 0, (cudaStream_t)stream>>>(
+        com, box, idx_a, na, idx_b, nb, xi, yi, exclude_self, N, out_pos, out_dist);
+    PBK_CHECK_LAUNCH(ctx, "k_ct_nearest");
+    return PBK_OK;
+}
+
+extern "C" int pbk_ct_adjacency(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx, int32_t n,
+                                int xi, int yi, double dist, int64_t F, int64_t N, uint32_t *bits, void *stream)
+{
+    if (!ctx || !com || !box || !bits || n < 0 || F < 0 || N <= 0 || xi < 0 || xi > 2 || yi < 0 || yi > 2 || (n > 0 && !idx))
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_ct_adjacency: bad argument");
+    if (F == 0 || n == 0) return PBK_OK;
+    if (F > 65535) return PBK_EUNSUPPORTED;
+    k_ct_adjacency<<<dim3((unsigned)((n + CT_THREADS - 1) / CT_THREADS), (unsigned)F), CT_THREADS, 0, (cudaStream_t)stream>>>(
+        com, box, idx, n, xi, yi, dist, N, bits);
+    PBK_CHECK_LAUNCH(ctx, "k_ct_adjacency");
+    return PBK_OK;
+}

@@ -585,6 +585,7 @@ k_frames3(F3Params P)
     // bead of this thread in the lipid phase (first round), kept in registers
     const int my_a0 = tid < P.N ? P.seg[tid] : 0, my_a1 = tid < P.N ? P.seg[tid + 1] : 0;
     const double my_lm = tid < P.N ? P.lipid_mass[tid] : 1.0;
+    const double my_rlm = 1.0 / my_lm;
     float Lp0, Lp1, Lp2, Ln0, Ln1, Ln2;
     {
         const int64_t tp = (kc == 0) ? 0 : f0 - 1;
@@ -880,10 +881,11 @@ k_frames3(F3Params P)
                         }
                     }
                     const double lm = i0 == 0 ? my_lm : __ldg(P.lipid_mass + i);
+                    const double rlm = i0 == 0 ? my_rlm : 1.0 / lm;        // pbk_div_r: RN(c / lm) without the division routine
                     double *ow = P.com + (t * (int64_t)P.N + i) * 3;
                     double *ou = P.com_unwrap + (t * (int64_t)P.N + i) * 3;
-                    ow[0] = __ddiv_rn(cw0, lm); ow[1] = __ddiv_rn(cw1, lm); ow[2] = __ddiv_rn(cw2, lm);
-                    const double u0 = __ddiv_rn(cu0, lm), u1 = __ddiv_rn(cu1, lm), u2 = __ddiv_rn(cu2, lm);
+                    ow[0] = pbk_div_r(cw0, lm, rlm); ow[1] = pbk_div_r(cw1, lm, rlm); ow[2] = pbk_div_r(cw2, lm, rlm);
+                    const double u0 = pbk_div_r(cu0, lm, rlm), u1 = pbk_div_r(cu1, lm, rlm), u2 = pbk_div_r(cu2, lm, rlm);
                     ou[0] = u0; ou[1] = u1; ou[2] = u2;
                     zv = P.norm == 0 ? u0 : (P.norm == 1 ? u1 : u2);
                     s_z[i] = zv;

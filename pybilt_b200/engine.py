@@ -451,6 +451,32 @@ class LipidReductionEngine:
         self.launches += 1
         return out
 
+    def ct_nearest(self, idx_a, idx_b, lateral=(0, 1), exclude_self: bool = False):
+        """COMTraj's nearest-partner search on the wrapped COMs of every resident frame
+        (pbk_ct_nearest): (position in idx_b int32 [F, na], distance float64 [F, na])."""
+        d, F = self.dev, self.n_done
+        a = torch.as_tensor(np.asarray(idx_a, dtype=np.int32), device=d)
+        b = torch.as_tensor(np.asarray(idx_b, dtype=np.int32), device=d)
+        pos = torch.empty((F, a.numel()), dtype=torch.int32, device=d)
+        dist = torch.empty((F, a.numel()), dtype=torch.float64, device=d)
+        self.ctx.call("pbk_ct_nearest", self.com.data_ptr(), self.box.data_ptr(), a.data_ptr(), a.numel(),
+                      b.data_ptr(), b.numel(), int(lateral[0]), int(lateral[1]), int(bool(exclude_self)), F, self.N,
+                      pos.data_ptr(), dist.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return pos, dist
+
+    def ct_adjacency(self, idx, dist: float, lateral=(0, 1)) -> torch.Tensor:
+        """uint32-packed adjacency rows [F, n, ceil(n/32)] of the lipids `idx` under COMTraj's
+        cluster criterion rxy <= dist (pbk_ct_adjacency)."""
+        d, F = self.dev, self.n_done
+        a = torch.as_tensor(np.asarray(idx, dtype=np.int32), device=d)
+        n = a.numel()
+        bits = torch.zeros((F, n, (n + 31) // 32), dtype=torch.int32, device=d)
+        self.ctx.call("pbk_ct_adjacency", self.com.data_ptr(), self.box.data_ptr(), a.data_ptr(), n,
+                      int(lateral[0]), int(lateral[1]), float(dist), F, self.N, bits.data_ptr(), self.stream_ptr())
+        self.launches += 1
+        return bits
+
     def msd_pairs(self, idx: np.ndarray, origins: Sequence[int], ends: Sequence[int],
                   lateral=(0, 1), lengths: bool = False) -> torch.Tensor:
         """mean squared displacement per (origin, end) pair; ``lengths``: mean displacement length."""

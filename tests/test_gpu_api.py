@@ -161,6 +161,45 @@ def test_comtraj_matches_reference(name):
     assert fr.lipidcom[0].type == top.resnames[0] and len(ct.frame) == ct.nframes
 
 
+@pytest.mark.parametrize("name", ["big_steps", "name_dict", "c2_prefix"])
+def test_comtraj_analyses_beyond_msd_match_reference(name):
+    """thickness from nearest cross-leaflet partners, closest-neighbour-circle and
+    box areas, clusters, step vectors, tessellation inputs, leaflet COM motion removal -- against the
+    literal COMTraj (oracle/ref_harness.run_comtraj_reference).  Partner choices and cluster lists are
+    exact; floating outputs to 1e-12 (they come out bit-identical)."""
+    from pybilt_b200.com_trajectory import COMTraj
+    gold = load("comtraj_" + name)
+    top, traj = cases.make_inputs(name)
+    ct = COMTraj(traj, top)
+    first = str(gold["first_group"])
+    zavgs, zmaps = ct.calc_membrane_thickness()
+    assert np.array_equal(zmaps, gold["thick_maps"])          # partner choice + host arithmetic: identical
+    close(zavgs, gold["thick_avgs"], 1e-12)
+    close(ct.calc_membrane_thickness_parallel(nprocs=3)[0], gold["thick_avgs"], 1e-12)
+    close(ct.calc_area_per_lipid_closest_neighbor_circle(), gold["apl_circle_both"], 1e-12)
+    close(ct.calc_area_per_lipid_closest_neighbor_circle(leaflet="upper", group=first), gold["apl_circle_upper_first"], 1e-12)
+    close(ct.calc_area_per_lipid_box(), gold["apl_box_both"], 1e-12)
+    close(ct.calc_area_per_lipid_box(leaflet="lower"), gold["apl_box_lower"], 1e-12)
+    close(ct.check_clustering(leaflet="upper", dist=9.0), gold["cluster_upper_9"], 1e-12)
+    rows = np.array([(f, c, m) for f, fr in enumerate(ct.clusters) for c, cl in enumerate(fr) for m in cl],
+                    dtype=np.int64).reshape(-1, 3)
+    assert np.array_equal(rows, gold["cluster_upper_9_lists"])  # same clusters, same member order
+    exported = ct.export_clusters_for_plotting()
+    assert len(exported) == ct.nframes and len(exported[0][0]) == int((rows[:, 0] == 0).sum())
+    close(ct.check_clustering(group=first, dist=12.0), gold["cluster_both_first_12"], 1e-12)
+    assert np.array_equal(np.array(ct.step_vector(fstep=2)), gold["step_vec_2"])
+    assert np.array_equal(np.array(ct.step_vector(leaflet="upper", fstep=3, wrapped=True)), gold["step_vec_2_wrapped_upper"])
+    assert np.array_equal(ct.step_vector_frames(fstep=2), gold["step_vec_frames_2"])
+    vor = ct.voronoi_tesselate(leaflet="upper")
+    assert np.array_equal(vor[0].points, gold["voronoi_upper_points0"])
+    assert np.array_equal(np.array([len(v.regions) for v in vor]), gold["voronoi_upper_nregions"])
+    tri = ct.delaunay_tesselate(leaflet="upper")
+    assert len(tri) == ct.nframes and np.array_equal(tri[0][0], gold["voronoi_upper_points0"][:, 0])
+    ct.remove_leaflet_com_motion()
+    assert np.array_equal(ct._engine.com_unwrap.cpu().numpy(), gold["com_unwrap_no_leaflet_motion"])
+    close(ct.calc_msd(), gold["msd_both_no_leaflet_motion"], 1e-9)
+
+
 @pytest.mark.parametrize("name", list(cases.CASES))
 @pytest.mark.parametrize("window", [3, 5, 1000])
 def test_windowed_run_matches_resident_run(name, window):
