@@ -197,21 +197,33 @@ int pbk_leaflet_distance(pbk_ctx *ctx, const double *com, const uint8_t *labels,
 int pbk_label_changes(pbk_ctx *ctx, const uint8_t *labels, const uint8_t *prev_row, int64_t F, int64_t N,
                       int32_t *changed, void *stream);
 
+/* ---- N3  com_frame:rewrap -----------------------------------------------------------------------
+ * COMFrame._rewrap                       pybilt/bilayer_analyzer/com_frame.py:233-270
+ * com[f, i] <- (com_unwrap[f, i] + mem_com[f]) moved by whole box edges into [0, box] wherever it lies
+ * more than 1 A from com[f, i]; in place. */
+int pbk_rewrap(pbk_ctx *ctx, double *com, const double *com_unwrap, const double *mem_com, const float *box,
+               int64_t F, int64_t N, int32_t *status, void *stream);
+
 /* ---- N4  pair searches of the stand-alone COM trajectory ---------------------------------------
  * COMTraj.calc_membrane_thickness                       pybilt/com_trajectory/COMTraj.py:1244-1408
  * COMTraj.calc_area_per_lipid_closest_neighbor_circle   pybilt/com_trajectory/COMTraj.py:1655-1766
  * COMTraj.check_clustering                              pybilt/com_trajectory/COMTraj.py:1411-1576
  * COMTraj's own minimum image on the wrapped COMs (d = a - b; |d| > h: d = L - |a - h| - |b - h| with
  * h = f32(L/2)), rxy = sqrt(dx*dx + dy*dy).
+ * mode 1 (N3: MSDDistProtocol._ordered_com_dists analysis_protocols.py:5776-5805, DCClusterProtocol
+ * :2936-2944 with distance_cutoff_clustering.py:27-71,127-143): the distance is
+ * distance_euclidean_pbc(a, b, box, center='box_half') instead.
  * pbk_ct_nearest: for every lipid idx_a[a] the candidates idx_b[0..nb) are scanned in list order
  * (idx_b[j] == idx_a[a] skipped when exclude_self); out_pos[f, a] = position j of the first strict
- * minimum below 10000.0 (-1: none), out_dist[f, a] = that distance (10000.0: none).
- * pbk_ct_adjacency: bits[f, a, w] bit b: rxy(candidate idx[32 w + b], seed idx[a]) <= dist. */
+ * minimum below 10000.0 (-1: none), out_dist[f, a] = that distance (10000.0: none), out_dist2[f, a]
+ * (may be NULL) = the second smallest distance.
+ * pbk_ct_adjacency: bits[f, a, w] bit b: rxy(candidate idx[32 w + b], seed idx[a]) <= dist; mode 1:
+ * dist(idx[min(a, b')], idx[max(a, b')]) <= dist for b' = 32 w + b != a (each pair evaluated once). */
 int pbk_ct_nearest(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx_a, int32_t na,
-                   const int32_t *idx_b, int32_t nb, int xi, int yi, int exclude_self, int64_t F, int64_t N,
-                   int32_t *out_pos, double *out_dist, void *stream);
+                   const int32_t *idx_b, int32_t nb, int xi, int yi, int exclude_self, int mode, int64_t F,
+                   int64_t N, int32_t *out_pos, double *out_dist, double *out_dist2, void *stream);
 int pbk_ct_adjacency(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx, int32_t n,
-                     int xi, int yi, double dist, int64_t F, int64_t N, uint32_t *bits, void *stream);
+                     int xi, int yi, double dist, int mode, int64_t F, int64_t N, uint32_t *bits, void *stream);
 
 /* ---- C1 / C2  mean squared displacement -------------------------------------------------
  * MSDProtocol.run_analysis / MSDMultiProtocol.run_analysis

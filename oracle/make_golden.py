@@ -105,6 +105,24 @@ def make_comtraj(name: str) -> str:
     return path
 
 
+def make_unwrap_up_to() -> str:
+    """BilayerAnalyzer.unwrap_coordinates_up_to (bilayer_analyzer.py:1034-1079) on the adversarial
+    unwrap case: frames 0..6 are only unwrapped, the analysis runs over frames 7.. and continues from
+    that state."""
+    top, traj = cases.make_inputs("big_steps")
+    ba = rh.make_analyzer(top, traj, ["msd msd_1", "msd msd_up leaflet upper"], "all", None, None, None)
+    with rh.quiet():
+        ba.unwrap_coordinates_up_to(6)
+        ba.set_frame_range(7, -1, 1)
+        ba.run_analysis()
+    flat = {"out/msd_1": ba.get_analysis_data("msd_1"), "out/msd_up": ba.get_analysis_data("msd_up"),
+            "rep/u_last": np.array(ba._oldcoords, dtype=np.float32),
+            "meta/input_sha256": np.array(cases.input_digest(traj))}
+    path = os.path.join(GOLDEN, "unwrap_up_to.npz")
+    np.savez_compressed(path, **flat)
+    return path
+
+
 def make_estimators() -> str:
     """The reference's diffusion estimators (pybilt/diffusion/diffusion_coefficients.py:17-167)
     on the msd rows of fixture c2_prefix and on a noisy straight line, with and without time_range."""
@@ -131,10 +149,12 @@ def make_estimators() -> str:
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES] + ["estimators"])
+    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES] + ["estimators", "unwrap_up_to"])
     for n in names:
         if n == "estimators":
             p = make_estimators()
+        elif n == "unwrap_up_to":
+            p = make_unwrap_up_to()
         else:
             p = make_comtraj(n.split(":", 1)[1]) if n.startswith("comtraj:") else make(n)
         print(n, "->", p, os.path.getsize(p), "bytes")

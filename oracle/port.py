@@ -824,6 +824,193 @@ def comtraj_msd(ct, leaflet="both", group="all", plane=(0, 1)):
 
 
 # --------------------------------------------------------------------------------------
+# N3: com_frame:rewrap, disp_vec, msd_dist, dc_cluster
+#   pybilt/bilayer_analyzer/com_frame.py:233-270; analysis_protocols.py:1655-1897, 5523-5830, 2826-2983;
+#   pybilt/common/distance_cutoff_clustering.py:27-71,127-205; pybilt/common/running_stats.py:364-431
+# (plain loops: these run on the small parity cases only)
+# --------------------------------------------------------------------------------------
+def rewrap(com, com_unwrap, mem_com, box):
+    out = com.copy()
+    for f in range(com.shape[0]):
+        for r in range(com.shape[1]):
+            pos_c = com_unwrap[f, r] + mem_com[f]
+            diff = pos_c - com[f, r]
+            if np.sqrt(np.dot(diff, diff)) > 1.0:
+                for i in range(3):
+                    p_i, b = pos_c[i], box[f, i]
+                    while p_i < 0.0:
+                        p_i += b
+                    while p_i > b:
+                        p_i -= b
+                    out[f, r, i] = p_i
+    return out
+
+
+def pbc_dist(v_a, v_b, bl):
+    """distance_euclidean_pbc(v_a, v_b, bl, center='box_half')"""
+    c = np.array(bl) / 2.0
+    v_a, v_b = v_a - c, v_b - c
+    d_v = v_a - v_b
+    for i in range(len(d_v)):
+        if np.absolute(d_v[i]) > bl[i] / 2.0:
+            d_v[i] = bl[i] - np.absolute(v_a[i]) - np.absolute(v_b[i])
+    return np.sqrt(np.dot(d_v, d_v))
+
+
+def interval_pairs(md_frames, interval):
+    pairs, last_g, last_md = [], 0, int(md_frames[0])
+    for g in range(1, len(md_frames)):
+        if int(md_frames[g]) - last_md == interval:
+            pairs.append((last_g, g))
+            last_g, last_md = g, int(md_frames[g])
+    return pairs
+
+
+def disp_vec(com, com_unwrap, labels, types, box, md_frames, kv, lateral=(0, 1)):
+    lat = list(lateral)
+    truth = lambda k: kv.get(k, "False") in ("True", "true")
+    scale, to_max, wrapped = truth("scale"), truth("scale_to_max"), truth("wrapped")
+    if scale and to_max:
+        scale = False
+    leaflet, resname = kv.get("leaflet", "both"), kv.get("resname", "all")
+    out, boxes = [], []
+    for gp, gc in interval_pairs(md_frames, int(kv.get("interval", 5))):
+        idx = list(_indices_for(leaflet_views(labels[gc], types), leaflet, resname))
+        bl = box[gp][lat]
+        boxes.append(bl)
+        ci, cj, cw = com_unwrap[gc][idx][:, lat], com_unwrap[gp][idx][:, lat], com[gp][idx][:, lat]
+        if scale:
+            ci, cj, cw = ci / bl, cj / bl, cw / bl
+        vec = np.zeros((len(idx), 4))
+        vec[:, 0:2] = cw if wrapped else cj
+        vec[:, 2:4] = ci - cj
+        out.append([vec, [types[i] for i in idx]])
+    if to_max and boxes:
+        b = np.array(boxes)
+        mx, my = b[:, 0].max(), b[:, 1].max()
+        scaled = []
+        for vec, names in out:
+            vec = vec.copy()
+            vec[:, 0] /= mx; vec[:, 2] /= mx; vec[:, 1] /= my; vec[:, 3] /= my
+            scaled.append([vec, names])
+        return scaled
+    return out
+
+
+def binned_average(data, positions, n_bins, position_range):
+    lower, upper = position_range
+    edges = np.linspace(lower, upper, num=n_bins + 1, endpoint=True)
+    bins = np.linspace(lower, upper, num=n_bins, endpoint=False)
+    counts, sums = np.zeros(len(bins)).astype(np.int64), np.zeros(len(bins))
+    for c_val, pos in zip(data, positions):
+        for j in range(1, len(bins) + 1):
+            if (pos >= edges[j - 1]) and (pos <= edges[j]):
+                counts[j - 1] += 1
+                sums[j - 1] += c_val
+                break
+    keep = [i for i in range(len(counts)) if counts[i] > 0]
+    return bins[keep], sums[keep] / counts[keep]
+
+
+def msd_dist(com, com_unwrap, labels, types, box, md_frames, kv, lateral=(0, 1)):
+    lat = list(lateral)
+    leaflet = kv.get("leaflet", "both")
+    views0 = leaflet_views(labels[0], types)
+    do_leaflet = ["upper", "lower"] if leaflet == "both" else [leaflet]
+    ltypes = []
+    for ln in do_leaflet:
+        for g in views0[ln].group_names:
+            if g not in ltypes:
+                ltypes.append(g)
+    r1n = ltypes[0] if kv.get("resname_1", "first") == "first" else kv["resname_1"]
+    r2n = ltypes[0] if kv.get("resname_2", "first") == "first" else kv["resname_2"]
+    r1, r2 = [], []
+    for ln in (["upper", "lower"] if leaflet == "both" else [leaflet]):
+        r1 += list(views0[ln].get_group_indices(r1n))
+        r2 += list(views0[ln].get_group_indices(r2n))
+    dist_avg = kv.get("dist_avg", "False") in ("True", "true")
+
+    def ordered(f):
+        bl = np.array([box[f][lat[0]], box[f][lat[1]]])
+        table = {}
+        for i in r1:
+            d = sorted(pbc_dist(com[f][i][lat], com[f][j][lat], bl) for j in r2)
+            table[i] = d
+        return table
+    sds, distances = [], []
+    pick = 1 if r1n == r2n else 0
+    for gp, gc in interval_pairs(md_frames, int(kv.get("interval", 5))):
+        for i in r1:
+            disp = com_unwrap[gc][i][lat] - com_unwrap[gp][i][lat]
+            sds.append(np.dot(disp, disp))
+        prev, curr = ordered(gp), ordered(gc)
+        for key in prev:
+            d = prev[key][pick]
+            if dist_avg:
+                d = (d + curr[key][pick]) / 2.0
+            distances.append(d)
+    return binned_average(np.array(sds), np.array(distances), int(kv.get("n_bins", 25)),
+                          [float(kv.get("range_inner", 0.0)), float(kv.get("range_outer", 25.0))])
+
+
+def dc_cluster(com, labels, types, box, times, kv, lateral=(0, 1)):
+    lat = list(lateral)
+    leaflet, cutoff = kv.get("leaflet", "upper"), float(kv.get("cutoff", 12.0))
+    do_leaflet = ["upper", "lower"] if leaflet == "both" else [leaflet]
+    resname = kv.get("resname", "first")
+    out = {k: [] for k in ("clusters", "nclusters", "max_size", "min_size", "avg_size")}
+    rs = {k: Welford() for k in ("nclusters", "max_size", "min_size", "avg_size")}
+    for f in range(com.shape[0]):
+        views = leaflet_views(labels[f], types)
+        if resname == "first":
+            names = []
+            for ln in do_leaflet:
+                for g in views[ln].group_names:
+                    if g not in names:
+                        names.append(g)
+            resname = names[0]
+        idx = []
+        for ln in do_leaflet:
+            idx += list(views[ln].get_group_indices(resname))
+        pos = [com[f][i][lat] for i in idx]
+        bl = box[f][lat]
+        n = len(pos)
+        adj = np.zeros((n, n), dtype=bool)
+        for i in range(n - 1):
+            for j in range(i + 1, n):
+                adj[i, j] = adj[j, i] = pbc_dist(pos[i], pos[j], bl) <= cutoff
+        clusters, master = [], list(range(n))
+        while master:
+            nb, taken, i = [master[0]], {master[0]}, 0
+            while i < len(nb):
+                for b in master:
+                    if b not in taken and adj[nb[i], b]:
+                        nb.append(b)
+                        taken.add(b)
+                i += 1
+            master = [b for b in master if b not in taken]
+            if len(nb) > 1:
+                clusters.append(nb)
+        ncl, mn, mx, avg = len(clusters), 0, 0, 0.0
+        for cl in clusters:
+            m = len(cl)
+            if m > mx:
+                mx = m
+            elif m > 0 and mx == 0:
+                mn = m
+            elif mx > 0 and m < mx:
+                mn = m
+            avg += m
+        if ncl > 0:
+            avg /= ncl
+        out["clusters"].append(clusters)
+        for key, val in (("nclusters", ncl), ("max_size", mx), ("min_size", mn), ("avg_size", avg)):
+            rs[key].push(val)
+            out[key].append([times[f], val, rs[key].mean(), rs[key].deviation()])
+    return {k: (v if k == "clusters" else np.array(v)) for k, v in out.items()}
+
+
+# --------------------------------------------------------------------------------------
 # driver: the BilayerAnalyzer frame loop over arrays (bilayer_analyzer.py:901-1031)
 # --------------------------------------------------------------------------------------
 def parse_analysis(s: str):
@@ -858,6 +1045,8 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
     times = np.asarray(traj.times)[fr]
     gather, seg, types, resids = build_beads(top, cf.get("name_dict"), cf.get("multi_bead", False))
     reps = com_frames(X, box, top.masses, gather, seg)
+    if cf.get("rewrap"):
+        reps["com"] = rewrap(reps["com"], reps["com_unwrap"], reps["mem_com"], box)
     com, comu = reps["com"], reps["com_unwrap"]
     labels = leaflet_labels(comu, norm, lf.get("update_interval", 1))
     out = {}
@@ -891,6 +1080,12 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
             out[a_id] = halperin_nelson(com, box, times, list(v.members), lateral)
         elif key == "flip_flop":
             out[a_id] = flip_flop(labels, types, resids, times, fr)
+        elif key == "disp_vec":
+            out[a_id] = disp_vec(com, comu, labels, types, box, fr, kv, lateral)
+        elif key == "msd_dist":
+            out[a_id] = msd_dist(com, comu, labels, types, box, fr, kv, lateral)
+        elif key == "dc_cluster":
+            out[a_id] = dc_cluster(com, labels, types, box, times, kv, lateral)
         elif key == "ald":
             idx = _indices_for(views0, kv.get("leaflet", "both"), kv.get("resname", "all"))
             out[a_id] = ald(comu, times, idx, lateral)

@@ -709,6 +709,291 @@ class LeaftoLeafDistProtocol(AnalysisProtocol):
 
 
 # ---------------------------------------------------------------------------------------
+def _truth(v):
+    return v in ['True', 'true']
+
+
+def _resident_only(batch, key):
+    if batch.windowed or batch.sharded:
+        raise RuntimeError("analysis '%s' needs every analysed frame resident on one device "
+                           "(no streamed windows / frame shards)" % key)
+
+
+def _frame_leaflets(batch, g):
+    """Host views of the leaflets of analysed frame g (rebuilt from the device labels)."""
+    from . import leaflet as lf
+    h = batch._analyzer._host_arrays()
+    return lf.leaflets_from_labels(h['labels'][batch.row_of_global(g)], batch.types, batch.resids)
+
+
+def _interval_pairs(batch, first_md_frame, interval):
+    """(previous, current) analysed-frame pairs the reference's interval bookkeeping selects: the last
+    used frame starts at frame_range[0] and moves to the current frame whenever the MD frame distance
+    equals `interval` (analysis_protocols.py:1772-1781, :5709-5713)."""
+    pairs, last_g, last_md = [], 0, int(first_md_frame)
+    for g in range(1, batch.n_frames):
+        md = int(batch.frame_numbers[g])
+        if md - last_md == interval:
+            pairs.append((last_g, g))
+            last_g, last_md = g, md
+    return pairs
+
+
+@_protocol('disp_vec', 'com_frame')
+class DispVecProtocol(AnalysisProtocol):
+    """Lateral displacement vectors between frames `interval` MD frames apart: per pair of frames
+    [[x, y, dx, dy] per lipid, resnames] with the lipids of the CURRENT frame's leaflets
+    (analysis_protocols.py:1655-1897).  Gathers of the resident COMs, formed on the host."""
+    _short_description = "Displacement vectors."
+    _related = list(['disp_vec_corr', 'disp_vec_nncorr', 'disp_vec_corr_avg', 'spatial_velocity_corr'])
+    _casts = {'interval': int, 'wrapped': _truth, 'scale': _truth, 'scale_to_max': _truth}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'leaflet': 'both', 'resname': 'all', 'wrapped': False, 'interval': 5, 'scale': False,
+                     'scale_to_max': False}, args)
+        if self.settings['scale'] and self.settings['scale_to_max']:
+            self.settings['scale'] = False
+        self.boxes = []
+        self.max_dim = None
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        pass                                  # everything happens in finish(), on the resident frames
+
+    def finish(self, batch):
+        _resident_only(batch, self.analysis_key)
+        h = batch._analyzer._host_arrays()
+        lat = list(batch.lateral)
+        if self.settings['leaflet'] not in ('both', 'upper', 'lower'):
+            warnings.warn("bad setting for \'leaflet\' in " + self.analysis_id + ". Using default \'both\'")
+            self.settings['leaflet'] = 'both'
+        for gp, gc in _interval_pairs(batch, batch._analyzer.settings['frame_range'][0], self.settings['interval']):
+            leaflets = _frame_leaflets(batch, gc)
+            if self.settings['leaflet'] == 'both':
+                indices = []
+                for name in leaflets:
+                    indices += leaflets[name].get_group_indices(self.settings['resname'])
+            else:
+                indices = leaflets[self.settings['leaflet']].get_group_indices(self.settings['resname'])
+            box_lateral = batch.box_host[gp][lat]
+            self.boxes.append(box_lateral)
+            rp, rc = batch.row_of_global(gp), batch.row_of_global(gc)
+            com_i = h['com_unwrap'][rc][indices][:, lat]
+            com_j = h['com_unwrap'][rp][indices][:, lat]
+            com_j_w = h['com'][rp][indices][:, lat]
+            if self.settings['scale']:
+                com_i, com_j, com_j_w = com_i / box_lateral, com_j / box_lateral, com_j_w / box_lateral
+            vec_ends = np.zeros((len(indices), 4))
+            vec_ends[:, 0:2] = com_j_w if self.settings['wrapped'] else com_j
+            vec_ends[:, 2:4] = com_i - com_j
+            self.analysis_output.append([vec_ends, [batch.types[i] for i in indices]])
+
+    def _process_output(self):
+        if self.settings['scale_to_max']:
+            boxes = np.array(self.boxes)
+            max_x, max_y = boxes[:, 0].max(), boxes[:, 1].max()
+            self.max_dim = [max_x, max_y]
+            scaled_out = []
+            for vec_ends, resnames in self.analysis_output:
+                vec_ends = vec_ends.copy()
+                vec_ends[:, 0] /= max_x
+                vec_ends[:, 2] /= max_x
+                vec_ends[:, 1] /= max_y
+                vec_ends[:, 3] /= max_y
+                scaled_out.append([vec_ends, resnames])
+            return scaled_out
+        return self.analysis_output
+
+    def get_data(self):
+        return self._process_output()
+
+    def reset(self):
+        self.analysis_output = []
+        self.boxes = []
+        self.max_dim = None
+
+
+def binned_average(data, positions, n_bins=25, position_range=None, min_count=0):
+    """(bin starts, averages) over the bins that received data; a position belongs to the FIRST bin whose
+    closed interval [edge_j, edge_j+1] holds it (pybilt/common/running_stats.py:364-431)."""
+    lower, upper = position_range if position_range is not None else (positions.min(), positions.max())
+    edges = np.linspace(lower, upper, num=n_bins + 1, endpoint=True)
+    bins = np.linspace(lower, upper, num=n_bins, endpoint=False)
+    counts = np.zeros(len(bins)).astype(np.int64)
+    sums = np.zeros(len(bins))
+    for c_val, pos in zip(data, positions):
+        hit = np.nonzero((pos >= edges[:-1]) & (pos <= edges[1:]))[0]
+        if len(hit):
+            counts[hit[0]] += 1
+            sums[hit[0]] += c_val
+    keep = np.nonzero(counts > 0)[0]
+    return bins[keep], sums[keep] / counts[keep]
+
+
+@_protocol('msd_dist', 'com_frame')
+class MSDDistProtocol(AnalysisProtocol):
+    """Squared lateral displacement over `interval` MD frames binned by the distance to the nearest
+    lipid of type resname_2 (second nearest when resname_1 == resname_2) in the earlier frame
+    (analysis_protocols.py:5523-5830).  The nearest distances of all frames come from one device search
+    (`pbk_ct_nearest`, distance_euclidean_pbc on the wrapped COMs)."""
+    _short_description = "Mean squared displacement as a function of distance."
+    _related = list(['disp_vec', 'msd'])
+    _casts = {'interval': int, 'n_bins': int, 'range_inner': float, 'range_outer': float, 'dist_avg': _truth}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'leaflet': 'both', 'interval': 5, 'resname_1': 'first', 'resname_2': 'first', 'n_bins': 25,
+                     'range_inner': 0.0, 'range_outer': 25.0, 'dist_avg': False}, args)
+        self.reset()
+
+    def reset(self):
+        self._sds, self._distances = [], []
+        self._r1_indices, self._r2_indices = [], []
+        self.analysis_output = []
+        self._processed_output = None
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        pass
+
+    def finish(self, batch):
+        _resident_only(batch, self.analysis_key)
+        st, leaflets = self.settings, batch.first_leaflets
+        do_leaflet = ['upper', 'lower'] if st['leaflet'] == 'both' else [st['leaflet']]
+        lipid_types, _n = _lipid_types_in(leaflets, do_leaflet)
+        if st['resname_1'] == 'first':
+            st['resname_1'] = lipid_types[0]
+        if st['resname_2'] == 'first':
+            st['resname_2'] = lipid_types[0]
+        r1, r2 = [], []
+        for name in (leaflets if st['leaflet'] == 'both' else [st['leaflet']]):
+            r1 += leaflets[name].get_group_indices(st['resname_1'])
+            r2 += leaflets[name].get_group_indices(st['resname_2'])
+        self._r1_indices, self._r2_indices = r1, r2
+        lat = list(batch.lateral)
+        _pos, d_first, d_second = batch.engine.ct_nearest(r1, r2, lat, d1=True, frames=batch.rows, second=True)
+        dist = (d_second if st['resname_1'] == st['resname_2'] else d_first).cpu().numpy()
+        h = batch._analyzer._host_arrays()
+        # the reference keys its neighbour table by lipid index: a lipid listed twice keeps one entry
+        keys = list(dict.fromkeys(r1))
+        col = {i: k for k, i in enumerate(r1)}
+        for gp, gc in _interval_pairs(batch, batch._analyzer.settings['frame_range'][0], st['interval']):
+            rp, rc = batch.row_of_global(gp), batch.row_of_global(gc)
+            disp = h['com_unwrap'][rc][r1][:, lat] - h['com_unwrap'][rp][r1][:, lat]
+            # np.dot of two float64: fused accumulation (DESIGN.md "Arithmetic"); x*x + y*y agrees with it
+            # to one rounding, far below the 1e-9 of the binned averages
+            self._sds += list(disp[:, 0] * disp[:, 0] + disp[:, 1] * disp[:, 1])
+            for i in keys:
+                d = dist[gp - batch.gframes.start][col[i]]
+                if st['dist_avg']:
+                    d = (d + dist[gc - batch.gframes.start][col[i]]) / 2.0
+                self._distances.append(d)
+
+    def _process_output(self):
+        if self._processed_output is None:
+            self._processed_output = binned_average(np.array(self._sds), np.array(self._distances),
+                                                    n_bins=self.settings['n_bins'],
+                                                    position_range=[self.settings['range_inner'], self.settings['range_outer']],
+                                                    min_count=0)
+
+    def get_data(self):
+        self._process_output()
+        return self._processed_output
+
+
+@_protocol('dc_cluster', 'com_frame')
+class DCClusterProtocol(AnalysisProtocol):
+    """Distance cut-off clusters of one lipid type per frame: {'clusters': per frame lists of positions in
+    the frame's index list, 'nclusters' / 'max_size' / 'min_size' / 'avg_size': rows [time, value, running
+    mean, running deviation]} (analysis_protocols.py:2826-2983, distance_cutoff_clustering.py:127-205).
+    The cut-off matrix comes from the device (`pbk_ct_adjacency`); clusters are grown on the host in the
+    reference's order."""
+    _short_description = "Hiearchical clustering of lipids based on distance."
+    _related = None
+    _casts = {'cutoff': float}
+    batched = True
+
+    def __init__(self, args):
+        self._setup({'resname': 'first', 'leaflet': 'upper', 'cutoff': 12.0}, args)
+        self.reset()
+
+    def reset(self):
+        self.converted = False
+        self.analysis_output = {k: [] for k in ('clusters', 'nclusters', 'max_size', 'min_size', 'avg_size')}
+        self.running_stats = {k: RunningStats() for k in ('nclusters', 'max_size', 'min_size', 'avg_size')}
+
+    def run_batch(self, ba_settings, batch, ba_mda_data):
+        pass
+
+    def finish(self, batch):
+        _resident_only(batch, self.analysis_key)
+        st = self.settings
+        do_leaflet = ['upper', 'lower'] if st['leaflet'] == 'both' else [st['leaflet']]
+        if st['resname'] == 'first':
+            st['resname'] = _lipid_types_in(batch.first_leaflets, do_leaflet)[0][0]
+        # index list per frame (it follows the frame's leaflets); frames that share a list share a launch
+        lists = []
+        for g in range(batch.n_frames):
+            leaflets = _frame_leaflets(batch, g)
+            idx = []
+            for name in do_leaflet:
+                idx += leaflets[name].get_group_indices(st['resname'])
+            lists.append(idx)
+        g = 0
+        while g < batch.n_frames:
+            g1 = g + 1
+            while g1 < batch.n_frames and lists[g1] == lists[g]:
+                g1 += 1
+            idx, n = lists[g], len(lists[g])
+            rows = slice(batch.row_of_global(g), batch.row_of_global(g1))
+            bits = batch.engine.ct_adjacency(idx, st['cutoff'], batch.lateral, d1=True, frames=rows).cpu().numpy() if n else None
+            for k in range(g1 - g):
+                adj = np.unpackbits(bits[k].view(np.uint8), axis=1, bitorder='little')[:, :n].astype(bool) if n else None
+                self._frame(batch.times[g + k], adj, n)
+            g = g1
+
+    def _frame(self, time, adj, n):
+        clusters, master = [], list(range(n))
+        while master:
+            neighbors, taken = [master[0]], {master[0]}
+            i = 0
+            while i < len(neighbors):
+                row = adj[neighbors[i]]
+                for b in master:
+                    if b not in taken and row[b]:
+                        neighbors.append(b)
+                        taken.add(b)
+                i += 1
+            master = [b for b in master if b not in taken]
+            if len(neighbors) > 1:
+                clusters.append(list(neighbors))
+        nclusters, min_size, max_size, avg_size = len(clusters), 0, 0, 0.0
+        for cluster in clusters:                  # (the reference's running min / max, as written)
+            m = len(cluster)
+            if m > max_size:
+                max_size = m
+            elif m > 0 and max_size == 0:
+                min_size = m
+            elif max_size > 0 and m < max_size:
+                min_size = m
+            avg_size += m
+        if nclusters > 0:
+            avg_size /= nclusters
+        out, rs = self.analysis_output, self.running_stats
+        out['clusters'].append(clusters)
+        for key, val in (('nclusters', nclusters), ('max_size', max_size), ('min_size', min_size), ('avg_size', avg_size)):
+            rs[key].push(val)
+            out[key].append([time, val, rs[key].mean(), rs[key].deviation()])
+
+    def get_data(self):
+        if not self.converted:
+            for key in self.analysis_output.keys():
+                if key != 'clusters':
+                    self.analysis_output[key] = np.array(self.analysis_output[key])
+            self.converted = True
+        return self.analysis_output
+
+
+# ---------------------------------------------------------------------------------------
 @_protocol('halperin_nelson', 'com_frame')
 class HalperinNelsonProtocol(AnalysisProtocol):
     """Halperin and Nelson's hexagonal-packing invariant averaged over a leaflet, rows

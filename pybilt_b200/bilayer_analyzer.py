@@ -512,6 +512,7 @@ class BilayerAnalyzer(object):
         self._engine = None
         self._batch = None
         self._host = None
+        self._unwrap_state = None           # unwrap_coordinates_up_to: unwrapped coordinates to continue from
         self._cursor = 0
 
     def __repr__(self):
@@ -668,8 +669,33 @@ class BilayerAnalyzer(object):
         self.settings['frame_index'] = 0
         self._current_frame = self.settings['frame_range'][0]
         self._frame_loop_count = 0
+        self._unwrap_state = None
         self._analysis_protocol.reset()
         self._invalidate()
+
+    def unwrap_coordinates_up_to(self, frame_index):
+        """Unwrap the trajectory from frame 0 up to ``frame_index`` (stepping by the frame interval)
+        without analysing anything, so that a run whose frame range starts later continues from
+        that unwrapped state instead of treating its first frame as the reference
+        (bilayer_analyzer.py:1034-1079).  ``reset()`` forgets the state, as it does there."""
+        md = self._mda_data
+        last = md.nframes if frame_index == -1 else int(frame_index)
+        frames = np.arange(0, min(last + 1, md.nframes), self.settings['frame_range'][2])
+        if len(frames) == 0:
+            return
+        cset = self.rep_settings['com_frame']
+        layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids,
+                                   cset['name_dict'], cset['multi_bead'])
+        nb = int(max(1, min(len(frames), (96 << 20) // max(1, md.natoms * 12))))
+        eng = LipidReductionEngine(md.masses, layout, 1, device=self.device, norm=self.settings['norm'],
+                                   batch_frames=nb, allow_fused=False)
+        if self._unwrap_state is not None:
+            eng.d_u_state.copy_(self._unwrap_state)
+            eng.stream_started = True
+        self._push_frames(eng, md, frames, unwrap_only=True)
+        eng.check_status()
+        self._unwrap_state = eng.d_u_state.clone()
+        self._feeder_cache = None
 
     def _invalidate(self):
         if getattr(self, '_engine', None) is not None:
@@ -701,8 +727,8 @@ class BilayerAnalyzer(object):
         if lset['assign_method'] != 'avg_norm':
             raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
                                "(only 'avg_norm')" % lset['assign_method'])
-        if self.rep_settings['com_frame']['rewrap'] or self.rep_settings['com_frame']['make_whole']:
-            raise RuntimeError("com_frame:rewrap / make_whole are outside the accelerated path")
+        if self.rep_settings['com_frame']['make_whole']:
+            raise RuntimeError("com_frame:make_whole is outside the accelerated path")
         md = self._mda_data
         cset = self.rep_settings['com_frame']
         layout = None
@@ -739,7 +765,7 @@ class BilayerAnalyzer(object):
             # reduction of batch k, and only the last batch's kernels are exposed
             batch_frames = int(max(64, min(len(fr), (96 << 20) // max(1, md.natoms * 12))))
         key = (id(md), repr(cset['name_dict']), bool(cset['multi_bead']), n_rows, self.device,
-               self.settings['norm'], int(lset['update_interval']), batch_frames)
+               self.settings['norm'], int(lset['update_interval']), batch_frames, bool(cset['rewrap']))
         cached = getattr(self, '_engine_cache', None)
         if cached is not None and cached[0] == key:
             eng = cached[1]
@@ -752,9 +778,14 @@ class BilayerAnalyzer(object):
             eng = LipidReductionEngine(md.masses, layout, n_rows, device=self.device,
                                        norm=self.settings['norm'],
                                        leaflet_update_interval=int(lset['update_interval']),
-                                       batch_frames=batch_frames, allow_fused=allow_fused)
+                                       batch_frames=batch_frames, allow_fused=allow_fused, rewrap=bool(cset['rewrap']))
         self._engine_key = key
         self._engine_cache = None
+        if self._unwrap_state is not None:
+            if shard is not None:
+                raise RuntimeError("unwrap_coordinates_up_to is not combined with frame shards")
+            eng.d_u_state.copy_(self._unwrap_state)
+            eng.stream_started = True
         if shard is not None:
             return self._reduce_sharded(eng, md, fr, fr_all, shard, layout)
         # host -> device in engine-batch sized pieces, double-buffered on a copy stream
@@ -863,8 +894,8 @@ class BilayerAnalyzer(object):
         if lset['assign_method'] != 'avg_norm':
             raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
                                "(only 'avg_norm')" % lset['assign_method'])
-        if self.rep_settings['com_frame']['rewrap'] or self.rep_settings['com_frame']['make_whole']:
-            raise RuntimeError("com_frame:rewrap / make_whole are outside the accelerated path")
+        if self.rep_settings['com_frame']['make_whole']:
+            raise RuntimeError("com_frame:make_whole is outside the accelerated path")
 
     def _default_batch_frames(self, n):
         md = self._mda_data
@@ -1010,7 +1041,7 @@ class BilayerAnalyzer(object):
             dims_all = np.zeros((F, 6), dtype=np.float32)
             times_all = np.zeros(F)
         ekey = (C + W + 1, self.device, self.settings['norm'], int(lset['update_interval']),
-                self._default_batch_frames(W))
+                self._default_batch_frames(W), bool(self.rep_settings['com_frame']['rewrap']))
         if wc.get('ekey') == ekey:                     # buffers, plan and context are reused across reset()
             eng = wc['engine']
             eng.reset()
@@ -1018,8 +1049,14 @@ class BilayerAnalyzer(object):
         else:
             eng = LipidReductionEngine(md.masses, layout, C + W + 1, device=self.device, norm=self.settings['norm'],
                                        leaflet_update_interval=int(lset['update_interval']),
-                                       batch_frames=self._default_batch_frames(W), allow_fused=allow_fused)
+                                       batch_frames=self._default_batch_frames(W), allow_fused=allow_fused,
+                                       rewrap=bool(self.rep_settings['com_frame']['rewrap']))
             wc['ekey'], wc['engine'] = ekey, eng
+        if self._unwrap_state is not None:
+            if world > 1:
+                raise RuntimeError("unwrap_coordinates_up_to is not combined with frame shards")
+            eng.d_u_state.copy_(self._unwrap_state)
+            eng.stream_started = True
         ref_row = C + W
         init = None
         retained = None

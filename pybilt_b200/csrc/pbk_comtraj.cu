@@ -10,6 +10,15 @@
 // scan the candidates in list order and keep the first strict minimum below the start value 10000.0.
 #include "pbk_common.cuh"
 
+// mode 1: distance_euclidean_pbc(a, b, box, center='box_half') of the BilayerAnalyzer protocols
+// (pybilt/common/distance_cutoff_clustering.py:27-71; msd_dist :5776-5805, dc_cluster :2936-2944 of
+// analysis_protocols.py): a' = a - c, b' = b - c with c = f32 box / 2, d^2 as np.dot forms it
+static __device__ __forceinline__ double ct_d1(double ax, double ay, double bx, double by, double Lx, double Ly,
+                                               double hx, double hy)
+{
+    return __dsqrt_rn(pbk_pbc_dist2(__dsub_rn(ax, hx), __dsub_rn(ay, hy), __dsub_rn(bx, hx), __dsub_rn(by, hy), Lx, Ly, hx, hy));
+}
+
 static __device__ __forceinline__ double ct_rxy(double ax, double ay, double bx, double by, double Lx, double Ly,
                                                 double hx, double hy)
 {
@@ -22,12 +31,53 @@ static __device__ __forceinline__ double ct_rxy(double ax, double ay, double bx,
 #define CT_THREADS 128
 #define CT_TILE 256
 
+// COMFrame._rewrap (pybilt/bilayer_analyzer/com_frame.py:233-270, rep setting com_frame:rewrap): the
+// wrapped COM of a lipid is rebuilt from its unwrapped one when the two disagree by more than 1 A:
+//   pos_c = com_unwrap + mem_com;  |pos_c - com| > 1  (np.dot of three float64: fma(c,c, fma(b,b, a*a)))
+//   every component is then moved by whole (float32) box edges into [0, box].
+__global__ void k_rewrap(double *__restrict__ com, const double *__restrict__ com_unwrap, const double *__restrict__ mem_com,
+                         const float *__restrict__ box, int64_t F, int64_t N, int32_t *__restrict__ status)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * N) return;
+    const int64_t f = t / N;
+    double pc[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        pc[k] = __dadd_rn(com_unwrap[3 * t + k], mem_com[3 * f + k]);
+        d[k] = __dsub_rn(pc[k], com[3 * t + k]);
+    }
+    const double d2 = fma(d[2], d[2], fma(d[1], d[1], __dmul_rn(d[0], d[0])));
+    if (!(__dsqrt_rn(d2) > 1.0)) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double b = (double)box[3 * f + k];
+        double p = pc[k];
+        if (!(b > 0.0)) { atomicOr(status, PBK_ST_IMAGE_OVERFLOW); com[3 * t + k] = p; continue; }
+        int it = 0;
+        while (p < 0.0 && ++it < (1 << 20)) p = __dadd_rn(p, b);
+        while (p > b && ++it < (1 << 20)) p = __dsub_rn(p, b);
+        com[3 * t + k] = p;
+    }
+}
+
+extern "C" int pbk_rewrap(pbk_ctx *ctx, double *com, const double *com_unwrap, const double *mem_com, const float *box,
+                          int64_t F, int64_t N, int32_t *status, void *stream)
+{
+    if (!ctx || !com || !com_unwrap || !mem_com || !box || !status || F < 0 || N <= 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_rewrap: bad argument");
+    if (F == 0) return PBK_OK;
+    k_rewrap<<<(unsigned)((F * N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(com, com_unwrap, mem_com, box, F, N, status);
+    PBK_CHECK_LAUNCH(ctx, "k_rewrap");
+    return PBK_OK;
+}
+
 // grid (ceil(na / CT_THREADS), F): thread = one lipid of list A, candidates of list B staged in
 // shared memory tile by tile, in list order
 __global__ void __launch_bounds__(CT_THREADS)
 k_ct_nearest(const double *__restrict__ com, const float *__restrict__ box, const int32_t *__restrict__ idx_a,
-             int na, const int32_t *__restrict__ idx_b, int nb, int xi, int yi, int exclude_self, int64_t N,
-             int32_t *__restrict__ out_pos, double *__restrict__ out_dist)
+             int na, const int32_t *__restrict__ idx_b, int nb, int xi, int yi, int exclude_self, int mode, int64_t N,
+             int32_t *__restrict__ out_pos, double *__restrict__ out_dist, double *__restrict__ out_dist2)
 {
     __shared__ double s_x[CT_TILE], s_y[CT_TILE];
     __shared__ int s_i[CT_TILE];
@@ -38,7 +88,7 @@ k_ct_nearest(const double *__restrict__ com, const float *__restrict__ box, cons
     const int a = blockIdx.x * CT_THREADS + threadIdx.x;
     const int ia = a < na ? idx_a[a] : -1;
     const double ax = ia >= 0 ? c[3 * (int64_t)ia + xi] : 0.0, ay = ia >= 0 ? c[3 * (int64_t)ia + yi] : 0.0;
-    double best = 10000.0;
+    double best = 10000.0, second = 10000.0;
     int pos = -1;
     for (int b0 = 0; b0 < nb; b0 += CT_TILE) {
         __syncthreads();
@@ -51,14 +101,17 @@ k_ct_nearest(const double *__restrict__ com, const float *__restrict__ box, cons
             const int m = min(CT_TILE, nb - b0);
             for (int j = 0; j < m; j++) {
                 if (exclude_self && s_i[j] == ia) continue;
-                const double r = ct_rxy(ax, ay, s_x[j], s_y[j], Lx, Ly, hx, hy);
-                if (r < best) { best = r; pos = b0 + j; }
+                const double r = mode ? ct_d1(ax, ay, s_x[j], s_y[j], Lx, Ly, hx, hy)
+                                      : ct_rxy(ax, ay, s_x[j], s_y[j], Lx, Ly, hx, hy);
+                if (r < best) { second = best; best = r; pos = b0 + j; }
+                else if (r < second) second = r;
             }
         }
     }
     if (ia >= 0) {
         out_pos[f * na + a] = pos;
         out_dist[f * na + a] = best;
+        if (out_dist2) out_dist2[f * na + a] = second;
     }
 }
 
@@ -66,7 +119,7 @@ k_ct_nearest(const double *__restrict__ com, const float *__restrict__ box, cons
 // rxy(idx[b], idx[a]) <= dist (evaluated as the reference does: candidate first, cluster seed second)
 __global__ void __launch_bounds__(CT_THREADS)
 k_ct_adjacency(const double *__restrict__ com, const float *__restrict__ box, const int32_t *__restrict__ idx, int n,
-               int xi, int yi, double dist, int64_t N, uint32_t *__restrict__ bits)
+               int xi, int yi, double dist, int mode, int64_t N, uint32_t *__restrict__ bits)
 {
     __shared__ double s_x[CT_TILE], s_y[CT_TILE];
     const int64_t f = blockIdx.y;
@@ -91,8 +144,12 @@ k_ct_adjacency(const double *__restrict__ com, const float *__restrict__ box, co
                 uint32_t word = 0u;
                 for (int j = w; j < min(m, w + 32); j++) {
                     // comc = candidate (b), coms = seed (a):  dx = comc - coms
-                    const double r = ct_rxy(s_x[j], s_y[j], ax, ay, Lx, Ly, hx, hy);
-                    if (r <= dist) word |= 1u << (j - w);
+                    // mode 1: the pair is evaluated once, dist(vectors[i], vectors[j]) with i < j
+                    const bool lower_first = a < b0 + j;
+                    const double r = !mode ? ct_rxy(s_x[j], s_y[j], ax, ay, Lx, Ly, hx, hy)
+                                   : (lower_first ? ct_d1(ax, ay, s_x[j], s_y[j], Lx, Ly, hx, hy)
+                                                  : ct_d1(s_x[j], s_y[j], ax, ay, Lx, Ly, hx, hy));
+                    if (r <= dist && (!mode || a != b0 + j)) word |= 1u << (j - w);
                 }
                 row[(b0 + w) / 32] = word;
             }
@@ -101,8 +158,8 @@ k_ct_adjacency(const double *__restrict__ com, const float *__restrict__ box, co
 }
 
 extern "C" int pbk_ct_nearest(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx_a, int32_t na,
-                              const int32_t *idx_b, int32_t nb, int xi, int yi, int exclude_self, int64_t F, int64_t N,
-                              int32_t *out_pos, double *out_dist, void *stream)
+                              const int32_t *idx_b, int32_t nb, int xi, int yi, int exclude_self, int mode, int64_t F,
+                              int64_t N, int32_t *out_pos, double *out_dist, double *out_dist2, void *stream)
 {
     if (!ctx || !com || !box || !out_pos || !out_dist || na < 0 || nb < 0 || F < 0 || N <= 0 || xi < 0 || xi > 2 ||
         yi < 0 || yi > 2 || (na > 0 && !idx_a) || (nb > 0 && !idx_b))
@@ -110,20 +167,20 @@ extern "C" int pbk_ct_nearest(pbk_ctx *ctx, const double *com, const float *box,
     if (F == 0 || na == 0) return PBK_OK;
     if (F > 65535) return PBK_EUNSUPPORTED;
     k_ct_nearest<<<dim3((unsigned)((na + CT_THREADS - 1) / CT_THREADS), (unsigned)F), CT_THREADS, 0, (cudaStream_t)stream>>>(
-        com, box, idx_a, na, idx_b, nb, xi, yi, exclude_self, N, out_pos, out_dist);
+        com, box, idx_a, na, idx_b, nb, xi, yi, exclude_self, mode, N, out_pos, out_dist, out_dist2);
     PBK_CHECK_LAUNCH(ctx, "k_ct_nearest");
     return PBK_OK;
 }
 
 extern "C" int pbk_ct_adjacency(pbk_ctx *ctx, const double *com, const float *box, const int32_t *idx, int32_t n,
-                                int xi, int yi, double dist, int64_t F, int64_t N, uint32_t *bits, void *stream)
+                                int xi, int yi, double dist, int mode, int64_t F, int64_t N, uint32_t *bits, void *stream)
 {
     if (!ctx || !com || !box || !bits || n < 0 || F < 0 || N <= 0 || xi < 0 || xi > 2 || yi < 0 || yi > 2 || (n > 0 && !idx))
         return pbk_fail(ctx, PBK_EINVAL, "pbk_ct_adjacency: bad argument");
     if (F == 0 || n == 0) return PBK_OK;
     if (F > 65535) return PBK_EUNSUPPORTED;
     k_ct_adjacency<<<dim3((unsigned)((n + CT_THREADS - 1) / CT_THREADS), (unsigned)F), CT_THREADS, 0, (cudaStream_t)stream>>>(
-        com, box, idx, n, xi, yi, dist, N, bits);
+        com, box, idx, n, xi, yi, dist, mode, N, bits);
     PBK_CHECK_LAUNCH(ctx, "k_ct_adjacency");
     return PBK_OK;
 }

@@ -133,7 +133,7 @@ class LipidReductionEngine:
 
     def __init__(self, masses, layout: BeadLayout, n_frames: int, device: int = 0, norm: int = 2,
                  leaflet_update_interval: int = 1, batch_frames: Optional[int] = None,
-                 scratch_bytes: int = 4 << 30, allow_fused: bool = True, comtraj_rules: bool = False,
+                 scratch_bytes: int = 4 << 30, allow_fused: bool = True, comtraj_rules: bool = False, rewrap: bool = False,
                  allow_stream: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pybilt_b200: a CUDA device is required (no CPU fallback)")
@@ -161,6 +161,7 @@ class LipidReductionEngine:
         self.d_level_off = torch.from_numpy(plan.level_off).to(d)
         # streamed reduction (frames that do not fit in shared memory): tiles of lipids
         self.comtraj_rules = bool(comtraj_rules)
+        self.rewrap = bool(rewrap)            # com_frame:rewrap (com_frame.py:233-270) after every reduction
         self.stream_plan = None if (self.comtraj_rules or not allow_stream) else stream_bead_limit(layout)
         # per-frame scratch: image counts (6 B/atom) + tree nodes (generic kernels), or tree nodes +
         # compact normal components + tile partials (streamed reduction)
@@ -323,6 +324,18 @@ class LipidReductionEngine:
             raise RuntimeError("init_images belongs to the first frame of the stream")
         st = self.stream_ptr()
         c = self.ctx
+        try:
+            n_before = self.n_done
+            self._push_batches(x, box, phase, init_images, net_out, net_frames, f_total, st, c)
+        finally:
+            if self.rewrap and self.n_done > n_before:
+                n = self.n_done - n_before
+                c.call("pbk_rewrap", self.com[n_before:].data_ptr(), self.com_unwrap[n_before:].data_ptr(),
+                       self.mem_com[n_before:].data_ptr(), self.box[n_before:].data_ptr(), n, self.N,
+                       self.d_status.data_ptr(), st)
+                self.launches += 1
+
+    def _push_batches(self, x, box, phase, init_images, net_out, net_frames, f_total, st, c):
         for b0 in range(0, f_total, self.B):
             b1 = min(f_total, b0 + self.B)
             nb = b1 - b0
@@ -451,29 +464,35 @@ class LipidReductionEngine:
         self.launches += 1
         return out
 
-    def ct_nearest(self, idx_a, idx_b, lateral=(0, 1), exclude_self: bool = False):
-        """COMTraj's nearest-partner search on the wrapped COMs of every resident frame
-        (pbk_ct_nearest): (position in idx_b int32 [F, na], distance float64 [F, na])."""
-        d, F = self.dev, self.n_done
+    def ct_nearest(self, idx_a, idx_b, lateral=(0, 1), exclude_self: bool = False, d1: bool = False,
+                   frames: Optional[slice] = None, second: bool = False):
+        """Nearest-partner search on the wrapped COMs (pbk_ct_nearest) over the resident rows `frames`:
+        (position in idx_b int32 [F, na], distance float64 [F, na][, second smallest distance]).
+        d1: distance_euclidean_pbc instead of COMTraj's minimum image."""
+        sl = frames or slice(0, self.n_done)
+        d, F = self.dev, sl.stop - sl.start
         a = torch.as_tensor(np.asarray(idx_a, dtype=np.int32), device=d)
         b = torch.as_tensor(np.asarray(idx_b, dtype=np.int32), device=d)
         pos = torch.empty((F, a.numel()), dtype=torch.int32, device=d)
         dist = torch.empty((F, a.numel()), dtype=torch.float64, device=d)
-        self.ctx.call("pbk_ct_nearest", self.com.data_ptr(), self.box.data_ptr(), a.data_ptr(), a.numel(),
-                      b.data_ptr(), b.numel(), int(lateral[0]), int(lateral[1]), int(bool(exclude_self)), F, self.N,
-                      pos.data_ptr(), dist.data_ptr(), self.stream_ptr())
+        dist2 = torch.empty((F, a.numel()), dtype=torch.float64, device=d) if second else None
+        self.ctx.call("pbk_ct_nearest", self.com[sl.start:].data_ptr(), self.box[sl.start:].data_ptr(), a.data_ptr(),
+                      a.numel(), b.data_ptr(), b.numel(), int(lateral[0]), int(lateral[1]), int(bool(exclude_self)),
+                      int(bool(d1)), F, self.N, pos.data_ptr(), dist.data_ptr(), _ptr(dist2), self.stream_ptr())
         self.launches += 1
-        return pos, dist
+        return (pos, dist, dist2) if second else (pos, dist)
 
-    def ct_adjacency(self, idx, dist: float, lateral=(0, 1)) -> torch.Tensor:
-        """uint32-packed adjacency rows [F, n, ceil(n/32)] of the lipids `idx` under COMTraj's
-        cluster criterion rxy <= dist (pbk_ct_adjacency)."""
-        d, F = self.dev, self.n_done
+    def ct_adjacency(self, idx, dist: float, lateral=(0, 1), d1: bool = False, frames: Optional[slice] = None) -> torch.Tensor:
+        """uint32-packed adjacency rows [F, n, ceil(n/32)] of the lipids `idx` under a lateral cut-off
+        (pbk_ct_adjacency): COMTraj's cluster criterion, or (d1) distance_cutoff_clustering's matrix."""
+        sl = frames or slice(0, self.n_done)
+        d, F = self.dev, sl.stop - sl.start
         a = torch.as_tensor(np.asarray(idx, dtype=np.int32), device=d)
         n = a.numel()
         bits = torch.zeros((F, n, (n + 31) // 32), dtype=torch.int32, device=d)
-        self.ctx.call("pbk_ct_adjacency", self.com.data_ptr(), self.box.data_ptr(), a.data_ptr(), n,
-                      int(lateral[0]), int(lateral[1]), float(dist), F, self.N, bits.data_ptr(), self.stream_ptr())
+        self.ctx.call("pbk_ct_adjacency", self.com[sl.start:].data_ptr(), self.box[sl.start:].data_ptr(), a.data_ptr(), n,
+                      int(lateral[0]), int(lateral[1]), float(dist), int(bool(d1)), F, self.N, bits.data_ptr(),
+                      self.stream_ptr())
         self.launches += 1
         return bits
 

@@ -38,7 +38,8 @@ def run_engine(name, batch_frames=None, fused=True, stream=True):
                                    cf.get("name_dict"), cf.get("multi_bead", False))
     e = eng.LipidReductionEngine(top.masses, layout, len(fr), norm=2,
                                  leaflet_update_interval=lf.get("update_interval", 1),
-                                 batch_frames=batch_frames, allow_fused=fused, allow_stream=stream)
+                                 batch_frames=batch_frames, allow_fused=fused, allow_stream=stream,
+                                 rewrap=cf.get("rewrap", False))
     x = torch.from_numpy(np.ascontiguousarray(traj.positions[fr])).cuda()
     box = torch.from_numpy(np.ascontiguousarray(traj.dimensions[fr][:, :3])).cuda()
     e.push(x, box)
