@@ -52,7 +52,8 @@ def test_registry_and_argument_parsing():
     from pybilt_b200 import analysis_protocols as ap
     assert set(ap.valid_analysis) == {"msd", "msd_multi", "com_lateral_rdf", "nnf", "apl_grid",
                                       "thickness_grid", "thickness_leaflet_distance", "area_fluctuation",
-                                      "halperin_nelson", "apl_box", "acm", "ald", "ac", "vcm", "flip_flop"}
+                                      "halperin_nelson", "apl_box", "acm", "ald", "ac", "vcm", "flip_flop",
+                                      "disp_vec", "msd_dist", "dc_cluster"}
     assert ap.analysis_obj_name_dict["apl_grid"] == "lipid_grid"
     a = ap.Analyses(["msd msd_1", "com_lateral_rdf r n_bins 80 range_outer 40.0 leaflet upper"])
     assert a.analysis_ids == ["msd_1", "r"] and not a.use_objects["lipid_grid"]
