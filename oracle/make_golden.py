@@ -123,6 +123,50 @@ def make_unwrap_up_to() -> str:
     return path
 
 
+PREFAB_RUNS = {
+    # driver -> (case whose inputs are used, keyword arguments)
+    "msd_diffusion": ("name_dict", dict(resnames=["POPC", "DOPE"])),
+    "area_per_lipid": ("tiny_all", dict(n_xbins=8, n_ybins=8)),
+    "nearest_neighbor_fraction": ("name_dict", dict(lipid_resnames=["POPC", "DOPE"], frame_interval=2)),
+    "com_lateral_rdf": ("c3_small", dict(resnames=["POPC", "CHOL"])),
+}
+
+
+def make_prefab() -> str:
+    """The reference's own prefab drivers (pybilt/bilayer_analyzer/prefab_analysis_protocols.py:34,313,834,
+    1463) executed unmodified on in-memory inputs: what they print and what dump_data pickles."""
+    import contextlib
+    import glob
+    import io
+    import pickle
+    import tempfile
+    rh.install()
+    with rh.quiet():
+        import pybilt.bilayer_analyzer.prefab_analysis_protocols as pap
+    flat = {}
+    for driver, (case, kw) in PREFAB_RUNS.items():
+        top, traj = cases.make_inputs(case)
+        tmp = tempfile.mkdtemp(prefix="prefab_") + "/"
+        buf = io.StringIO()
+        cwd = os.getcwd()
+        os.chdir(tmp)                      # figures / plot files land in the scratch directory
+        try:
+            with contextlib.redirect_stdout(buf):
+                getattr(pap, driver)(top, (traj.positions, traj.dimensions, traj.times), "all", dump_path=tmp, **kw)
+        finally:
+            os.chdir(cwd)
+        flat[f"{driver}/stdout"] = np.array(buf.getvalue().splitlines())
+        dumped = {}
+        for path in sorted(glob.glob(tmp + "*.pickle")):
+            with open(path, "rb") as fh:
+                dumped[os.path.basename(path)[:-len(".pickle")]] = pickle.load(fh)
+        for k, v in cases.flatten_outputs(dumped).items():
+            flat[f"{driver}/{k}"] = v
+    path = os.path.join(GOLDEN, "prefab.npz")
+    np.savez_compressed(path, **flat)
+    return path
+
+
 def make_estimators() -> str:
     """The reference's diffusion estimators (pybilt/diffusion/diffusion_coefficients.py:17-167)
     on the msd rows of fixture c2_prefix and on a noisy straight line, with and without time_range."""
@@ -149,12 +193,14 @@ def make_estimators() -> str:
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES] + ["estimators", "unwrap_up_to"])
+    names = sys.argv[1:] or (list(cases.CASES) + ["comtraj:" + n for n in COMTRAJ_CASES] + ["estimators", "unwrap_up_to", "prefab"])
     for n in names:
         if n == "estimators":
             p = make_estimators()
         elif n == "unwrap_up_to":
             p = make_unwrap_up_to()
+        elif n == "prefab":
+            p = make_prefab()
         else:
             p = make_comtraj(n.split(":", 1)[1]) if n.startswith("comtraj:") else make(n)
         print(n, "->", p, os.path.getsize(p), "bytes")

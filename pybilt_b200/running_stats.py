@@ -62,3 +62,45 @@ def running_rows(times, values):
         stats.push(v)
         rows[f] = (times[f], v, stats.mean(), stats.deviation())
     return rows, stats
+
+
+class BlockAverager(object):
+    """Block averages of a series: consecutive blocks of ``points_per_block`` values, each reduced by a
+    RunningStats; blocks with fewer than ``min_points_in_block`` values are left out of the estimate
+    (pybilt/common/running_stats.py:114-300; the drivers only use the running form)."""
+
+    def __init__(self, points_per_block=1000, min_points_in_block=500, store_data=False):
+        if store_data:
+            raise RuntimeError("BlockAverager(store_data=True) is not provided")
+        self._blocks = [RunningStats()]
+        self.n_blocks = 1
+        self._points_per_block = points_per_block
+        self._min_points_in_block = points_per_block - 1 if min_points_in_block > points_per_block \
+            else min_points_in_block
+
+    def push_single(self, datum):
+        self._blocks[self.n_blocks - 1].push(datum)
+        if self._blocks[self.n_blocks - 1].n >= self._points_per_block:
+            self._blocks.append(RunningStats())
+            self.n_blocks += 1
+
+    def push_container(self, data):
+        for datum in data:
+            self.push_single(datum)
+
+    def _means(self):
+        return np.array([b.mean() for b in self._blocks if b.n >= self._min_points_in_block])
+
+    def get(self):
+        means = self._means()
+        if len(means) > 1:
+            return means.mean(), means.std() / np.sqrt(len(means))
+        if len(means) == 1:
+            return means[0], 0.0
+        return 0.0, 0.0
+
+    def averages_of_blocks(self):
+        return self._means()
+
+    def number_of_blocks(self):
+        return self.n_blocks

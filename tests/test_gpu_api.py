@@ -359,3 +359,52 @@ def test_unwrap_coordinates_up_to_continues_the_unwrap():
     ba.reset()
     ba.run_analysis()
     assert not np.array_equal(ba._engine.d_u_state.cpu().numpy(), gold["rep/u_last"])
+
+
+_REPORT = ("Composite for", "Values from", "  Basic", "    Diffusion coefficient", "  Linear fit", "  Anomalous",
+           "Final running", "  via the", "Will do block", "Block Averaged", "Nearest neighbor fraction")
+
+
+def _report_lines(lines):
+    import re
+    per_type = re.compile(r"^    \w+: -?\d+\.\d{4} \+- ")          # '    POPC: 67.6784 +- 2.1069'
+    return [l for l in lines if l.startswith(_REPORT) or per_type.match(l)]
+
+
+@pytest.mark.parametrize("driver", ["msd_diffusion", "area_per_lipid", "nearest_neighbor_fraction", "com_lateral_rdf"])
+def test_prefab_drivers_match_the_reference_drivers(driver, tmp_path, capsys):
+    """the prefab drivers on the device analyzer against the reference's own drivers
+    executed unmodified (oracle/make_golden.py make_prefab): the summary they print (numbers to 1e-6, they
+    are formatted or come out of scipy fits) and the pickles dump_data writes (1e-9)."""
+    import pickle
+    import re
+    from pybilt_b200 import prefab_analysis_protocols as pap
+    from oracle.make_golden import PREFAB_RUNS
+    gold = load("prefab")
+    case, kw = PREFAB_RUNS[driver]
+    top, traj = cases.make_inputs(case)
+    dump = str(tmp_path) + "/"
+    cwd = os.getcwd()
+    os.chdir(dump)
+    try:
+        getattr(pap, driver)(top, traj, "all", dump_path=dump, **kw)
+    finally:
+        os.chdir(cwd)
+    got_lines = _report_lines(capsys.readouterr().out.splitlines())
+    want_lines = _report_lines([str(l) for l in gold[driver + "/stdout"]])
+    assert len(got_lines) == len(want_lines) and (len(want_lines) > 0 or driver == "com_lateral_rdf")
+    num = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?|nan|inf")
+    for g, w in zip(got_lines, want_lines):
+        assert num.sub("#", g) == num.sub("#", w), (g, w)
+        gv, wv = [float(x) for x in num.findall(g)], [float(x) for x in num.findall(w)]
+        close(gv, wv, 1e-6, atol=1e-4)
+    dumped = {}
+    for name in os.listdir(dump):
+        if name.endswith(".pickle"):
+            with open(os.path.join(dump, name), "rb") as fh:
+                dumped[name[:-len(".pickle")]] = pickle.load(fh)
+    flat = cases.flatten_outputs(dumped)
+    keys = [k[len(driver) + 1:] for k in gold if k.startswith(driver + "/out/")]
+    assert keys and sorted(keys) == sorted(flat)
+    for k in keys:
+        close(flat[k], gold[driver + "/" + k], 1e-9, atol=cases.output_atol(k, gold[driver + "/" + k]))
