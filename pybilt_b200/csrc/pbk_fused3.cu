@@ -33,6 +33,9 @@
 #define F3_LPW 4                    // leaves per warp in the leaf phase (8 lanes each, 6 of them active)
 #define F3_NQ 16                    // 8-atom rows per leaf (128 / 8)
 #define F3_TAB 1024                 // ints of summation-plan tables staged in shared memory
+#define F4_TAB 384                  // the same for k_frames4 (two CTAs per SM: every KB counts)
+#define F4_EVCAP 4096               // count moves per chunk that k_frames4 takes (more: the batch is handed back)
+#define F4_MAXCHUNK 1024            // frames per chunk that k_evsort buckets
 #define F3_PIECES 4                 // bulk copies per frame (all complete on one mbarrier)
 
 int pbk_reduce_fused_v1(pbk_ctx *ctx, const float *x, const float *box, const double *mass,
@@ -89,8 +92,17 @@ struct __align__(16) ImgCol {
 
 // one frame of one column: same-image test of the 4 chains at once; the exact rule only when
 // one of them fails (rare)
+// a count move of chain c at local frame tl: appended to the chunk's list (k_frames4 reads it)
+static __device__ __noinline__ void img3_event(uint2 *ev, int *ev_n, int c, int tl, int ds)
+{
+    if (!ev || ds == 0) return;
+    const int slot = atomicAdd(ev_n, 1);
+    if (slot < F4_EVCAP) ev[slot] = make_uint2((uint32_t)c, ((uint32_t)tl << 8) | ((uint32_t)ds & 0xffu));
+}
+
 static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], const float he[4], const float Le[4],
-                                                 int acc[4], int &am, float &smin, int &bad)
+                                                 int acc[4], int &am, float &smin, int &bad, uint2 *ev, int *ev_n,
+                                                 int c0, int tl)
 {
     const float xv[4] = {v.x, v.y, v.z, v.w};
     float sl[4];
@@ -102,7 +114,10 @@ static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], co
         for (int e = 0; e < 4; e++) {
             if (!(sl[e] > 0.0f)) {                          // |jump| >= L/2 (or bad box)
                 float s2;
-                acc[e] += f3_shift_far(__fsub_rn(xv[e], pv[e]), Le[e], &s2, &bad);
+                const int ds = f3_shift_far(__fsub_rn(xv[e], pv[e]), Le[e], &s2, &bad);
+                if (ds > 127 || ds < -127) bad |= 2;
+                img3_event(ev, ev_n, c0 + e, tl, ds);
+                acc[e] += ds;
                 am = max(am, abs(acc[e]));
                 smin = fminf(smin, s2);
             } else {
@@ -132,47 +147,61 @@ static __device__ __forceinline__ void f3_chunk_range(int kc, int chunk, int64_t
     }
 }
 
-__global__ void __launch_bounds__(IMG_THREADS)
-k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float4 *__restrict__ u4,
-       int first_frame, int64_t F, int64_t split, int C3q, int chunk, ImgCol *__restrict__ cols,
-       float *__restrict__ chunk_box, int32_t *status)
+// per chunk: largest box edge, largest frame-to-frame change of an edge (for the slack check of
+// k_scan3) and whether the box is the same in every frame of the chunk (NVT runs)
+__global__ void __launch_bounds__(128)
+k_chunk_box(const float *__restrict__ box, int64_t F, int64_t split, int chunk, float *__restrict__ chunk_box,
+            int *__restrict__ chunk_const)
 {
-    __shared__ float s_L[IMG_MAXF * 3];
-    __shared__ int s_red[3];                     // Lmax bits, dL bits, "box differs" flag
-    const int kc = blockIdx.y;                   // column blocks vary fastest: neighbouring CTAs read one frame
+    __shared__ int s_red[3];
+    const int kc = blockIdx.x;
     int64_t f0, f1;
     f3_chunk_range(kc, chunk, split, F, &f0, &f1);
     const int nf = (int)(f1 - f0);
-    const bool staged = nf <= IMG_MAXF;
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
     __syncthreads();
-    {   // box rows of the chunk: largest edge, largest frame-to-frame change, constant or not
-        float Lmax = 0.f, dL = 0.f;
-        int diff = 0;
-        for (int r = threadIdx.x; r < nf * 3; r += IMG_THREADS) {
-            const int64_t t = f0 + r / 3;
-            const int k = r % 3;
-            const float L = box[t * 3 + k];
-            if (staged) s_L[r] = L;
-            Lmax = fmaxf(Lmax, L);
-            if (t > 0) dL = fmaxf(dL, fabsf(L - box[(t - 1) * 3 + k]));
-            diff |= (L != box[f0 * 3 + k]);
-        }
-        atomicMax(&s_red[0], __float_as_int(Lmax));      // (non-negative floats order like their bits; NaN/negative
-        atomicMax(&s_red[1], __float_as_int(dL));        //  boxes are caught by the L > 0 tests below)
-        if (diff) atomicOr(&s_red[2], 1);
+    float Lmax = 0.f, dL = 0.f;
+    int diff = 0;
+    for (int r = threadIdx.x; r < nf * 3; r += 128) {
+        const int64_t t = f0 + r / 3;
+        const int k = r % 3;
+        const float L = box[t * 3 + k];
+        Lmax = fmaxf(Lmax, L);
+        if (t > 0) dL = fmaxf(dL, fabsf(L - box[(t - 1) * 3 + k]));
+        diff |= (L != box[f0 * 3 + k]);
     }
+    atomicMax(&s_red[0], __float_as_int(Lmax));      // (non-negative floats order like their bits; NaN/negative
+    atomicMax(&s_red[1], __float_as_int(dL));        //  boxes are caught by the L > 0 tests of k_img3)
+    if (diff) atomicOr(&s_red[2], 1);
     __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
         chunk_box[kc * 2] = __int_as_float(s_red[0]);
         chunk_box[kc * 2 + 1] = __int_as_float(s_red[1]);
+        chunk_const[kc] = s_red[2] == 0;
     }
-    const bool cbox = s_red[2] == 0;
-    const int q4 = blockIdx.x * IMG_THREADS + threadIdx.x;
+}
+
+__global__ void __launch_bounds__(IMG_THREADS, 8)
+k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float4 *__restrict__ u4,
+       int first_frame, int64_t F, int64_t split, int C3q, int chunk, ImgCol *__restrict__ cols,
+       const int *__restrict__ chunk_const, int32_t *status, uint2 *__restrict__ events, int *__restrict__ ev_count,
+       int8_t *__restrict__ first_shift, int n_chunks, int span)
+{
+    // a thread walks `span` consecutive chunks (they are contiguous in time, also across `split`): the last
+    // frame of one chunk is the previous frame of the next, and the per-thread set-up is paid once
+    const int q4 = blockIdx.x * IMG_THREADS + threadIdx.x;      // column blocks vary fastest: neighbouring CTAs read one frame
     if (q4 >= C3q) return;
     const int k0 = (4 * q4) % 3;                 // axis of the column's first chain
     int bad = 0;
-    float pv[4];
+    float pv[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sub = 0; sub < span; sub++) {
+    const int kc = blockIdx.y * span + sub;
+    if (kc >= n_chunks) break;
+    int64_t f0, f1;
+    f3_chunk_range(kc, chunk, split, F, &f0, &f1);
+    const bool cbox = chunk_const[kc] != 0;
+    uint2 *ev = events ? events + (int64_t)kc * F4_EVCAP : nullptr;
+    int *ev_n = ev_count ? ev_count + kc : nullptr;
     int acc[4] = {0, 0, 0, 0};
     int am = 0;
     float smin = 3.0e38f;
@@ -187,11 +216,16 @@ k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float
             for (int e = 0; e < 4; e++) {
                 float sl;
                 acc[e] = f3_shift(__fsub_rn(pv[e], uv[e]), box[(k0 + e) % 3], &sl, &bad);
+                // (k_frames4 starts chunk 0 from these counts: they are the whole state, not a few moves)
+                if (first_shift) {
+                    if (acc[e] > 127 || acc[e] < -127) bad |= 2;
+                    first_shift[4 * q4 + e] = (int8_t)max(-127, min(127, acc[e]));
+                }
                 am = max(am, abs(acc[e]));
             }
         }
         t = 1;
-    } else {
+    } else if (sub == 0) {
         const float4 p = x4[(f0 - 1) * C3q + q4];
         pv[0] = p.x; pv[1] = p.y; pv[2] = p.z; pv[3] = p.w;
     }
@@ -210,12 +244,12 @@ k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float
             for (int j = 0; j < IMG_UNR; j++) v[j] = __ldg(ptr + (int64_t)j * C3q);
             ptr += (int64_t)IMG_UNR * C3q;
 #pragma unroll
-            for (int j = 0; j < IMG_UNR; j++) img3_step(v[j], pv, he, Le, acc, am, smin, bad);
+            for (int j = 0; j < IMG_UNR; j++) img3_step(v[j], pv, he, Le, acc, am, smin, bad, ev, ev_n, 4 * q4, (int)(t + j - f0));
         }
         for (; t < f1; t++) {
             const float4 v = __ldg(ptr);
             ptr += C3q;
-            img3_step(v, pv, he, Le, acc, am, smin, bad);
+            img3_step(v, pv, he, Le, acc, am, smin, bad, ev, ev_n, 4 * q4, (int)(t - f0));
         }
     } else {
         for (; t < f1; t += IMG_UNR) {
@@ -230,10 +264,10 @@ k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int k = (k0 + e) % 3;
-                        Le[e] = staged ? s_L[(int)(t + j - f0) * 3 + k] : __ldg(box + (t + j) * 3 + k);
+                        Le[e] = __ldg(box + (t + j) * 3 + k);
                         he[e] = Le[e] > 0.0f ? Le[e] * 0.5f : -1.0f;
                     }
-                    img3_step(v[j], pv, he, Le, acc, am, smin, bad);
+                    img3_step(v[j], pv, he, Le, acc, am, smin, bad, ev, ev_n, 4 * q4, (int)(t + j - f0));
                 }
             }
         }
@@ -247,7 +281,10 @@ k_img3(const float4 *__restrict__ x4, const float *__restrict__ box, const float
     c.smin = smin;
     c.amax = am;
     cols[(int64_t)kc * C3q + q4] = c;
-    if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
+    if ((bad & 2) && !ev) bad &= ~2;
+    }
+    if (bad & 1) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
+    if (bad & 2) atomicOr(status, PBK_ST_FUSED_RANGE);     // a move of more than 127 images in one frame (k_frames4 only)
 }
 
 // k_scan3: per chain, exclusive prefix of the chunk totals (= image count at every chunk start,
@@ -315,6 +352,41 @@ k_scan3(const ImgCol *__restrict__ cols, const float *__restrict__ chunk_box, in
     if (flags) atomicOr(status, flags);
 }
 
+// k_evsort: one CTA per chunk -- the chunk's count moves bucketed by frame (counting sort):
+// sorted[off[tl] .. off[tl + 1]) are the moves of local frame tl.  Too many moves, or a chunk longer
+// than the buckets: the batch is handed back (PBK_ST_FUSED_RANGE) and the generic kernels take it.
+__global__ void __launch_bounds__(256)
+k_evsort(const uint2 *__restrict__ events, const int *__restrict__ ev_count, int chunk, uint2 *__restrict__ sorted,
+         int *__restrict__ off, int32_t *status)
+{
+    __shared__ int s_cnt[F4_MAXCHUNK + 1];
+    const int kc = blockIdx.x, tid = threadIdx.x;
+    int n = ev_count[kc];
+    int *o = off + (int64_t)kc * (chunk + 1);
+    if (n > F4_EVCAP || chunk > F4_MAXCHUNK) {
+        if (tid == 0) atomicOr(status, PBK_ST_FUSED_RANGE);
+        for (int t = tid; t <= chunk; t += 256) o[t] = 0;
+        return;
+    }
+    for (int t = tid; t <= chunk; t += 256) s_cnt[t] = 0;
+    __syncthreads();
+    const uint2 *ev = events + (int64_t)kc * F4_EVCAP;
+    for (int j = tid; j < n; j += 256) atomicAdd(&s_cnt[min((int)(ev[j].y >> 8), chunk - 1) + 1], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t <= chunk; t++) { run += s_cnt[t]; s_cnt[t] = run; o[t] = run; }   // s_cnt[t] = start of bucket t
+    }
+    __syncthreads();
+    // (the order inside a bucket does not matter: a chain moves at most once per frame)
+    uint2 *so = sorted + (int64_t)kc * F4_EVCAP;
+    for (int j = tid; j < n; j += 256) {
+        const uint2 e = ev[j];
+        const int tl = min((int)(e.y >> 8), chunk - 1);
+        so[atomicAdd(&s_cnt[tl], 1)] = e;
+    }
+}
+
 // net image-count change over the whole batch: what a frame shard hands to the ranks after it
 __global__ void k_net3(const ImgCol *__restrict__ cols, int C3, int n_chunks, int32_t *__restrict__ net)
 {
@@ -370,6 +442,8 @@ struct F3Params {
     const int32_t *init_images;
     double *com, *com_unwrap, *mem_com; uint8_t *labels; int32_t *status;
     long long *prof;            // optional [n_chunks][8] phase cycle counters (debug), may be NULL
+    const uint2 *ev_sorted; const int *ev_off; int ev_cap;   // k_frames4: count moves per chunk, sorted by frame
+    const int8_t *first_shift;   // k_frames4, later batches: counts of frame 0 against the carried state
 };
 
 // Image counts live in shared memory as BIASED bytes (s + 128): byte e of a word drops straight
@@ -924,6 +998,384 @@ k_frames3(F3Params P)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_frames4: the same three phases per frame, TWO CTAs per SM.  The image counts do not come from a
+// same-image test against the previous frame any more: k_img3 already looks at every jump, so it now
+// also notes WHEN a count moves (an event list per chunk, sorted by frame in k_evsort), and a frame
+// only has to apply its few events to the shared int8 counts.  That frees the 48 registers and the
+// second frame buffer the previous frame took: one frame buffer (the next frame's bulk copy is issued
+// when the lipid phase is done and hides under the other CTA of the SM), 64 registers per thread,
+// 32 warps per SM whose phases interleave instead of waiting on each other's barriers.
+// ------------------------------------------------------------------------------------------
+template <int NQ, bool FULL>
+__global__ void __launch_bounds__(F3_THREADS, 2)
+k_frames4(F3Params P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C3 = 3 * P.M;                       // multiple of 12
+    // doubles first, then the two frame buffers (128-byte aligned), then the image counts
+    double *s_acc = reinterpret_cast<double *>(smem_raw);               // L*24 accumulators
+    double *s_leaf = s_acc + (size_t)P.L * 24;                          // (L+K)*3
+    double *s_z = s_leaf + (size_t)(P.L + P.K) * 3;                     // N   com_unwrap[norm]
+    double *s_tail = s_z + P.N;                                         // 24
+    size_t off = ((size_t)(reinterpret_cast<unsigned char *>(s_tail + 24) - smem_raw) + 127) & ~(size_t)127;
+    float *XB0 = reinterpret_cast<float *>(smem_raw + off);
+    uint32_t *S32 = reinterpret_cast<uint32_t *>(XB0 + C3);             // C3 biased int8 image counts
+    unsigned char *S8 = reinterpret_cast<unsigned char *>(S32);
+    __shared__ int s_tab[F4_TAB];               // leaf_start | leaf_len | node_left | node_right | level_off
+    __shared__ uint64_t bar[1];
+    __shared__ double s_mem[3];
+    __shared__ double red[F3_WARPS];
+    __shared__ double s_pmax[F3_WARPS];
+    __shared__ int s_nnz[3];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kc = blockIdx.x;
+    int64_t f0, f1;
+    f3_chunk_range(kc, P.chunk, P.split, P.F, &f0, &f1);
+    if (f0 >= f1) return;
+    const uint32_t frame_bytes = (uint32_t)C3 * 4u;
+    int bad = 0;
+
+    if (tid == 0) f3_mbar_init(&bar[0], 1);
+    if (tid < 3) s_nnz[tid] = 0;
+    __syncthreads();
+    int *t_ls = s_tab, *t_ll = t_ls + P.L, *t_nl = t_ll + P.L, *t_nr = t_nl + P.K, *t_lo = t_nr + P.K;
+    for (int i = tid; i < P.L; i += F3_THREADS) { t_ls[i] = P.leaf_start[i]; t_ll[i] = P.leaf_len[i]; }
+    for (int i = tid; i < P.K; i += F3_THREADS) { t_nl[i] = P.node_left[i]; t_nr[i] = P.node_right[i]; }
+    for (int i = tid; i <= P.H; i += F3_THREADS) t_lo[i] = P.level_off[i];
+    // uniform masses (coarse-grained models): the mass is a register, not a load
+    int uni = 1;
+    const double m_first = P.mass[0];
+    for (int a = tid; a < P.M; a += F3_THREADS) if (P.mass[a] != m_first) uni = 0;
+    // vector lipid phase: contiguous beads, every start and length a multiple of 4 atoms
+    int vec = P.gather ? 0 : 1;
+    for (int i = tid; i < P.N; i += F3_THREADS) {
+        const int a0 = P.seg[i], a1 = P.seg[i + 1];
+        if ((a0 & 3) || ((a1 - a0) & 3)) vec = 0;
+    }
+    // image counts before the chunk's first frame: 0 / init_images for chunk 0 (a later batch's jump from
+    // the carried state is frame 0's event), the scan's counts otherwise
+    for (int c = tid; c < C3; c += F3_THREADS) {
+        int s0 = (kc == 0) ? (P.init_images ? P.init_images[c] : (P.first_frame ? 0 : (int)P.first_shift[c]))
+                           : (int)P.sstart[(int64_t)kc * C3 + c];
+        if (s0 > 127 || s0 < -127) { bad |= 4; s0 = 0; }
+        S8[c] = (unsigned char)(s0 + 128);
+        if (s0 != 0) atomicAdd(&s_nnz[c % 3], 1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const bool um = __syncthreads_and(uni) != 0;        // also publishes tables, S, the barriers
+    const bool vec_beads = __syncthreads_and(vec) != 0;
+    const double um_val = m_first;
+    const double *__restrict__ gmass = P.mass;
+#define F3_MASS(a) (um ? um_val : __ldg(gmass + (a)))
+
+    // ---- leaf-phase role: lane -> (leaf, li); column li of the leaf's 6-float4 rows ----------
+    const int lsub = lane >> 3, li = lane & 7;
+    const int leaf = warp * F3_LPW + lsub;
+    const bool leaf_on = li < 6 && leaf < P.L;
+    int ls = 0, nq = 0, rem = 0;
+    if (leaf_on) {
+        ls = t_ls[leaf];
+        const int n = t_ll[leaf];
+        nq = n >= 8 ? n / 8 : 0;
+        rem = n - 8 * nq;
+    }
+    const int tail_valid = leaf_on ? max(0, min(4, 3 * rem - 4 * li)) : 0;   // comps of the tail row in this column
+    const int base4 = 6 * (ls >> 3) + li;          // float4 index of the lane's column in row 0
+    const int ke0 = li % 3;                        // axis of comp e is (ke0 + e) % 3
+    const int n_first = 3 - ke0;                   // comps e < n_first belong to the column's first atom
+    const int a_first = (4 * li) / 3;              // ... which is atom a_first of the 8-atom row
+    // this chunk's events, sorted by frame: ev_off[t - f0] .. ev_off[t - f0 + 1]
+    const uint2 *__restrict__ evs = P.ev_sorted + (int64_t)kc * P.ev_cap;
+    const int *__restrict__ ev_off = P.ev_off + (int64_t)kc * (P.chunk + 1);
+    // bead of this thread in the lipid phase (first round), kept in registers
+    const int my_a0 = tid < P.N ? P.seg[tid] : 0, my_a1 = tid < P.N ? P.seg[tid + 1] : 0;
+    const double my_lm = tid < P.N ? P.lipid_mass[tid] : 1.0;
+    const double my_rlm = 1.0 / my_lm;
+    float Ln0, Ln1, Ln2;
+    Ln0 = __ldg(P.box + f0 * 3); Ln1 = __ldg(P.box + f0 * 3 + 1); Ln2 = __ldg(P.box + f0 * 3 + 2);
+    auto issue_frame = [&](float *dst, int64_t t, uint64_t *b) {
+        f3_mbar_expect_tx(b, frame_bytes);
+        const uint32_t piece = ((frame_bytes / F3_PIECES) + 15u) & ~15u;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(P.x + t * (int64_t)C3);
+        for (uint32_t o = 0; o < frame_bytes; o += piece)
+            f3_bulk_g2s(reinterpret_cast<unsigned char *>(dst) + o, src + o, min(piece, frame_bytes - o), b);
+    };
+    if (tid == 0) issue_frame(XB0, f0, &bar[0]);
+
+    unsigned pc[5] = {0u, 0u, 0u, 0u, 0u};
+    unsigned tk = (unsigned)clock();
+// (a barrier only blocks at the next use of protected state: the clock read is made to depend
+// on a shared-memory load issued after it)
+#define F3_MARK(i) do { if (P.prof && tid == 0) { unsigned n_; const int dep_ = *(volatile int *)&s_tab[0]; \
+        asm volatile("mov.u32 %0, %%clock;" : "=r"(n_) : "r"(dep_)); pc[i] += n_ - tk; tk = n_; } } while (0)
+
+    // leaflet labels of frame tf from s_z / red / s_pmax (written by the lipid phase of tf);
+    // thread zt of nzt label threads.  The tree mean decides unless a lipid is within the
+    // rounding bound of it; then the warp replays the sequential Welford mean (running_stats.py:34-52).
+    auto write_labels = [&](int64_t tf, int zt, int nzt) {
+        double s2 = lane < F3_WARPS ? red[lane] : 0.0, m2 = lane < F3_WARPS ? s_pmax[lane] : 0.0;
+        s2 = pbk_warp_sum(s2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        double mean = s2 / (double)P.N;
+        const double tol = 64.0 * (double)P.N * 2.220446049250313e-16 * m2;
+        int close = 0;
+        for (int i = zt; i < P.N; i += nzt) if (fabs(s_z[i] - mean) <= tol) close = 1;
+        if (__any_sync(0xffffffffu, close)) {
+            double m = 0.0;
+            if (lane == 0)
+                for (int i = 0; i < P.N; i++) {
+                    const double v = s_z[i];
+                    m = (i == 0) ? v : __dadd_rn(m, __ddiv_rn(__dsub_rn(v, m), (double)(i + 1)));
+                }
+            mean = __shfl_sync(0xffffffffu, m, 0);
+        }
+        uint8_t *out = P.labels + tf * (int64_t)P.N;
+        for (int i = zt; i < P.N; i += nzt) {
+            const double v = s_z[i];
+            if (v > mean) out[i] = 1;
+            else if (v < mean) out[i] = 0;
+            else { out[i] = 0; bad |= 8; }
+        }
+    };
+
+    for (int64_t t = f0; t < f1; t++) {
+        float *cur = XB0;
+        const float Lc0 = Ln0, Lc1 = Ln1, Lc2 = Ln2;
+        const bool Lbig = !(Lc0 < 8192.0f && Lc1 < 8192.0f && Lc2 < 8192.0f);
+        {   // the frame's events: count moves of a few chains (k_img3 found them, k_evsort ordered them)
+            const int e0 = __ldg(ev_off + (int)(t - f0)), e1 = __ldg(ev_off + (int)(t - f0) + 1);
+            for (int j = e0 + tid; j < e1; j += F3_THREADS) {
+                const uint2 ev = __ldg(evs + j);
+                const int c = (int)ev.x, sn = (int)S8[c] - 128 + (int)(int8_t)(ev.y & 0xffu);
+                if (sn > 127 || sn < -127) { bad |= 4; continue; }
+                if ((S8[c] == 128) != (sn == 0)) atomicAdd(&s_nnz[c % 3], sn == 0 ? -1 : 1);
+                S8[c] = (unsigned char)(sn + 128);
+            }
+        }
+        if (!f3_mbar_wait(&bar[0], (uint32_t)(t - f0) & 1u)) bad |= 2;
+        __syncthreads();                        // the counts of frame t are in place
+        F3_MARK(0);                             // wait for the frame
+        // ---- leaf phase: the NumPy-pairwise leaf sums of m*f64(u), u from the frame's counts -------
+        if (leaf_on) {
+            float Le[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = (ke0 + e) % 3;
+                Le[e] = k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2);
+            }
+            const float4 *cur4 = reinterpret_cast<const float4 *>(cur);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (um) {
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    if (FULL || q < nq) {
+                        const int f4 = base4 + 6 * q;
+                        const float4 cv = cur4[f4];
+                        const uint32_t sw = S32[f4];
+                        const float xv[4] = {cv.x, cv.y, cv.z, cv.w};
+                        float uv[4];
+                        f3_unwrap4(xv, sw, Le, Lbig, uv);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const double pr = __dmul_rn(um_val, (double)uv[e]);
+                            acc[e] = (q == 0) ? pr : __dadd_rn(acc[e], pr);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    if (FULL || q < nq) {
+                        const int f4 = base4 + 6 * q;
+                        const float4 cv = cur4[f4];
+                        const uint32_t sw = S32[f4];
+                        const float xv[4] = {cv.x, cv.y, cv.z, cv.w};
+                        float uv[4];
+                        f3_unwrap4(xv, sw, Le, Lbig, uv);
+                        const int arow = ls + 8 * q + a_first;
+                        const double ma = __ldg(gmass + arow), mb = __ldg(gmass + arow + 1);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const double pr = __dmul_rn(e < n_first ? ma : mb, (double)uv[e]);
+                            acc[e] = (q == 0) ? pr : __dadd_rn(acc[e], pr);
+                        }
+                    }
+                }
+            }
+            if (FULL || nq > 0) {
+                double *my = s_acc + (size_t)leaf * 24 + 4 * li;
+                my[0] = acc[0]; my[1] = acc[1]; my[2] = acc[2]; my[3] = acc[3];
+            }
+            if (!FULL && tail_valid) {          // the n % 8 atoms after the last full row (last leaf only)
+                const int f4 = base4 + 6 * nq;
+                const float4 cv = cur4[f4];
+                const uint32_t sw = S32[f4];
+                const float xv[4] = {cv.x, cv.y, cv.z, cv.w};
+                const int arow = ls + 8 * nq + a_first;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (e < tail_valid) {
+                        const float u = f3_unwrap_slow(xv[e], f3_sint(sw, e), Le[e]);
+                        s_tail[4 * li + e] = __dmul_rn(F3_MASS(e < n_first ? arow : arow + 1), (double)u);
+                    }
+            }
+        }
+        __syncwarp();
+        if (leaf_on && li < 3) {                // lane li combines axis li of its leaf
+            const double *r = s_acc + (size_t)leaf * 24 + li;
+            double v = 0.0;
+            if (FULL || nq > 0)
+                v = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[3]), __dadd_rn(r[6], r[9])),
+                              __dadd_rn(__dadd_rn(r[12], r[15]), __dadd_rn(r[18], r[21])));
+            if (!FULL) for (int a = 0; a < rem; a++) v = __dadd_rn(v, s_tail[3 * a + li]);
+            s_leaf[leaf * 3 + li] = v;
+        }
+        __syncthreads();
+        F3_MARK(1);                             // leaf phase
+        if (warp == 0) {                        // summation tree + division in one warp
+            if (P.perfect >= 0) {
+                // perfect binary tree over L = 2^perfect leaves in order: butterfly (IEEE addition is
+                // commutative, so every lane ends with the root of NumPy's recursion)
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                if (P.L == 64) {
+                    const double *a = s_leaf + 6 * lane;
+                    v0 = __dadd_rn(a[0], a[3]); v1 = __dadd_rn(a[1], a[4]); v2 = __dadd_rn(a[2], a[5]);
+                } else if (lane < P.L) {
+                    const double *a = s_leaf + 3 * lane;
+                    v0 = a[0]; v1 = a[1]; v2 = a[2];
+                }
+                const int top = P.L == 64 ? 16 : (P.L >> 1);
+                for (int o = 1; o <= top; o <<= 1) {
+                    v0 = __dadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                    v1 = __dadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                    v2 = __dadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                }
+                v1 = __shfl_sync(0xffffffffu, v1, 0);       // (lanes >= L hold nothing when L < 32)
+                v2 = __shfl_sync(0xffffffffu, v2, 0);
+                if (lane < 3) {
+                    const double mc = __ddiv_rn(lane == 0 ? v0 : (lane == 1 ? v1 : v2), P.total_mass);
+                    s_mem[lane] = mc;
+                    P.mem_com[t * 3 + lane] = mc;
+                }
+            } else {
+                for (int h = 0; h < P.H; h++) {
+                    const int a = t_lo[h], bnd = t_lo[h + 1];
+                    for (int w = lane; w < (bnd - a) * 3; w += 32) {
+                        const int node = a + w / 3, k = w % 3;
+                        s_leaf[(P.L + node) * 3 + k] = __dadd_rn(s_leaf[t_nl[node] * 3 + k], s_leaf[t_nr[node] * 3 + k]);
+                    }
+                    __syncwarp();
+                }
+                if (lane < 3) {
+                    const double mc = __ddiv_rn(s_leaf[(P.L + P.K - 1) * 3 + lane], P.total_mass);
+                    s_mem[lane] = mc;
+                    P.mem_com[t * 3 + lane] = mc;
+                }
+            }
+        } else {
+            // meanwhile: leaflet labels of the previous frame
+            if (P.do_labels && t > f0) write_labels(t - 1, tid - 32, F3_THREADS - 32);
+        }
+        if (t + 1 < f1) {                       // box of the next frame (latency hidden by the lipid phase)
+            Ln0 = __ldg(P.box + (t + 1) * 3); Ln1 = __ldg(P.box + (t + 1) * 3 + 1); Ln2 = __ldg(P.box + (t + 1) * 3 + 2);
+        }
+        __syncthreads();
+        F3_MARK(2);                             // tree (+ labels of t-1)
+        // ---- lipid phase: wrapped and unwrapped COM of every lipid, atoms in order -------------
+        {
+            const double m0 = s_mem[0], m1 = s_mem[1], m2 = s_mem[2];
+            // axes on which no atom carries an image count: u == x there, f64(u) is f64(x)
+            const int zmask = (s_nnz[0] == 0 ? 1 : 0) | (s_nnz[1] == 0 ? 2 : 0) | (s_nnz[2] == 0 ? 4 : 0);
+            const int32_t *__restrict__ gat = P.gather;
+            double sacc = 0.0, macc = 0.0;
+            for (int i0 = 0; i0 < P.N; i0 += F3_THREADS) {
+                const int i = i0 + tid;
+                double zv = 0.0;
+                if (i < P.N) {
+                    const int a0 = i0 == 0 ? my_a0 : __ldg(P.seg + i), a1 = i0 == 0 ? my_a1 : __ldg(P.seg + i + 1);
+                    double cw0 = 0, cw1 = 0, cw2 = 0, cu0 = 0, cu1 = 0, cu2 = 0;
+                    if (vec_beads) {
+                        const float4 *x4 = reinterpret_cast<const float4 *>(cur) + (a0 * 3) / 4;
+                        const uint32_t *s4 = S32 + (a0 * 3) / 4;
+                        const int ng = (a1 - a0) >> 2;
+                        if (zmask == 7) {
+                            for (int g = 0; g < ng; g++)
+                                f3_lipid_group<7>(x4 + 3 * g, s4 + 3 * g, F3_MASS(a0 + 4 * g), F3_MASS(a0 + 4 * g + 1), F3_MASS(a0 + 4 * g + 2),
+                                                  F3_MASS(a0 + 4 * g + 3), Lc0, Lc1, Lc2, Lbig, m0, m1, m2, cw0, cw1, cw2, cu0, cu1, cu2);
+                        } else if (zmask == 4) {
+                            for (int g = 0; g < ng; g++)
+                                f3_lipid_group<4>(x4 + 3 * g, s4 + 3 * g, F3_MASS(a0 + 4 * g), F3_MASS(a0 + 4 * g + 1), F3_MASS(a0 + 4 * g + 2),
+                                                  F3_MASS(a0 + 4 * g + 3), Lc0, Lc1, Lc2, Lbig, m0, m1, m2, cw0, cw1, cw2, cu0, cu1, cu2);
+                        } else {
+                            for (int g = 0; g < ng; g++)
+                                f3_lipid_group<0>(x4 + 3 * g, s4 + 3 * g, F3_MASS(a0 + 4 * g), F3_MASS(a0 + 4 * g + 1), F3_MASS(a0 + 4 * g + 2),
+                                                  F3_MASS(a0 + 4 * g + 3), Lc0, Lc1, Lc2, Lbig, m0, m1, m2, cw0, cw1, cw2, cu0, cu1, cu2);
+                        }
+                    } else {
+                        for (int p = a0; p < a1; p++) {
+                            const int a = gat ? __ldg(gat + p) : p;
+                            const double m = F3_MASS(a);
+                            const float x0 = cur[a * 3], x1 = cur[a * 3 + 1], x2 = cur[a * 3 + 2];
+                            const int s0 = (int)S8[a * 3] - 128, s1 = (int)S8[a * 3 + 1] - 128, s2 = (int)S8[a * 3 + 2] - 128;
+                            if ((s0 | s1 | s2) == 0) {
+                                f3_comp0(x0, m0, m, cw0, cu0); f3_comp0(x1, m1, m, cw1, cu1); f3_comp0(x2, m2, m, cw2, cu2);
+                            } else {
+                                f3_comp1(x0, pbk_unwrapped(x0, s0, Lc0), m0, m, cw0, cu0);
+                                f3_comp1(x1, pbk_unwrapped(x1, s1, Lc1), m1, m, cw1, cu1);
+                                f3_comp1(x2, pbk_unwrapped(x2, s2, Lc2), m2, m, cw2, cu2);
+                            }
+                        }
+                    }
+                    const double lm = i0 == 0 ? my_lm : __ldg(P.lipid_mass + i);
+                    const double rlm = i0 == 0 ? my_rlm : 1.0 / lm;        // pbk_div_r: RN(c / lm) without the division routine
+                    double *ow = P.com + (t * (int64_t)P.N + i) * 3;
+                    double *ou = P.com_unwrap + (t * (int64_t)P.N + i) * 3;
+                    ow[0] = pbk_div_r(cw0, lm, rlm); ow[1] = pbk_div_r(cw1, lm, rlm); ow[2] = pbk_div_r(cw2, lm, rlm);
+                    const double u0 = pbk_div_r(cu0, lm, rlm), u1 = pbk_div_r(cu1, lm, rlm), u2 = pbk_div_r(cu2, lm, rlm);
+                    ou[0] = u0; ou[1] = u1; ou[2] = u2;
+                    zv = P.norm == 0 ? u0 : (P.norm == 1 ? u1 : u2);
+                    s_z[i] = zv;
+                }
+                if (P.do_labels) {              // warp partials of z for the tree mean of the labels
+                    double mx = fabs(zv);
+                    sacc += pbk_warp_sum(zv);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    macc = fmax(macc, mx);
+                }
+            }
+            if (P.do_labels && lane == 0) { red[warp] = sacc; s_pmax[warp] = macc; }
+        }
+        // carried state for the next batch: u of the last frame of the batch
+        if (t == P.F - 1) {
+            for (int c = tid; c < C3; c += F3_THREADS) {
+                const int k = c % 3;
+                P.u_out[c] = pbk_unwrapped(cur[c], (int)S8[c] - 128, k == 0 ? Lc0 : (k == 1 ? Lc1 : Lc2));
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of `cur` before the async write
+        __syncthreads();
+        // the frame buffer is free: the next frame's bulk copy runs while the SM's other CTA computes
+        if (tid == 0 && t + 1 < f1) issue_frame(XB0, t + 1, &bar[0]);
+        F3_MARK(3);                             // lipid phase
+    }
+    if (P.do_labels) write_labels(f1 - 1, tid, F3_THREADS);
+    F3_MARK(4);
+    if (P.prof && tid == 0) for (int i = 0; i < 8; i++) P.prof[kc * 8 + i] = i < 5 ? (long long)pc[i] : 0;
+    if (bad) {
+        int st = 0;
+        if (bad & 1) st |= PBK_ST_IMAGE_OVERFLOW;
+        if (bad & 2) st |= PBK_ST_INTERNAL;
+        if (bad & 4) st |= PBK_ST_FUSED_RANGE;
+        if (bad & 8) st |= PBK_ST_LEAFLET_TIE;
+        atomicOr(P.status, st);
+    }
+}
+
+
 // largest leaf of NumPy's pairwise split of m elements (pybilt_b200/pairwise.py: build_plan)
 static int64_t f3_max_leaf(int64_t m)
 {
@@ -947,15 +1399,29 @@ static int f3_perfect(int64_t m)
     return lv;
 }
 
+// chunks per SM: two when the two-CTA kernel (k_frames4) may run -- sized for that case always
+static void f3_tiling(int64_t F, int sm_count, int per_sm, int64_t *chunk, int64_t *n_chunks)
+{
+    const int64_t slots = (int64_t)sm_count * per_sm;
+    int64_t c = (F + slots - 1) / slots;
+    if (c < 4) c = 4;
+    *chunk = c;
+    *n_chunks = (F + c - 1) / c;
+}
+
 extern "C" int pbk_reduce_fused_scratch_bytes(int64_t F, int64_t M, int sm_count, int64_t *bytes,
                                              int32_t *n_chunks_out, int32_t *chunk_out)
 {
     if (F <= 0 || M <= 0 || sm_count <= 0 || !bytes) return PBK_EINVAL;
-    int64_t chunk = (F + sm_count - 1) / sm_count;
-    if (chunk < 4) chunk = 4;
-    int64_t n_chunks = (F + chunk - 1) / chunk;
+    int64_t chunk, n_chunks, chunk2, n_chunks2;
+    f3_tiling(F, sm_count, 1, &chunk, &n_chunks);
+    f3_tiling(F, sm_count, 2, &chunk2, &n_chunks2);
     // sized for the v1 layout (the larger) and for one extra chunk (a split tiling, see f3_chunk_range)
-    *bytes = 4 * ((n_chunks + 1) * 3 * M * 16 + (n_chunks + 1) * 8) + 3 * M * 4 + 256;
+    const int64_t v1 = 4 * ((n_chunks + 1) * 3 * M * 16 + (n_chunks + 1) * 8) + 3 * M * 4 + 256;
+    // k_frames4: two chunks per SM -- columns, counts at the chunk starts, the event lists (raw + sorted) and offsets
+    const int64_t v4 = (n_chunks2 + 2) * (3 * M / 4 + 1) * 16 + 3 * M * 4 + (n_chunks2 + 2) * 8 + 64 +
+                       (n_chunks2 + 2) * 3 * M + (n_chunks2 + 2) * ((int64_t)F4_EVCAP * 16 + 8 + (chunk2 + 1) * 4) + 3 * M + 1024;
+    *bytes = v1 > v4 ? v1 : v4;
     if (n_chunks_out) *n_chunks_out = (int32_t)n_chunks;
     if (chunk_out) *chunk_out = (int32_t)chunk;
     return PBK_OK;
@@ -997,6 +1463,16 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     int64_t need; int32_t n_chunks, chunk;
     pbk_reduce_fused_scratch_bytes(F, M, ctx->sm_count, &need, &n_chunks, &chunk);
     if (scratch_bytes < need) return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small");
+    // two CTAs per SM (k_frames4) when a CTA with ONE frame buffer and the small table fits twice
+    const size_t smem4 = smem - (size_t)C3 * 4;
+    bool v4 = !getenv("PBK_FUSED_V3") && 2 * (int64_t)L + 2 * (int64_t)K + H + 1 <= F4_TAB &&
+              2 * (smem4 + 3 * 1024) <= 228 * 1024;
+    if (v4) {
+        int64_t c2, n2;
+        f3_tiling(F, ctx->sm_count, 2, &c2, &n2);
+        if (c2 <= F4_MAXCHUNK) { chunk = (int32_t)c2; n_chunks = (int32_t)n2; }
+        else v4 = false;
+    }
     const int32_t n_net = (int32_t)((split + chunk - 1) / chunk);       // chunks tiling [0, split)
     n_chunks = n_net + (int32_t)((F - split + chunk - 1) / chunk);
     const int C3q = C3 / 4;
@@ -1008,11 +1484,33 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     sp += (size_t)C3 * 4;
     float *chunk_box = reinterpret_cast<float *>(sp);
     sp += (((size_t)n_chunks * 8) + 15) & ~(size_t)15;
+    int *chunk_const = reinterpret_cast<int *>(sp);
+    sp += (((size_t)n_chunks * 4) + 15) & ~(size_t)15;
     int8_t *sstart = reinterpret_cast<int8_t *>(sp);
+    sp += (((size_t)n_chunks * C3) + 15) & ~(size_t)15;
+    uint2 *ev_raw = nullptr, *ev_sorted = nullptr;
+    int *ev_count = nullptr, *ev_off = nullptr;
+    int8_t *first_shift = nullptr;
+    if (v4) {
+        ev_raw = reinterpret_cast<uint2 *>(sp); sp += (size_t)n_chunks * F4_EVCAP * 8;
+        ev_sorted = reinterpret_cast<uint2 *>(sp); sp += (size_t)n_chunks * F4_EVCAP * 8;
+        ev_count = reinterpret_cast<int *>(sp); sp += (((size_t)n_chunks * 4) + 15) & ~(size_t)15;
+        ev_off = reinterpret_cast<int *>(sp); sp += (((size_t)n_chunks * (chunk + 1) * 4) + 15) & ~(size_t)15;
+        first_shift = reinterpret_cast<int8_t *>(sp); sp += (size_t)C3;
+        if ((int64_t)(sp - reinterpret_cast<unsigned char *>(scratch)) > scratch_bytes)
+            return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small (events)");
+    }
     if (phase & 1) {
-        k_img3<<<dim3((C3q + IMG_THREADS - 1) / IMG_THREADS, n_chunks), IMG_THREADS, 0, st>>>(
+        if (v4) {
+            cudaError_t e0 = cudaMemsetAsync(ev_count, 0, (size_t)n_chunks * 4, st);
+            if (e0 != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "event counters", e0);
+        }
+        k_chunk_box<<<n_chunks, 128, 0, st>>>(box, F, split, chunk, chunk_box, chunk_const);
+        PBK_CHECK_LAUNCH(ctx, "k_chunk_box");
+        const int span = getenv("PBK_IMG_SPAN") ? atoi(getenv("PBK_IMG_SPAN")) : 1;
+        k_img3<<<dim3((C3q + IMG_THREADS - 1) / IMG_THREADS, (n_chunks + span - 1) / span), IMG_THREADS, 0, st>>>(
             reinterpret_cast<const float4 *>(x), box, reinterpret_cast<const float4 *>(u_state), first_frame, F,
-            split, C3q, chunk, cols, chunk_box, status);
+            split, C3q, chunk, cols, chunk_const, status, ev_raw, ev_count, first_shift, n_chunks, span);
         PBK_CHECK_LAUNCH(ctx, "k_img3");
         if (net_images) {
             k_net3<<<(C3 + 255) / 256, 256, 0, st>>>(cols, C3, n_net, net_images);
@@ -1040,10 +1538,27 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
     if (full && mleaf == 96) kern = k_frames3<12, true>;
     else if (full && mleaf == 128) kern = k_frames3<16, true>;
     else if (mleaf <= 96) kern = k_frames3<12, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_frames3 smem attribute", e);
-    kern<<<n_chunks, F3_THREADS, smem, st>>>(P);
-    PBK_CHECK_LAUNCH(ctx, "k_frames3");
+    cudaError_t e;
+    if (v4) {
+        k_evsort<<<n_chunks, 256, 0, st>>>(ev_raw, ev_count, chunk, ev_sorted, ev_off, status);
+        PBK_CHECK_LAUNCH(ctx, "k_evsort");
+        P.ev_sorted = ev_sorted; P.ev_off = ev_off; P.ev_cap = F4_EVCAP; P.first_shift = first_shift;
+        kern = k_frames4<F3_NQ, false>;
+        if (full && mleaf == 96) kern = k_frames4<12, true>;
+        else if (full && mleaf == 128) kern = k_frames4<16, true>;
+        else if (mleaf <= 96) kern = k_frames4<12, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_frames4 smem attribute", e);
+        kern<<<n_chunks, F3_THREADS, smem4, st>>>(P);
+        PBK_CHECK_LAUNCH(ctx, "k_frames4");
+    } else {
+        P.ev_sorted = nullptr; P.ev_off = nullptr; P.ev_cap = 0; P.first_shift = nullptr;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "k_frames3 smem attribute", e);
+        kern<<<n_chunks, F3_THREADS, smem, st>>>(P);
+        PBK_CHECK_LAUNCH(ctx, "k_frames3");
+    }
     // u_state is read by chunk 0 and replaced by the last chunk: the new state is produced in
     // scratch and copied over once the kernel is done
     e = cudaMemcpyAsync(u_state, u_out, (size_t)C3 * 4, cudaMemcpyDeviceToDevice, st);
