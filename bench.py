@@ -59,7 +59,7 @@ def peaks():
 def ncu_traffic(stage: str):
     """dram read+write bytes per step of a stage, from the committed ncu capture
     (profiles/traffic.json: per-launch bytes of each kernel); None if not captured."""
-    kernels = {"reduce(unwrap+memCOM+lipidCOM+leaflets)": ["k_img3", "k_scan3", "k_frames3<12, 1>"],
+    kernels = {"reduce(unwrap+memCOM+lipidCOM+leaflets)": ["k_chunk_box", "k_img3", "k_scan3", "k_evsort", "k_frames4<12, 1>"],
                "rdf": ["k_rdf5<1>"], "msd": ["k_msd_pairs"], "msd_multi": ["k_msd_pairs"]}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
