@@ -1147,23 +1147,26 @@ static __device__ __forceinline__ void sb_accumulate(float xv, int s, float Lc, 
     cu = __dadd_rn(cu, __dmul_rn((double)v, m));
 }
 
+// (CTA size by bead size: this kernel is launched after every time-parallel reduction only to find
+//  the flag clear, so few large CTAs for the common single-atom shapes)
+#define SBS_THREADS(NA) ((NA) == 0 ? 128 : ((NA) <= 4 ? 512 : 256))
 template <int NA>
-__global__ void __launch_bounds__(SB_THREADS)
+__global__ void __launch_bounds__(SBS_THREADS(NA))
 k_sweep_b(SweepBParams P)
 {
     extern __shared__ __align__(16) unsigned char sb_raw[];
     __shared__ float s_box[SW_CHUNK][8];
     __shared__ double s_mem[SW_CHUNK][3];
-    int16_t *s_img = reinterpret_cast<int16_t *>(sb_raw);       // NA == 0: [max_atoms][SB_THREADS]
+    int16_t *s_img = reinterpret_cast<int16_t *>(sb_raw);       // NA == 0: [max_atoms][SBS_THREADS(NA)]
     if (P.fb_flag && *P.fb_flag == 0) return;
     const int tid = threadIdx.x;
     const int64_t C3 = 3 * P.M;
     const int64_t f0 = (int64_t)blockIdx.y * SW_CHUNK, f1 = min(P.F, f0 + SW_CHUNK);
     const int nf = (int)(f1 - f0);
-    for (int r = tid; r < nf * 8; r += SB_THREADS) s_box[r >> 3][r & 7] = P.boxtab[f0 * 8 + r];
-    for (int r = tid; r < nf * 3; r += SB_THREADS) s_mem[r / 3][r % 3] = P.mem_com[f0 * 3 + r];
+    for (int r = tid; r < nf * 8; r += SBS_THREADS(NA)) s_box[r >> 3][r & 7] = P.boxtab[f0 * 8 + r];
+    for (int r = tid; r < nf * 3; r += SBS_THREADS(NA)) s_mem[r / 3][r % 3] = P.mem_com[f0 * 3 + r];
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * SB_THREADS + tid;
+    const int64_t g = (int64_t)blockIdx.x * SBS_THREADS(NA) + tid;
     if (g >= 3 * P.N) return;
     const int64_t i = g / 3;
     const int k = (int)(g - 3 * i);
@@ -1289,7 +1292,7 @@ k_sweep_b(SweepBParams P)
             int s0 = first_chunk ? (P.init_images ? P.init_images[3 * a + k] : 0) : (int)P.snap[(int64_t)blockIdx.y * C3 + 3 * a + k];
             if (s0 > 32767 || s0 < -32767) { bad |= 1; s0 = 0; }
             if (s0 > 127 || s0 < -127) wide = 1;
-            s_img[j * SB_THREADS + tid] = (int16_t)s0;
+            s_img[j * SBS_THREADS(NA) + tid] = (int16_t)s0;
         }
         for (int f = 0; f < nf; f++) {
             const float *cur = P.x + (f0 + f) * C3;
@@ -1300,10 +1303,10 @@ k_sweep_b(SweepBParams P)
             for (int j = 0; j < n; j++) {
                 const int a = gat ? __ldg(gat + p0 + j) : p0 + j;
                 const float xv = __ldg(cur + 3 * a + k), pvv = prow[3 * a + k];
-                const int s = (int)s_img[j * SB_THREADS + tid];
+                const int s = (int)s_img[j * SBS_THREADS(NA) + tid];
                 const int sn = sb_count(xv, pvv, s, hc, Lc, Lp, wide != 0, &bad);
                 if (sn != s) {
-                    s_img[j * SB_THREADS + tid] = (int16_t)sn;
+                    s_img[j * SBS_THREADS(NA) + tid] = (int16_t)sn;
                     if (sn > 127 || sn < -127) wide = 1;
                 }
                 sb_accumulate(xv, sn, Lc, Lbig, mem, __ldg(gm + a), cw, cu);
@@ -1669,13 +1672,13 @@ extern "C" int pbk_reduce_stream_scratch_bytes(int64_t F, int64_t M, int64_t N, 
 template <int NA>
 static cudaError_t sw_launch_b(const SweepBParams &B, int64_t nch, cudaStream_t st)
 {
-    dim3 g((unsigned)((3 * B.N + SB_THREADS - 1) / SB_THREADS), (unsigned)nch);
-    const size_t smem = NA == 0 ? (size_t)B.max_atoms * SB_THREADS * 2 : 0;
+    dim3 g((unsigned)((3 * B.N + SBS_THREADS(NA) - 1) / SBS_THREADS(NA)), (unsigned)nch);
+    const size_t smem = NA == 0 ? (size_t)B.max_atoms * SBS_THREADS(NA) * 2 : 0;
     if (NA == 0) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep_b<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_sweep_b<NA><<<g, SB_THREADS, smem, st>>>(B);
+    k_sweep_b<NA><<<g, SBS_THREADS(NA), smem, st>>>(B);
     return cudaGetLastError();
 }
 
