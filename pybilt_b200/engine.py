@@ -234,7 +234,9 @@ class LipidReductionEngine:
             int(scratch.numel()), self.com[g0:].data_ptr(), self.com_unwrap[g0:].data_ptr(),
             self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(), self.d_status.data_ptr(), self.stream_ptr())
         if ok:
-            self.launches += 5 if (phase & 2) else 2
+            # k_box_table, k_sweep_p, k_sweep_s, k_sweep_a2 (flag-gated) [+ k_sweep_l, k_mem_tree, k_sweep_bt,
+            # k_sweep_b (flag-gated), k_zpart, k_zmean, k_labels, k_leaflets_c]
+            self.launches += 12 if (phase & 2) else 4
             self.used_stream = True
         return ok
 
@@ -361,7 +363,8 @@ class LipidReductionEngine:
                                 self.mem_com[g0:].data_ptr(), self.labels[g0:].data_ptr(),
                                 self.d_status.data_ptr(), st)
                 if ok:
-                    self.launches += 3 if phase == 3 else (2 if phase == 1 else 2)
+                    # k_chunk_box, k_img3 | k_scan3, k_evsort, k_frames4 (two CTAs per SM; one fewer without k_evsort)
+                    self.launches += 5 if phase == 3 else (2 if phase == 1 else 3)
                     self.used_fused = True
                     if not (phase & 2):
                         continue
