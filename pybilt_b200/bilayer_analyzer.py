@@ -674,6 +674,10 @@ class BilayerAnalyzer(object):
         self._invalidate()
 
     def unwrap_coordinates_up_to(self, frame_index):
+        with torch.cuda.device(self.device):       # libpbk launches on the current device
+            return self._unwrap_coordinates_up_to(frame_index)
+
+    def _unwrap_coordinates_up_to(self, frame_index):
         """Unwrap the trajectory from frame 0 up to ``frame_index`` (stepping by the frame interval)
         without analysing anything, so that a run whose frame range starts later continues from
         that unwrapped state instead of treating its first frame as the reference
@@ -1235,6 +1239,10 @@ class BilayerAnalyzer(object):
         return frame, leaflets, grid
 
     def __next__(self):
+        with torch.cuda.device(self.device):
+            return self._next_frame()
+
+    def _next_frame(self):
         if self._batch is None or not getattr(self, '_started', False):
             if self._current_frame > self._last_frame:
                 raise StopIteration()
@@ -1267,6 +1275,10 @@ class BilayerAnalyzer(object):
     _iterating_for_user = True
 
     def run_analysis(self):
+        with torch.cuda.device(self.device):
+            return self._run_analysis()
+
+    def _run_analysis(self):
         """Run every registered analysis over the analysed frames (bilayer_analyzer.py:777-790).
         Batched run: no per-frame host views unless a plain per-frame plugin needs them."""
         if self._current_frame > self._last_frame and not getattr(self, '_started', False):

@@ -179,6 +179,7 @@ class COMTraj(object):
         self.nframes = len(self._frames)
         self._layout = build_bead_layout(md.masses, md.names, md.resindex, md.resnames, md.resids)
         self.nlipids = self._layout.n_beads
+        torch.cuda.set_device(device)             # libpbk launches on the current device
         eng = LipidReductionEngine(md.masses, self._layout, self.nframes, device=device, norm=self.norm,
                                    leaflet_update_interval=1, comtraj_rules=True)
         x, d, t = md.frames(self._frames)

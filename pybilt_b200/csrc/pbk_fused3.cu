@@ -114,9 +114,21 @@ static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], co
         for (int e = 0; e < 4; e++) {
             if (!(sl[e] > 0.0f)) {                          // |jump| >= L/2 (or bad box)
                 float s2;
-                const int ds = f3_shift_far(__fsub_rn(xv[e], pv[e]), Le[e], &s2, &bad);
-                if (ds > 127 || ds < -127) bad |= 2;
-                img3_event(ev, ev_n, c0 + e, tl, ds);
+                int ds;
+                const float d = __fsub_rn(xv[e], pv[e]), h = Le[e] * 0.5f;
+                if (fabsf(d) > h && fabsf(d) < 3.0f * h) {
+                    // the usual crossing: one image (the loop of the reference rule stops after its first step,
+                    // d -+ L lies inside the window); same float64 expressions as f3_shift, no call
+                    ds = d > 0.0f ? -1 : 1;
+                    s2 = (float)((double)h - fabs(__dadd_rn((double)d, __dmul_rn((double)ds, (double)Le[e]))));
+                } else {
+                    ds = f3_shift_far(d, Le[e], &s2, &bad);
+                    if (ds > 127 || ds < -127) bad |= 2;
+                }
+                if (ev && ds != 0) {
+                    const int slot = atomicAdd(ev_n, 1);
+                    if (slot < F4_EVCAP) ev[slot] = make_uint2((uint32_t)(c0 + e), ((uint32_t)tl << 8) | ((uint32_t)ds & 0xffu));
+                }
                 acc[e] += ds;
                 am = max(am, abs(acc[e]));
                 smin = fminf(smin, s2);
