@@ -204,6 +204,19 @@ int pbk_label_changes(pbk_ctx *ctx, const uint8_t *labels, const uint8_t *prev_r
 int pbk_rewrap(pbk_ctx *ctx, double *com, const double *com_unwrap, const double *mem_com, const float *box,
                int64_t F, int64_t N, int32_t *status, void *stream);
 
+/* ---- N3  leaflets from the lipids' orientation -----------------------------------------------------
+ * BilayerAnalyzer._build_leaflets_orientation   pybilt/bilayer_analyzer/bilayer_analyzer.py:849-876
+ * labels[f, i] = 1 / 0 by the sign of (COM of the head atoms - COM of the tail atoms)[norm], both taken
+ * from the unwrapped, membrane-COM-free float32 coordinates of the frame, on the frames where the
+ * leaflets are rebuilt ((frame0 + f) % interval == 0; other rows are left alone).  seg[2 i .. 2 i + 2]
+ * delimits lipid i's tail and head atoms in sel_atom / sel_mass; u_state[n_sel] carries the unwrapped
+ * normal components from batch to batch (first_frame: frame 0 is its own reference).  A zero component:
+ * PBK_ST_LEAFLET_TIE (the reference raises KeyError('')). */
+int pbk_orient_labels(pbk_ctx *ctx, const float *x, const float *box, const double *mem_com,
+                      const int32_t *sel_atom, const double *sel_mass, const int32_t *seg, float *u_state,
+                      int first_frame, int64_t F, int64_t M, int64_t N, int norm, int64_t frame0, int interval,
+                      uint8_t *labels, int32_t *status, void *stream);
+
 /* ---- N4  pair searches of the stand-alone COM trajectory ---------------------------------------
  * COMTraj.calc_membrane_thickness                       pybilt/com_trajectory/COMTraj.py:1244-1408
  * COMTraj.calc_area_per_lipid_closest_neighbor_circle   pybilt/com_trajectory/COMTraj.py:1655-1766

@@ -139,7 +139,17 @@ class AtomGroup:
         return AtomGroup(self.universe, np.concatenate([self._ix, other._ix]))
 
     def select_atoms(self, sel):
+        if " and " in sel:
+            # "resname X and resid R and name A" (bilayer_analyzer.py:857-861): the intersection
+            out = self
+            for part in sel.split(" and "):
+                out = out.select_atoms(part.strip())
+            return out
         words = sel.split()
+        if words[0] == "resid":
+            rid = np.asarray(self.universe._resids)[self.universe._resindex[self._ix]]
+            keep = np.isin(rid, [int(w) for w in words[1:]])
+            return AtomGroup(self.universe, self._ix[keep])
         if words[0] == "all":
             return AtomGroup(self.universe, self._ix.copy())
         if words[0] == "name":

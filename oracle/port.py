@@ -187,7 +187,7 @@ def membrane_com(U: np.ndarray, masses: np.ndarray) -> np.ndarray:
     return mem
 
 
-def com_frames(X, box, masses, gather, seg, u_state=None, chunk=64):
+def com_frames(X, box, masses, gather, seg, u_state=None, chunk=64, keep_v=None):
     """COMFrame for every analysed frame: wrapped COM from raw x, unwrap, membrane COM,
     v=f32(f64(u)-mem), unwrapped COM from v (com_frame.py:152-186).
     Returns dict(com, com_unwrap, mem_com, u_last)."""
@@ -197,6 +197,7 @@ def com_frames(X, box, masses, gather, seg, u_state=None, chunk=64):
     comu = np.empty((F, nb, 3))
     mem = np.empty((F, 3))
     prev = u_state
+    vs = []
     for c0 in range(0, F, chunk):
         c1 = min(F, c0 + chunk)
         U = unwrap(X[c0:c1], box[c0:c1], prev)
@@ -206,7 +207,12 @@ def com_frames(X, box, masses, gather, seg, u_state=None, chunk=64):
         com[c0:c1] = lipid_coms(X[c0:c1], masses, gather, seg)
         comu[c0:c1] = lipid_coms(V, masses, gather, seg)
         mem[c0:c1] = m
-    return {"com": com, "com_unwrap": comu, "mem_com": mem, "u_last": prev}
+        if keep_v is not None:              # the timestep as COMFrame leaves it, for the listed atoms
+            vs.append(V[:, keep_v, :].copy())
+    out = {"com": com, "com_unwrap": comu, "mem_com": mem, "u_last": prev}
+    if keep_v is not None:
+        out["v"] = np.concatenate(vs, axis=0)
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -224,6 +230,49 @@ def leaflet_labels(com_unwrap: np.ndarray, norm: int = 2, update_interval: int =
         else:
             lab[f] = lab[f - 1]
     return lab
+
+
+def orientation_labels(v_sel, sel_mass, seg, norm=2, update_interval=1):
+    """BilayerAnalyzer._build_leaflets_orientation (bilayer_analyzer.py:849-876) on the rebuild frames:
+    v_sel [F, n_sel, 3] the COMFrame-modified coordinates of the selected atoms, seg[2 i .. 2 i + 2] the
+    tail / head atoms of lipid i."""
+    F, N = v_sel.shape[0], (len(seg) - 1) // 2
+    lab = np.empty((F, N), dtype=np.uint8)
+    nv = np.zeros(3)
+    nv[norm] = 1.0
+    for f in range(F):
+        if f != 0 and (f % update_interval) != 0:
+            lab[f] = lab[f - 1]
+            continue
+        for i in range(N):
+            com = []
+            for a0, a1 in ((seg[2 * i], seg[2 * i + 1]), (seg[2 * i + 1], seg[2 * i + 2])):
+                c = v_sel[f, a0:a1].astype(np.float64)
+                w = sel_mass[a0:a1]
+                com.append((c * w[:, None]).sum(axis=0) / w.sum())
+            vec = com[1] - com[0]
+            cost = np.dot(vec, nv) / np.sqrt(np.dot(vec, vec))
+            if cost > 0.0:
+                lab[f, i] = 1
+            elif cost < 0.0:
+                lab[f, i] = 0
+            else:
+                raise KeyError("")
+    return lab
+
+
+def orientation_selection(top, types, resids, orientation_atoms):
+    names = np.asarray(top.names, dtype=object)
+    resindex = np.asarray(top.resindex)
+    sel, seg = [], [0]
+    for resname, resid in zip(types, resids):
+        res = [r for r in range(len(top.resnames)) if top.resnames[r] == resname and int(top.resids[r]) == int(resid)]
+        for which in (0, 1):
+            for r in res:
+                sel += [int(a) for a in np.nonzero((resindex == r) & (names == orientation_atoms[resname][which]))[0]]
+            seg.append(len(sel))
+    sel = np.asarray(sel, dtype=np.int64)
+    return sel, np.asarray(top.masses, dtype=np.float64)[sel], seg
 
 
 class LeafletView:
@@ -1044,11 +1093,15 @@ def run(top, traj, analyses=(), rep_settings=None, settings=None, frame_range=(0
     box = dims[:, :3]
     times = np.asarray(traj.times)[fr]
     gather, seg, types, resids = build_beads(top, cf.get("name_dict"), cf.get("multi_bead", False))
-    reps = com_frames(X, box, top.masses, gather, seg)
+    orient = lf.get("assign_method", "avg_norm") == "orientation"
+    if orient:
+        o_sel, o_mass, o_seg = orientation_selection(top, types, resids, lf["orientation_atoms"])
+    reps = com_frames(X, box, top.masses, gather, seg, keep_v=o_sel if orient else None)
     if cf.get("rewrap"):
         reps["com"] = rewrap(reps["com"], reps["com_unwrap"], reps["mem_com"], box)
     com, comu = reps["com"], reps["com_unwrap"]
-    labels = leaflet_labels(comu, norm, lf.get("update_interval", 1))
+    labels = (orientation_labels(reps["v"], o_mass, o_seg, norm, lf.get("update_interval", 1)) if orient
+              else leaflet_labels(comu, norm, lf.get("update_interval", 1)))
     out = {}
     views0 = leaflet_views(labels[0], types)
     grids = None

@@ -56,6 +56,8 @@ _SIGNATURES = {
                              c_void_p, c_void_p, c_void_p]),
     "pbk_leaflet_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "pbk_label_changes": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "pbk_orient_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_rewrap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "pbk_ct_nearest": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int, c_int, c_int,
                                c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

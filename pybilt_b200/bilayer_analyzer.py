@@ -701,6 +701,30 @@ class BilayerAnalyzer(object):
         self._unwrap_state = eng.d_u_state.clone()
         self._feeder_cache = None
 
+    @staticmethod
+    def _orientation_selection(md, layout, orientation_atoms):
+        """Atoms behind ``"resname R and resid I and name A"`` (bilayer_analyzer.py:857-861) for the tail
+        (``orientation_atoms[R][0]``) and head (``[1]``) of every lipid, as indices into the selected atoms."""
+        names = np.asarray(md.names, dtype=object)
+        res_of_atom = np.asarray(md.resindex)
+        resnames = np.asarray(md.resnames, dtype=object)
+        resids = np.asarray(md.resids)
+        by_res = {}
+        for r in range(len(resnames)):
+            by_res.setdefault((resnames[r], int(resids[r])), []).append(r)
+        order = np.argsort(res_of_atom, kind="stable")
+        starts = np.searchsorted(res_of_atom[order], np.arange(len(resnames) + 1))
+        sel_atom, seg = [], [0]
+        for i, (resname, resid) in enumerate(zip(layout.types, layout.resids)):
+            pair = orientation_atoms[resname]                 # KeyError for a lipid type without an entry, as there
+            for which in (0, 1):
+                for r in by_res.get((resname, int(resid)), []):
+                    atoms = order[starts[r]:starts[r + 1]]
+                    sel_atom += [int(a) for a in np.sort(atoms[names[atoms] == pair[which]])]
+                seg.append(len(sel_atom))
+        sel_atom = np.asarray(sel_atom, dtype=np.int32)
+        return sel_atom, np.asarray(md.masses, dtype=np.float64)[sel_atom], np.asarray(seg, dtype=np.int32)
+
     def _invalidate(self):
         if getattr(self, '_engine', None) is not None:
             self._engine_cache = (self._engine_key, self._engine)
@@ -728,9 +752,9 @@ class BilayerAnalyzer(object):
 
     def _reduce_with(self, allow_fused):
         lset = self.rep_settings['leaflets']
-        if lset['assign_method'] != 'avg_norm':
+        if lset['assign_method'] not in ('avg_norm', 'orientation'):
             raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
-                               "(only 'avg_norm')" % lset['assign_method'])
+                               "('avg_norm', 'orientation')" % lset['assign_method'])
         if self.rep_settings['com_frame']['make_whole']:
             raise RuntimeError("com_frame:make_whole is outside the accelerated path")
         md = self._mda_data
@@ -785,6 +809,11 @@ class BilayerAnalyzer(object):
                                        batch_frames=batch_frames, allow_fused=allow_fused, rewrap=bool(cset['rewrap']))
         self._engine_key = key
         self._engine_cache = None
+        eng._orient = None
+        if lset['assign_method'] == 'orientation':
+            if shard is not None:
+                raise RuntimeError("leaflets:assign_method 'orientation' is not combined with frame shards")
+            eng.set_orientation(*self._orientation_selection(md, layout, lset['orientation_atoms']))
         if self._unwrap_state is not None:
             if shard is not None:
                 raise RuntimeError("unwrap_coordinates_up_to is not combined with frame shards")
@@ -896,8 +925,8 @@ class BilayerAnalyzer(object):
     def _check_rep_settings(self):
         lset = self.rep_settings['leaflets']
         if lset['assign_method'] != 'avg_norm':
-            raise RuntimeError("leaflets:assign_method '%s' is outside the accelerated path "
-                               "(only 'avg_norm')" % lset['assign_method'])
+            raise RuntimeError("leaflets:assign_method '%s' needs a resident run on one device "
+                               "(streamed windows build their leaflets with 'avg_norm')" % lset['assign_method'])
         if self.rep_settings['com_frame']['make_whole']:
             raise RuntimeError("com_frame:make_whole is outside the accelerated path")
 

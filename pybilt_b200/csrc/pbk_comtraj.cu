@@ -184,3 +184,87 @@ extern "C" int pbk_ct_adjacency(pbk_ctx *ctx, const double *com, const float *bo
     PBK_CHECK_LAUNCH(ctx, "k_ct_adjacency");
     return PBK_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// leaflets:assign_method = 'orientation'   (BilayerAnalyzer._build_leaflets_orientation,
+// pybilt/bilayer_analyzer/bilayer_analyzer.py:849-876)
+// The reference takes the head and tail atoms of every lipid out of the CURRENT timestep, which COMFrame
+// has overwritten with v = f32(f64(u) - mem_com) (com_frame.py:172-181), forms their centres of mass
+// (rows added in atom order, divided by the mass sum) and labels the lipid by the sign of
+// (head - tail)[norm] (the cosine's denominator is positive; a zero or NaN vector component leaves the
+// label empty -> KeyError('')).  Only the normal component of the selected atoms is needed, so one
+// thread per lipid walks the frames in order with the exact unwrap rule (mda_unwrap_vectorized.py:12-93)
+// for its few atoms; labels are written on the frames where the leaflets are rebuilt.
+// ------------------------------------------------------------------------------------------
+static __device__ int ct_shift(float d, float L, int *bad)
+{
+    const float h = L * 0.5f;
+    int s = 0;
+    if (!(L > 0.0f)) { *bad = 1; return 0; }
+    const double dd = (double)d, Ld = (double)L, hd = (double)h;
+    if (d > h) {
+        do { s -= 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) > hd && s > -32768);
+    } else if (d < -h) {
+        do { s += 1; } while (__dadd_rn(dd, __dmul_rn((double)s, Ld)) < -hd && s < 32768);
+    }
+    if (s <= -32768 || s >= 32768) { *bad = 1; s = 0; }
+    return s;
+}
+
+__global__ void k_orient_labels(const float *__restrict__ x, const float *__restrict__ box, const double *__restrict__ mem_com,
+                                const int32_t *__restrict__ sel_atom, const double *__restrict__ sel_mass,
+                                const int32_t *__restrict__ seg, float *__restrict__ u_state, int first_frame,
+                                int64_t F, int64_t M, int64_t N, int norm, int64_t frame0, int interval,
+                                uint8_t *__restrict__ labels, int32_t *__restrict__ status)
+{
+    // seg[2 i] .. seg[2 i + 1]: tail atoms of lipid i in sel_*, seg[2 i + 1] .. seg[2 i + 2]: head atoms
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int a0 = seg[2 * i], a1 = seg[2 * i + 1], a2 = seg[2 * i + 2];
+    int bad = 0, tie = 0;
+    for (int64_t t = 0; t < F; t++) {
+        const float L = box[t * 3 + norm];
+        const double mem = mem_com[t * 3 + norm];
+        const bool rebuild = ((frame0 + t) % interval) == 0;
+        double st = 0.0, mt = 0.0, sh = 0.0, mh = 0.0;
+        for (int a = a0; a < a2; a++) {
+            const float xv = x[(t * M + sel_atom[a]) * 3 + norm];
+            float u = xv;
+            if (!(first_frame && t == 0)) {
+                const int s = ct_shift(__fsub_rn(xv, u_state[a]), L, &bad);
+                u = pbk_unwrapped(xv, s, L);
+            }
+            u_state[a] = u;
+            if (rebuild) {
+                const double v = (double)__double2float_rn(__dsub_rn((double)u, mem));
+                const double m = sel_mass[a];
+                if (a < a1) { st = (a == a0) ? __dmul_rn(v, m) : __dadd_rn(st, __dmul_rn(v, m)); mt = (a == a0) ? m : __dadd_rn(mt, m); }
+                else { sh = (a == a1) ? __dmul_rn(v, m) : __dadd_rn(sh, __dmul_rn(v, m)); mh = (a == a1) ? m : __dadd_rn(mh, m); }
+            }
+        }
+        if (rebuild) {
+            const double vec = __dsub_rn(__ddiv_rn(sh, mh), __ddiv_rn(st, mt));
+            if (vec > 0.0) labels[t * N + i] = 1;
+            else if (vec < 0.0) labels[t * N + i] = 0;
+            else { labels[t * N + i] = 0; tie = 1; }
+        }
+    }
+    if (bad) atomicOr(status, PBK_ST_IMAGE_OVERFLOW);
+    if (tie) atomicOr(status, PBK_ST_LEAFLET_TIE);
+}
+
+extern "C" int pbk_orient_labels(pbk_ctx *ctx, const float *x, const float *box, const double *mem_com,
+                                 const int32_t *sel_atom, const double *sel_mass, const int32_t *seg, float *u_state,
+                                 int first_frame, int64_t F, int64_t M, int64_t N, int norm, int64_t frame0, int interval,
+                                 uint8_t *labels, int32_t *status, void *stream)
+{
+    if (!ctx || !x || !box || !mem_com || !sel_atom || !sel_mass || !seg || !u_state || !labels || !status || F < 0 ||
+        M <= 0 || N <= 0 || norm < 0 || norm > 2 || interval < 1 || frame0 < 0)
+        return pbk_fail(ctx, PBK_EINVAL, "pbk_orient_labels: bad argument");
+    if (F == 0) return PBK_OK;
+    k_orient_labels<<<(unsigned)((N + 63) / 64), 64, 0, (cudaStream_t)stream>>>(x, box, mem_com, sel_atom, sel_mass, seg, u_state,
+                                                                               first_frame, F, M, N, norm, frame0, interval,
+                                                                               labels, status);
+    PBK_CHECK_LAUNCH(ctx, "k_orient_labels");
+    return PBK_OK;
+}

@@ -162,6 +162,7 @@ class LipidReductionEngine:
         # streamed reduction (frames that do not fit in shared memory): tiles of lipids
         self.comtraj_rules = bool(comtraj_rules)
         self.rewrap = bool(rewrap)            # com_frame:rewrap (com_frame.py:233-270) after every reduction
+        self._orient = None                   # leaflets:assign_method 'orientation' (set_orientation)
         self.stream_plan = None if (self.comtraj_rules or not allow_stream) else stream_bead_limit(layout)
         # per-frame scratch: image counts (6 B/atom) + tree nodes (generic kernels), or tree nodes +
         # compact normal components + tile partials (streamed reduction)
@@ -326,9 +327,14 @@ class LipidReductionEngine:
             raise RuntimeError("init_images belongs to the first frame of the stream")
         st = self.stream_ptr()
         c = self.ctx
+        first_frame = not self.stream_started
+        if self._orient is not None and phase != 3:
+            raise RuntimeError("orientation leaflets are not combined with frame shards")
         try:
             n_before = self.n_done
             self._push_batches(x, box, phase, init_images, net_out, net_frames, f_total, st, c)
+            if self._orient is not None and self.n_done > n_before:
+                self._orientation_labels(x, box, n_before, first_frame, st)
         finally:
             if self.rewrap and self.n_done > n_before:
                 n = self.n_done - n_before
@@ -336,6 +342,34 @@ class LipidReductionEngine:
                        self.mem_com[n_before:].data_ptr(), self.box[n_before:].data_ptr(), n, self.N,
                        self.d_status.data_ptr(), st)
                 self.launches += 1
+
+    def set_orientation(self, sel_atom, sel_mass, seg):
+        """Label the leaflets by lipid orientation (bilayer_analyzer.py:849-876) instead of the normal
+        position: ``seg[2 i .. 2 i + 2]`` delimits lipid i's tail and head atoms in ``sel_atom`` (indices
+        into the pushed atoms) / ``sel_mass``."""
+        d = self.dev
+        self._orient = (torch.as_tensor(np.asarray(sel_atom, dtype=np.int32), device=d),
+                        torch.as_tensor(np.asarray(sel_mass, dtype=np.float64), device=d),
+                        torch.as_tensor(np.asarray(seg, dtype=np.int32), device=d),
+                        torch.zeros(max(1, len(sel_atom)), dtype=torch.float32, device=d))
+
+    def _orientation_labels(self, x, box, n_before, first_frame, st):
+        sel_atom, sel_mass, seg, u_state = self._orient
+        n = self.n_done - n_before
+        self.ctx.call("pbk_orient_labels", x.data_ptr(), box.data_ptr(), self.mem_com[n_before:].data_ptr(),
+                      sel_atom.data_ptr(), sel_mass.data_ptr(), seg.data_ptr(), u_state.data_ptr(),
+                      1 if first_frame else 0, n, self.M, self.N, self.norm, n_before + self.row_offset,
+                      self.update_interval, self.labels[n_before:].data_ptr(), self.d_status.data_ptr(), st)
+        self.launches += 1
+        if self.update_interval > 1:
+            # frames between rebuilds carry the labels of the last rebuild frame (bilayer_analyzer.py:969-981)
+            rows = torch.arange(n_before, self.n_done, device=self.dev)
+            g = rows + self.row_offset
+            src = g - g % self.update_interval - self.row_offset
+            keep = src != rows
+            if bool((src[keep] < 0).any()):
+                raise RuntimeError("orientation leaflets: the last rebuild frame is not resident")
+            self.labels[rows[keep]] = self.labels[src[keep]]
 
     def _push_batches(self, x, box, phase, init_images, net_out, net_frames, f_total, st, c):
         for b0 in range(0, f_total, self.B):

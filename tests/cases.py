@@ -118,6 +118,16 @@ CASES = {
         analyses=["msd msd_1", "nnf nnf_pd resname_1 POPC resname_2 DOPE n_neighbors 4",
                   "com_lateral_rdf rdf resname_1 all resname_2 all n_bins 20 range_outer 20.0"],
         rep_settings={"com_frame": {"rewrap": True}}),
+    # leaflets from the lipids' orientation (head above or below the tail; bilayer_analyzer.py:849-876),
+    # rebuilt every other frame, fast motion along the normal so that image counts matter there too
+    "orientation": dict(
+        spec=syn.BilayerSpec(60, MIX3, seed=37, box_z=50.0, z_step=1.5, npt=1e-3, drift=(0.02, -0.015, 0.9)), n_frames=14,
+        analyses=["msd msd_1", "msd msd_up leaflet upper",
+                  "nnf nnf_pd resname_1 POPC resname_2 DOPE n_neighbors 4",
+                  "com_lateral_rdf rdf resname_1 all resname_2 all n_bins 20 range_outer 20.0"],
+        rep_settings={"leaflets": {"assign_method": "orientation", "update_interval": 2,
+                                   "orientation_atoms": {"POPC": ["H2", "N"], "DOPE": ["H1", "N"],
+                                                         "TLCL2": ["H3", "P1"]}}}),
     # CG 3-component mixture, per-leaflet RDF/NNF as the prefab drivers request them
     "c3_small": dict(
         spec=syn.BilayerSpec(512, CG3, seed=9), n_frames=4,

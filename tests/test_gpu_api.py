@@ -214,6 +214,10 @@ def test_windowed_run_matches_resident_run(name, window):
     want = cases.flatten_outputs({a_id: ba.get_analysis_data(a_id) for a_id in ba.get_analysis_ids()})
     bw, c = make_analyzer(name)
     bw.window_frames = window
+    if name == "orientation":
+        with pytest.raises(RuntimeError, match="resident"):     # orientation leaflets: resident runs only
+            bw.run_analysis()
+        return
     if name == "n3_rest":
         # disp_vec / msd_dist / dc_cluster look at pairs of frames far apart and at per-frame host
         # views: they say so instead of running on a window

@@ -40,6 +40,9 @@ def run_engine(name, batch_frames=None, fused=True, stream=True):
                                  leaflet_update_interval=lf.get("update_interval", 1),
                                  batch_frames=batch_frames, allow_fused=fused, allow_stream=stream,
                                  rewrap=cf.get("rewrap", False))
+    if lf.get("assign_method") == "orientation":
+        from pybilt_b200 import BilayerAnalyzer
+        e.set_orientation(*BilayerAnalyzer._orientation_selection(top, layout, lf["orientation_atoms"]))
     x = torch.from_numpy(np.ascontiguousarray(traj.positions[fr])).cuda()
     box = torch.from_numpy(np.ascontiguousarray(traj.dimensions[fr][:, :3])).cuda()
     e.push(x, box)
