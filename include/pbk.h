@@ -204,6 +204,12 @@ int pbk_label_changes(pbk_ctx *ctx, const uint8_t *labels, const uint8_t *prev_r
 int pbk_rewrap(pbk_ctx *ctx, double *com, const double *com_unwrap, const double *mem_com, const float *box,
                int64_t F, int64_t N, int32_t *status, void *stream);
 
+/* ---- self-check: division by a reused mass ---------------------------------------------------------
+ * The per-lipid COM division (com_frame.py:91-96, MDAnalysis center_of_mass) is done as pbk_div_r: a
+ * reciprocal formed once per lipid and two FMA corrections.  mismatches[0] (device, caller zeroes it) +=
+ * number of n pseudo-random operand pairs for which that differs from the correctly rounded quotient. */
+int pbk_debug_div_check(pbk_ctx *ctx, uint64_t seed, int64_t n, uint64_t *mismatches, void *stream);
+
 /* ---- N3  leaflets from the lipids' orientation -----------------------------------------------------
  * BilayerAnalyzer._build_leaflets_orientation   pybilt/bilayer_analyzer/bilayer_analyzer.py:849-876
  * labels[f, i] = 1 / 0 by the sign of (COM of the head atoms - COM of the tail atoms)[norm], both taken

@@ -56,6 +56,7 @@ _SIGNATURES = {
                              c_void_p, c_void_p, c_void_p]),
     "pbk_leaflet_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "pbk_label_changes": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "pbk_debug_div_check": (c_int, [c_void_p, ctypes.c_uint64, c_int64, c_void_p, c_void_p]),
     "pbk_orient_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pbk_rewrap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

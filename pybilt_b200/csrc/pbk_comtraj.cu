@@ -268,3 +268,35 @@ extern "C" int pbk_orient_labels(pbk_ctx *ctx, const float *x, const float *box,
     PBK_CHECK_LAUNCH(ctx, "k_orient_labels");
     return PBK_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// self-check of pbk_div_r (pbk_common.cuh) against the hardware's correctly rounded division on
+// pseudo-random operands: mismatches[0] = number of (a, b) with pbk_div_r(a, b, 1/b) != a / b.
+// b cycles through typical bead masses and random values in [2^-4, 2^16), a through +-[2^-10, 2^30).
+// ------------------------------------------------------------------------------------------
+__global__ void k_div_check(unsigned long long seed, int64_t n, unsigned long long *mismatches)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    next(); next();
+    const double masses[8] = {72.0, 864.0, 576.0, 760.076, 1.008, 30.974, 786.113, 12.011};
+    unsigned long long r = next();
+    double b = masses[r & 7];
+    if (r & 8) b = ldexp((double)(next() >> 11) * 0x1p-53 + 0.5, (int)(next() % 20) - 4);
+    r = next();
+    double a = ldexp((double)(r >> 11) * 0x1p-53 + 0.5, (int)(next() % 40) - 10);
+    if (r & 1) a = -a;
+    const double rb = __ddiv_rn(1.0, b);
+    if (pbk_div_r(a, b, rb) != __ddiv_rn(a, b)) atomicAdd(mismatches, 1ull);
+}
+
+extern "C" int pbk_debug_div_check(pbk_ctx *ctx, uint64_t seed, int64_t n, uint64_t *mismatches, void *stream)
+{
+    if (!ctx || !mismatches || n < 0) return pbk_fail(ctx, PBK_EINVAL, "pbk_debug_div_check: bad argument");
+    if (n == 0) return PBK_OK;
+    k_div_check<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, n, reinterpret_cast<unsigned long long *>(mismatches));
+    PBK_CHECK_LAUNCH(ctx, "k_div_check");
+    return PBK_OK;
+}

@@ -267,3 +267,15 @@ def test_rdf_out_of_box_coordinates_follow_reference_formula():
         edges = np.histogram([-1], bins=nb, range=[lo, hi])[1]
         count, fc = e.rdf(d_codes, ca, cb, mask, edges)
         assert np.array_equal(count.cpu().numpy(), want)
+
+
+def test_division_by_reused_mass_is_correctly_rounded():
+    """pbk_div_r (reciprocal once per lipid + two FMA corrections) against the device's own correctly
+    rounded division on 2^27 pseudo-random operand pairs: not one differs."""
+    from pybilt_b200 import _native
+    ctx = _native.Context(0)
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 2):
+        ctx.call("pbk_debug_div_check", seed, 1 << 26, bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
