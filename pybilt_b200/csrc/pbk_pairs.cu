@@ -273,24 +273,29 @@ k_nnf_frame_mean(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ la
 // Parallel form of the frame mean (default; PBK_SEQ_WELFORD=1 selects the sequential replays): the
 // running mean of RunningStats.push equals sum / n in exact arithmetic, and the values are the
 // k + 1 quotients c / k, so a lane-strided float64 sum with a fixed combination tree differs from
-// the sequential recurrence by rounding noise only (~1e-15 relative).  One warp per (analysis, frame).
-__global__ void __launch_bounds__(128)
+// the sequential recurrence by rounding noise only (~1e-15 relative).  One CTA per (analysis, frame).
+__global__ void __launch_bounds__(256)
 k_nnf_frame_mean_par(const int32_t *__restrict__ n_b, const uint8_t *__restrict__ labels, int64_t AF, int64_t F,
                      int64_t N, int k, double *__restrict__ frac)
 {
-    const int64_t af = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (af >= AF) return;
+    // one CTA per (analysis, frame); the k + 1 possible quotients c / k come from a table (one division each,
+    // not one per lipid); fixed combination tree (pbk_block_sum)
+    __shared__ double s_q[65];
+    __shared__ double red[32];
+    const int64_t af = blockIdx.x;
+    const int tid = threadIdx.x;
+    const double kd = (double)k;
+    if (tid <= 64) s_q[tid] = __ddiv_rn((double)tid, kd);
+    __syncthreads();
     const int32_t *c = n_b + af * N;
     double s = 0.0, n = 0.0;
-    const double kd = (double)k;
-    for (int64_t i = lane; i < N; i += 32) {
+    for (int64_t i = tid; i < N; i += 256) {
         const int ci = c[i];
-        if (ci >= 0) { s += __ddiv_rn((double)ci, kd); n += 1.0; }
+        if (ci >= 0) { s += ci <= 64 ? s_q[ci] : __ddiv_rn((double)ci, kd); n += 1.0; }
     }
-    s = pbk_warp_sum(s);
-    n = pbk_warp_sum(n);
-    if (lane == 0) frac[af] = n > 0.0 ? s / n : 0.0;
+    s = pbk_block_sum(s, red);
+    n = pbk_block_sum(n, red);
+    if (tid == 0) frac[af] = n > 0.0 ? s / n : 0.0;
 }
 
 static bool pbk_seq_welford() { return getenv("PBK_SEQ_WELFORD") != nullptr; }
@@ -423,7 +428,7 @@ extern "C" int pbk_nnf_select_many(pbk_ctx *ctx, const int32_t *type_hits, const
     PBK_CHECK_LAUNCH(ctx, "k_nnf_select_many");
     const int64_t n_af = (int64_t)n_specs * F;
     if (!pbk_seq_welford()) {
-        k_nnf_frame_mean_par<<<(unsigned)((n_af + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, n_af, F, N, k, frac);
+        k_nnf_frame_mean_par<<<(unsigned)n_af, 256, 0, (cudaStream_t)stream>>>(n_b, labels, n_af, F, N, k, frac);
         PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean_par");
         return PBK_OK;
     }
@@ -447,7 +452,7 @@ extern "C" int pbk_nnf_select(pbk_ctx *ctx, const int32_t *type_hits, const int3
                                                       type_a, type_b, leaflet_mask, n_b);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_select");
     if (pbk_seq_welford()) k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
-    else k_nnf_frame_mean_par<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
+    else k_nnf_frame_mean_par<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;
 }
@@ -476,7 +481,7 @@ extern "C" int pbk_nnf(pbk_ctx *ctx, const double *com, const uint8_t *labels,
                                    leaflet_mask, k, n_b, nullptr, 0, (cudaStream_t)stream);
     if (rc) return rc;
     if (pbk_seq_welford()) k_nnf_frame_mean<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, N, k, frac);
-    else k_nnf_frame_mean_par<<<(unsigned)((F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
+    else k_nnf_frame_mean_par<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(n_b, labels, F, F, N, k, frac);
     PBK_CHECK_LAUNCH(ctx, "k_nnf_frame_mean");
     return PBK_OK;
 }
