@@ -88,18 +88,11 @@ struct __align__(16) ImgCol {
 
 #define IMG_THREADS 128
 #define IMG_UNR 8
-#define IMG_MAXF 512                // frames of box rows staged in shared memory per chunk
 
 // one frame of one column: same-image test of the 4 chains at once; the exact rule only when
 // one of them fails (rare)
-// a count move of chain c at local frame tl: appended to the chunk's list (k_frames4 reads it)
-static __device__ __noinline__ void img3_event(uint2 *ev, int *ev_n, int c, int tl, int ds)
-{
-    if (!ev || ds == 0) return;
-    const int slot = atomicAdd(ev_n, 1);
-    if (slot < F4_EVCAP) ev[slot] = make_uint2((uint32_t)c, ((uint32_t)tl << 8) | ((uint32_t)ds & 0xffu));
-}
-
+// (a count move of chain c at local frame tl is appended to the chunk's event list inside img3_step: k_frames4
+//  reads it)
 static __device__ __forceinline__ void img3_step(const float4 v, float pv[4], const float he[4], const float Le[4],
                                                  int acc[4], int &am, float &smin, int &bad, uint2 *ev, int *ev_n,
                                                  int c0, int tl)
@@ -1530,6 +1523,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
         }
         k_chunk_box<<<n_chunks, 128, 0, st>>>(box, F, split, chunk, chunk_box, chunk_const);
         PBK_CHECK_LAUNCH(ctx, "k_chunk_box");
+        // chunks walked per thread: 1 measured best (2 saves the re-read of a chunk's previous frame but costs registers)
         const int span = getenv("PBK_IMG_SPAN") ? atoi(getenv("PBK_IMG_SPAN")) : 1;
         k_img3<<<dim3((C3q + IMG_THREADS - 1) / IMG_THREADS, (n_chunks + span - 1) / span), IMG_THREADS, 0, st>>>(
             reinterpret_cast<const float4 *>(x), box, reinterpret_cast<const float4 *>(u_state), first_frame, F,
