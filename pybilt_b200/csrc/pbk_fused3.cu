@@ -87,7 +87,7 @@ struct __align__(16) ImgCol {
 };
 
 #define IMG_THREADS 128
-#define IMG_UNR 8
+#define IMG_UNR 4                   // frames of loads in flight per thread (8 spilled at 64 registers and was slower)
 
 // one frame of one column: same-image test of the 4 chains at once; the exact rule only when
 // one of them fails (rare)
