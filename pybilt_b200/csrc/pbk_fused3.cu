@@ -156,7 +156,7 @@ static __device__ __forceinline__ void f3_chunk_range(int kc, int chunk, int64_t
 // k_scan3) and whether the box is the same in every frame of the chunk (NVT runs)
 __global__ void __launch_bounds__(128)
 k_chunk_box(const float *__restrict__ box, int64_t F, int64_t split, int chunk, float *__restrict__ chunk_box,
-            int *__restrict__ chunk_const)
+            int *__restrict__ chunk_const, int *__restrict__ ev_count)
 {
     __shared__ int s_red[3];
     const int kc = blockIdx.x;
@@ -183,6 +183,7 @@ k_chunk_box(const float *__restrict__ box, int64_t F, int64_t split, int chunk, 
         chunk_box[kc * 2] = __int_as_float(s_red[0]);
         chunk_box[kc * 2 + 1] = __int_as_float(s_red[1]);
         chunk_const[kc] = s_red[2] == 0;
+        if (ev_count) ev_count[kc] = 0;              // the chunk's event list starts empty (k_img3 appends)
     }
 }
 
@@ -1517,11 +1518,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
             return pbk_fail(ctx, PBK_EINVAL, "pbk_reduce_fused: scratch too small (events)");
     }
     if (phase & 1) {
-        if (v4) {
-            cudaError_t e0 = cudaMemsetAsync(ev_count, 0, (size_t)n_chunks * 4, st);
-            if (e0 != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "event counters", e0);
-        }
-        k_chunk_box<<<n_chunks, 128, 0, st>>>(box, F, split, chunk, chunk_box, chunk_const);
+        k_chunk_box<<<n_chunks, 128, 0, st>>>(box, F, split, chunk, chunk_box, chunk_const, ev_count);
         PBK_CHECK_LAUNCH(ctx, "k_chunk_box");
         // chunks walked per thread: 1 measured best (2 saves the re-read of a chunk's previous frame but costs registers)
         const int span = getenv("PBK_IMG_SPAN") ? atoi(getenv("PBK_IMG_SPAN")) : 1;
@@ -1560,6 +1557,7 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
         k_evsort<<<n_chunks, 256, 0, st>>>(ev_raw, ev_count, chunk, ev_sorted, ev_off, status);
         PBK_CHECK_LAUNCH(ctx, "k_evsort");
         P.ev_sorted = ev_sorted; P.ev_off = ev_off; P.ev_cap = F4_EVCAP; P.first_shift = first_shift;
+        P.u_out = u_state;      // k_frames4 never reads the carried state (k_img3 did): the new one goes straight there
         kern = k_frames4<F3_NQ, false>;
         if (full && mleaf == 96) kern = k_frames4<12, true>;
         else if (full && mleaf == 128) kern = k_frames4<16, true>;
@@ -1576,9 +1574,11 @@ extern "C" int pbk_reduce_fused(pbk_ctx *ctx, const float *x, const float *box, 
         kern<<<n_chunks, F3_THREADS, smem, st>>>(P);
         PBK_CHECK_LAUNCH(ctx, "k_frames3");
     }
-    // u_state is read by chunk 0 and replaced by the last chunk: the new state is produced in
+    // k_frames3: u_state is read by chunk 0 and replaced by the last chunk, so the new state is produced in
     // scratch and copied over once the kernel is done
-    e = cudaMemcpyAsync(u_state, u_out, (size_t)C3 * 4, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "u_state copy", e);
+    if (!v4) {
+        e = cudaMemcpyAsync(u_state, u_out, (size_t)C3 * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return pbk_fail(ctx, PBK_ECUDA, "u_state copy", e);
+    }
     return PBK_OK;
 }
