@@ -240,3 +240,36 @@ def test_host_blas_ddot_fuses_like_the_fixtures_assume():
         plain += got == a * a + b * b
     assert fused == len(v), "np.dot(float64[2]) is not fma(b, b, a*a) on this host (%d/%d; a*a+b*b: %d)" % (
         fused, len(v), plain)
+
+
+def test_binned_average_and_block_averager_host_logic():
+    """Host pieces of the round-2 analyses against the oracle's restatement (no GPU): msd_dist's
+    binned_average (first closed bin that holds a position wins, empty bins dropped) and the prefab
+    drivers' BlockAverager."""
+    from oracle import port
+    from pybilt_b200.analysis_protocols import binned_average, _interval_pairs
+    from pybilt_b200.running_stats import BlockAverager, RunningStats
+    rng = np.random.default_rng(5)
+    data, pos = rng.normal(size=400), rng.uniform(-2.0, 27.0, size=400)
+    pos[:5] = [0.0, 25.0, 5.0, 10.0, 12.5]                    # bin edges: the lower bin takes them
+    got = binned_average(data, pos, n_bins=10, position_range=[0.0, 25.0])
+    want = port.binned_average(data, pos, 10, [0.0, 25.0])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    # interval bookkeeping: frames 3, 5, 7, ... with interval 4 pair up every other analysed frame
+    class B:                                                  # the two attributes _interval_pairs reads
+        n_frames = 8
+        frame_numbers = np.arange(3, 19, 2)
+    assert _interval_pairs(B, 3, 4) == port.interval_pairs(B.frame_numbers, 4) == [(0, 2), (2, 4), (4, 6)]
+    assert _interval_pairs(B, 3, 3) == []
+    # block averages: 10 values per block, the last short block (3 < min 5 points) is left out
+    vals = rng.normal(size=53)
+    ba = BlockAverager(points_per_block=10, min_points_in_block=5)
+    ba.push_container(vals)
+    means = np.array([vals[i:i + 10].mean() for i in range(0, 50, 10)])
+    avg, err = ba.get()
+    assert ba.number_of_blocks() == 6 and len(ba.averages_of_blocks()) == 5
+    assert abs(avg - means.mean()) < 1e-12 and abs(err - means.std() / np.sqrt(5)) < 1e-12
+    rs = RunningStats()
+    for v in vals[:10]:
+        rs.push(v)
+    assert abs(ba.averages_of_blocks()[0] - rs.mean()) == 0.0
