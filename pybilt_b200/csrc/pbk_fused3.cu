@@ -10,8 +10,9 @@
 //
 // Three kernels, as in pbk_fused.cu (which stays as the fallback for shapes this file does
 // not take: atom counts that are not a multiple of 4, more than 80 summation leaves):
-//   k_img3     streams the positions once (one thread per float4 column of a frame chunk, 8
-//              frames of loads in flight) and sums the image-count increments per chunk;
+//   k_img3     streams the positions once (one thread per float4 column of a frame chunk, 4
+//              frames of loads in flight), sums the image-count increments per chunk and lists
+//              the moves of the counts for k_frames4;
 //   k_scan3    exclusive prefix over the chunks -> int8 image counts at every chunk start,
 //              plus the slack check that makes the chunk-local increments exact;
 //   k_frames3  one 512-thread CTA per chunk.  Per frame:
